@@ -1,0 +1,184 @@
+/*
+ * ptb200.h -- C ABI of libptb200.so: the B200-native (sm_100a) batched RoadRunner / TSModel transit
+ * model evaluation and fused white-noise population log-likelihood.
+ *
+ * This is the drop-in boundary for the hot path of hpparvi/PyTransit (v2.8.1).  Every entry point
+ * cites the reference interface it replaces (paths relative to the PyTransit tree).  The reference
+ * is pure Python + Numba, so "the FFI for this path" is what a ctypes/cffi binding inside
+ * pytransit/models/roadrunner/ would call; INTEGRATION.md shows that binding.
+ *
+ * Conventions
+ *  - Plain C types only: pointers and sizes.  No torch / numpy types cross this boundary.
+ *  - Every data pointer may be a HOST pointer or a DEVICE pointer on the model's device; the
+ *    library detects which (cudaPointerGetAttributes).  Device pointers are used in place
+ *    (zero copy); host pointers are staged through buffers owned by the handle.
+ *  - All floating-point arrays are C-contiguous float64, all index arrays int64 (what the
+ *    reference's TransitModel.set_data produces, models/transitmodel.py:88-125).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls whose
+ *    outputs are device pointers are asynchronous on that stream; calls with host outputs return
+ *    after the device-to-host copy has completed.
+ *  - Return value: 0 on success, a negative ptb_status otherwise; ptb_last_error() gives the text.
+ *    Numerical invalidity (a<=1, e<0, NaN) is DATA, not an error: the affected rows are NaN, as in
+ *    the reference (models/roadrunner/model_full.py:40-42,80-82).
+ *  - A handle is not thread safe (neither is the reference object); use one handle per host thread.
+ *  - There is no CPU fallback: every entry point that computes fails with PTB_ECUDA when no
+ *    CUDA device is usable.
+ */
+#ifndef PTB200_H
+#define PTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB_VERSION 100 /* 0.1.0 */
+
+typedef struct ptb_model ptb_model; /* opaque */
+
+enum ptb_status {
+    PTB_OK = 0,
+    PTB_EINVAL = -1, /* bad argument value        -> Python ValueError            */
+    PTB_ESHAPE = -2, /* inconsistent array shapes -> Python ValueError            */
+    PTB_ECUDA = -3,  /* CUDA runtime failure      -> Python RuntimeError          */
+    PTB_ENOMEM = -4, /* allocation failure        -> Python MemoryError           */
+    PTB_ESTATE = -5, /* call order (no set_data)  -> Python RuntimeError          */
+    PTB_ENOTIMPL = -6 /* unknown limb darkening law -> Python NotImplementedError  */
+};
+
+/* Limb-darkening laws of RoadRunnerModel.ldmodels (models/roadrunner/rrmodel.py:48-58), evaluated
+ * on the device from coefficient arrays (models/numba/ldmodels.py:22-175).  PTB_LD_PROFILES means
+ * the caller supplies the tabulated profile ldp[npv,npb,nz] at ptb_get_tables().mu together with
+ * istar[npv,npb] -- the LDModel protocol (models/ldmodel.py:21-39) and custom callables. */
+enum ptb_ldlaw {
+    PTB_LD_UNIFORM = 0, PTB_LD_LINEAR = 1, PTB_LD_QUADRATIC = 2, PTB_LD_QUADRATIC_TRI = 3,
+    PTB_LD_NONLINEAR = 4, PTB_LD_GENERAL = 5, PTB_LD_SQUARE_ROOT = 6, PTB_LD_LOGARITHMIC = 7,
+    PTB_LD_EXPONENTIAL = 8, PTB_LD_POWER_2 = 9, PTB_LD_POWER_2_PM = 10,
+    PTB_LD_PROFILES = 100
+};
+
+/* Debug / parity taps for ptb_get_stage(): the per-vector intermediates of
+ * models/roadrunner/model_full.py:34-70. */
+enum ptb_stage {
+    PTB_STAGE_LDP = 0,   /* [npv,npb,nz]   limb-darkening profile at the mu nodes              */
+    PTB_STAGE_ISTAR = 1, /* [npv,npb]      disk-integrated intensity                           */
+    PTB_STAGE_LDM = 2,   /* [npv,npb,ng]   limb-darkening means                                */
+    PTB_STAGE_XYC = 3,   /* [npv,2,5]      Taylor-series orbit coefficients (solve2d)           */
+    PTB_STAGE_BBOX = 4,  /* [npv,2]        un-padded contact times T1,T4 (bounding_box)         */
+    PTB_STAGE_GOOD = 5   /* [npv]          1.0 valid / 0.0 invalid parameter vector            */
+};
+
+/* Constructor arguments: RoadRunnerModel.__init__ (models/roadrunner/rrmodel.py:60-63). */
+typedef struct ptb_config {
+    int32_t device;             /* CUDA device ordinal                                          */
+    int32_t ldlaw;              /* enum ptb_ldlaw                                                */
+    int32_t nk, nzin, nzlimb, ng; /* defaults 256, 20, 20, 100                                  */
+    double kmin, kmax, zcut;    /* klims = (0.005, 0.5), zcut = 0.7                              */
+    int32_t precompute_weights; /* TSModel only (models/roadrunner/tsmodel.py:117-120)           */
+    int32_t precision;          /* 0 = fp64 (default); 1 = opt-in fp32 sample arithmetic         */
+} ptb_config;
+
+/* Fill *cfg with the reference defaults (rrmodel.py:60-63). */
+void ptb_default_config(ptb_config *cfg);
+
+int ptb_version(void);
+
+/* Text of the last error on this handle (or of the last failed ptb_create when h is NULL). */
+const char *ptb_last_error(const ptb_model *h);
+
+/* RoadRunnerModel.__init__ + init_integration (rrmodel.py:60-173): builds the z grid
+ * (common.py:131-149) on the host and the weight table W[nk,ng,nz] (common.py:188-223) on the
+ * device. */
+int ptb_create(const ptb_config *cfg, ptb_model **out);
+void ptb_destroy(ptb_model *h);
+
+/* The attributes RoadRunnerModel exposes after init_integration (rrmodel.py:165-173):
+ * ze[nz], zm[nz], mu[nz], weights[nk,ng,nz], dk, dg.  Any output pointer may be NULL. */
+int ptb_get_tables(ptb_model *h, double *ze, double *zm, double *mu, double *weights, double *dk,
+                   double *dg);
+
+/* TransitModel.set_data / RoadRunnerModel.set_data (models/transitmodel.py:56-125,
+ * rrmodel.py:156-163).  lcids[npt] in [0,nlc); pbids[nlc] in [0,npb); epids[nlc] in [0,nep);
+ * nsamples[nlc] >= 1; exptimes[nlc].  lcids may be NULL (all zeros, nlc must be 1). */
+int ptb_set_data(ptb_model *h, const double *time, int64_t npt, const int64_t *lcids, int64_t nlc,
+                 const int64_t *pbids, int64_t npb, const int64_t *epids, int64_t nep,
+                 const int64_t *nsamples, const double *exptimes);
+
+/* RoadRunnerModel.evaluate -> rr_full / rr_simple (rrmodel.py:175-238, model_full.py:9-100,
+ * model_simple.py:11-80) on fully expanded arrays:
+ *   k[npv,kcols] (kcols 1 or npb); ld = ldc[npv,npb,nld] for a named law, or ldp[npv,npb,nz] with
+ *   istar[npv,npb] for PTB_LD_PROFILES (istar NULL otherwise); t0[npv,nep]; p,a,inc,e,w[npv].
+ * flux[npv,npt] may be a device pointer (written in place), a host pointer, or NULL (the flux
+ * stays in the handle's device buffer: ptb_flux_device_ptr). */
+int ptb_rr_evaluate(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld,
+                    int64_t nld, const double *istar, const double *t0, const double *p,
+                    const double *a, const double *inc, const double *e, const double *w,
+                    double *flux, void *stream);
+
+/* Observed fluxes and noise blocks for the fused likelihood: the (o, slices, nids) arguments of
+ * lnlike_normal (lpf/loglikelihood/wnloglikelihood.py:22-35,43-55).  obs[npt]; slices[nsl,2]
+ * half-open point ranges; nids[nsl] in [0,nblocks).  Points outside every slice do not contribute.
+ * slices NULL = one slice covering all points with noise id 0. */
+int ptb_set_obs(ptb_model *h, const double *obs, const int64_t *slices, const int64_t *nids,
+                int64_t nsl, int64_t nblocks);
+
+/* BaseLPF.lnlikelihood with WNLogLikelihood (lpf/lpf.py:454-475, wnloglikelihood.py:79-81) fused
+ * with the model: lnl[npv] = sum_j -log(s) - 0.5 log(2 pi) - 0.5 ((obs_j - model_ij)/s)^2 with
+ * s = sigma[npv,nblocks] (already 10**pv).  No [npv,npt] flux is materialised.  Model arguments as
+ * ptb_rr_evaluate. */
+int ptb_rr_lnlike(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld,
+                  int64_t nld, const double *istar, const double *t0, const double *p,
+                  const double *a, const double *inc, const double *e, const double *w,
+                  const double *sigma, double *lnl, void *stream);
+
+/* lnlike_normal (wnloglikelihood.py:22-35) on an existing model flux m[npv,npt] (device or host),
+ * e.g. baseline-multiplied flux produced by the caller (lpf/lpf.py:445-449). */
+int ptb_lnlike_normal(ptb_model *h, int64_t npv, const double *model, const double *sigma,
+                      double *lnl, void *stream);
+
+/* TransmissionSpectroscopyModel.evaluate -> tsmodel_serial (models/roadrunner/tsmodel.py:46-130,
+ * model_trspec.py:11-93): k[npv,npb]; ld as above with npb = the spectroscopic channel count;
+ * t0,p,a,inc,e,w[npv]; flux[npv,npb,npt].  Uses nsamples[0], exptimes[0] of set_data. */
+int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, const double *ld,
+                    int64_t nld, const double *istar, const double *t0, const double *p,
+                    const double *a, const double *inc, const double *e, const double *w,
+                    double *flux, void *stream);
+
+/* LDTkLDModel.__call__ (models/ldtkldm.py:74-89) -> trilinear_interpolation_set +
+ * integrate_profiles_set (models/numba/ldtkldm.py:53-60,77-91): profiles[nx,ny,nz3,npb,nmu],
+ * stellar parameters xs,ys,zs[npv] -> ldp[npv,npb,nmu], istar[npv,npb] (device or host). */
+int ptb_ldtk_profiles(ptb_model *h, const double *profiles, int64_t nx, int64_t ny, int64_t nz3,
+                      int64_t npb, int64_t nmu, const double *xs, const double *ys,
+                      const double *zs, int64_t npv, double x0, double dx, double y0, double dy,
+                      double z0, double dz, const double *mu, double *ldp, double *istar,
+                      void *stream);
+
+/* Parity taps: copy a per-vector intermediate of the LAST evaluate/lnlike call to out (host or
+ * device).  See enum ptb_stage for shapes. */
+int ptb_get_stage(ptb_model *h, int32_t stage, double *out);
+
+/* Inject Taylor coefficients xyc[npv,2,5] to be used instead of the device solve2d for the
+ * following evaluations (NULL clears).  Lets everything downstream of the third-party
+ * meepmeep.solve2d be pinned independently. */
+int ptb_inject_xyc(ptb_model *h, const double *xyc, int64_t npv);
+
+/* Device pointer / element count of the handle-owned result of the last evaluate call whose
+ * output pointer was NULL (the RoadRunnerModelCL `_b_f` analogue, rrmodel_cl.py:365-369). */
+int ptb_flux_device_ptr(ptb_model *h, double **ptr, int64_t *count);
+
+/* Page-locked host memory for results (so device-to-host copies run at full PCIe rate). */
+int ptb_host_alloc(void **ptr, size_t bytes);
+int ptb_host_free(void *ptr);
+
+/* Kernels launched by this handle since creation (bench.py's gpu_launches evidence). */
+int64_t ptb_launch_count(const ptb_model *h);
+
+/* Block until all work queued by this handle on `stream` has finished. */
+int ptb_synchronize(ptb_model *h, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB200_H */

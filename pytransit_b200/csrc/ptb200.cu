@@ -1,0 +1,827 @@
+// ptb200.cu -- host side of libptb200.so: the C ABI declared in include/ptb200.h.
+//
+// Owns the handle (tables, dataset, per-vector workspaces, staging buffers), validates shapes the
+// way the reference's Python layer does, stages host inputs through one pinned block, and launches
+// the kernels in ptb_kernels.cuh / ptb_ts_kernels.cuh.  No CPU compute path exists here: without a
+// CUDA device every computing entry point fails with PTB_ECUDA.
+#include "../../include/ptb200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ptb_kernels.cuh"
+#include "ptb_ts_kernels.cuh"
+
+using namespace ptb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {  // grow-only device buffer
+    void *ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const { return static_cast<T *>(ptr); }
+};
+
+struct PinBuf {  // grow-only pinned host buffer
+    void *ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&ptr, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct ptb_model {
+    ptb_config cfg{};
+    int sm_count = 148;
+    int nz = 0;
+    double dk = 0, dg = 0;
+    std::vector<double> ze, zm, mu, ks, gs;
+    DevBuf d_tab;  // ze | mu | gs | ks | ldmu200 | ldz200
+    double *d_ze = nullptr, *d_mu = nullptr, *d_gs = nullptr, *d_ks = nullptr, *d_ldmu = nullptr, *d_ldz = nullptr;
+    DevBuf d_W;
+
+    // dataset (set_data)
+    bool has_data = false;
+    int64_t npt = 0, nlc = 0, npb = 0, nep = 0;
+    const double *d_time = nullptr;  // borrowed device pointer or d_time_own
+    DevBuf d_time_own, d_meta;       // meta: lcids32[npt] | pbids | epids | nsamples | exptimes
+    int32_t *d_lcids = nullptr, *d_pbids = nullptr, *d_epids = nullptr, *d_nsamples = nullptr;
+    double *d_exptimes = nullptr;
+    int ns_max = 1;
+    std::vector<int64_t> h_nsamples;
+    std::vector<double> h_exptimes;
+
+    // observations (set_obs)
+    bool has_obs = false;
+    int64_t nblocks = 0;
+    const double *d_obs = nullptr;
+    DevBuf d_obs_own, d_blk, d_nblk;
+    bool blk_trivial = true;
+
+    // per-vector workspaces
+    DevBuf d_orb, d_ldrec, d_ldp, d_istar, d_flux, d_partial, d_isig2, d_lnl, d_xyc;
+    DevBuf d_tsw, d_tsrec;
+    bool xyc_injected = false;
+    int64_t xyc_npv = 0;
+    int64_t last_npv = 0, last_npb = 0, last_flux_count = 0;
+
+    // staging of host inputs: one pinned block + one device block per call
+    PinBuf h_stage;
+    DevBuf d_stage;
+    cudaEvent_t stage_ev = nullptr;  // completion of the last copy out of h_stage
+    bool stage_pending = false;
+
+    std::string err;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(ptb_model *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return fail(h, _e == cudaErrorMemoryAllocation ? PTB_ENOMEM : PTB_ECUDA, "%s failed: %s", \
+                        #call, cudaGetErrorString(_e));                                               \
+    } while (0)
+
+bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// Stager: host arrays are packed into the pinned block and shipped with ONE async copy;
+// device arrays are used in place.
+struct Stager {
+    ptb_model *h;
+    cudaStream_t st;
+    struct Item { const void *src; size_t off, bytes; };
+    std::vector<Item> items;
+    size_t total = 0;
+    explicit Stager(ptb_model *h_, cudaStream_t s) : h(h_), st(s) {}
+    // returns a token: device pointers pass through, host ones are resolved after commit()
+    struct Ref { const void *dev; size_t off; bool staged; };
+    Ref add(const void *p, size_t bytes) {
+        if (!p) return {nullptr, 0, false};
+        if (is_device_ptr(p)) return {p, 0, false};
+        const size_t off = total;
+        items.push_back({p, off, bytes});
+        total += (bytes + 255) & ~size_t(255);
+        return {nullptr, off, true};
+    }
+    int commit() {
+        if (total == 0) return PTB_OK;
+        if (h->stage_pending) {  // the previous call's copy must have left the pinned block
+            CU(cudaEventSynchronize(h->stage_ev));
+            h->stage_pending = false;
+        }
+        CU(h->h_stage.reserve(total));
+        CU(h->d_stage.reserve(total));
+        for (auto &it : items) memcpy(static_cast<char *>(h->h_stage.ptr) + it.off, it.src, it.bytes);
+        CU(cudaMemcpyAsync(h->d_stage.ptr, h->h_stage.ptr, total, cudaMemcpyHostToDevice, st));
+        if (!h->stage_ev) CU(cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming));
+        CU(cudaEventRecord(h->stage_ev, st));
+        h->stage_pending = true;
+        return PTB_OK;
+    }
+    template <class T>
+    const T *get(const Ref &r) const {
+        if (!r.staged) return static_cast<const T *>(r.dev);
+        return reinterpret_cast<const T *>(static_cast<const char *>(h->d_stage.ptr) + r.off);
+    }
+};
+
+int set_device(ptb_model *h) {
+    CU(cudaSetDevice(h->cfg.device));
+    return PTB_OK;
+}
+
+// create_z_grid (common.py:131-149)
+void make_z_grid(double zcut, int nin, int nedge, std::vector<double> &ze, std::vector<double> &zm) {
+    const int n = nin + nedge;
+    ze.assign(n, 0.0);
+    zm.assign(n, 0.0);
+    const double mucut = std::sqrt(1.0 - zcut * zcut);
+    const double dz = zcut / nin, dmu = mucut / nedge;
+    for (int i = 0; i < nin - 1; ++i) ze[i] = (i + 1) * dz;
+    for (int i = 0; i <= nedge; ++i) {
+        const double v = i * dmu;
+        ze[n - 1 - i] = std::sqrt(1 - v * v);
+    }
+    for (int i = 0; i + 1 < n; ++i) zm[i + 1] = 0.5 * (ze[i] + ze[i + 1]);
+}
+
+// numpy/numba linspace: start + i*step, last element = stop
+std::vector<double> linspace(double a, double b, int n) {
+    std::vector<double> v(n);
+    if (n > 1) {
+        const double step = (b - a) / (n - 1);
+        for (int i = 0; i < n; ++i) v[i] = a + i * step;
+        v[n - 1] = b;
+    } else if (n == 1) v[0] = a;
+    return v;
+}
+
+int copy_out(ptb_model *h, double *dst, const double *dsrc, size_t count, cudaStream_t st) {
+    if (!dst || dst == dsrc) return PTB_OK;
+    if (is_device_ptr(dst)) {
+        CU(cudaMemcpyAsync(dst, dsrc, count * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    } else {
+        CU(cudaMemcpyAsync(dst, dsrc, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return PTB_OK;
+}
+
+struct ModelArgs {
+    int64_t npv, kcols, nld;
+    const double *k, *ld, *istar, *t0, *p, *a, *inc, *e, *w;
+};
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+void ptb_default_config(ptb_config *cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->device = 0;
+    cfg->ldlaw = PTB_LD_QUADRATIC;
+    cfg->nk = 256;
+    cfg->nzin = 20;
+    cfg->nzlimb = 20;
+    cfg->ng = 100;
+    cfg->kmin = 0.005;
+    cfg->kmax = 0.5;
+    cfg->zcut = 0.7;
+    cfg->precompute_weights = 0;
+    cfg->precision = 0;
+}
+
+int ptb_version(void) { return PTB_VERSION; }
+
+const char *ptb_last_error(const ptb_model *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ptb_create(const ptb_config *cfg, ptb_model **out) {
+    ptb_model *h = nullptr;
+    if (!cfg || !out) return fail(h, PTB_EINVAL, "ptb_create: null argument");
+    *out = nullptr;
+    const bool law_ok = (cfg->ldlaw >= 0 && cfg->ldlaw <= PTB_LD_POWER_2_PM) || cfg->ldlaw == PTB_LD_PROFILES;
+    if (!law_ok) return fail(h, PTB_ENOTIMPL, "unknown limb darkening law id %d", cfg->ldlaw);
+    if (cfg->nk < 2 || cfg->ng < 2 || cfg->nzin < 2 || cfg->nzlimb < 1 || !(cfg->kmax > cfg->kmin) || !(cfg->kmin > 0) ||
+        !(cfg->zcut > 0 && cfg->zcut < 1))
+        return fail(h, PTB_EINVAL, "invalid integration grid (nk=%d ng=%d nzin=%d nzlimb=%d klims=(%g,%g) zcut=%g)",
+                    cfg->nk, cfg->ng, cfg->nzin, cfg->nzlimb, cfg->kmin, cfg->kmax, cfg->zcut);
+    if (cfg->precision != 0) return fail(h, PTB_ENOTIMPL, "precision=%d: only fp64 (0) is implemented", cfg->precision);
+    const int nz = cfg->nzin + cfg->nzlimb;
+    if (((size_t)cfg->ng * nz) % 2 != 0 || (size_t)cfg->ng * nz * 16 > 200 * 1024)
+        return fail(h, PTB_EINVAL, "ng*nz = %d*%d: two table rows must fit 200 KB of shared memory and be 16-byte multiples",
+                    cfg->ng, nz);
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(h, PTB_ECUDA, "no CUDA device available (%s); libptb200 has no CPU fallback",
+                    ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(h, PTB_EINVAL, "device %d out of range [0,%d)", cfg->device, ndev);
+
+    h = new ptb_model();
+    h->cfg = *cfg;
+    h->nz = nz;
+    auto bail = [&](int code) {
+        g_create_error = h->err;
+        ptb_destroy(h);
+        return code;
+    };
+    if (set_device(h) != PTB_OK) return bail(PTB_ECUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        fail(h, PTB_ECUDA, "device %d is sm_%d%d; libptb200 is built for sm_100a only", cfg->device, prop.major, prop.minor);
+        return bail(PTB_ECUDA);
+    }
+
+    make_z_grid(cfg->zcut, cfg->nzin, cfg->nzlimb, h->ze, h->zm);
+    h->mu.resize(nz);
+    for (int i = 0; i < nz; ++i) h->mu[i] = std::sqrt(1 - h->zm[i] * h->zm[i]);
+    h->ks = linspace(cfg->kmin, cfg->kmax, cfg->nk);
+    h->gs = linspace(0.0, 1.0 - 1e-7, cfg->ng);
+    h->dk = (cfg->kmax - cfg->kmin) / cfg->nk;  // NOT the linspace step (common.py:223)
+    h->dg = h->gs[1] - h->gs[0];
+    std::vector<double> ldmu = linspace(1.0, 0.0, 200), ldz(200);
+    for (int i = 0; i < 200; ++i) ldz[i] = std::sqrt(1 - ldmu[i] * ldmu[i]);
+
+    std::vector<double> tab;
+    auto push = [&](const std::vector<double> &v) {
+        size_t off = tab.size();
+        tab.insert(tab.end(), v.begin(), v.end());
+        if (tab.size() % 2) tab.push_back(0.0);
+        return off;
+    };
+    const size_t o_ze = push(h->ze), o_mu = push(h->mu), o_gs = push(h->gs), o_ks = push(h->ks), o_lm = push(ldmu),
+                 o_lz = push(ldz);
+    auto cu = [&](cudaError_t e, const char *what) {
+        if (e == cudaSuccess) return true;
+        fail(h, e == cudaErrorMemoryAllocation ? PTB_ENOMEM : PTB_ECUDA, "%s failed: %s", what, cudaGetErrorString(e));
+        return false;
+    };
+    if (!cu(h->d_tab.reserve(tab.size() * 8), "cudaMalloc(tables)")) return bail(PTB_ECUDA);
+    if (!cu(cudaMemcpy(h->d_tab.ptr, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice), "cudaMemcpy(tables)"))
+        return bail(PTB_ECUDA);
+    double *base = h->d_tab.as<double>();
+    h->d_ze = base + o_ze;
+    h->d_mu = base + o_mu;
+    h->d_gs = base + o_gs;
+    h->d_ks = base + o_ks;
+    h->d_ldmu = base + o_lm;
+    h->d_ldz = base + o_lz;
+
+    const size_t wcount = (size_t)cfg->nk * cfg->ng * nz;
+    if (!cu(h->d_W.reserve(wcount * 8), "cudaMalloc(weights)")) return bail(PTB_ENOMEM);
+    const int rows = cfg->nk * cfg->ng;
+    k_weight_table<<<(rows + 127) / 128, 128>>>(h->d_ks, h->d_gs, h->d_ze, cfg->nk, cfg->ng, nz, h->d_W.as<double>());
+    h->launches++;
+    if (!cu(cudaGetLastError(), "k_weight_table launch")) return bail(PTB_ECUDA);
+    if (!cu(cudaDeviceSynchronize(), "k_weight_table")) return bail(PTB_ECUDA);
+
+    const int smem_setup = (int)(2 * (size_t)cfg->ng * nz * 8 + 64 * 1024);
+    cudaFuncSetAttribute(k_rr_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(smem_setup, 227 * 1024));
+    *out = h;
+    return PTB_OK;
+}
+
+void ptb_destroy(ptb_model *h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    for (DevBuf *b : {&h->d_tab, &h->d_W, &h->d_time_own, &h->d_meta, &h->d_obs_own, &h->d_blk, &h->d_nblk, &h->d_orb,
+                      &h->d_ldrec, &h->d_ldp, &h->d_istar, &h->d_flux, &h->d_partial, &h->d_isig2, &h->d_lnl, &h->d_xyc,
+                      &h->d_tsw, &h->d_tsrec, &h->d_stage})
+        b->release();
+    h->h_stage.release();
+    if (h->stage_ev) cudaEventDestroy(h->stage_ev);
+    delete h;
+}
+
+int ptb_get_tables(ptb_model *h, double *ze, double *zm, double *mu, double *weights, double *dk, double *dg) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    if (ze) memcpy(ze, h->ze.data(), h->nz * 8);
+    if (zm) memcpy(zm, h->zm.data(), h->nz * 8);
+    if (mu) memcpy(mu, h->mu.data(), h->nz * 8);
+    if (dk) *dk = h->dk;
+    if (dg) *dg = h->dg;
+    if (weights) {
+        const size_t n = (size_t)h->cfg.nk * h->cfg.ng * h->nz;
+        CU(cudaMemcpy(weights, h->d_W.ptr, n * 8, is_device_ptr(weights) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
+    }
+    return PTB_OK;
+}
+
+int ptb_set_data(ptb_model *h, const double *time, int64_t npt, const int64_t *lcids, int64_t nlc, const int64_t *pbids,
+                 int64_t npb, const int64_t *epids, int64_t nep, const int64_t *nsamples, const double *exptimes) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    if (!time || npt <= 0) return fail(h, PTB_EINVAL, "set_data: time array is empty");
+    if (npt > 0x7fffffffLL) return fail(h, PTB_EINVAL, "set_data: npt=%lld exceeds the 2^31-1 points per dataset limit", (long long)npt);
+    if (nlc < 1 || npb < 1 || nep < 1) return fail(h, PTB_ESHAPE, "set_data: nlc, npb, nep must be >= 1");
+    if (!lcids && nlc != 1) return fail(h, PTB_ESHAPE, "set_data: lcids missing but nlc=%lld", (long long)nlc);
+    if (npb > 256) return fail(h, PTB_EINVAL, "set_data: npb=%lld > 256 passbands (use the TSModel entry point for spectroscopy)", (long long)npb);
+
+    // host views of the small per-light-curve arrays (they may live on the device)
+    auto fetch64 = [&](const int64_t *p, int64_t n, std::vector<int64_t> &v, int64_t def) -> int {
+        v.assign(n, def);
+        if (!p) return PTB_OK;
+        CU(cudaMemcpy(v.data(), p, n * 8, cudaMemcpyDefault));
+        return PTB_OK;
+    };
+    std::vector<int64_t> hpb, hep, hns;
+    if (int rc = fetch64(pbids, nlc, hpb, 0)) return rc;
+    if (int rc = fetch64(epids, nlc, hep, 0)) return rc;
+    if (int rc = fetch64(nsamples, nlc, hns, 1)) return rc;
+    std::vector<double> het(nlc, 0.0);
+    if (exptimes) CU(cudaMemcpy(het.data(), exptimes, nlc * 8, cudaMemcpyDefault));
+    int nsmax = 1;
+    for (int64_t i = 0; i < nlc; ++i) {
+        if (hpb[i] < 0 || hpb[i] >= npb)
+            return fail(h, PTB_EINVAL, "Passband indices (`pbids`) for %lld unique passbands should be given as integers between 0 and %lld.",
+                        (long long)npb, (long long)npb - 1);
+        if (hep[i] < 0 || hep[i] >= nep) return fail(h, PTB_EINVAL, "set_data: epids[%lld]=%lld outside [0,%lld)", (long long)i, (long long)hep[i], (long long)nep);
+        if (hns[i] < 1 || hns[i] > 100000) return fail(h, PTB_EINVAL, "set_data: nsamples[%lld]=%lld must be in [1,100000]", (long long)i, (long long)hns[i]);
+        nsmax = std::max<int>(nsmax, (int)hns[i]);
+    }
+
+    // light-curve ids -> int32 on the device (validated against [0,nlc))
+    std::vector<int32_t> meta;
+    const size_t n_lc32 = lcids ? (size_t)npt : 0;
+    const size_t lc_pad = (n_lc32 + 3) & ~size_t(3);
+    meta.resize(lc_pad + 3 * ((nlc + 3) & ~int64_t(3)) + 2 * nlc + 8, 0);
+    if (lcids) {
+        std::vector<int64_t> hl(npt);
+        CU(cudaMemcpy(hl.data(), lcids, npt * 8, cudaMemcpyDefault));
+        for (int64_t i = 0; i < npt; ++i) {
+            if (hl[i] < 0 || hl[i] >= nlc)
+                return fail(h, PTB_EINVAL, "set_data: lcids[%lld]=%lld outside [0,%lld)", (long long)i, (long long)hl[i], (long long)nlc);
+            meta[i] = (int32_t)hl[i];
+        }
+    }
+    const size_t nlc4 = (nlc + 3) & ~int64_t(3);
+    const size_t o_pb = lc_pad, o_ep = o_pb + nlc4, o_ns = o_ep + nlc4, o_et = o_ns + nlc4;  // o_et: 16-byte aligned
+    for (int64_t i = 0; i < nlc; ++i) {
+        meta[o_pb + i] = (int32_t)hpb[i];
+        meta[o_ep + i] = (int32_t)hep[i];
+        meta[o_ns + i] = (int32_t)hns[i];
+    }
+    memcpy(&meta[o_et], het.data(), nlc * 8);
+    CU(h->d_meta.reserve(meta.size() * 4));
+    CU(cudaMemcpy(h->d_meta.ptr, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
+    int32_t *mb = h->d_meta.as<int32_t>();
+    h->d_lcids = lcids ? mb : nullptr;
+    h->d_pbids = mb + o_pb;
+    h->d_epids = mb + o_ep;
+    h->d_nsamples = mb + o_ns;
+    h->d_exptimes = reinterpret_cast<double *>(mb + o_et);
+
+    if (is_device_ptr(time)) {
+        h->d_time = time;  // zero copy: the caller keeps the tensor alive (as with RoadRunnerModelCL buffers)
+    } else {
+        CU(h->d_time_own.reserve(npt * 8 + 16));
+        CU(cudaMemcpy(h->d_time_own.ptr, time, npt * 8, cudaMemcpyHostToDevice));
+        h->d_time = h->d_time_own.as<double>();
+    }
+    h->npt = npt;
+    h->nlc = nlc;
+    h->npb = npb;
+    h->nep = nep;
+    h->ns_max = nsmax;
+    h->h_nsamples = hns;
+    h->h_exptimes = het;
+    h->has_data = true;
+    h->has_obs = false;  // observations are tied to the time axis
+    return PTB_OK;
+}
+
+int ptb_set_obs(ptb_model *h, const double *obs, const int64_t *slices, const int64_t *nids, int64_t nsl, int64_t nblocks) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    if (!h->has_data) return fail(h, PTB_ESTATE, "set_obs: call set_data first");
+    if (!obs) return fail(h, PTB_EINVAL, "set_obs: obs is null");
+    const int64_t npt = h->npt;
+    std::vector<int32_t> blk(npt, -1);
+    std::vector<double> cnt;
+    bool trivial = false;
+    if (!slices) {
+        nblocks = 1;
+        cnt.assign(1, (double)npt);
+        trivial = true;
+    } else {
+        if (nsl < 1 || nblocks < 1 || !nids) return fail(h, PTB_ESHAPE, "set_obs: slices given but nsl/nblocks/nids invalid");
+        std::vector<int64_t> hs(2 * nsl), hn(nsl);
+        CU(cudaMemcpy(hs.data(), slices, 16 * nsl, cudaMemcpyDefault));
+        CU(cudaMemcpy(hn.data(), nids, 8 * nsl, cudaMemcpyDefault));
+        cnt.assign(nblocks, 0.0);
+        for (int64_t s = 0; s < nsl; ++s) {
+            if (hn[s] < 0 || hn[s] >= nblocks) return fail(h, PTB_EINVAL, "set_obs: nids[%lld]=%lld outside [0,%lld)", (long long)s, (long long)hn[s], (long long)nblocks);
+            if (hs[2 * s] < 0 || hs[2 * s + 1] > npt || hs[2 * s] > hs[2 * s + 1])
+                return fail(h, PTB_EINVAL, "set_obs: slice %lld = [%lld,%lld) outside [0,%lld]", (long long)s, (long long)hs[2 * s], (long long)hs[2 * s + 1], (long long)npt);
+            for (int64_t j = hs[2 * s]; j < hs[2 * s + 1]; ++j) {
+                if (blk[j] >= 0) return fail(h, PTB_EINVAL, "set_obs: overlapping slices at point %lld are not supported", (long long)j);
+                blk[j] = (int32_t)hn[s];
+            }
+            cnt[hn[s]] += (double)(hs[2 * s + 1] - hs[2 * s]);
+        }
+        trivial = (nblocks == 1 && cnt[0] == (double)npt);
+    }
+    if (!trivial) {
+        CU(h->d_blk.reserve(npt * 4));
+        CU(cudaMemcpy(h->d_blk.ptr, blk.data(), npt * 4, cudaMemcpyHostToDevice));
+    }
+    CU(h->d_nblk.reserve(nblocks * 8));
+    CU(cudaMemcpy(h->d_nblk.ptr, cnt.data(), nblocks * 8, cudaMemcpyHostToDevice));
+    if (is_device_ptr(obs)) {
+        h->d_obs = obs;
+    } else {
+        CU(h->d_obs_own.reserve(npt * 8 + 16));
+        CU(cudaMemcpy(h->d_obs_own.ptr, obs, npt * 8, cudaMemcpyHostToDevice));
+        h->d_obs = h->d_obs_own.as<double>();
+    }
+    h->blk_trivial = trivial;
+    h->nblocks = nblocks;
+    h->has_obs = true;
+    return PTB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+int check_model_args(ptb_model *h, const char *who, const ModelArgs &A, int64_t npb) {
+    if (!h->has_data) return fail(h, PTB_ESTATE, "%s: call set_data first", who);
+    if (A.npv < 1) return fail(h, PTB_ESHAPE, "%s: npv must be >= 1", who);
+    if (A.npv > 0x7fffffffLL / 64) return fail(h, PTB_EINVAL, "%s: npv=%lld too large for one call", who, (long long)A.npv);
+    if (!A.k || !A.ld || !A.t0 || !A.p || !A.a || !A.inc || !A.e || !A.w) return fail(h, PTB_EINVAL, "%s: null parameter array", who);
+    if (A.kcols != 1 && A.kcols != npb)
+        return fail(h, PTB_ESHAPE, "Radius ratios should be given either as an [npv, 1] or [npv, npb] array.");
+    if (h->cfg.ldlaw == PTB_LD_PROFILES) {
+        if (A.nld != h->nz) return fail(h, PTB_ESHAPE, "%s: tabulated profiles need %d mu nodes per passband, got %lld", who, h->nz, (long long)A.nld);
+        if (!A.istar) return fail(h, PTB_EINVAL, "%s: istar is required with tabulated profiles", who);
+    } else {
+        static const int need[] = {0, 1, 2, 2, 4, 1, 2, 2, 2, 2, 2};
+        if (A.nld < need[h->cfg.ldlaw]) return fail(h, PTB_ESHAPE, "%s: limb darkening law %d needs %d coefficients, got %lld", who, h->cfg.ldlaw, need[h->cfg.ldlaw], (long long)A.nld);
+        if (A.nld < 1) return fail(h, PTB_ESHAPE, "%s: nld must be >= 1", who);
+    }
+    return PTB_OK;
+}
+
+struct Staged {
+    const double *k, *ld, *istar, *t0, *p, *a, *inc, *e, *w, *sigma;
+};
+
+int stage_model_args(ptb_model *h, const ModelArgs &A, int64_t npb, int64_t nep, const double *sigma, int64_t nsig,
+                     cudaStream_t st, Staged &D) {
+    Stager S(h, st);
+    const size_t npv = A.npv;
+    auto rk = S.add(A.k, npv * A.kcols * 8);
+    auto rld = S.add(A.ld, npv * npb * A.nld * 8);
+    auto ris = S.add(A.istar, npv * npb * 8);
+    auto rt0 = S.add(A.t0, npv * nep * 8);
+    auto rp = S.add(A.p, npv * 8), ra = S.add(A.a, npv * 8), ri = S.add(A.inc, npv * 8), re = S.add(A.e, npv * 8),
+         rw = S.add(A.w, npv * 8);
+    auto rs = S.add(sigma, npv * nsig * 8);
+    if (int rc = S.commit()) return rc;
+    D.k = S.get<double>(rk);
+    D.ld = S.get<double>(rld);
+    D.istar = S.get<double>(ris);
+    D.t0 = S.get<double>(rt0);
+    D.p = S.get<double>(rp);
+    D.a = S.get<double>(ra);
+    D.inc = S.get<double>(ri);
+    D.e = S.get<double>(re);
+    D.w = S.get<double>(rw);
+    D.sigma = S.get<double>(rs);
+    return PTB_OK;
+}
+
+int launch_rr_setup(ptb_model *h, const ModelArgs &A, const Staged &D, cudaStream_t st) {
+    const int64_t npv = A.npv, npb = h->npb;
+    const int ng = h->cfg.ng, nz = h->nz;
+    const int lds = (ng + 4 + 1) & ~1;
+    CU(h->d_orb.reserve(npv * ORB_STRIDE * 8));
+    CU(h->d_ldrec.reserve((size_t)npv * npb * lds * 8));
+    CU(h->d_ldp.reserve((size_t)npv * npb * nz * 8));
+    CU(h->d_istar.reserve((size_t)npv * npb * 8));
+    if (h->xyc_injected && h->xyc_npv != npv)
+        return fail(h, PTB_ESHAPE, "injected xyc has npv=%lld but evaluate was called with npv=%lld", (long long)h->xyc_npv, (long long)npv);
+    SetupParams P{};
+    P.k = D.k; P.ld = D.ld; P.istar = D.istar; P.p = D.p; P.a = D.a; P.inc = D.inc; P.e = D.e; P.w = D.w;
+    P.xyc_in = h->xyc_injected ? h->d_xyc.as<double>() : nullptr;
+    P.W = h->d_W.as<double>(); P.ze = h->d_ze; P.mu = h->d_mu; P.gs = h->d_gs; P.ldmu200 = h->d_ldmu; P.ldz200 = h->d_ldz;
+    P.orb = h->d_orb.as<double>(); P.ldrec = h->d_ldrec.as<double>(); P.ldp_out = h->d_ldp.as<double>();
+    P.istar_out = h->d_istar.as<double>();
+    P.npv = (int)npv; P.kcols = (int)A.kcols; P.npb = (int)npb; P.nld = (int)A.nld; P.law = h->cfg.ldlaw;
+    P.nk = h->cfg.nk; P.ng = ng; P.nz = nz; P.lds = lds;
+    P.kmin = h->cfg.kmin; P.kmax = h->cfg.kmax; P.dk = h->dk;
+    P.check_ldp_nan = 1;
+    const size_t smem = (2 * (size_t)ng * nz + (size_t)npb * nz + npb + 600) * 8 + 16;
+    if (smem > 227 * 1024) return fail(h, PTB_EINVAL, "setup kernel needs %zu bytes of shared memory (> 227 KB)", smem);
+    k_rr_setup<<<(unsigned)npv, 128, smem, st>>>(P);
+    h->launches++;
+    CU(cudaGetLastError());
+    h->last_npv = npv;
+    h->last_npb = npb;
+    return PTB_OK;
+}
+
+template <int VEC, bool SINGLE, bool LNL>
+int launch_points_t(ptb_model *h, const PointsParams &P, size_t smem, cudaStream_t st) {
+    auto kern = k_rr_points<VEC, SINGLE, LNL>;
+    if (smem > 48 * 1024 - 12 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = (long long)P.npv * P.nchunks;
+    kern<<<(unsigned)grid, PT_THREADS, smem, st>>>(P);
+    h->launches++;
+    CU(cudaGetLastError());
+    return PTB_OK;
+}
+
+// flux != nullptr -> flux mode; else lnL mode (partials into h->d_partial)
+int launch_points(ptb_model *h, int64_t npv, const double *t0, double *flux, const double *isig2, cudaStream_t st, int *nchunks_out) {
+    const int ng = h->cfg.ng;
+    const int lds = (ng + 4 + 1) & ~1;
+    PointsParams P{};
+    P.time = h->d_time; P.lcids = h->d_lcids; P.pbids = h->d_pbids; P.epids = h->d_epids; P.nsamples = h->d_nsamples;
+    P.exptimes = h->d_exptimes; P.orb = h->d_orb.as<double>(); P.t0 = t0; P.ldrec = h->d_ldrec.as<double>();
+    P.flux = flux; P.obs = h->d_obs; P.blk = h->blk_trivial ? nullptr : h->d_blk.as<int32_t>(); P.isig2 = isig2;
+    P.npt = h->npt; P.npv = (int)npv; P.nlc = (int)h->nlc; P.npb = (int)h->npb; P.nep = (int)h->nep; P.ng = ng; P.lds = lds;
+    P.nblocks = (int)h->nblocks; P.ns_max = h->ns_max; P.dg = h->dg; P.inv_dg = 1.0 / h->dg;
+
+    const bool single = (h->nlc == 1);
+    const bool lnl = (flux == nullptr);
+    const bool aligned = (h->npt % 2 == 0) && ((reinterpret_cast<uintptr_t>(h->d_time) & 15) == 0) &&
+                         (lnl || (reinterpret_cast<uintptr_t>(flux) & 15) == 0);
+    const int vec = aligned ? 2 : 1;
+    const long long tile = (long long)PT_THREADS * vec;
+    const long long ntiles = (h->npt + tile - 1) / tile;
+    // enough CTAs to fill the machine ~8 deep; otherwise one CTA walks a whole row
+    const long long want = (long long)h->sm_count * 8;
+    long long nchunks = std::min<long long>(ntiles, std::max<long long>(1, (want + npv - 1) / npv));
+    long long tpc = (ntiles + nchunks - 1) / nchunks;
+    nchunks = (ntiles + tpc - 1) / tpc;
+    P.nchunks = (int)nchunks;
+    P.tiles_per_chunk = (int)tpc;
+    if (nchunks_out) *nchunks_out = (int)nchunks;
+    if (lnl) {
+        CU(h->d_partial.reserve((size_t)npv * nchunks * 8));
+        P.partial = h->d_partial.as<double>();
+    }
+    const size_t ldbytes = (size_t)h->npb * lds * 8;
+    P.stage_ld = ldbytes <= 64 * 1024 ? 1 : 0;
+    const size_t smem = (P.stage_ld ? ldbytes : 0) + (single ? 0 : 3 * (size_t)h->nlc * 8) + 16;
+    if (smem > 160 * 1024) return fail(h, PTB_EINVAL, "nlc=%lld light curves need %zu bytes of shared memory", (long long)h->nlc, smem);
+
+#define PTB_DISPATCH(V, S, L) return launch_points_t<V, S, L>(h, P, smem, st)
+    if (vec == 2) {
+        if (single) { if (lnl) PTB_DISPATCH(2, true, true); else PTB_DISPATCH(2, true, false); }
+        else        { if (lnl) PTB_DISPATCH(2, false, true); else PTB_DISPATCH(2, false, false); }
+    } else {
+        if (single) { if (lnl) PTB_DISPATCH(1, true, true); else PTB_DISPATCH(1, true, false); }
+        else        { if (lnl) PTB_DISPATCH(1, false, true); else PTB_DISPATCH(1, false, false); }
+    }
+#undef PTB_DISPATCH
+}
+
+}  // namespace
+
+extern "C" {
+
+int ptb_rr_evaluate(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld, int64_t nld,
+                    const double *istar, const double *t0, const double *p, const double *a, const double *inc,
+                    const double *e, const double *w, double *flux, void *stream) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ModelArgs A{npv, kcols, nld, k, ld, istar, t0, p, a, inc, e, w};
+    if (int rc = check_model_args(h, "rr_evaluate", A, h->npb)) return rc;
+    Staged D{};
+    if (int rc = stage_model_args(h, A, h->npb, h->nep, nullptr, 0, st, D)) return rc;
+    if (int rc = launch_rr_setup(h, A, D, st)) return rc;
+    const size_t count = (size_t)npv * h->npt;
+    double *dflux = flux;
+    const bool direct = flux && is_device_ptr(flux);
+    if (!direct) {
+        CU(h->d_flux.reserve(count * 8));
+        dflux = h->d_flux.as<double>();
+    }
+    if (int rc = launch_points(h, npv, D.t0, dflux, nullptr, st, nullptr)) return rc;
+    h->last_flux_count = direct ? 0 : (int64_t)count;
+    if (flux && !direct) {
+        CU(cudaMemcpyAsync(flux, dflux, count * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return PTB_OK;
+}
+
+int ptb_rr_lnlike(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld, int64_t nld,
+                  const double *istar, const double *t0, const double *p, const double *a, const double *inc,
+                  const double *e, const double *w, const double *sigma, double *lnl, void *stream) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!h->has_obs) return fail(h, PTB_ESTATE, "rr_lnlike: call set_obs first");
+    if (!sigma || !lnl) return fail(h, PTB_EINVAL, "rr_lnlike: sigma / lnl is null");
+    ModelArgs A{npv, kcols, nld, k, ld, istar, t0, p, a, inc, e, w};
+    if (int rc = check_model_args(h, "rr_lnlike", A, h->npb)) return rc;
+    Staged D{};
+    if (int rc = stage_model_args(h, A, h->npb, h->nep, sigma, h->nblocks, st, D)) return rc;
+    if (int rc = launch_rr_setup(h, A, D, st)) return rc;
+    const long long nsig = (long long)npv * h->nblocks;
+    CU(h->d_isig2.reserve(nsig * 8));
+    k_inv_sigma2<<<(unsigned)((nsig + 255) / 256), 256, 0, st>>>(D.sigma, nsig, h->d_isig2.as<double>());
+    h->launches++;
+    int nchunks = 1;
+    if (int rc = launch_points(h, npv, D.t0, nullptr, h->d_isig2.as<double>(), st, &nchunks)) return rc;
+    const bool direct = is_device_ptr(lnl);
+    double *dl = lnl;
+    if (!direct) {
+        CU(h->d_lnl.reserve(npv * 8));
+        dl = h->d_lnl.as<double>();
+    }
+    k_lnl_finish<<<(unsigned)((npv + 127) / 128), 128, 0, st>>>(h->d_partial.as<double>(), nchunks, D.sigma,
+                                                                 h->d_nblk.as<double>(), (int)h->nblocks, (int)npv, dl);
+    h->launches++;
+    CU(cudaGetLastError());
+    if (!direct) {
+        CU(cudaMemcpyAsync(lnl, dl, npv * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return PTB_OK;
+}
+
+int ptb_lnlike_normal(ptb_model *h, int64_t npv, const double *model, const double *sigma, double *lnl, void *stream) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!h->has_obs) return fail(h, PTB_ESTATE, "lnlike_normal: call set_obs first");
+    if (!model || !sigma || !lnl || npv < 1) return fail(h, PTB_EINVAL, "lnlike_normal: null argument or npv < 1");
+    Stager S(h, st);
+    auto rm = S.add(model, (size_t)npv * h->npt * 8);
+    auto rs = S.add(sigma, (size_t)npv * h->nblocks * 8);
+    if (int rc = S.commit()) return rc;
+    const double *dm = S.get<double>(rm), *ds = S.get<double>(rs);
+    const long long nsig = (long long)npv * h->nblocks;
+    CU(h->d_isig2.reserve(nsig * 8));
+    CU(h->d_partial.reserve(npv * 8));
+    k_inv_sigma2<<<(unsigned)((nsig + 255) / 256), 256, 0, st>>>(ds, nsig, h->d_isig2.as<double>());
+    k_lnl_model<<<(unsigned)npv, 256, 0, st>>>(dm, h->d_obs, h->blk_trivial ? nullptr : h->d_blk.as<int32_t>(),
+                                               h->d_isig2.as<double>(), h->npt, (int)h->nblocks, h->d_partial.as<double>());
+    const bool direct = is_device_ptr(lnl);
+    double *dl = lnl;
+    if (!direct) {
+        CU(h->d_lnl.reserve(npv * 8));
+        dl = h->d_lnl.as<double>();
+    }
+    k_lnl_finish<<<(unsigned)((npv + 127) / 128), 128, 0, st>>>(h->d_partial.as<double>(), 1, ds, h->d_nblk.as<double>(),
+                                                                 (int)h->nblocks, (int)npv, dl);
+    h->launches += 3;
+    CU(cudaGetLastError());
+    if (!direct) {
+        CU(cudaMemcpyAsync(lnl, dl, npv * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return PTB_OK;
+}
+
+int ptb_get_stage(ptb_model *h, int32_t stage, double *out) {
+    if (!h || !out) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    if (h->last_npv == 0) return fail(h, PTB_ESTATE, "get_stage: no evaluation has run yet");
+    CU(cudaDeviceSynchronize());
+    const int64_t npv = h->last_npv, npb = h->last_npb;
+    const int ng = h->cfg.ng, nz = h->nz, lds = (ng + 4 + 1) & ~1;
+    const cudaMemcpyKind kind = cudaMemcpyDefault;
+    switch (stage) {
+    case PTB_STAGE_LDP: CU(cudaMemcpy(out, h->d_ldp.ptr, (size_t)npv * npb * nz * 8, kind)); break;
+    case PTB_STAGE_ISTAR: CU(cudaMemcpy(out, h->d_istar.ptr, (size_t)npv * npb * 8, kind)); break;
+    case PTB_STAGE_LDM:
+        CU(cudaMemcpy2D(out, ng * 8, h->d_ldrec.ptr, lds * 8, ng * 8, (size_t)npv * npb, kind));
+        break;
+    case PTB_STAGE_XYC: CU(cudaMemcpy2D(out, 80, h->d_orb.ptr, ORB_STRIDE * 8, 80, npv, kind)); break;
+    case PTB_STAGE_BBOX:
+        CU(cudaMemcpy2D(out, 16, h->d_orb.as<double>() + ORB_T1, ORB_STRIDE * 8, 16, npv, kind));
+        break;
+    case PTB_STAGE_GOOD:
+        CU(cudaMemcpy2D(out, 8, h->d_orb.as<double>() + ORB_GOOD, ORB_STRIDE * 8, 8, npv, kind));
+        break;
+    default: return fail(h, PTB_EINVAL, "get_stage: unknown stage %d", stage);
+    }
+    return PTB_OK;
+}
+
+int ptb_inject_xyc(ptb_model *h, const double *xyc, int64_t npv) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    if (!xyc) {
+        h->xyc_injected = false;
+        h->xyc_npv = 0;
+        return PTB_OK;
+    }
+    if (npv < 1) return fail(h, PTB_ESHAPE, "inject_xyc: npv must be >= 1");
+    CU(h->d_xyc.reserve(npv * 80));
+    CU(cudaMemcpy(h->d_xyc.ptr, xyc, npv * 80, cudaMemcpyDefault));
+    h->xyc_injected = true;
+    h->xyc_npv = npv;
+    return PTB_OK;
+}
+
+int ptb_flux_device_ptr(ptb_model *h, double **ptr, int64_t *count) {
+    if (!h || !ptr || !count) return PTB_EINVAL;
+    *ptr = h->d_flux.as<double>();
+    *count = h->last_flux_count;
+    return PTB_OK;
+}
+
+int ptb_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return PTB_EINVAL;
+    cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        g_create_error = std::string("cudaMallocHost failed: ") + cudaGetErrorString(e);
+        return PTB_ENOMEM;
+    }
+    return PTB_OK;
+}
+
+int ptb_host_free(void *ptr) {
+    if (!ptr) return PTB_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? PTB_OK : PTB_ECUDA;
+}
+
+int64_t ptb_launch_count(const ptb_model *h) { return h ? h->launches : 0; }
+
+int ptb_synchronize(ptb_model *h, void *stream) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    CU(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return PTB_OK;
+}
+
+}  // extern "C"
+
+#include "ptb_ts_host.inl"

@@ -1,0 +1,534 @@
+// ptb_kernels.cuh -- sm_100a kernels of the RoadRunner population path.
+//
+//   k_weight_table   W[nk,ng,nz]  (common.py:188-223)                         once per model
+//   k_rr_setup       per-vector state: LD profile, I*, LD means (TMA-staged table rows), Taylor
+//                    orbit coefficients, contact times (model_full.py:39-70)   once per evaluate
+//   k_rr_points      the npv x npt pass: phase fold, box test, supersampled flux, optional fused
+//                    chi^2 reduction (model_full.py:76-99, wnloglikelihood.py:22-35)
+//   k_lnl_finish     chi^2 partials -> lnL[npv]
+//   k_lnl_model      lnlike_normal on a materialised model flux
+//
+// HBM layout (all fp64 unless noted):
+//   orb  [npv][16]            cx[5] cy[5] p 1/p T1 T4 good -
+//   ldrec[npv][npb][lds]      ldm[ng] | k 1/(1+k) 1/I* k^2 | pad      (lds = ng+4 rounded up to even)
+//   flux [npv][npt]           row-major, written with 16-byte stores
+#pragma once
+#include "ptb_math.cuh"
+
+namespace ptb {
+
+constexpr int ORB_STRIDE = 16;
+constexpr int ORB_P = 10, ORB_INVP = 11, ORB_T1 = 12, ORB_T4 = 13, ORB_GOOD = 14;
+
+// ---------------------------------------------------------------------------------------------
+// Weight table: one thread per (ik, ig) row; annuli in index order with the reference's running
+// difference and running-sum normalisation (common.py:152-185).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void weight_row(double k, double g, const double *__restrict__ ze, int nz, double *w,
+                                           int stride) {
+    const double b = g * (1.0 + k);
+    double a0 = ccia_acos(ze[0], k, b);
+    w[0] = a0;
+    double s = a0;
+    for (int i = 1; i < nz; ++i) {
+        const double a1 = ccia_acos(ze[i], k, b);
+        const double d = a1 - a0;
+        w[i * stride] = d;
+        a0 = a1;
+        s += d;
+    }
+    for (int i = 0; i < nz; ++i) w[i * stride] /= s;
+}
+
+__global__ void k_weight_table(const double *__restrict__ ks, const double *__restrict__ gs,
+                               const double *__restrict__ ze, int nk, int ng, int nz, double *__restrict__ W) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nk * ng) return;
+    const int ik = idx / ng, ig = idx % ng;
+    weight_row(ks[ik], gs[ig], ze, nz, W + (size_t)idx * nz, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-vector setup.  One CTA (128 threads) per parameter vector:
+//   thread 0      arms an mbarrier and starts two TMA bulk copies of the table rows W[ik], W[ik+1]
+//                 (ng*nz*8 bytes each) into shared memory;
+//   warp 0        meanwhile solves the orbit: lanes 0..6 each do one Kepler solve of the 7-point
+//                 stencil, the coefficients are formed from shuffles, lanes 0/1 bisect T1/T4;
+//   warps 1..3    evaluate the limb-darkening profile at the nz mu nodes and I* per passband;
+//   all           wait on the mbarrier, then contract (ng x nz).(nz) per passband -> ldm.
+// ---------------------------------------------------------------------------------------------
+struct SetupParams {
+    const double *k;      // [npv][kcols]
+    const double *ld;     // ldc[npv][npb][nld] or ldp[npv][npb][nz]
+    const double *istar;  // [npv][npb] (profiles only)
+    const double *p, *a, *inc, *e, *w;
+    const double *xyc_in;  // optional injected coefficients [npv][10]
+    const double *W, *ze, *mu, *gs, *ldmu200, *ldz200;
+    double *orb, *ldrec, *ldp_out, *istar_out;
+    int npv, kcols, npb, nld, law, nk, ng, nz, lds;
+    double kmin, kmax, dk;
+    int check_ldp_nan;  // RoadRunner: 1 (model_full.py:40); TSModel: 0 (model_trspec.py:37)
+};
+
+__device__ __forceinline__ void solve_orbit_warp(int lane, double p, double a, double inc, double e, double w,
+                                                 double kbox, const double *xyc_in, double *orb_out) {
+    double cx[5], cy[5];
+    if (xyc_in != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { cx[j] = xyc_in[j]; cy[j] = xyc_in[5 + j]; }
+    } else {
+        double x = 0.0, y = 0.0;
+        const double offset = mean_anomaly_offset(e, w);
+        if (lane < 7) sky_position((lane - 3) * 2e-2, p, a * (1.0 - e * e), cos(inc), e, w, offset, x, y);
+        double vx[7], vy[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            vx[j] = __shfl_sync(0xffffffffu, x, j);
+            vy[j] = __shfl_sync(0xffffffffu, y, j);
+        }
+        stencil_to_coeffs(vx, cx);
+        stencil_to_coeffs(vy, cy);
+    }
+    double tcon = 0.0;
+    if (lane < 2) tcon = contact_point(kbox, lane == 0 ? -1.0 : 1.0, cx, cy);
+    const double t1 = __shfl_sync(0xffffffffu, tcon, 0);
+    const double t4 = __shfl_sync(0xffffffffu, tcon, 1);
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { orb_out[j] = cx[j]; orb_out[5 + j] = cy[j]; }
+        orb_out[ORB_P] = p;
+        orb_out[ORB_INVP] = 1.0 / p;
+        orb_out[ORB_T1] = t1;
+        orb_out[ORB_T4] = t4;
+        orb_out[15] = 0.0;
+    }
+}
+
+// I* by the reference's numeric fallback, 2 pi trapezoid(z I(mu(z)), z) on 200 nodes
+// (rrmodel.py:151-152,223-227); one warp per (pv, pb), scratch[200] in shared memory.
+__device__ __forceinline__ double istar_numeric_warp(int lane, int law, const double *pv, int nld,
+                                                     const double *__restrict__ ldmu, const double *__restrict__ ldz,
+                                                     double *scratch) {
+    for (int i = lane; i < 200; i += 32) scratch[i] = ldz[i] * ld_intensity(law, ldmu[i], pv, nld);
+    __syncwarp();
+    double s = 0.0;
+    for (int i = 1 + lane; i < 200; i += 32) s += (ldz[i] - ldz[i - 1]) * (scratch[i] + scratch[i - 1]) * 0.5;
+    __syncwarp();
+    return 2.0 * kPi * warp_sum(s);
+}
+
+__global__ void __launch_bounds__(128) k_rr_setup(const __grid_constant__ SetupParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int ng = P.ng, nz = P.nz, npb = P.npb;
+    const int rowlen = ng * nz;
+    double *sW0 = reinterpret_cast<double *>(smem_raw);
+    double *sW1 = sW0 + rowlen;
+    double *sLdp = sW1 + rowlen;             // [npb][nz]
+    double *sIstar = sLdp + npb * nz;        // [npb]
+    double *sScr = sIstar + npb;             // [3][200] trapezoid scratch
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sScr + 600);
+
+    const int ipv = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double a = P.a[ipv], e = P.e[ipv];
+    const double k0 = P.k[(size_t)ipv * P.kcols];
+    const bool good0 = !(isnan(a) || (a <= 1.0) || (e < 0.0));
+    const bool in_table = (P.kmin <= k0) && (k0 <= P.kmax);
+    int ik = 0, ik1 = 0;
+    double ak = 0.0;
+    if (in_table) {
+        ik = (int)floor((k0 - P.kmin) / P.dk);
+        ak = (k0 - P.kmin - ik * P.dk) / P.dk;
+        ik = min(ik, P.nk - 1);
+        ik1 = min(ik + 1, P.nk - 1);  // the reference reads weights[nk] here
+    }
+    const bool use_tma = good0 && in_table;
+
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (use_tma && tid == 0) {
+        const uint32_t bytes = (uint32_t)rowlen * 8u;
+        mbar_expect_tx(bar, 2u * bytes);
+        tma_load_1d(sW0, P.W + (size_t)ik * rowlen, bytes, bar);
+        tma_load_1d(sW1, P.W + (size_t)ik1 * rowlen, bytes, bar);
+    }
+
+    double *orb = P.orb + (size_t)ipv * ORB_STRIDE;
+    if (warp == 0) {
+        if (good0) {
+            solve_orbit_warp(lane, P.p[ipv], a, P.inc[ipv], e, P.w[ipv], k0,
+                             P.xyc_in ? P.xyc_in + (size_t)ipv * 10 : nullptr, orb);
+        } else if (lane < ORB_STRIDE) {
+            orb[lane] = (lane == ORB_GOOD) ? 0.0 : nan("");
+        }
+    } else {
+        // limb-darkening profile at the mu nodes (evaluate_ld, ldmodels.py:142-157)
+        const int t = tid - 32;
+        for (int idx = t; idx < npb * nz; idx += 96) {
+            const int pb = idx / nz, iz = idx - pb * nz;
+            double v;
+            if (P.law == LD_PROFILES) v = P.ld[((size_t)ipv * npb + pb) * nz + iz];
+            else v = ld_intensity(P.law, P.mu[iz], P.ld + ((size_t)ipv * npb + pb) * P.nld, P.nld);
+            sLdp[idx] = v;
+            if (P.ldp_out) P.ldp_out[((size_t)ipv * npb + pb) * nz + iz] = v;
+        }
+        // disk-integrated intensity (evaluate_ldi, ldmodels.py:160-175; numeric fallback)
+        for (int pb = warp - 1; pb < npb; pb += 3) {
+            double is;
+            if (P.law == LD_PROFILES) {
+                is = P.istar[(size_t)ipv * npb + pb];
+            } else {
+                const double *pv = P.ld + ((size_t)ipv * npb + pb) * P.nld;
+                if (!ld_integral(P.law, pv, is))
+                    is = istar_numeric_warp(lane, P.law, pv, P.nld, P.ldmu200, P.ldz200, sScr + (warp - 1) * 200);
+            }
+            if (lane == 0) {
+                sIstar[pb] = is;
+                if (P.istar_out) P.istar_out[(size_t)ipv * npb + pb] = is;
+            }
+        }
+    }
+    __syncthreads();
+
+    const bool good = good0 && !(P.check_ldp_nan && isnan(sLdp[0]));
+    if (tid == 0 && good0) orb[ORB_GOOD] = good ? 1.0 : 0.0;
+
+    if (use_tma) mbar_wait(bar, 0);  // every thread observes completion before reading / exiting
+    if (!good) return;
+
+    if (!in_table) {
+        // direct weights for this radius ratio (calculate_weights_2d, common.py:152-185)
+        for (int ig = tid; ig < ng; ig += 128) weight_row(k0, P.gs[ig], P.ze, nz, sW0 + (size_t)ig * nz, 1);
+        __syncthreads();
+    }
+
+    double *rec = P.ldrec + (size_t)ipv * npb * P.lds;
+    for (int ig = tid; ig < ng; ig += 128) {
+        const double *w0 = sW0 + (size_t)ig * nz;
+        const double *w1 = sW1 + (size_t)ig * nz;
+        for (int pb = 0; pb < npb; ++pb) {
+            const double *l = sLdp + pb * nz;
+            double d0 = 0.0, d1 = 0.0;
+            int iz = ig % nz;  // rotated start: lanes of a warp hit distinct banks
+            if (in_table) {
+                for (int j = 0; j < nz; ++j) {
+                    d0 = fma(w0[iz], l[iz], d0);
+                    d1 = fma(w1[iz], l[iz], d1);
+                    iz = (iz + 1 == nz) ? 0 : iz + 1;
+                }
+                rec[(size_t)pb * P.lds + ig] = (1.0 - ak) * d0 + ak * d1;
+            } else {
+                for (int j = 0; j < nz; ++j) {
+                    d0 = fma(w0[iz], l[iz], d0);
+                    iz = (iz + 1 == nz) ? 0 : iz + 1;
+                }
+                rec[(size_t)pb * P.lds + ig] = d0;
+            }
+        }
+    }
+    for (int pb = tid; pb < npb; pb += 128) {
+        const double kk = (P.kcols == npb) ? P.k[(size_t)ipv * P.kcols + pb] : k0;
+        double *tail = rec + (size_t)pb * P.lds + ng;
+        tail[0] = kk;
+        tail[1] = 1.0 / (1.0 + kk);
+        tail[2] = 1.0 / sIstar[pb];
+        tail[3] = kk * kk;
+        for (int j = ng + 4; j < P.lds; ++j) rec[(size_t)pb * P.lds + j] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The npv x npt pass.
+//
+// One CTA = one parameter vector x one chunk of the time axis, 8 warps.  The per-vector record
+// (ldm rows + k, 1/(1+k), 1/I*, k^2 per passband) is staged into shared memory with one TMA bulk
+// copy.  Each tile of 256*VEC consecutive points is folded and box-tested (fp64, reference
+// operation order) and the flux row is written with 16-byte stores; in-box points are pushed to
+// a warp-private queue in shared memory and evaluated by full warps (one lane per exposure
+// sub-sample), so the 3 % of points that cost 50x the rest do not serialise the warp.
+// ---------------------------------------------------------------------------------------------
+struct PointsParams {
+    const double *time;
+    const int32_t *lcids, *pbids, *epids, *nsamples;
+    const double *exptimes;
+    const double *orb, *t0, *ldrec;
+    double *flux;
+    const double *obs;
+    const int32_t *blk;
+    const double *isig2;  // [npv][nblocks]
+    double *partial;      // [npv][nchunks]
+    long long npt;
+    int npv, nlc, npb, nep, ng, lds, nblocks, ns_max, nchunks, tiles_per_chunk, stage_ld;
+    double dg, inv_dg;
+};
+
+constexpr int PT_THREADS = 256;
+constexpr int PT_WARPS = PT_THREADS / 32;
+constexpr int PT_QCAP = 128;
+
+template <int VEC>
+struct VecIO;
+template <>
+struct VecIO<1> {
+    __device__ static __forceinline__ void load(const double *p, double *v) { v[0] = __ldg(p); }
+    __device__ static __forceinline__ void store(double *p, const double *v) { __stcs(p, v[0]); }
+};
+template <>
+struct VecIO<2> {
+    __device__ static __forceinline__ void load(const double *p, double *v) {
+        const double2 t = __ldg(reinterpret_cast<const double2 *>(p));
+        v[0] = t.x;
+        v[1] = t.y;
+    }
+    __device__ static __forceinline__ void store(double *p, const double *v) {
+        __stcs(reinterpret_cast<double2 *>(p), make_double2(v[0], v[1]));
+    }
+};
+
+// One exposure sub-sample: separation -> mean limb darkening under the planet -> lens area
+// (model_full.py:94-98).  Returns (I* - I_p A)/I* as 1 - I_p A / I*.
+__device__ __forceinline__ double sample_flux(double t, const double *cx, const double *cy, const double *row, int ng,
+                                              double dg, double inv_dg) {
+    const double z = sep_poly(t, cx, cy);
+    const double k = row[ng], inv1k = row[ng + 1], inv_istar = row[ng + 2], k2 = row[ng + 3];
+    const double ip = ldm_lerp(z * inv1k, dg, inv_dg, row, ng);
+    double area, kap;
+    kite_area(k, k2, z, area, kap);
+    return 1.0 - ip * area * inv_istar;
+}
+
+template <int VEC, bool SINGLE_LC, bool LNL>
+__global__ void __launch_bounds__(PT_THREADS) k_rr_points(const __grid_constant__ PointsParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int q_ipt[PT_WARPS][PT_QCAP];
+    __shared__ double q_tc[PT_WARPS][PT_QCAP];
+    __shared__ double s_part[PT_WARPS][32];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ipv = blockIdx.x / P.nchunks;
+    const int chunk = blockIdx.x - ipv * P.nchunks;
+    const long long npt = P.npt;
+    constexpr int TILE = PT_THREADS * VEC;
+
+    // dynamic smem: [ldrec copy npb*lds] [lc_lo nlc] [lc_hi nlc] [lc_t0 nlc]
+    double *sLd = reinterpret_cast<double *>(smem_raw);
+    double *sLo = sLd + (P.stage_ld ? (size_t)P.npb * P.lds : 0);
+    double *sHi = sLo + (SINGLE_LC ? 0 : P.nlc);
+    double *sT0 = sHi + (SINGLE_LC ? 0 : P.nlc);
+
+    const double *orb = P.orb + (size_t)ipv * ORB_STRIDE;
+    const bool good = orb[ORB_GOOD] != 0.0;
+    const double *ldg = P.ldrec + (size_t)ipv * P.npb * P.lds;
+
+    const long long cbeg = (long long)chunk * P.tiles_per_chunk * TILE;
+    const long long cend = min(npt, cbeg + (long long)P.tiles_per_chunk * TILE);
+
+    if (!good) {  // invalid parameter vector: NaN row (model_full.py:80-82)
+        if (LNL) {
+            if (tid == 0) P.partial[(size_t)ipv * P.nchunks + chunk] = nan("");
+        } else {
+            double *frow = P.flux + (size_t)ipv * npt;
+            double v[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) v[j] = nan("");
+            for (long long i = cbeg + (long long)tid * VEC; i < cend; i += TILE) VecIO<VEC>::store(frow + i, v);
+        }
+        return;
+    }
+
+    if (P.stage_ld) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            const uint32_t bytes = (uint32_t)(P.npb * P.lds * 8);
+            mbar_expect_tx(&bar, bytes);
+            tma_load_1d(sLd, ldg, bytes, &bar);
+        }
+    }
+    const double p = orb[ORB_P], invp = orb[ORB_INVP], T1 = orb[ORB_T1], T4 = orb[ORB_T4];
+    double lo1 = 0, hi1 = 0, t01 = 0;
+    if (SINGLE_LC) {
+        const double pad = 0.003 + P.exptimes[0];
+        lo1 = T1 - pad;
+        hi1 = T4 + pad;
+        t01 = P.t0[(size_t)ipv * P.nep + P.epids[0]];
+    } else {
+        for (int lc = tid; lc < P.nlc; lc += PT_THREADS) {
+            const double pad = 0.003 + P.exptimes[lc];
+            sLo[lc] = T1 - pad;
+            sHi[lc] = T4 + pad;
+            sT0[lc] = P.t0[(size_t)ipv * P.nep + P.epids[lc]];
+        }
+    }
+    __syncthreads();  // mbarrier init + per-light-curve tables visible
+
+    const double *ldrow_base = P.stage_ld ? sLd : ldg;
+    bool ld_ready = !P.stage_ld;
+
+    const int L = min(P.ns_max, 32);  // lanes per queued point
+    const int PPW = 32 / L;           // points per warp pass
+    int qn = 0;
+    double chi = 0.0;
+    const double *isig2 = LNL ? P.isig2 + (size_t)ipv * P.nblocks : nullptr;
+    double *frow = LNL ? nullptr : P.flux + (size_t)ipv * npt;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    // evaluate `npts` queued points starting at queue slot `base` (warp-cooperative)
+    auto drain = [&](int base, int npts) {
+        if (!ld_ready) {
+            mbar_wait(&bar, 0);
+            ld_ready = true;
+        }
+        double cx[5], cy[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { cx[j] = orb[j]; cy[j] = orb[5 + j]; }
+        const int pt = lane / L, s = lane - pt * L;
+        const bool active = pt < npts;
+        double acc = 0.0;
+        int ipt = 0, ns = 1;
+        if (active) {
+            ipt = q_ipt[warp][base + pt];
+            const double tc = q_tc[warp][base + pt];
+            const int lc = SINGLE_LC ? 0 : P.lcids[ipt];
+            ns = P.nsamples[lc];
+            const double et = P.exptimes[lc];
+            const double *row = ldrow_base + (size_t)P.pbids[lc] * P.lds;
+            for (int ss = s; ss < ns; ss += L) {
+                const double off = et * (((ss + 1) - 0.5) / ns - 0.5);
+                acc += sample_flux(tc + off, cx, cy, row, P.ng, P.dg, P.inv_dg);
+            }
+        }
+        if (L > 1) {  // sum the sub-samples of each point in exposure order
+            s_part[warp][lane] = acc;
+            __syncwarp();
+            if (active && s == 0) {
+                double sum = 0.0;
+                const int m = min(L, ns);
+                for (int j = 0; j < m; ++j) sum += s_part[warp][lane + j];
+                acc = sum / ns;
+            }
+            __syncwarp();
+        }
+        if (active && s == 0) {
+            if (LNL) {
+                const int b = P.blk ? P.blk[ipt] : 0;
+                if (b >= 0) {
+                    const double d = P.obs[ipt] - acc;
+                    chi = fma(d * d, isig2[b], chi);
+                }
+            } else {
+                frow[ipt] = acc;
+            }
+        }
+    };
+
+    for (long long tbeg = cbeg; tbeg < cend; tbeg += TILE) {
+        const long long i0 = tbeg + (long long)tid * VEC;
+        double tv[VEC], fv[VEC];
+        const bool inr = i0 < cend;  // VEC > 1 requires npt % VEC == 0: vectors are all-in or all-out
+        if (inr) VecIO<VEC>::load(P.time + i0, tv);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            bool inbox = false;
+            double tc = 0.0;
+            if (inr) {
+                double lo = lo1, hi = hi1, t0 = t01;
+                if (!SINGLE_LC) {
+                    const int lc = P.lcids[i0 + j];
+                    lo = sLo[lc];
+                    hi = sHi[lc];
+                    t0 = sT0[lc];
+                }
+                // epoch = floor((t - t0 + p/2)/p); tc = t - (t0 + epoch p)   (model_full.py:88-89)
+                // The division is a multiplication by 1/p: the two can only disagree half a period
+                // away from the transit, where the point is outside the box either way.
+                const double epoch = floor(fma(tv[j] - t0, invp, 0.5));
+                tc = tv[j] - __dadd_rn(t0, __dmul_rn(epoch, p));
+                inbox = (lo <= tc) && (tc <= hi);
+                fv[j] = 1.0;
+                if (LNL && !inbox) {
+                    const int b = P.blk ? P.blk[i0 + j] : 0;
+                    if (b >= 0) {
+                        const double d = P.obs[i0 + j] - 1.0;
+                        chi = fma(d * d, isig2[b], chi);
+                    }
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, inbox);
+            if (inbox) {
+                const int pos = qn + __popc(m & lt_mask);
+                q_ipt[warp][pos] = (int)(i0 + j);
+                q_tc[warp][pos] = tc;
+            }
+            qn += __popc(m);
+        }
+        if (!LNL && inr) VecIO<VEC>::store(frow + i0, fv);
+        __syncwarp();
+        // drain full passes; keep the remainder (< PPW points) for the next tile
+        while (qn >= PPW) {
+            qn -= PPW;
+            drain(qn, PPW);
+        }
+    }
+    if (qn > 0) drain(0, qn);
+    if (P.stage_ld && !ld_ready) mbar_wait(&bar, 0);  // never exit with the bulk copy in flight
+
+    if (LNL) {
+        chi = warp_sum(chi);
+        __syncthreads();
+        if (lane == 0) s_part[0][warp] = chi;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int wq = 0; wq < PT_WARPS; ++wq) s += s_part[0][wq];
+            P.partial[(size_t)ipv * P.nchunks + chunk] = s;
+        }
+    }
+}
+
+// chi^2 partials -> lnL (wnloglikelihood.py:34): lnL = sum_b n_b (-log s_b - log(2 pi)/2) - chi^2/2
+__global__ void k_lnl_finish(const double *__restrict__ partial, int nchunks, const double *__restrict__ sigma,
+                             const double *__restrict__ nblk, int nblocks, int npv, double *__restrict__ lnl) {
+    const int ipv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ipv >= npv) return;
+    double chi = 0.0;
+    for (int c = 0; c < nchunks; ++c) chi += partial[(size_t)ipv * nchunks + c];
+    double cst = 0.0;
+    for (int b = 0; b < nblocks; ++b) cst += nblk[b] * (-log(sigma[(size_t)ipv * nblocks + b]) - 0.5 * log(kTwoPi));
+    lnl[ipv] = cst - 0.5 * chi;
+}
+
+__global__ void k_inv_sigma2(const double *__restrict__ sigma, long long n, double *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const double s = sigma[i];
+        out[i] = 1.0 / (s * s);
+    }
+}
+
+// lnlike_normal on a materialised model (wnloglikelihood.py:22-35): one CTA per vector.
+__global__ void __launch_bounds__(256) k_lnl_model(const double *__restrict__ model, const double *__restrict__ obs,
+                                                   const int32_t *__restrict__ blk, const double *__restrict__ isig2,
+                                                   long long npt, int nblocks, double *__restrict__ partial) {
+    __shared__ double s_w[8];
+    const int ipv = blockIdx.x;
+    const double *m = model + (size_t)ipv * npt;
+    const double *w = isig2 + (size_t)ipv * nblocks;
+    double chi = 0.0;
+    for (long long j = threadIdx.x; j < npt; j += 256) {
+        const int b = blk ? blk[j] : 0;
+        if (b >= 0) {
+            const double d = obs[j] - m[j];
+            chi = fma(d * d, w[b], chi);
+        }
+    }
+    chi = warp_sum(chi);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = chi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += s_w[i];
+        partial[ipv] = s;
+    }
+}
+
+}  // namespace ptb

@@ -1,0 +1,269 @@
+// ptb_math.cuh -- device-side scalar arithmetic of the RoadRunner path (fp64).
+//
+// Each function names the reference arithmetic it implements (paths relative to the PyTransit
+// v2.8.1 tree).  These are new implementations written for the GPU: reciprocals are hoisted into
+// per-vector constants, branches are arranged for warp coherence, and table indices are clamped
+// where the reference reads one element out of bounds.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace ptb {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kTwoPi = 6.28318530717958647692;
+constexpr double kHalfPi = 1.57079632679489661923;
+
+// ---------------------------------------------------------------------------------------------
+// Geometry (models/roadrunner/common.py)
+// ---------------------------------------------------------------------------------------------
+
+// circle_circle_intersection_area, acos form (common.py:36-49).  Table construction only.
+__device__ __forceinline__ double ccia_acos(double r1, double r2, double b) {
+    if (r1 < b - r2) return 0.0;
+    if (r1 >= b + r2) return kPi * (r2 * r2);
+    if (b - r2 <= -r1) return kPi * (r1 * r1);
+    const double b2 = b * b, r12 = r1 * r1, r22 = r2 * r2;
+    return r22 * acos((b2 + r22 - r12) / (2.0 * b * r2)) + r12 * acos((b2 + r12 - r22) / (2.0 * b * r1)) -
+           0.5 * sqrt((-b + r2 + r1) * (b + r2 - r1) * (b - r2 + r1) * (b + r2 + r1));
+}
+
+// circle_circle_intersection_area_kite(1, k, z) (common.py:52-73, tsort :5-33): lens area of the
+// unit star and a planet of radius k at separation z, and kappa0.  k2 = k*k is passed in.
+// The Kahan-ordered product keeps the reference's parenthesisation.
+__device__ __forceinline__ void kite_area(double k, double k2, double z, double &area, double &kappa0) {
+    if (1.0 + k <= z) {
+        area = 0.0;
+        kappa0 = 0.0;
+    } else if (fabs(1.0 - k) < z) {
+        // descending sort of (1, k, z) as a 3-element min/max network (branch free)
+        const double hi = fmax(1.0, k), lo = fmin(1.0, k);
+        const double x = fmax(hi, z), t = fmin(hi, z);
+        const double y = fmax(lo, t), zz = fmin(lo, t);
+        const double akite = 0.5 * sqrt((x + (y + zz)) * (zz - (x - y)) * (zz + (x - y)) * (x + (y - zz)));
+        const double z2 = z * z;
+        const double k0 = atan2(2.0 * akite, (k - 1.0) * (k + 1.0) + z2);
+        const double k1 = atan2(2.0 * akite, (1.0 - k) * (1.0 + k) + z2);
+        area = k1 + k2 * k0 - akite;
+        kappa0 = k0;
+    } else if (z <= 1.0 - k) {
+        area = kPi * k2;
+        kappa0 = kPi;
+    } else if (z <= k - 1.0) {
+        area = kPi;
+        kappa0 = 0.0;
+    } else {
+        area = nan("");
+        kappa0 = nan("");
+    }
+}
+
+// interpolate_mean_limb_darkening_s (common.py:225-233) with inv_dg = 1/dg hoisted and the upper
+// node clamped to ng-1 (the reference reads lda[ng] for g in (1-1e-7, 1]; that term multiplies a
+// lens area < 1e-10).  `row` may point to shared or global memory.
+__device__ __forceinline__ double ldm_lerp(double g, double dg, double inv_dg, const double *row, int ng) {
+    if (g < 0.0) return nan("");
+    if (g > 1.0) return 0.0;
+    int i = (int)floor(g * inv_dg);
+    const double a = (g - i * dg) * inv_dg;
+    const int i0 = min(i, ng - 1);
+    const int i1 = min(i + 1, ng - 1);
+    return (1.0 - a) * row[i0] + a * row[i1];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Limb-darkening laws (models/numba/ldmodels.py:22-139) and analytic disk integrals (:27-123)
+// ---------------------------------------------------------------------------------------------
+enum : int {
+    LD_UNIFORM = 0, LD_LINEAR = 1, LD_QUADRATIC = 2, LD_QUADRATIC_TRI = 3, LD_NONLINEAR = 4, LD_GENERAL = 5,
+    LD_SQUARE_ROOT = 6, LD_LOGARITHMIC = 7, LD_EXPONENTIAL = 8, LD_POWER_2 = 9, LD_POWER_2_PM = 10,
+    LD_PROFILES = 100
+};
+
+__device__ __forceinline__ double ld_intensity(int law, double mu, const double *pv, int nldc) {
+    const double om = 1.0 - mu;
+    switch (law) {
+    case LD_UNIFORM: return 1.0;
+    case LD_LINEAR: return 1.0 - pv[0] * om;
+    case LD_QUADRATIC: return 1.0 - pv[0] * om - pv[1] * (om * om);
+    case LD_QUADRATIC_TRI: {
+        const double a = sqrt(pv[0]), b = 2.0 * pv[1];
+        const double u = a * b, v = a * (1.0 - b);
+        return 1.0 - u * om - v * (om * om);
+    }
+    case LD_NONLINEAR:
+        return 1.0 - pv[0] * (1.0 - sqrt(mu)) - pv[1] * om - pv[2] * (1.0 - pow(mu, 1.5)) - pv[3] * (1.0 - mu * mu);
+    case LD_GENERAL: {
+        double s = 0.0;
+        for (int i = 0; i < nldc; ++i) s += pv[i] * (1.0 - pow(mu, (double)(i + 1)));
+        return s;
+    }
+    case LD_SQUARE_ROOT: return 1.0 - pv[0] * om - pv[1] * (1.0 - sqrt(mu));
+    case LD_LOGARITHMIC: return 1.0 - pv[0] * om - pv[1] * mu * log(mu);
+    case LD_EXPONENTIAL: return 1.0 - pv[0] * om - pv[1] / (1.0 - exp(mu));
+    case LD_POWER_2: return 1.0 - pv[0] * (1.0 - pow(mu, pv[1]));
+    case LD_POWER_2_PM: {
+        const double c = 1.0 - pv[0] + pv[1];
+        const double al = log2(c / pv[1]);
+        return 1.0 - c * (1.0 - pow(mu, al));
+    }
+    default: return nan("");
+    }
+}
+
+// true when the reference registry has an analytic integral for the law (rrmodel.py:48-58);
+// 'linear' keeps the reference's 2 pi / 6 (3 - 2u) as coded (ldmodels.py:37-39).
+__device__ __forceinline__ bool ld_integral(int law, const double *pv, double &istar) {
+    switch (law) {
+    case LD_UNIFORM: istar = kPi; return true;
+    case LD_LINEAR: istar = 2.0 * kPi * 1.0 / 6.0 * (3.0 - 2.0 * pv[0]); return true;
+    case LD_QUADRATIC: istar = 2.0 * kPi * 1.0 / 12.0 * (-2.0 * pv[0] - pv[1] + 6.0); return true;
+    case LD_QUADRATIC_TRI: {
+        const double a = sqrt(pv[0]), b = 2.0 * pv[1];
+        const double u = a * b, v = a * (1.0 - b);
+        istar = 2.0 * kPi * 1.0 / 12.0 * (-2.0 * u - v + 6.0);
+        return true;
+    }
+    case LD_POWER_2: istar = 2.0 * kPi * (-pv[0] * pv[1] + pv[1] + 2.0) / (2.0 * pv[1] + 4.0); return true;
+    default: return false;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Orbit (meepmeep.backends.numba.point2d, restated from pytransit/orbits/taylor_z.py and
+// orbits/orbits_py.py)
+// ---------------------------------------------------------------------------------------------
+
+// numpy.mod semantics (result has the sign of the divisor).
+__device__ __forceinline__ double pymod(double a, double b) {
+    double r = fmod(a, b);
+    if (r != 0.0 && ((r < 0.0) != (b < 0.0))) r += b;
+    return r;
+}
+
+// mean_anomaly_offset (orbits_py.py:82-86)
+__device__ __forceinline__ double mean_anomaly_offset(double e, double w) {
+    double s, c;
+    sincos(kHalfPi - w, &s, &c);
+    double off = atan2(sqrt(1.0 - e * e) * s, e + c);
+    off -= e * sin(off);
+    return off;
+}
+
+// ta_newton_s (orbits_py.py:115-119,144-154,191-200) with t0 = 0: true anomaly at time t.
+// `offset` = mean_anomaly_offset(e, w) is hoisted by the caller.
+__device__ __forceinline__ double true_anomaly(double t, double p, double e, double offset) {
+    const double Ma = pymod(kTwoPi * (t - (0.0 - offset * p / kTwoPi)) / p, kTwoPi);
+    double Ea = Ma, err = 0.05, s, c;
+    int it = 0;
+    while (fabs(err) > 1e-8 && it < 1000) {
+        sincos(Ea, &s, &c);
+        err = Ea - e * s - Ma;
+        Ea = Ea - err / (1.0 - e * c);
+        ++it;
+    }
+    sincos(Ea, &s, &c);
+    const double den = 1.0 - e * c;
+    return atan2(sqrt(1.0 - e * e) * s / den, (c - e) / den);
+}
+
+// sky-plane position at time t (taylor_z.py:60-75)
+__device__ __forceinline__ void sky_position(double t, double p, double ae, double ci, double e, double w,
+                                             double offset, double &x, double &y) {
+    const double f = true_anomaly(t, p, e, offset);
+    const double r = ae / (1.0 + e * cos(f));
+    double s, c;
+    sincos(w + f, &s, &c);
+    x = -r * c;
+    y = -r * s * ci;
+}
+
+// 7-point central differences (taylor_z.py:77-100) -> monomial coefficients incl. 1/n!
+// (layout evidenced by models/numba/gdmodel.py:441-442).
+__device__ __forceinline__ void stencil_to_coeffs(const double *v, double *o) {
+    const double dt = 2e-2;
+    o[0] = v[3];
+    o[1] = (1. / 60 * (v[6] - v[0]) + 9. / 60 * (v[1] - v[5]) + 45. / 60 * (v[4] - v[2])) / dt;
+    o[2] = 0.5 * (1. / 90 * (v[0] + v[6]) - 3. / 20 * (v[1] + v[5]) + 3. / 2 * (v[2] + v[4]) - 49. / 18 * v[3]) /
+           (dt * dt);
+    o[3] = (1. / 8 * (v[0] - v[6]) + (v[5] - v[1]) + 13. / 8 * (v[2] - v[4])) / (dt * dt * dt) / 6.0;
+    o[4] = (-1. / 6 * (v[0] + v[6]) + 2 * (v[1] + v[5]) - 13. / 2 * (v[2] + v[4]) + 28. / 3 * v[3]) /
+           (dt * dt * dt * dt) / 24.0;
+}
+
+// sep_c (taylor_z.py:229-255): projected separation from the two quartics, Horner form.
+__device__ __forceinline__ double sep_poly(double t, const double *cx, const double *cy) {
+    const double px = fma(t, fma(t, fma(t, fma(t, cx[4], cx[3]), cx[2]), cx[1]), cx[0]);
+    const double py = fma(t, fma(t, fma(t, fma(t, cy[4], cy[3]), cy[2]), cy[1]), cy[0]);
+    return sqrt(px * px + py * py);
+}
+
+// find_contact_point for points 1 (s=-1) and 4 (s=+1), target z = 1 + k (taylor_z.py:298-328).
+__device__ __forceinline__ double contact_point(double k, double s, const double *cx, const double *cy) {
+    const double zt = 1.0 + k;
+    double t0 = 0.0;
+    double t2 = s * 2.0 / cx[1];
+    double t1 = 0.5 * t2;
+    double z0 = sep_poly(t0, cx, cy) - zt;
+    double z1 = sep_poly(t1, cx, cy) - zt;
+    int i = 0;
+    while (fabs(t2 - t0) > 1e-6 && i < 100) {
+        if (z0 * z1 < 0.0) {
+            t2 = t1;
+            t1 = 0.5 * (t0 + t1);
+        } else {
+            t0 = t1;
+            t1 = 0.5 * (t1 + t2);
+            z0 = z1;
+        }
+        z1 = sep_poly(t1, cx, cy) - zt;
+        ++i;
+    }
+    return t1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA bulk copy + mbarrier (sm_90+/sm_100a PTX; SASS: UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// global -> shared bulk copy through the TMA engine; completion is signalled on `bar`.
+// dst, src 16-byte aligned; bytes a multiple of 16.
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace ptb

@@ -1,0 +1,354 @@
+"""GPU parity tests (-m gpu): the CUDA path through the C ABI / Python classes against
+ (1) the golden fixtures produced by the reference's own Numba files (tests/golden/make_golden.py),
+ (2) the CPU oracle (oracle/rr_oracle.c) on the same seeded inputs, and
+ (3) size-independent properties at the full BASELINE.json sizes.
+
+Tolerances (BASELINE.json north_star): max |d flux| <= 1e-9 in fp64, lnL within 1e-8 relative.  The
+CUDA kernels follow the reference's algorithm step for step, so the observed differences are ~1e-14;
+the tests assert the contractual 1e-9 and, where the arithmetic is identical by construction
+(injected orbit coefficients), a much tighter 1e-12.
+"""
+import numpy as np
+import pytest
+
+import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+FLUX_TOL = 1e-9       # north-star fp64 tolerance
+TIGHT = 1e-12         # same algorithm, different libm / summation order
+LNL_RTOL = 1e-8
+
+
+@pytest.fixture(scope='module')
+def pb():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import pytransit_b200 as pb
+    return pb
+
+
+def _full_args(d):
+    return d['k'], d['ldc'], d['t0'], d['p'], d['a'], d['i'], d['e'], d['w']
+
+
+def _set_data(m, d):
+    m.set_data(d['time'], d['lcids'], d['pbids'], d['nsamples'], d['exptimes'], d['epids'])
+
+
+# ---------------------------------------------------------------------------------------------
+# tables and stages
+# ---------------------------------------------------------------------------------------------
+def test_tables(pb, golden, tab):
+    m = pb.RoadRunnerModelCUDA('quadratic')
+    g = golden('tables')
+    assert m.dk == float(g['dk']) and m.dg == float(g['dg'])
+    assert np.array_equal(m.ze, g['ze']) and np.array_equal(m.zm, g['zm'])
+    np.testing.assert_allclose(m.mu, g['mu'], rtol=0, atol=1e-16)
+    w = m.weights
+    assert w.shape == (256, 100, 40)
+    np.testing.assert_allclose(w[np.ix_(g['weights_ik'], g['weights_ig'])], g['weights_sub'], rtol=0, atol=5e-15)
+    np.testing.assert_allclose(w[37], g['weights_k37'], rtol=0, atol=5e-15)
+    np.testing.assert_allclose(w, tab.weights, rtol=0, atol=5e-15)
+    np.testing.assert_allclose(w.sum(-1), 1.0, rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize('law', ['uniform', 'linear', 'quadratic', 'quadratic-tri', 'nonlinear', 'general',
+                                 'square_root', 'logarithmic', 'exponential', 'power-2', 'power-2-pm'])
+def test_ld_laws(pb, golden, law):
+    g = golden('ldlaws')
+    ldc = g[f'{law}__ldc']                      # [3, 2, nldc]
+    m = pb.RoadRunnerModelCUDA(law)
+    time = np.linspace(-0.1, 0.1, 64)
+    m.set_data(time, lcids=np.arange(64) % 2, pbids=[0, 1])
+    m.evaluate(np.full((3, 1), 0.1), ldc, np.zeros(3), np.full(3, 1.0), np.full(3, 3.0), np.full(3, 0.5 * np.pi),
+               np.zeros(3), np.zeros(3))
+    np.testing.assert_allclose(m.stage('ldp'), g[f'{law}__ldp'], rtol=5e-15, atol=1e-15)
+    ref = g[f'{law}__istar']
+    fin = np.isfinite(ref)
+    ist = m.stage('istar')
+    assert np.array_equal(np.isfinite(ist), fin)
+    np.testing.assert_allclose(ist[fin], ref[fin], rtol=1e-13)
+
+
+@pytest.mark.parametrize('name,law', [('c2', 'power-2'), ('c3', 'quadratic'), ('c5', 'power-2'), ('edge', 'power-2'),
+                                      ('ttv', 'quadratic'), ('conftest', 'quadratic')])
+def test_rr_population_vs_reference_golden(pb, orc, tab, golden, name, law):
+    d = golden(name)
+    ref = np.atleast_2d(d['flux'])
+    m = pb.RoadRunnerModelCUDA(law)
+    _set_data(m, d)
+    flux = np.atleast_2d(m.evaluate(*_full_args(d))).copy()
+    assert flux.shape == ref.shape
+    assert np.array_equal(np.isnan(flux), np.isnan(ref))
+    err = np.nanmax(np.abs(flux - ref))
+    assert err <= FLUX_TOL, err
+
+    # stage-level parity against the oracle's intermediates
+    ldp, istar = orc.evaluate_ld(law, tab.mu, d['ldc'])
+    _, st = orc.rr_full(tab, d['time'], d['k'], d['t0'], d['p'], d['a'], d['i'], d['e'], d['w'], d['lcids'],
+                        d['pbids'], d['epids'], d['nsamples'], d['exptimes'], ldp, istar, stages=True)
+    good = m.stage('good') > 0
+    assert np.array_equal(good, ~np.isnan(ref[:, 0]))
+    np.testing.assert_allclose(m.stage('ldm')[good], st['ldm'][good], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(m.stage('xyc')[good], d['xyc'][good], rtol=1e-9, atol=1e-9)
+    bb = m.stage('bbox')[good]
+    np.testing.assert_allclose(bb[:, 0] - (0.003 + d['exptimes'][0]), st['bbs'][good, 0, 0], atol=2e-6)
+    np.testing.assert_allclose(bb[:, 1] + (0.003 + d['exptimes'][0]), st['bbs'][good, 0, 1], atol=2e-6)
+
+    # with the reference run's own Taylor coefficients injected everything downstream is pinned tightly
+    m.inject_xyc(np.where(np.isnan(d['xyc']), 0.0, d['xyc']))
+    flux2 = np.atleast_2d(m.evaluate(*_full_args(d))).copy()
+    m.inject_xyc(None)
+    err2 = np.nanmax(np.abs(flux2 - ref))
+    assert err2 <= TIGHT, err2
+
+
+def test_c1_readme_example(pb, golden):
+    c, g = wl.config1(), golden('c1')
+    m = pb.RoadRunnerModelCUDA('quadratic')
+    m.set_data(c.time)
+    f = m.evaluate(c.k, c.ldc, c.t0, c.p, c.a, c.i)
+    assert f.shape == (10_000,)
+    assert np.abs(f - g['flux']).max() <= FLUX_TOL
+    m.set_data(c.time, nsamples=7, exptimes=0.01)
+    f = m.evaluate(c.k, c.ldc, c.t0, c.p, c.a, c.i, 0.1, 0.3)
+    assert np.abs(f - g['flux_ss7']).max() <= FLUX_TOL
+    # odd npt exercises the scalar-store path
+    m.set_data(c.time[:9999])
+    f = m.evaluate(c.k, c.ldc, c.t0, c.p, c.a, c.i)
+    assert np.abs(f - g['flux'][:9999]).max() <= FLUX_TOL
+
+
+def test_broadcasting_and_errors(pb, golden):
+    d = golden('c3')
+    m = pb.RoadRunnerModelCUDA('quadratic')
+    _set_data(m, d)
+    ref = m.evaluate(*_full_args(d)).copy()
+    # scalar e, w and a 1-D t0[npv] broadcast to the population
+    f = m.evaluate(d['k'], d['ldc'], d['t0'][:, 0], d['p'], d['a'], d['i'], 0.0, 0.0)
+    assert np.array_equal(f, ref)
+    # shared coefficients: [npb, nldc] applies to every vector
+    f1 = m.evaluate(d['k'], d['ldc'][0], d['t0'], d['p'], d['a'], d['i'], d['e'], d['w'])
+    assert np.array_equal(f1[0], ref[0])
+    # evaluate_pv row layout [k..., t0, p, a, i, e, w]
+    pvp = np.column_stack([d['k'], d['t0'][:, 0], d['p'], d['a'], d['i'], d['e'], d['w']])
+    assert np.array_equal(m.evaluate_pv(pvp, d['ldc']), ref)
+    with pytest.raises(ValueError):
+        m.evaluate(d['k'][:, :3], d['ldc'], d['t0'], d['p'], d['a'], d['i'], d['e'], d['w'])   # k with 3 of 4 passbands
+    with pytest.raises(ValueError):
+        m.evaluate(d['k'], d['ldc'], d['t0'], d['p'], d['a'][:5], d['i'], d['e'], d['w'])
+    with pytest.raises(ValueError):
+        m.set_data(d['time'], d['lcids'], [0, 1, 2, 4], d['nsamples'], d['exptimes'])
+    with pytest.raises(ValueError):
+        m.set_data(d['time'], d['lcids'].astype(float), d['pbids'])
+    with pytest.raises(KeyError):
+        pb.RoadRunnerModelCUDA('no-such-law')
+
+
+def test_device_resident_io(pb, golden):
+    import torch
+    d = golden('c2')
+    m = pb.RoadRunnerModelCUDA('power-2')
+    _set_data(m, d)
+    ref = m.evaluate(*_full_args(d)).copy()
+    dev = 'cuda:0'
+    t = {k: torch.as_tensor(d[k], device=dev) for k in ('k', 'ldc', 't0', 'p', 'a', 'i', 'e', 'w')}
+    m2 = pb.RoadRunnerModelCUDA('power-2')
+    m2.set_data(torch.as_tensor(d['time'], device=dev))
+    out = m2.evaluate(t['k'], t['ldc'], t['t0'], t['p'], t['a'], t['i'], t['e'], t['w'], copy=False)
+    assert isinstance(out, torch.Tensor) and out.is_cuda
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_custom_ld_callable_and_ldmodel(pb, golden):
+    d = golden('c2')
+
+    def quad(mu, pv):
+        return 1. - pv[0] * (1. - mu) - pv[1] * (1. - mu) ** 2
+
+    ldc = np.random.default_rng(3).uniform(0.1, 0.4, size=(d['k'].shape[0], 1, 2))
+    ma = pb.RoadRunnerModelCUDA('quadratic')
+    _set_data(ma, d)
+    ref = ma.evaluate(d['k'], ldc, d['t0'], d['p'], d['a'], d['i'], d['e'], d['w']).copy()
+    mb = pb.RoadRunnerModelCUDA((quad, lambda pv: 2 * np.pi / 12 * (-2 * pv[0] - pv[1] + 6)))
+    _set_data(mb, d)
+    f = mb.evaluate(d['k'], ldc, d['t0'], d['p'], d['a'], d['i'], d['e'], d['w'])
+    assert np.abs(f - ref).max() < 1e-13
+    mc = pb.RoadRunnerModelCUDA(quad)          # numeric I* on 200 nodes: ~1e-5 relative
+    _set_data(mc, d)
+    f = mc.evaluate(d['k'], ldc, d['t0'], d['p'], d['a'], d['i'], d['e'], d['w'])
+    assert np.abs(f - ref).max() < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# fused log likelihood
+# ---------------------------------------------------------------------------------------------
+def test_lnlike_vs_reference_golden(pb, golden):
+    d = golden('c5')
+    m = pb.RoadRunnerModelCUDA('power-2')
+    _set_data(m, d)
+    m.set_obs(d['obs'], d['slices'], d['nids'])
+    lnl = m.lnlikelihood(*_full_args(d), sigma=d['sigma']).copy()
+    np.testing.assert_allclose(lnl, d['lnl'], rtol=LNL_RTOL)
+    # unfused: lnlike_normal on the reference flux
+    lnl2 = m.lnlike_normal(d['flux'], d['sigma']).copy()
+    np.testing.assert_allclose(lnl2, d['lnl'], rtol=1e-12)
+
+
+def test_lnlike_blocks_nan_rows_and_supersampling(pb, orc, tab, golden):
+    d = golden('ttv')     # 3 light curves, unsorted times, per-light-curve nsamples
+    npt = d['time'].size
+    rng = np.random.default_rng(5)
+    obs = 1 + rng.normal(0, 1e-3, npt)
+    # two noise blocks over three slices, and a gap that belongs to no slice
+    slices = np.array([[0, 300], [300, 700], [750, npt]])
+    nids = np.array([0, 1, 0])
+    npv = d['k'].shape[0]
+    sigma = 10 ** rng.uniform(-3.2, -2.8, size=(npv, 2))
+    a = d['a'].copy()
+    a[2] = 0.5           # invalid vector: lnL must be NaN for this row only
+    m = pb.RoadRunnerModelCUDA('quadratic')
+    _set_data(m, d)
+    m.set_obs(obs, slices, nids)
+    lnl = m.lnlikelihood(d['k'], d['ldc'], d['t0'], d['p'], a, d['i'], d['e'], d['w'], sigma=sigma).copy()
+    ldp, istar = orc.evaluate_ld('quadratic', tab.mu, d['ldc'])
+    flux = orc.rr_full(tab, d['time'], d['k'], d['t0'], d['p'], a, d['i'], d['e'], d['w'], d['lcids'], d['pbids'],
+                       d['epids'], d['nsamples'], d['exptimes'], ldp, istar)
+    ref = orc.lnlike_normal(obs, flux, sigma, slices, nids)
+    assert np.isnan(lnl[2]) and np.isnan(ref[2])
+    ok = np.arange(npv) != 2
+    np.testing.assert_allclose(lnl[ok], ref[ok], rtol=LNL_RTOL)
+    from pytransit_b200 import CUDALogLikelihood
+    ll = CUDALogLikelihood(m, obs, slices, nids)
+    pvp = np.log10(sigma)
+    np.testing.assert_allclose(ll.lnlikelihood(pvp, d['k'], d['ldc'], d['t0'], d['p'], a, d['i'], d['e'], d['w'])[ok],
+                               ref[ok], rtol=LNL_RTOL)
+    np.testing.assert_allclose(ll(pvp, flux)[ok], ref[ok], rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# transmission spectroscopy
+# ---------------------------------------------------------------------------------------------
+def test_tsmodel_vs_reference_golden(pb, golden):
+    d = golden('c4')
+    for pw in (False, True):
+        for ns, et in ((1, 0.0), (4, 0.012)):
+            class Tab(pb.LDModel):
+                def __call__(self, mu, x):
+                    return d['ldp'], d['istar']
+            m = pb.TSModelCUDA(Tab(), precompute_weights=pw)
+            m.set_data(d['time'], nsamples=[ns], exptimes=[et])
+            f = m.evaluate(d['k'], np.zeros((6, 24, 3)), d['t0'], d['p'], d['a'], d['i'], d['e'], d['w']).copy()
+            ref = d[f'flux_pw{int(pw)}_ns{ns}']
+            assert f.shape == ref.shape == (6, 24, 500)
+            assert np.array_equal(np.isnan(f), np.isnan(ref))
+            err = np.nanmax(np.abs(f - ref))
+            assert err <= FLUX_TOL, (pw, ns, err)
+    m = pb.TSModelCUDA('power-2')
+    m.set_data(d['time'])
+    f = m.evaluate(d['k'], d['ldc_named'], d['t0'], d['p'], d['a'], d['i'], d['e'], d['w'])
+    assert np.nanmax(np.abs(f - d['flux_named'])) <= FLUX_TOL
+    with pytest.raises(ValueError):
+        m.evaluate(d['k'], d['ldc_named'][:, :5], d['t0'], d['p'], d['a'], d['i'], d['e'], d['w'])
+    with pytest.raises(ValueError):
+        m.evaluate(d['k'], d['ldc_named'][0], d['t0'], d['p'], d['a'], d['i'], d['e'], d['w'])
+
+
+def test_tabulated_ld_model_on_device(pb, golden):
+    d = golden('c4')
+    m = pb.TSModelCUDA('uniform')
+    prof, (x0, dx), (y0, dy), (z0, dz) = wl.ldtk_style_table(24, m.mu)
+    ldm = pb.TabulatedLDModel(prof, x0, dx, y0, dy, z0, dz)
+    x = np.column_stack([d['teff'], d['logg'], d['metal']])
+    ldp, istar = ldm(m.mu, x)
+    np.testing.assert_allclose(ldp.cpu().numpy(), d['ldp'], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(istar.cpu().numpy(), d['istar'], rtol=1e-13)
+    mt = pb.TSModelCUDA(ldm)
+    mt.set_data(d['time'])
+    f = mt.evaluate(d['k'], x, d['t0'], d['p'], d['a'], d['i'], d['e'], d['w'])
+    assert np.nanmax(np.abs(f - d['flux_pw0_ns1'])) <= FLUX_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle comparisons on fresh seeded inputs + properties at full size
+# ---------------------------------------------------------------------------------------------
+def test_c2_shaped_population_vs_oracle(pb, orc, tab):
+    c = wl.config2(npv=192, npt=20_000)
+    m = pb.RoadRunnerModelCUDA('power-2')
+    m.set_data(c.time)
+    f = m.evaluate(c.k, c.ldc, c.t0, c.p, c.a, c.i, c.e, c.w).copy()
+    ldp, istar = orc.evaluate_ld('power-2', tab.mu, c.ldc)
+    ref = orc.rr_full(tab, c.time, c.k, c.t0, c.p, c.a, c.i, c.e, c.w, c.lcids, c.pbids, c.epids, c.nsamples,
+                      c.exptimes, ldp, istar)
+    err = np.abs(f - ref).max()
+    assert err <= FLUX_TOL, err
+    assert (ref < 1).mean() > 0.01
+
+
+def test_c3_shaped_population_vs_oracle(pb, orc, tab):
+    c = wl.config3(npv=64, npt_per_lc=4096)
+    m = pb.RoadRunnerModelCUDA('quadratic')
+    m.set_data(c.time, c.lcids, c.pbids, c.nsamples, c.exptimes, c.epids)
+    f = m.evaluate(c.k, c.ldc, c.t0, c.p, c.a, c.i, c.e, c.w).copy()
+    ldp, istar = orc.evaluate_ld('quadratic', tab.mu, c.ldc)
+    ref = orc.rr_full(tab, c.time, c.k, c.t0, c.p, c.a, c.i, c.e, c.w, c.lcids, c.pbids, c.epids, c.nsamples,
+                      c.exptimes, ldp, istar)
+    err = np.abs(f - ref).max()
+    assert err <= FLUX_TOL, err
+
+
+def test_c5_shaped_lnlike_vs_oracle(pb, orc, tab):
+    c = wl.config5(npv=96, npt=100_000)
+    m = pb.RoadRunnerModelCUDA('power-2')
+    m.set_data(c.time)
+    m.set_obs(c.obs)
+    lnl = m.lnlikelihood(c.k, c.ldc, c.t0, c.p, c.a, c.i, c.e, c.w, sigma=c.sigma).copy()
+    ldp, istar = orc.evaluate_ld('power-2', tab.mu, c.ldc)
+    flux = orc.rr_full(tab, c.time, c.k, c.t0, c.p, c.a, c.i, c.e, c.w, c.lcids, c.pbids, c.epids, c.nsamples,
+                       c.exptimes, ldp, istar)
+    ref = orc.lnlike_normal(c.obs, flux, c.sigma, c.slices, c.nids)
+    np.testing.assert_allclose(lnl, ref, rtol=LNL_RTOL)
+
+
+def test_c4_shaped_tsmodel_vs_oracle(pb, orc, tab):
+    c = wl.config4(npv=8, npb=200, npt=2000)
+    prof, (x0, dx), (y0, dy), (z0, dz) = wl.ldtk_style_table(c.npb, tab.mu)
+    ldp, istar = orc.ldtk_profiles(prof, c.teff, c.logg, c.metal, x0, dx, y0, dy, z0, dz, tab.mu)
+    ref = orc.tsmodel(tab, c.time, c.k, c.t0, c.p, c.a, c.i, c.e, c.w, 1, 0.0, ldp, istar)
+    ldm = pb.TabulatedLDModel(prof, x0, dx, y0, dy, z0, dz)
+    m = pb.TSModelCUDA(ldm)
+    m.set_data(c.time)
+    f = m.evaluate(c.k, np.column_stack([c.teff, c.logg, c.metal]), c.t0, c.p, c.a, c.i, c.e, c.w)
+    err = np.abs(f - ref).max()
+    assert err <= FLUX_TOL, err
+
+
+def test_full_size_c2_properties(pb, orc, tab):
+    """BASELINE configs[1] at full size (8192 x 20000): properties that do not need the oracle on all rows,
+    plus the oracle on a strided sample of rows."""
+    import torch
+    c = wl.config2()
+    m = pb.RoadRunnerModelCUDA('power-2')
+    m.set_data(c.time)
+    f = m.evaluate(c.k, c.ldc, c.t0, c.p, c.a, c.i, c.e, c.w, copy=False)
+    assert f.shape == (8192, 20000)
+    assert bool(torch.isfinite(f).all()) and float(f.max()) == 1.0 and float(f.min()) > 0.97
+    frac = float((f < 1).double().mean())
+    assert 0.02 < frac < 0.05
+    # evaluating a row subset gives bit-identical rows (no cross-vector coupling)
+    rows = np.arange(0, 8192, 257)
+    fs = m.evaluate(c.k[rows], c.ldc[rows], c.t0[rows], c.p[rows], c.a[rows], c.i[rows], c.e[rows], c.w[rows]).copy()
+    assert np.array_equal(fs, f[torch.as_tensor(rows, device=f.device)].cpu().numpy())
+    ldp, istar = orc.evaluate_ld('power-2', tab.mu, c.ldc[rows])
+    ref = orc.rr_full(tab, c.time, c.k[rows], c.t0[rows], c.p[rows], c.a[rows], c.i[rows], c.e[rows], c.w[rows],
+                      c.lcids, c.pbids, c.epids, c.nsamples, c.exptimes, ldp, istar)
+    assert np.abs(fs - ref).max() <= FLUX_TOL
+    # fused likelihood equals lnlike_normal on the materialised flux
+    obs = 1 + np.random.default_rng(1).normal(0, 1e-3, c.npt)
+    sigma = np.full((8192, 1), 1e-3)
+    m.set_obs(obs)
+    l1 = m.lnlikelihood(c.k, c.ldc, c.t0, c.p, c.a, c.i, c.e, c.w, sigma=sigma).copy()
+    l2 = m.lnlike_normal(f, sigma).copy()
+    np.testing.assert_allclose(l1, l2, rtol=1e-11)

@@ -1,0 +1,125 @@
+"""CPU tests: the oracle (oracle/rr_oracle.c) against the golden fixtures produced by executing the
+reference's own files (tests/golden/make_golden.py) and against the reference's known-answer tests.
+
+Tolerances: the oracle restates the reference in the same operation order, so flux agrees to a few
+ulp (2e-15); the 1e-9 parity bar of BASELINE.json is checked with a wide margin.
+"""
+import numpy as np
+import pytest
+
+FLUX_TOL = 2e-15
+
+
+def test_tables_match_reference(tab, golden):
+    g = golden('tables')
+    assert tab.dk == float(g['dk']) and tab.dg == float(g['dg'])
+    assert np.array_equal(tab.ze, g['ze']) and np.array_equal(tab.zm, g['zm'])
+    np.testing.assert_allclose(tab.mu, g['mu'], rtol=0, atol=1e-16)
+    sub = tab.weights[np.ix_(g['weights_ik'], g['weights_ig'])]
+    np.testing.assert_allclose(sub, g['weights_sub'], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(tab.weights[37], g['weights_k37'], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(tab.weights.sum(-1), g['weights_rowsum'], rtol=0, atol=1e-14)
+
+
+def test_known_answer_uniform_model(orc):
+    # reference tests/test_uniform_model_nb.py:24-25: uniform_z_s(1.0, 0.1) = 0.9951061298
+    a = orc.ccia(1.0, 0.1, 1.0)
+    ak, _ = orc.ccia_kite(1.0, 0.1, 1.0)
+    assert abs(1 - a / np.pi - 0.9951061298) < 1e-10
+    assert abs(1 - ak / np.pi - 0.9951061298) < 1e-10
+    assert abs(a - ak) < 1e-15
+
+
+def test_kite_branches(orc):
+    assert orc.ccia_kite(1.0, 0.1, 1.2) == (0.0, 0.0)                       # no overlap
+    a, k = orc.ccia_kite(1.0, 0.1, 0.3)
+    assert a == np.pi * 0.1 ** 2 and k == np.pi                              # planet inside the disk
+    a, k = orc.ccia_kite(1.0, 1.5, 0.2)
+    assert a == np.pi and k == 0.0                                           # star inside the planet
+
+
+@pytest.mark.parametrize('law', ['uniform', 'linear', 'quadratic', 'quadratic-tri', 'nonlinear', 'general',
+                                 'square_root', 'logarithmic', 'exponential', 'power-2', 'power-2-pm'])
+def test_ld_laws_match_reference(orc, tab, golden, law):
+    g = golden('ldlaws')
+    ldp, istar = orc.evaluate_ld(law, tab.mu, g[f'{law}__ldc'])
+    np.testing.assert_allclose(ldp, g[f'{law}__ldp'], rtol=2e-15, atol=1e-15)
+    ref = g[f'{law}__istar']
+    fin = np.isfinite(ref)
+    # 'exponential' is singular at mu = 0: the reference's numeric I* is +-inf (sign decided by fastmath)
+    assert np.array_equal(np.isfinite(istar), fin)
+    np.testing.assert_allclose(istar[fin], ref[fin], rtol=2e-15, atol=5e-15)
+
+
+def test_known_answer_ld_integrals(orc, tab):
+    # reference tests/test_limb_darkening.py: quadratic disk integral vs closed form; the 'linear' law used
+    # by RoadRunner keeps the reference's as-coded 2 pi / 6 (3 - 2u)
+    ldc = np.array([[[0.3, 0.2]]])
+    _, istar = orc.evaluate_ld('quadratic', tab.mu, ldc)
+    assert abs(istar[0, 0] - np.pi * (1 - 0.3 / 3 - 0.2 / 6)) < 1e-15
+    _, istar = orc.evaluate_ld('linear', tab.mu, np.array([[[0.4]]]))
+    assert abs(istar[0, 0] - 2 * np.pi / 6 * (3 - 2 * 0.4)) < 1e-15
+
+
+def _run_full(orc, tab, d, law, xyc=None):
+    ldp, istar = orc.evaluate_ld(law, tab.mu, d['ldc'])
+    return orc.rr_full(tab, d['time'], d['k'], d['t0'], d['p'], d['a'], d['i'], d['e'], d['w'], d['lcids'],
+                       d['pbids'], d['epids'], d['nsamples'], d['exptimes'], ldp, istar, xyc=xyc, stages=True)
+
+
+@pytest.mark.parametrize('name,law', [('c2', 'power-2'), ('c3', 'quadratic'), ('c5', 'power-2'), ('edge', 'power-2'),
+                                      ('ttv', 'quadratic'), ('conftest', 'quadratic')])
+def test_rr_full_matches_reference(orc, tab, golden, name, law):
+    d = golden(name)
+    ref = np.atleast_2d(d['flux'])
+    flux, st = _run_full(orc, tab, d, law)
+    assert np.array_equal(np.isnan(flux), np.isnan(ref))
+    assert np.nanmax(np.abs(flux - ref)) <= FLUX_TOL
+    good = ~np.isnan(ref[:, 0])
+    np.testing.assert_allclose(st['xyc'][good], d['xyc'][good], rtol=0, atol=1e-9)
+    # with the reference's own coefficients injected the result is unchanged
+    flux2, _ = _run_full(orc, tab, d, law, xyc=d['xyc'])
+    assert np.nanmax(np.abs(flux2 - ref)) <= FLUX_TOL
+    assert (ref[good] < 1.0).any()
+
+
+def test_edge_rows(golden):
+    d = golden('edge')
+    assert np.isnan(d['flux'][1:5]).all() and not np.isnan(d['flux'][[0, 5, 6]]).any()
+
+
+def test_rr_simple_matches_reference(orc, tab, golden):
+    import workloads as wl
+    c, g = wl.config1(), golden('c1')
+    ldp, istar = orc.evaluate_ld('quadratic', tab.mu, c.ldc.reshape(1, 1, 2))
+    f = orc.rr_simple(tab, c.time, c.k, c.t0, c.p, c.a, c.i, c.e, c.w, 1, 0.0, ldp[0, 0], istar[0, 0])
+    assert np.abs(f - g['flux']).max() <= FLUX_TOL
+    f = orc.rr_simple(tab, c.time, c.k, c.t0, c.p, c.a, c.i, 0.1, 0.3, 7, 0.01, ldp[0, 0], istar[0, 0])
+    assert np.abs(f - g['flux_ss7']).max() <= FLUX_TOL
+    # README sanity: depth of a k=0.1 quadratic transit (reference tests/test_ma_quadratic_nb.py:29-53)
+    assert abs(g['flux'].min() - 0.98909638) < 1e-6
+
+
+def test_lnlike_matches_reference(orc, golden):
+    d = golden('c5')
+    lnl = orc.lnlike_normal(d['obs'], d['flux'], d['sigma'], d['slices'], d['nids'])
+    np.testing.assert_allclose(lnl, d['lnl'], rtol=1e-12)
+
+
+def test_tsmodel_matches_reference(orc, tab, golden):
+    import workloads as wl
+    d = golden('c4')
+    prof, (x0, dx), (y0, dy), (z0, dz) = wl.ldtk_style_table(d['k'].shape[1], tab.mu)
+    ldp, istar = orc.ldtk_profiles(prof, d['teff'], d['logg'], d['metal'], x0, dx, y0, dy, z0, dz, tab.mu)
+    np.testing.assert_allclose(ldp, d['ldp'], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(istar, d['istar'], rtol=0, atol=1e-14)
+    for pw in (0, 1):
+        for ns, et in ((1, 0.0), (4, 0.012)):
+            f = orc.tsmodel(tab, d['time'], d['k'], d['t0'], d['p'], d['a'], d['i'], d['e'], d['w'], ns, et, ldp,
+                            istar, precompute_weights=bool(pw))
+            ref = d[f'flux_pw{pw}_ns{ns}']
+            assert np.array_equal(np.isnan(f), np.isnan(ref))
+            assert np.nanmax(np.abs(f - ref)) <= 5e-15
+    ldpn, istarn = orc.evaluate_ld('power-2', tab.mu, d['ldc_named'])
+    f = orc.tsmodel(tab, d['time'], d['k'], d['t0'], d['p'], d['a'], d['i'], d['e'], d['w'], 1, 0.0, ldpn, istarn)
+    assert np.nanmax(np.abs(f - d['flux_named'])) <= 5e-15
