@@ -463,13 +463,16 @@ __global__ void __launch_bounds__(PT_THREADS) k_rr_points(const __grid_constant_
         }
         if (!LNL && inr) VecIO<VEC>::store(frow + i0, fv);
         __syncwarp();
-        // drain full passes; keep the remainder (< PPW points) for the next tile
-        while (qn >= PPW) {
-            qn -= PPW;
-            drain(qn, PPW);
+        // Drain full passes; keep the remainder (< PPW points) for the next tile, except after the last
+        // tile.  There is exactly ONE call site, so every point goes through the same instruction
+        // sequence whatever the chunking: results are bit-reproducible across population splits.
+        const bool last = tbeg + TILE >= cend;
+        while (qn >= PPW || (last && qn > 0)) {
+            const int n = min(qn, PPW);
+            qn -= n;
+            drain(qn, n);
         }
     }
-    if (qn > 0) drain(0, qn);
     if (P.stage_ld && !ld_ready) mbar_wait(&bar, 0);  // never exit with the bulk copy in flight
 
     if (LNL) {

@@ -20,13 +20,20 @@ constexpr double kHalfPi = 1.57079632679489661923;
 // ---------------------------------------------------------------------------------------------
 
 // circle_circle_intersection_area, acos form (common.py:36-49).  Table construction only.
+// The acos arguments approach +-1 at tangency, where a 1-ulp change of the argument is amplified
+// ~1e4-fold, so the reference's operation order is kept rounding for rounding (explicit
+// round-to-nearest intrinsics: no FMA contraction).
 __device__ __forceinline__ double ccia_acos(double r1, double r2, double b) {
     if (r1 < b - r2) return 0.0;
     if (r1 >= b + r2) return kPi * (r2 * r2);
     if (b - r2 <= -r1) return kPi * (r1 * r1);
-    const double b2 = b * b, r12 = r1 * r1, r22 = r2 * r2;
-    return r22 * acos((b2 + r22 - r12) / (2.0 * b * r2)) + r12 * acos((b2 + r12 - r22) / (2.0 * b * r1)) -
-           0.5 * sqrt((-b + r2 + r1) * (b + r2 - r1) * (b - r2 + r1) * (b + r2 + r1));
+    const double b2 = __dmul_rn(b, b), r12 = __dmul_rn(r1, r1), r22 = __dmul_rn(r2, r2);
+    const double x2 = __ddiv_rn(__dsub_rn(__dadd_rn(b2, r22), r12), __dmul_rn(__dmul_rn(2.0, b), r2));
+    const double x1 = __ddiv_rn(__dsub_rn(__dadd_rn(b2, r12), r22), __dmul_rn(__dmul_rn(2.0, b), r1));
+    const double q = __dmul_rn(__dmul_rn(__dmul_rn(__dadd_rn(__dadd_rn(-b, r2), r1), __dsub_rn(__dadd_rn(b, r2), r1)),
+                                         __dadd_rn(__dsub_rn(b, r2), r1)),
+                               __dadd_rn(__dadd_rn(b, r2), r1));
+    return __dsub_rn(__dadd_rn(__dmul_rn(r22, acos(x2)), __dmul_rn(r12, acos(x1))), __dmul_rn(0.5, sqrt(q)));
 }
 
 // circle_circle_intersection_area_kite(1, k, z) (common.py:52-73, tsort :5-33): lens area of the
