@@ -175,6 +175,16 @@ int ptb_host_free(void *ptr);
 /* Kernels launched by this handle since creation (bench.py's gpu_launches evidence). */
 int64_t ptb_launch_count(const ptb_model *h);
 
+/* Per-kernel device timing for bench.py's roofline: when enabled, CUDA events are recorded on the
+ * launching stream around the per-vector setup kernel(s) and around the dominant npv x npt kernel of
+ * every evaluate / lnlike call.  ptb_last_timing waits for the last call and returns both durations
+ * in milliseconds. */
+int ptb_set_profiling(ptb_model *h, int32_t enabled);
+int ptb_last_timing(ptb_model *h, double *setup_ms, double *points_ms);
+/* Totals over the calls since ptb_set_profiling(h, 1) (at most the last 256): no host
+ * synchronisation happens between calls, only here. */
+int ptb_timing_summary(ptb_model *h, int64_t *ncalls, double *setup_ms_total, double *points_ms_total);
+
 /* Block until all work queued by this handle on `stream` has finished. */
 int ptb_synchronize(ptb_model *h, void *stream);
 

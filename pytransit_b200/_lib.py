@@ -47,6 +47,9 @@ SIGNATURES = {
     'ptb_host_free': (C.c_int, [_vp]),
     'ptb_launch_count': (_i64, [_vp]),
     'ptb_synchronize': (C.c_int, [_vp, _vp]),
+    'ptb_set_profiling': (C.c_int, [_vp, C.c_int32]),
+    'ptb_last_timing': (C.c_int, [_vp, C.POINTER(_dbl), C.POINTER(_dbl)]),
+    'ptb_timing_summary': (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_dbl), C.POINTER(_dbl)]),
 }
 
 _LIB = None

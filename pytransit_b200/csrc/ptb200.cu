@@ -110,6 +110,12 @@ struct ptb_model {
     cudaEvent_t stage_ev = nullptr;  // completion of the last copy out of h_stage
     bool stage_pending = false;
 
+    // optional per-kernel timing (ptb_set_profiling)
+    bool profiling = false;
+    static constexpr int TRING = 256;
+    std::vector<cudaEvent_t> tev;  // TRING x 4 events
+    int64_t tcalls = 0;            // timed calls since profiling was enabled
+
     std::string err;
     int64_t launches = 0;
 };
@@ -188,6 +194,14 @@ struct Stager {
 
 int set_device(ptb_model *h) {
     CU(cudaSetDevice(h->cfg.device));
+    return PTB_OK;
+}
+
+// timing marks: 0/1 bracket the per-vector setup, 2/3 the dominant kernel
+int mark(ptb_model *h, int i, cudaStream_t st) {
+    if (!h->profiling) return PTB_OK;
+    CU(cudaEventRecord(h->tev[(h->tcalls % ptb_model::TRING) * 4 + i], st));
+    if (i == 3) h->tcalls++;
     return PTB_OK;
 }
 
@@ -358,6 +372,8 @@ void ptb_destroy(ptb_model *h) {
         b->release();
     h->h_stage.release();
     if (h->stage_ev) cudaEventDestroy(h->stage_ev);
+    for (auto &e : h->tev) if (e) cudaEventDestroy(e);
+    h->tev.clear();
     delete h;
 }
 
@@ -661,7 +677,9 @@ int ptb_rr_evaluate(ptb_model *h, int64_t npv, const double *k, int64_t kcols, c
     if (int rc = check_model_args(h, "rr_evaluate", A, h->npb)) return rc;
     Staged D{};
     if (int rc = stage_model_args(h, A, h->npb, h->nep, nullptr, 0, st, D)) return rc;
+    mark(h, 0, st);
     if (int rc = launch_rr_setup(h, A, D, st)) return rc;
+    mark(h, 1, st);
     const size_t count = (size_t)npv * h->npt;
     double *dflux = flux;
     const bool direct = flux && is_device_ptr(flux);
@@ -669,7 +687,9 @@ int ptb_rr_evaluate(ptb_model *h, int64_t npv, const double *k, int64_t kcols, c
         CU(h->d_flux.reserve(count * 8));
         dflux = h->d_flux.as<double>();
     }
+    mark(h, 2, st);
     if (int rc = launch_points(h, npv, D.t0, dflux, nullptr, st, nullptr)) return rc;
+    mark(h, 3, st);
     h->last_flux_count = direct ? 0 : (int64_t)count;
     if (flux && !direct) {
         CU(cudaMemcpyAsync(flux, dflux, count * 8, cudaMemcpyDeviceToHost, st));
@@ -690,13 +710,17 @@ int ptb_rr_lnlike(ptb_model *h, int64_t npv, const double *k, int64_t kcols, con
     if (int rc = check_model_args(h, "rr_lnlike", A, h->npb)) return rc;
     Staged D{};
     if (int rc = stage_model_args(h, A, h->npb, h->nep, sigma, h->nblocks, st, D)) return rc;
+    mark(h, 0, st);
     if (int rc = launch_rr_setup(h, A, D, st)) return rc;
     const long long nsig = (long long)npv * h->nblocks;
     CU(h->d_isig2.reserve(nsig * 8));
     k_inv_sigma2<<<(unsigned)((nsig + 255) / 256), 256, 0, st>>>(D.sigma, nsig, h->d_isig2.as<double>());
     h->launches++;
+    mark(h, 1, st);
     int nchunks = 1;
+    mark(h, 2, st);
     if (int rc = launch_points(h, npv, D.t0, nullptr, h->d_isig2.as<double>(), st, &nchunks)) return rc;
+    mark(h, 3, st);
     const bool direct = is_device_ptr(lnl);
     double *dl = lnl;
     if (!direct) {
@@ -814,6 +838,53 @@ int ptb_host_free(void *ptr) {
 }
 
 int64_t ptb_launch_count(const ptb_model *h) { return h ? h->launches : 0; }
+
+int ptb_set_profiling(ptb_model *h, int32_t enabled) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    if (enabled && h->tev.empty()) {
+        h->tev.assign(ptb_model::TRING * 4, nullptr);
+        for (auto &e : h->tev) CU(cudaEventCreate(&e));
+    }
+    h->profiling = enabled != 0;
+    h->tcalls = 0;
+    return PTB_OK;
+}
+
+int ptb_timing_summary(ptb_model *h, int64_t *ncalls, double *setup_ms_total, double *points_ms_total) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    if (h->tev.empty() || h->tcalls == 0) return fail(h, PTB_ESTATE, "timing: profiling is off or no call has been timed");
+    const int64_t n = std::min<int64_t>(h->tcalls, ptb_model::TRING);
+    double a = 0, b = 0;
+    for (int64_t c = h->tcalls - n; c < h->tcalls; ++c) {
+        cudaEvent_t *e = &h->tev[(c % ptb_model::TRING) * 4];
+        CU(cudaEventSynchronize(e[3]));
+        float x = 0, y = 0;
+        CU(cudaEventElapsedTime(&x, e[0], e[1]));
+        CU(cudaEventElapsedTime(&y, e[2], e[3]));
+        a += x;
+        b += y;
+    }
+    if (ncalls) *ncalls = n;
+    if (setup_ms_total) *setup_ms_total = a;
+    if (points_ms_total) *points_ms_total = b;
+    return PTB_OK;
+}
+
+int ptb_last_timing(ptb_model *h, double *setup_ms, double *points_ms) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    if (h->tev.empty() || h->tcalls == 0) return fail(h, PTB_ESTATE, "last_timing: profiling is off or no call has been timed");
+    cudaEvent_t *e = &h->tev[((h->tcalls - 1) % ptb_model::TRING) * 4];
+    CU(cudaEventSynchronize(e[3]));
+    float a = 0, b = 0;
+    CU(cudaEventElapsedTime(&a, e[0], e[1]));
+    CU(cudaEventElapsedTime(&b, e[2], e[3]));
+    if (setup_ms) *setup_ms = a;
+    if (points_ms) *points_ms = b;
+    return PTB_OK;
+}
 
 int ptb_synchronize(ptb_model *h, void *stream) {
     if (!h) return PTB_EINVAL;

@@ -69,6 +69,7 @@ int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, con
     SP.npv = (int)npv; SP.npb = (int)npb; SP.nk = h->cfg.nk; SP.ng = ng; SP.nz = nz;
     SP.use_table = h->cfg.precompute_weights ? 1 : 0;
     SP.kmin = h->cfg.kmin; SP.dk = h->dk;
+    mark(h, 0, st);
     k_ts_setup<<<(unsigned)npv, 128, 0, st>>>(SP);
     h->launches++;
     CU(cudaGetLastError());
@@ -109,6 +110,7 @@ int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, con
     default: rc = launch_ts_ldm_t<16>(h, MP, smem_ldm, grid_ldm, st); break;
     }
     if (rc) return rc;
+    mark(h, 1, st);
 
     // 4. flux
     const size_t count = (size_t)npv * npb * h->npt;
@@ -134,10 +136,12 @@ int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, con
     const long long grid = base_ctas * FP.pbsplit;
     if (grid > 0x7fffffffLL) return fail(h, PTB_EINVAL, "ts_evaluate: grid too large");
     const size_t smem_fl = multi ? (size_t)ns * 256 * sizeof(TsGeo) : 0;
+    mark(h, 2, st);
     if (vec == 2) rc = launch_ts_flux_t<2, false>(h, FP, smem_fl, (unsigned)grid, st);
     else if (!multi) rc = launch_ts_flux_t<1, false>(h, FP, smem_fl, (unsigned)grid, st);
     else rc = launch_ts_flux_t<1, true>(h, FP, smem_fl, (unsigned)grid, st);
     if (rc) return rc;
+    mark(h, 3, st);
     h->last_npv = 0;  // RoadRunner stage taps do not describe a TS evaluation
     h->last_flux_count = direct ? 0 : (int64_t)count;
     if (flux && !direct) {

@@ -137,6 +137,22 @@ class RoadRunnerModelCUDA(TransitModel):
     def launch_count(self) -> int:
         return int(lib().ptb_launch_count(self._h))
 
+    def set_profiling(self, enabled: bool = True) -> None:
+        """Record CUDA events around the setup kernel(s) and the dominant kernel of every call."""
+        check(lib().ptb_set_profiling(self._h, int(enabled)), self._h)
+
+    def last_timing(self):
+        """(setup_ms, points_ms) of the last call, measured with CUDA events on the launching stream."""
+        a, b = C.c_double(), C.c_double()
+        check(lib().ptb_last_timing(self._h, C.byref(a), C.byref(b)), self._h)
+        return a.value, b.value
+
+    def timing_summary(self):
+        """(ncalls, setup_ms_total, points_ms_total) over the calls since set_profiling(True)."""
+        n, a, b = C.c_int64(), C.c_double(), C.c_double()
+        check(lib().ptb_timing_summary(self._h, C.byref(n), C.byref(a), C.byref(b)), self._h)
+        return n.value, a.value, b.value
+
     def synchronize(self) -> None:
         check(lib().ptb_synchronize(self._h, _current_stream(self.device)), self._h)
 

@@ -1,0 +1,183 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/ptb200.h declares
+(no compute calls without a GPU), the error path when no device exists, and the Python layer's dataset
+validation / broadcasting rules (reference: models/transitmodel.py:88-125, rrmodel.py:212-230)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    txt = (ROOT / 'include' / 'ptb200.h').read_text()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    return sorted(set(re.findall(r'\b(ptb_[a-z0-9_]+)\s*\(', txt)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from pytransit_b200 import build, _lib
+    build.build()
+    return _lib.lib()
+
+
+def test_header_symbols_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in include/ptb200.h but not exported by libptb200.so'
+
+
+def test_binding_covers_header():
+    from pytransit_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+
+
+def test_version_and_default_config(lib):
+    from pytransit_b200._lib import PtbConfig
+    assert lib.ptb_version() == 100
+    cfg = PtbConfig()
+    lib.ptb_default_config(C.byref(cfg))
+    assert (cfg.nk, cfg.nzin, cfg.nzlimb, cfg.ng) == (256, 20, 20, 100)
+    assert (cfg.kmin, cfg.kmax, cfg.zcut) == (0.005, 0.5, 0.7)
+    assert cfg.ldlaw == 2 and cfg.precision == 0
+
+
+def test_no_cpu_fallback_without_device(lib):
+    """Without a CUDA device model construction must fail loudly (RuntimeError), never fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    import pytransit_b200 as pb
+    with pytest.raises(RuntimeError, match='no CUDA device'):
+        pb.RoadRunnerModelCUDA('quadratic')
+    with pytest.raises(KeyError):
+        pb.RoadRunnerModelCUDA('not-a-law')
+
+
+def test_bad_config_rejected(lib):
+    from pytransit_b200._lib import PtbConfig
+    cfg = PtbConfig()
+    lib.ptb_default_config(C.byref(cfg))
+    h = C.c_void_p()
+    cfg.ldlaw = 55
+    assert lib.ptb_create(C.byref(cfg), C.byref(h)) == -6 and not h.value      # PTB_ENOTIMPL
+    cfg.ldlaw, cfg.kmax = 2, 0.001
+    assert lib.ptb_create(C.byref(cfg), C.byref(h)) == -1                      # PTB_EINVAL
+    assert b'invalid integration grid' in lib.ptb_last_error(None)
+    cfg.kmax, cfg.precision = 0.5, 1
+    assert lib.ptb_create(C.byref(cfg), C.byref(h)) == -6
+
+
+def test_product_never_imports_oracle():
+    """The product package must not reference oracle/ (the checker) anywhere."""
+    for f in (ROOT / 'pytransit_b200').rglob('*'):
+        if f.suffix in ('.py', '.cu', '.cuh', '.inl', '.h'):
+            txt = f.read_text()
+            assert 'oracle' not in txt.lower() or f.name == '__never__', f'{f} mentions the oracle'
+
+
+# ---------------------------------------------------------------------------------------------
+# TransitModel.set_data validation (pure host logic)
+# ---------------------------------------------------------------------------------------------
+def test_set_data_validation_matches_reference_rules():
+    from pytransit_b200.transitmodel import TransitModel
+    tm = TransitModel()
+    t = np.linspace(0, 1, 30)
+    tm.set_data(t)
+    assert (tm.npt, tm.nlc, tm.npb) == (30, 1, 1)
+    assert tm.lcids.dtype == np.int64 and tm.nsamples.tolist() == [1] and tm.exptimes.tolist() == [0.0]
+    lc = np.repeat([0, 1, 2], 10)
+    tm.set_data(t, lc, [0, 1, 1], nsamples=3, exptimes=0.02)
+    assert (tm.nlc, tm.npb) == (3, 2)
+    assert tm.nsamples.tolist() == [3, 3, 3] and tm.exptimes.tolist() == [0.02] * 3     # scalars broadcast (Q16)
+    with pytest.raises(ValueError, match='integers'):
+        tm.set_data(t, lc.astype(float))
+    with pytest.raises(ValueError, match='number of datapoints'):
+        tm.set_data(t, lc[:-1])
+    with pytest.raises(ValueError, match='Passband index array size'):
+        tm.set_data(t, lc, [0, 1])
+    with pytest.raises(ValueError, match='between 0 and'):
+        tm.set_data(t, lc, [0, 2, 2])
+    with pytest.raises(ValueError, match='integers'):
+        tm.set_data(t, lc, [0.0, 1.0, 1.0])
+    with pytest.raises(ValueError):
+        tm.set_data(t, np.repeat([0, 1, 5], 10))       # gaps in the light-curve ids
+    # same time object and nothing else: early out (transitmodel.py:83-84)
+    tm.set_data(t, lc, [0, 1, 1])
+    before = tm.lcids
+    tm.set_data(t)
+    assert tm.lcids is before
+
+
+def _bare_model(npb=2, nep=1, law='quadratic'):
+    """RoadRunnerModelCUDA without a device handle: enough state for the broadcasting helpers."""
+    from pytransit_b200 import _lib
+    from pytransit_b200.rrmodel import RoadRunnerModelCUDA
+    m = object.__new__(RoadRunnerModelCUDA)
+    m._h = None
+    m.npb, m.nep, m.nz = npb, nep, 40
+    m._law = _lib.LD_LAWS[law]
+    return m
+
+
+def test_parameter_broadcasting():
+    m = _bare_model(npb=2, nep=1)
+    npv, k, t0, p, a, i, e, w = m._expand(0.1, 0.0, 1.0, 3.0, 1.5, 0.0, 0.0)
+    assert npv == 1 and k.shape == (1, 1) and t0.shape == (1, 1) and all(v.shape == (1,) for v in (p, a, i, e, w))
+    # 1-D k = per-passband radius ratios of ONE vector
+    npv, k, *_ = m._expand([0.1, 0.11], 0.0, 1.0, 3.0, 1.5, 0.0, 0.0)
+    assert npv == 1 and k.shape == (1, 2)
+    # population: scalar e, w broadcast (Q5), 1-D t0[npv] is one epoch per vector (Q4)
+    pv = np.full(5, 1.0)
+    npv, k, t0, p, a, i, e, w = m._expand(np.full((5, 1), 0.1), np.arange(5.0), pv, pv * 3, pv, 0.0, 0.1)
+    assert npv == 5 and k.shape == (5, 1) and t0.shape == (5, 1) and t0[:, 0].tolist() == [0, 1, 2, 3, 4]
+    assert e.shape == (5,) and w.tolist() == [0.1] * 5
+    # shared per-passband k broadcast over the population
+    npv, k, *_ = m._expand(np.array([[0.1, 0.2]]), 0.0, pv, pv, pv, 0.0, 0.0)
+    assert k.shape == (5, 2) and k[3].tolist() == [0.1, 0.2]
+    with pytest.raises(ValueError, match='Radius ratios'):
+        m._expand(np.full((5, 3), 0.1), 0.0, pv, pv, pv, 0.0, 0.0)
+    with pytest.raises(ValueError, match='Radius ratios'):
+        m._expand(np.full((4, 1), 0.1), 0.0, pv, pv, pv, 0.0, 0.0)
+    with pytest.raises(ValueError, match='`a`'):
+        m._expand(np.full((5, 1), 0.1), 0.0, pv, pv[:3], pv, 0.0, 0.0)
+    # TTV epochs: t0[npv, nep]
+    m2 = _bare_model(npb=1, nep=3)
+    npv, _, t0, *_ = m2._expand(0.1, [0.0, 0.01, 0.02], 1.0, 3.0, 1.5, 0.0, 0.0)
+    assert t0.shape == (1, 3)
+    npv, _, t0, *_ = m2._expand(np.full((5, 1), 0.1), np.zeros((5, 3)), pv, pv, pv, 0.0, 0.0)
+    assert t0.shape == (5, 3)
+    with pytest.raises(ValueError):
+        m2._expand(np.full((5, 1), 0.1), np.zeros((5, 2)), pv, pv, pv, 0.0, 0.0)
+
+
+def test_ldc_broadcasting():
+    m = _bare_model(npb=2)
+    ld, nld, istar = m._limb_darkening([0.2, 0.1], 4, 2)
+    assert ld.shape == (4, 2, 2) and nld == 2 and istar is None and ld[3, 1].tolist() == [0.2, 0.1]
+    ld, *_ = m._limb_darkening(np.array([[0.2, 0.1], [0.3, 0.2]]), 4, 2)          # [npb, nldc]
+    assert ld.shape == (4, 2, 2) and ld[2, 1].tolist() == [0.3, 0.2]
+    ld, *_ = m._limb_darkening(np.zeros((4, 2, 2)), 4, 2)
+    assert ld.shape == (4, 2, 2)
+    with pytest.raises(ValueError):
+        m._limb_darkening(np.zeros((3, 2)), 4, 2)
+    with pytest.raises(ValueError):
+        m._limb_darkening(np.zeros((3, 2, 2)), 4, 2)
+
+
+def test_ldmodel_protocol():
+    from pytransit_b200 import LDModel
+
+    class Quad(LDModel):
+        def _evaluate(self, mu, x):
+            x = np.asarray(x)
+            return 1 - x[..., 0:1] * (1 - mu) - x[..., 1:2] * (1 - mu) ** 2
+
+    x = np.array([[[0.3, 0.2]]])
+    ldp, istar = Quad()(np.linspace(1, 0.1, 40), x)
+    assert ldp.shape == (1, 1, 40) and istar.shape == (1, 1)
+    assert abs(istar[0, 0] - np.pi * (1 - 0.3 / 3 - 0.2 / 6)) < 1e-3      # trapezoid on 200 nodes in z
