@@ -87,6 +87,11 @@ struct ptb_model {
     int32_t *d_lcids = nullptr, *d_pbids = nullptr, *d_epids = nullptr, *d_nsamples = nullptr;
     double *d_exptimes = nullptr;
     int ns_max = 1;
+    int64_t nblk64 = 0;                // 64-point classification blocks
+    DevBuf d_bmeta;                    // bmin[nblk64] | bmax[nblk64] | blc[nblk64]
+    double *d_bmin = nullptr, *d_bmax = nullptr;
+    int32_t *d_blc = nullptr;
+    std::vector<int32_t> h_lcids;      // host copy (empty when nlc == 1)
     std::vector<int64_t> h_nsamples;
     std::vector<double> h_exptimes;
 
@@ -94,7 +99,9 @@ struct ptb_model {
     bool has_obs = false;
     int64_t nblocks = 0;
     const double *d_obs = nullptr;
-    DevBuf d_obs_own, d_blk, d_nblk;
+    DevBuf d_obs_own, d_blk, d_nblk, d_bobs;  // d_bobs: bchi[nblk64] | bnoise[nblk64]
+    double *d_bchi = nullptr;
+    int32_t *d_bnoise = nullptr;
     bool blk_trivial = true;
 
     // per-vector workspaces
@@ -368,7 +375,7 @@ void ptb_destroy(ptb_model *h) {
     cudaSetDevice(h->cfg.device);
     for (DevBuf *b : {&h->d_tab, &h->d_W, &h->d_time_own, &h->d_meta, &h->d_obs_own, &h->d_blk, &h->d_nblk, &h->d_orb,
                       &h->d_ldrec, &h->d_ldp, &h->d_istar, &h->d_flux, &h->d_partial, &h->d_isig2, &h->d_lnl, &h->d_xyc,
-                      &h->d_tsw, &h->d_tsrec, &h->d_stage})
+                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs})
         b->release();
     h->h_stage.release();
     if (h->stage_ev) cudaEventDestroy(h->stage_ev);
@@ -456,12 +463,46 @@ int ptb_set_data(ptb_model *h, const double *time, int64_t npt, const int64_t *l
     h->d_nsamples = mb + o_ns;
     h->d_exptimes = reinterpret_cast<double *>(mb + o_et);
 
+    std::vector<double> htime;
+    const double *ht = time;
     if (is_device_ptr(time)) {
         h->d_time = time;  // zero copy: the caller keeps the tensor alive (as with RoadRunnerModelCL buffers)
+        htime.resize(npt);
+        CU(cudaMemcpy(htime.data(), time, npt * 8, cudaMemcpyDeviceToHost));
+        ht = htime.data();
     } else {
         CU(h->d_time_own.reserve(npt * 8 + 16));
         CU(cudaMemcpy(h->d_time_own.ptr, time, npt * 8, cudaMemcpyHostToDevice));
         h->d_time = h->d_time_own.as<double>();
+    }
+    // per 64-point block: time range and light curve (k_rr_points block classification)
+    {
+        const int64_t nb = (npt + 63) / 64;
+        std::vector<double> bm(2 * nb);
+        std::vector<int32_t> bl(nb, 0);
+        for (int64_t b = 0; b < nb; ++b) {
+            const int64_t j0 = b * 64, j1 = std::min<int64_t>(npt, j0 + 64);
+            double mn = ht[j0], mx = ht[j0];
+            bool nanv = false;
+            int32_t lc = lcids ? meta[j0] : 0;
+            for (int64_t j = j0; j < j1; ++j) {
+                nanv |= std::isnan(ht[j]);
+                mn = std::min(mn, ht[j]);
+                mx = std::max(mx, ht[j]);
+                if (lcids && meta[j] != lc) lc = -1;
+            }
+            if (nanv) lc = -1;  // force the exact per-point path
+            bm[b] = mn;
+            bm[nb + b] = mx;
+            bl[b] = lc;
+        }
+        CU(h->d_bmeta.reserve(nb * 20 + 64));
+        CU(cudaMemcpy(h->d_bmeta.ptr, bm.data(), nb * 16, cudaMemcpyHostToDevice));
+        h->d_bmin = h->d_bmeta.as<double>();
+        h->d_bmax = h->d_bmin + nb;
+        h->d_blc = reinterpret_cast<int32_t *>(h->d_bmax + nb);
+        CU(cudaMemcpy(h->d_blc, bl.data(), nb * 4, cudaMemcpyHostToDevice));
+        h->nblk64 = nb;
     }
     h->npt = npt;
     h->nlc = nlc;
@@ -512,12 +553,44 @@ int ptb_set_obs(ptb_model *h, const double *obs, const int64_t *slices, const in
     }
     CU(h->d_nblk.reserve(nblocks * 8));
     CU(cudaMemcpy(h->d_nblk.ptr, cnt.data(), nblocks * 8, cudaMemcpyHostToDevice));
+    std::vector<double> hobs;
+    const double *ho = obs;
     if (is_device_ptr(obs)) {
         h->d_obs = obs;
+        hobs.resize(npt);
+        CU(cudaMemcpy(hobs.data(), obs, npt * 8, cudaMemcpyDeviceToHost));
+        ho = hobs.data();
     } else {
         CU(h->d_obs_own.reserve(npt * 8 + 16));
         CU(cudaMemcpy(h->d_obs_own.ptr, obs, npt * 8, cudaMemcpyHostToDevice));
         h->d_obs = h->d_obs_own.as<double>();
+    }
+    // per 64-point block: sum of (obs-1)^2 and the block's noise id (k_rr_points likelihood fast path)
+    {
+        const int64_t nb = h->nblk64;
+        std::vector<double> bc(nb, 0.0);
+        std::vector<int32_t> bn(nb, -1);
+        for (int64_t b = 0; b < nb; ++b) {
+            const int64_t j0 = b * 64, j1 = std::min<int64_t>(npt, j0 + 64);
+            int32_t id = -1;
+            bool mixed = false;
+            double sum = 0.0;
+            for (int64_t j = j0; j < j1; ++j) {
+                const int32_t bj = trivial ? 0 : blk[j];
+                if (bj < 0) continue;
+                if (id < 0) id = bj;
+                else if (id != bj) mixed = true;
+                const double d = ho[j] - 1.0;
+                sum += d * d;
+            }
+            bc[b] = sum;
+            bn[b] = mixed ? -2 : id;
+        }
+        CU(h->d_bobs.reserve(nb * 12 + 64));
+        h->d_bchi = h->d_bobs.as<double>();
+        h->d_bnoise = reinterpret_cast<int32_t *>(h->d_bchi + nb);
+        CU(cudaMemcpy(h->d_bchi, bc.data(), nb * 8, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->d_bnoise, bn.data(), nb * 4, cudaMemcpyHostToDevice));
     }
     h->blk_trivial = trivial;
     h->nblocks = nblocks;
@@ -609,7 +682,7 @@ int launch_rr_setup(ptb_model *h, const ModelArgs &A, const Staged &D, cudaStrea
 template <int VEC, bool SINGLE, bool LNL>
 int launch_points_t(ptb_model *h, const PointsParams &P, size_t smem, cudaStream_t st) {
     auto kern = k_rr_points<VEC, SINGLE, LNL>;
-    if (smem > 48 * 1024 - 12 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (long long)P.npv * P.nchunks;
     kern<<<(unsigned)grid, PT_THREADS, smem, st>>>(P);
     h->launches++;
@@ -628,29 +701,32 @@ int launch_points(ptb_model *h, int64_t npv, const double *t0, double *flux, con
     P.npt = h->npt; P.npv = (int)npv; P.nlc = (int)h->nlc; P.npb = (int)h->npb; P.nep = (int)h->nep; P.ng = ng; P.lds = lds;
     P.nblocks = (int)h->nblocks; P.ns_max = h->ns_max; P.dg = h->dg; P.inv_dg = 1.0 / h->dg;
 
+    P.bmin = h->d_bmin; P.bmax = h->d_bmax; P.blc = h->d_blc; P.bchi = h->d_bchi; P.bnoise = h->d_bnoise;
+    P.nblk64 = (int)h->nblk64;
     const bool single = (h->nlc == 1);
     const bool lnl = (flux == nullptr);
     const bool aligned = (h->npt % 2 == 0) && ((reinterpret_cast<uintptr_t>(h->d_time) & 15) == 0) &&
                          (lnl || (reinterpret_cast<uintptr_t>(flux) & 15) == 0);
     const int vec = aligned ? 2 : 1;
-    const long long tile = (long long)PT_THREADS * vec;
-    const long long ntiles = (h->npt + tile - 1) / tile;
-    // enough CTAs to fill the machine ~8 deep; otherwise one CTA walks a whole row
+    // Enough CTAs to fill the machine ~8 deep, otherwise one CTA walks a whole row; a chunk is a
+    // multiple of 8 blocks (one block per warp and pass).
+    const long long nb = h->nblk64;
     const long long want = (long long)h->sm_count * 8;
-    long long nchunks = std::min<long long>(ntiles, std::max<long long>(1, (want + npv - 1) / npv));
-    long long tpc = (ntiles + nchunks - 1) / nchunks;
-    nchunks = (ntiles + tpc - 1) / tpc;
+    long long nchunks = std::min<long long>((nb + 7) / 8, std::max<long long>(1, (want + npv - 1) / npv));
+    long long bpc = (nb + nchunks - 1) / nchunks;
+    bpc = (bpc + 7) / 8 * 8;
+    nchunks = (nb + bpc - 1) / bpc;
     P.nchunks = (int)nchunks;
-    P.tiles_per_chunk = (int)tpc;
+    P.blocks_per_chunk = (int)bpc;
     if (nchunks_out) *nchunks_out = (int)nchunks;
     if (lnl) {
         CU(h->d_partial.reserve((size_t)npv * nchunks * 8));
         P.partial = h->d_partial.as<double>();
     }
     const size_t ldbytes = (size_t)h->npb * lds * 8;
-    P.stage_ld = ldbytes <= 64 * 1024 ? 1 : 0;
-    const size_t smem = (P.stage_ld ? ldbytes : 0) + (single ? 0 : 3 * (size_t)h->nlc * 8) + 16;
-    if (smem > 160 * 1024) return fail(h, PTB_EINVAL, "nlc=%lld light curves need %zu bytes of shared memory", (long long)h->nlc, smem);
+    P.stage_ld = ldbytes <= 32 * 1024 ? 1 : 0;
+    const size_t smem = sizeof(WarpScratch) * PT_WARPS + (P.stage_ld ? ldbytes : 0) + (single ? 0 : 3 * (size_t)h->nlc * 8) + 16;
+    if (smem > 200 * 1024) return fail(h, PTB_EINVAL, "nlc=%lld light curves need %zu bytes of shared memory", (long long)h->nlc, smem);
 
 #define PTB_DISPATCH(V, S, L) return launch_points_t<V, S, L>(h, P, smem, st)
     if (vec == 2) {

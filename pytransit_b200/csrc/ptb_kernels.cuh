@@ -239,12 +239,23 @@ __global__ void __launch_bounds__(128) k_rr_setup(const __grid_constant__ SetupP
 // ---------------------------------------------------------------------------------------------
 // The npv x npt pass.
 //
-// One CTA = one parameter vector x one chunk of the time axis, 8 warps.  The per-vector record
-// (ldm rows + k, 1/(1+k), 1/I*, k^2 per passband) is staged into shared memory with one TMA bulk
-// copy.  Each tile of 256*VEC consecutive points is folded and box-tested (fp64, reference
-// operation order) and the flux row is written with 16-byte stores; in-box points are pushed to
-// a warp-private queue in shared memory and evaluated by full warps (one lane per exposure
-// sub-sample), so the 3 % of points that cost 50x the rest do not serialise the warp.
+// One CTA = one parameter vector x one chunk of the time axis, 8 warps; the time axis is cut into
+// blocks of 64 consecutive points and each warp walks its own blocks.
+//
+//  * Block classification (warp-uniform, ~10 fp64 ops per 64 points): set_data stores the smallest and
+//    largest time stamp of every block.  A block whose [tmin, tmax] misses every transit window
+//    [t0 + n p + lo, t0 + n p + hi] holds no in-box point, so its 64 fluxes are 1.0: the warp issues
+//    one 16-byte streaming store per lane and moves on (likelihood mode: adds the block's
+//    pre-summed (obs-1)^2).  ~93 % of a TESS sector takes this path at HBM-store speed.
+//  * Other blocks: each point is folded and box-tested in fp64 in the reference's operation order
+//    (model_full.py:88-91); in-box points go to a warp-private queue in shared memory.
+//  * Batched drain: when >= 128 exposure sub-samples are queued the warp evaluates them together --
+//    separation + limb-darkening lerp for every sample, then the samples on the stellar limb (the
+//    ones that need the sqrt + 2 atan2 lens area, ~1/4 of them) are compacted a second time so the
+//    expensive code runs with full warps; per-point sums over sub-samples are taken in exposure order.
+//
+// The per-vector record (ldm rows + k, 1/(1+k), 1/I*, k^2 per passband) is staged into shared memory
+// with one TMA bulk copy per CTA.
 // ---------------------------------------------------------------------------------------------
 struct PointsParams {
     const double *time;
@@ -256,14 +267,29 @@ struct PointsParams {
     const int32_t *blk;
     const double *isig2;  // [npv][nblocks]
     double *partial;      // [npv][nchunks]
+    const double *bmin, *bmax;  // per 64-point block: smallest / largest time stamp
+    const int32_t *blc;         // light curve of the block, -1 when it straddles light curves
+    const double *bchi;         // likelihood: sum of (obs-1)^2 over the block's points
+    const int32_t *bnoise;      // likelihood: noise id of the block, -1 none, -2 mixed (slow path)
     long long npt;
-    int npv, nlc, npb, nep, ng, lds, nblocks, ns_max, nchunks, tiles_per_chunk, stage_ld;
+    int npv, nlc, npb, nep, ng, lds, nblocks, ns_max, nchunks, blocks_per_chunk, nblk64, stage_ld;
     double dg, inv_dg;
 };
 
 constexpr int PT_THREADS = 256;
 constexpr int PT_WARPS = PT_THREADS / 32;
-constexpr int PT_QCAP = 128;
+constexpr int PT_BLOCK = 64;           // points per classification block
+constexpr int PT_BATCH = 128;          // exposure sub-samples evaluated per drain
+constexpr int PT_QCAP = PT_BATCH + PT_BLOCK;
+constexpr double PT_EPS = 1e-9;        // classification margin, in periods (>> rounding, << the 0.003 d pad)
+
+struct alignas(16) WarpScratch {
+    double q_tc[PT_QCAP];
+    double contrib[PT_BATCH];
+    double l_z[PT_BATCH], l_ip[PT_BATCH];
+    int q_ipt[PT_QCAP];
+    int l_it[PT_BATCH];
+};
 
 template <int VEC>
 struct VecIO;
@@ -284,34 +310,20 @@ struct VecIO<2> {
     }
 };
 
-// One exposure sub-sample: separation -> mean limb darkening under the planet -> lens area
-// (model_full.py:94-98).  Returns (I* - I_p A)/I* as 1 - I_p A / I*.
-__device__ __forceinline__ double sample_flux(double t, const double *cx, const double *cy, const double *row, int ng,
-                                              double dg, double inv_dg) {
-    const double z = sep_poly(t, cx, cy);
-    const double k = row[ng], inv1k = row[ng + 1], inv_istar = row[ng + 2], k2 = row[ng + 3];
-    const double ip = ldm_lerp(z * inv1k, dg, inv_dg, row, ng);
-    double area, kap;
-    kite_area(k, k2, z, area, kap);
-    return 1.0 - ip * area * inv_istar;
-}
-
 template <int VEC, bool SINGLE_LC, bool LNL>
-__global__ void __launch_bounds__(PT_THREADS) k_rr_points(const __grid_constant__ PointsParams P) {
+__global__ void __launch_bounds__(PT_THREADS, 3) k_rr_points(const __grid_constant__ PointsParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ int q_ipt[PT_WARPS][PT_QCAP];
-    __shared__ double q_tc[PT_WARPS][PT_QCAP];
-    __shared__ double s_part[PT_WARPS][32];
+    __shared__ double s_red[PT_WARPS];
     __shared__ __align__(8) uint64_t bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ipv = blockIdx.x / P.nchunks;
     const int chunk = blockIdx.x - ipv * P.nchunks;
     const long long npt = P.npt;
-    constexpr int TILE = PT_THREADS * VEC;
 
-    // dynamic smem: [ldrec copy npb*lds] [lc_lo nlc] [lc_hi nlc] [lc_t0 nlc]
-    double *sLd = reinterpret_cast<double *>(smem_raw);
+    // dynamic smem: [WarpScratch x 8] [ldrec copy npb*lds] [lc_lo nlc] [lc_hi nlc] [lc_t0 nlc]
+    WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem_raw)[warp];
+    double *sLd = reinterpret_cast<double *>(smem_raw + sizeof(WarpScratch) * PT_WARPS);
     double *sLo = sLd + (P.stage_ld ? (size_t)P.npb * P.lds : 0);
     double *sHi = sLo + (SINGLE_LC ? 0 : P.nlc);
     double *sT0 = sHi + (SINGLE_LC ? 0 : P.nlc);
@@ -320,8 +332,8 @@ __global__ void __launch_bounds__(PT_THREADS) k_rr_points(const __grid_constant_
     const bool good = orb[ORB_GOOD] != 0.0;
     const double *ldg = P.ldrec + (size_t)ipv * P.npb * P.lds;
 
-    const long long cbeg = (long long)chunk * P.tiles_per_chunk * TILE;
-    const long long cend = min(npt, cbeg + (long long)P.tiles_per_chunk * TILE);
+    const int bbeg = chunk * P.blocks_per_chunk;
+    const int bend = min(P.nblk64, bbeg + P.blocks_per_chunk);
 
     if (!good) {  // invalid parameter vector: NaN row (model_full.py:80-82)
         if (LNL) {
@@ -331,18 +343,18 @@ __global__ void __launch_bounds__(PT_THREADS) k_rr_points(const __grid_constant_
             double v[VEC];
 #pragma unroll
             for (int j = 0; j < VEC; ++j) v[j] = nan("");
-            for (long long i = cbeg + (long long)tid * VEC; i < cend; i += TILE) VecIO<VEC>::store(frow + i, v);
+            const long long cend = min(npt, (long long)bend * PT_BLOCK);
+            for (long long i = (long long)bbeg * PT_BLOCK + (long long)tid * VEC; i < cend; i += PT_THREADS * VEC)
+                VecIO<VEC>::store(frow + i, v);
         }
         return;
     }
 
-    if (P.stage_ld) {
-        if (tid == 0) {
-            mbar_init(&bar, 1);
-            const uint32_t bytes = (uint32_t)(P.npb * P.lds * 8);
-            mbar_expect_tx(&bar, bytes);
-            tma_load_1d(sLd, ldg, bytes, &bar);
-        }
+    if (P.stage_ld && tid == 0) {
+        mbar_init(&bar, 1);
+        const uint32_t bytes = (uint32_t)(P.npb * P.lds * 8);
+        mbar_expect_tx(&bar, bytes);
+        tma_load_1d(sLd, ldg, bytes, &bar);
     }
     const double p = orb[ORB_P], invp = orb[ORB_INVP], T1 = orb[ORB_T1], T4 = orb[ORB_T4];
     double lo1 = 0, hi1 = 0, t01 = 0;
@@ -364,16 +376,16 @@ __global__ void __launch_bounds__(PT_THREADS) k_rr_points(const __grid_constant_
     const double *ldrow_base = P.stage_ld ? sLd : ldg;
     bool ld_ready = !P.stage_ld;
 
-    const int L = min(P.ns_max, 32);  // lanes per queued point
-    const int PPW = 32 / L;           // points per warp pass
+    const int S = P.ns_max;                        // sub-sample slots per queued point
+    const int PB = S >= PT_BATCH ? 1 : PT_BATCH / S;  // points per drain batch
     int qn = 0;
     double chi = 0.0;
     const double *isig2 = LNL ? P.isig2 + (size_t)ipv * P.nblocks : nullptr;
     double *frow = LNL ? nullptr : P.flux + (size_t)ipv * npt;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    // evaluate `npts` queued points starting at queue slot `base` (warp-cooperative)
-    auto drain = [&](int base, int npts) {
+    // evaluate the `np` queued points starting at queue slot `base` (warp-cooperative)
+    auto drain = [&](int base, int np) {
         if (!ld_ready) {
             mbar_wait(&bar, 0);
             ld_ready = true;
@@ -381,108 +393,182 @@ __global__ void __launch_bounds__(PT_THREADS) k_rr_points(const __grid_constant_
         double cx[5], cy[5];
 #pragma unroll
         for (int j = 0; j < 5; ++j) { cx[j] = orb[j]; cy[j] = orb[5 + j]; }
-        const int pt = lane / L, s = lane - pt * L;
-        const bool active = pt < npts;
-        double acc = 0.0;
-        int ipt = 0, ns = 1;
-        if (active) {
-            ipt = q_ipt[warp][base + pt];
-            const double tc = q_tc[warp][base + pt];
-            const int lc = SINGLE_LC ? 0 : P.lcids[ipt];
-            ns = P.nsamples[lc];
-            const double et = P.exptimes[lc];
-            const double *row = ldrow_base + (size_t)P.pbids[lc] * P.lds;
-            for (int ss = s; ss < ns; ss += L) {
-                const double off = et * (((ss + 1) - 0.5) / ns - 0.5);
-                acc += sample_flux(tc + off, cx, cy, row, P.ng, P.dg, P.inv_dg);
-            }
-        }
-        if (L > 1) {  // sum the sub-samples of each point in exposure order
-            s_part[warp][lane] = acc;
-            __syncwarp();
-            if (active && s == 0) {
-                double sum = 0.0;
-                const int m = min(L, ns);
-                for (int j = 0; j < m; ++j) sum += s_part[warp][lane + j];
-                acc = sum / ns;
-            }
-            __syncwarp();
-        }
-        if (active && s == 0) {
-            if (LNL) {
-                const int b = P.blk ? P.blk[ipt] : 0;
-                if (b >= 0) {
-                    const double d = P.obs[ipt] - acc;
-                    chi = fma(d * d, isig2[b], chi);
+        double bigsum = 0.0;  // S > PT_BATCH only: running sum over sample chunks (np == 1)
+        for (int s0 = 0; s0 < S; s0 += PT_BATCH) {
+            const int SS = min(S - s0, PT_BATCH);  // sample slots in this pass
+            const int nitems = np * SS;
+            // stage A: separation, limb-darkening lerp, cheap area cases; limb samples -> second queue
+            int nl = 0;
+            for (int it0 = 0; it0 < nitems; it0 += 32) {
+                const int it = it0 + lane;
+                bool limb = false;
+                double z = 0.0, ip = 0.0;
+                if (it < nitems) {
+                    const int pt = (SS == 1) ? it : it / SS;
+                    const int s = s0 + (it - pt * SS);
+                    const int ipt = ws.q_ipt[base + pt];
+                    const int lc = SINGLE_LC ? 0 : P.lcids[ipt];
+                    const int ns = P.nsamples[lc];
+                    double c = 0.0;
+                    if (s < ns) {
+                        const double off = P.exptimes[lc] * (((s + 1) - 0.5) / ns - 0.5);
+                        z = sep_poly(ws.q_tc[base + pt] + off, cx, cy);
+                        const double *row = ldrow_base + (size_t)P.pbids[lc] * P.lds;
+                        const double k = row[P.ng];
+                        ip = ldm_lerp(z * row[P.ng + 1], P.dg, P.inv_dg, row, P.ng);
+                        if (1.0 + k <= z) c = 1.0;                                   // no overlap: area 0
+                        else if (fabs(1.0 - k) < z) limb = true;                     // lens: kite formula
+                        else if (z <= 1.0 - k) c = 1.0 - ip * (kPi * row[P.ng + 3]) * row[P.ng + 2];
+                        else if (z <= k - 1.0) c = 1.0 - ip * kPi * row[P.ng + 2];   // planet covers the star
+                        else c = nan("");
+                    }
+                    ws.contrib[it] = c;
                 }
-            } else {
-                frow[ipt] = acc;
+                const unsigned m = __ballot_sync(0xffffffffu, limb);
+                if (limb) {
+                    const int pos = nl + __popc(m & lt_mask);
+                    ws.l_it[pos] = it;
+                    ws.l_z[pos] = z;
+                    ws.l_ip[pos] = ip;
+                }
+                nl += __popc(m);
             }
+            __syncwarp();
+            // stage B: lens area on the limb (sqrt + 2 atan2), full warps
+            for (int j = lane; j < nl; j += 32) {
+                const int it = ws.l_it[j];
+                const int pt = (SS == 1) ? it : it / SS;
+                const int lc = SINGLE_LC ? 0 : P.lcids[ws.q_ipt[base + pt]];
+                const double *row = ldrow_base + (size_t)P.pbids[lc] * P.lds;
+                double area, kap;
+                kite_area(row[P.ng], row[P.ng + 3], ws.l_z[j], area, kap);
+                ws.contrib[it] = 1.0 - ws.l_ip[j] * area * row[P.ng + 2];
+            }
+            __syncwarp();
+            // stage C: per-point sum over sub-samples in exposure order (model_full.py:93-99)
+            for (int pt = lane; pt < np; pt += 32) {
+                const int ipt = ws.q_ipt[base + pt];
+                const int lc = SINGLE_LC ? 0 : P.lcids[ipt];
+                const int ns = P.nsamples[lc];
+                const int m = min(SS, ns - s0);
+                double sum = bigsum;
+                for (int j = 0; j < m; ++j) sum += ws.contrib[pt * SS + j];
+                if (s0 + SS >= S) {
+                    const double f = sum / ns;
+                    if (LNL) {
+                        const int b = P.blk ? P.blk[ipt] : 0;
+                        if (b >= 0) {
+                            const double d = P.obs[ipt] - f;
+                            chi = fma(d * d, isig2[b], chi);
+                        }
+                    } else {
+                        frow[ipt] = f;
+                    }
+                } else {
+                    bigsum = sum;  // only reached with np == 1 (lane 0)
+                }
+            }
+            __syncwarp();
         }
     };
 
-    for (long long tbeg = cbeg; tbeg < cend; tbeg += TILE) {
-        const long long i0 = tbeg + (long long)tid * VEC;
-        double tv[VEC], fv[VEC];
-        const bool inr = i0 < cend;  // VEC > 1 requires npt % VEC == 0: vectors are all-in or all-out
-        if (inr) VecIO<VEC>::load(P.time + i0, tv);
+    // One extra pass after the last block flushes the queue, so that drain() has exactly ONE call site
+    // and batches are always cut from the top of the queue: a point's arithmetic does not depend on the
+    // chunking and results are bit-reproducible across population splits.
+    for (int b = bbeg + warp;; b += PT_WARPS) {
+        const bool live = b < bend;
+        if (live) {
+        const long long base = (long long)b * PT_BLOCK;
+        // ---- classification: can any transit window touch this block? --------------------------
+        bool hit = true;
+        const int lcb = SINGLE_LC ? 0 : P.blc[b];
+        int nz_id = 0;
+        if (LNL) nz_id = P.bnoise ? P.bnoise[b] : 0;
+        if (lcb >= 0 && nz_id != -2) {
+            const double lo = SINGLE_LC ? lo1 : sLo[lcb], hi = SINGLE_LC ? hi1 : sHi[lcb];
+            const double t0 = SINGLE_LC ? t01 : sT0[lcb];
+            const double n1 = ceil(fma(P.bmin[b] - t0 - hi, invp, -PT_EPS));
+            const double n2 = floor(fma(P.bmax[b] - t0 - lo, invp, PT_EPS));
+            hit = !(n1 > n2) || !(p > 0.0);  // NaNs and p <= 0 fall through to the exact per-point path
+        }
+        if (!hit) {
+            if (LNL) {
+                if (lane == 0 && nz_id >= 0) chi = fma(P.bchi[b], isig2[nz_id], chi);
+            } else {
+                double one[VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            bool inbox = false;
-            double tc = 0.0;
-            if (inr) {
-                double lo = lo1, hi = hi1, t0 = t01;
-                if (!SINGLE_LC) {
-                    const int lc = P.lcids[i0 + j];
-                    lo = sLo[lc];
-                    hi = sHi[lc];
-                    t0 = sT0[lc];
+                for (int j = 0; j < VEC; ++j) one[j] = 1.0;
+#pragma unroll
+                for (int h = 0; h < 2 / VEC; ++h) {
+                    const long long i0 = base + (long long)(h * 32 + lane) * VEC;
+                    if (i0 < npt) VecIO<VEC>::store(frow + i0, one);
                 }
-                // epoch = floor((t - t0 + p/2)/p); tc = t - (t0 + epoch p)   (model_full.py:88-89)
-                // The division is a multiplication by 1/p: the two can only disagree half a period
-                // away from the transit, where the point is outside the box either way.
-                const double epoch = floor(fma(tv[j] - t0, invp, 0.5));
-                tc = tv[j] - __dadd_rn(t0, __dmul_rn(epoch, p));
-                inbox = (lo <= tc) && (tc <= hi);
-                fv[j] = 1.0;
-                if (LNL && !inbox) {
-                    const int b = P.blk ? P.blk[i0 + j] : 0;
-                    if (b >= 0) {
-                        const double d = P.obs[i0 + j] - 1.0;
-                        chi = fma(d * d, isig2[b], chi);
+            }
+            continue;
+        }
+        // ---- exact per-point path -------------------------------------------------------------------
+#pragma unroll
+        for (int h = 0; h < 2 / VEC; ++h) {
+            const long long i0 = base + (long long)(h * 32 + lane) * VEC;
+            double tv[VEC], fv[VEC];
+            const bool inr = i0 < npt;  // VEC == 2 requires an even npt: vectors are all-in or all-out
+            if (inr) VecIO<VEC>::load(P.time + i0, tv);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                bool inbox = false;
+                double tc = 0.0;
+                if (inr) {
+                    double lo = lo1, hi = hi1, t0 = t01;
+                    if (!SINGLE_LC) {
+                        const int lc = P.lcids[i0 + j];
+                        lo = sLo[lc];
+                        hi = sHi[lc];
+                        t0 = sT0[lc];
+                    }
+                    // epoch = floor((t - t0 + p/2)/p); tc = t - (t0 + epoch p)   (model_full.py:88-89)
+                    // The division is a multiplication by 1/p: the two can only disagree half a period
+                    // away from the transit, where the point is outside the box either way.
+                    const double epoch = floor(fma(tv[j] - t0, invp, 0.5));
+                    tc = tv[j] - __dadd_rn(t0, __dmul_rn(epoch, p));
+                    inbox = (lo <= tc) && (tc <= hi);
+                    fv[j] = 1.0;
+                    if (LNL && !inbox) {
+                        const int nb = P.blk ? P.blk[i0 + j] : 0;
+                        if (nb >= 0) {
+                            const double d = P.obs[i0 + j] - 1.0;
+                            chi = fma(d * d, isig2[nb], chi);
+                        }
                     }
                 }
+                const unsigned m = __ballot_sync(0xffffffffu, inbox);
+                if (inbox) {
+                    const int pos = qn + __popc(m & lt_mask);
+                    ws.q_ipt[pos] = (int)(i0 + j);
+                    ws.q_tc[pos] = tc;
+                }
+                qn += __popc(m);
             }
-            const unsigned m = __ballot_sync(0xffffffffu, inbox);
-            if (inbox) {
-                const int pos = qn + __popc(m & lt_mask);
-                q_ipt[warp][pos] = (int)(i0 + j);
-                q_tc[warp][pos] = tc;
-            }
-            qn += __popc(m);
+            if (!LNL && inr) VecIO<VEC>::store(frow + i0, fv);
         }
-        if (!LNL && inr) VecIO<VEC>::store(frow + i0, fv);
         __syncwarp();
-        // Drain full passes; keep the remainder (< PPW points) for the next tile, except after the last
-        // tile.  There is exactly ONE call site, so every point goes through the same instruction
-        // sequence whatever the chunking: results are bit-reproducible across population splits.
-        const bool last = tbeg + TILE >= cend;
-        while (qn >= PPW || (last && qn > 0)) {
-            const int n = min(qn, PPW);
+        }  // live
+        // drain full batches; the remainder (< PB points) waits for more, except on the flush pass
+        while (qn >= PB || (!live && qn > 0)) {
+            const int n = min(qn, PB);
             qn -= n;
             drain(qn, n);
         }
+        if (!live) break;
     }
     if (P.stage_ld && !ld_ready) mbar_wait(&bar, 0);  // never exit with the bulk copy in flight
 
     if (LNL) {
         chi = warp_sum(chi);
-        __syncthreads();
-        if (lane == 0) s_part[0][warp] = chi;
+        if (lane == 0) s_red[warp] = chi;
         __syncthreads();
         if (tid == 0) {
             double s = 0.0;
-            for (int wq = 0; wq < PT_WARPS; ++wq) s += s_part[0][wq];
+            for (int wq = 0; wq < PT_WARPS; ++wq) s += s_red[wq];
             P.partial[(size_t)ipv * P.nchunks + chunk] = s;
         }
     }
