@@ -712,9 +712,10 @@ int launch_points(ptb_model *h, int64_t npv, const double *t0, double *flux, con
     // multiple of 8 blocks (one block per warp and pass).
     const long long nb = h->nblk64;
     const long long want = (long long)h->sm_count * 8;
-    long long nchunks = std::min<long long>((nb + 7) / 8, std::max<long long>(1, (want + npv - 1) / npv));
+    long long nchunks = std::min<long long>((nb + 63) / 64, std::max<long long>(1, (want + npv - 1) / npv));
+    nchunks = std::max<long long>(nchunks, (nb + PT_MAXBLK - 1) / PT_MAXBLK);
     long long bpc = (nb + nchunks - 1) / nchunks;
-    bpc = (bpc + 7) / 8 * 8;
+    bpc = std::min<long long>((bpc + 63) / 64 * 64, PT_MAXBLK);  // whole 8-block groups per warp and pass
     nchunks = (nb + bpc - 1) / bpc;
     P.nchunks = (int)nchunks;
     P.blocks_per_chunk = (int)bpc;

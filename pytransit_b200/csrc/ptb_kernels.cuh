@@ -281,6 +281,7 @@ constexpr int PT_WARPS = PT_THREADS / 32;
 constexpr int PT_BLOCK = 64;           // points per classification block
 constexpr int PT_BATCH = 128;          // exposure sub-samples evaluated per drain
 constexpr int PT_QCAP = PT_BATCH + PT_BLOCK;
+constexpr int PT_MAXBLK = 8192;        // blocks per CTA chunk (hit bitmap in shared memory)
 constexpr double PT_EPS = 1e-9;        // classification margin, in periods (>> rounding, << the 0.003 d pad)
 
 struct alignas(16) WarpScratch {
@@ -314,6 +315,7 @@ template <int VEC, bool SINGLE_LC, bool LNL>
 __global__ void __launch_bounds__(PT_THREADS, 3) k_rr_points(const __grid_constant__ PointsParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_red[PT_WARPS];
+    __shared__ unsigned s_hit[PT_MAXBLK / 32];
     __shared__ __align__(8) uint64_t bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -472,92 +474,115 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_rr_points(const __grid_consta
         }
     };
 
-    // One extra pass after the last block flushes the queue, so that drain() has exactly ONE call site
+    // ---- classification of every block of this chunk, in parallel over the CTA -----------------------
+    // Can any transit window [t0 + n p + lo, t0 + n p + hi] touch [tmin, tmax] of the block?  If not, the
+    // block holds no in-box point.  One bit per block goes to shared memory; in likelihood mode the
+    // pre-summed (obs-1)^2 of the untouched blocks is added right here.
+    const int nbc = bend - bbeg;
+    for (int bb0 = 0; bb0 < nbc; bb0 += PT_THREADS) {
+        const int bb = bb0 + tid, b = bbeg + bb;
+        bool hit = false;
+        if (bb < nbc) {
+            hit = true;
+            const int lcb = SINGLE_LC ? 0 : P.blc[b];
+            int nz_id = 0;
+            if (LNL) nz_id = P.bnoise ? P.bnoise[b] : 0;
+            const bool partial = (b == P.nblk64 - 1) && (npt % PT_BLOCK != 0);
+            if (lcb >= 0 && nz_id != -2 && !partial) {
+                const double lo = SINGLE_LC ? lo1 : sLo[lcb], hi = SINGLE_LC ? hi1 : sHi[lcb];
+                const double t0 = SINGLE_LC ? t01 : sT0[lcb];
+                const double n1 = ceil(fma(P.bmin[b] - t0 - hi, invp, -PT_EPS));
+                const double n2 = floor(fma(P.bmax[b] - t0 - lo, invp, PT_EPS));
+                hit = !(n1 > n2) || !(p > 0.0);  // NaNs and p <= 0 fall through to the exact per-point path
+            }
+            if (LNL && !hit && nz_id >= 0) chi = fma(P.bchi[b], isig2[nz_id], chi);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_hit[bb >> 5] = m;
+    }
+    __syncthreads();
+
+    // ---- main loop: a warp takes groups of 8 blocks (512 points) ------------------------------------
+    // One extra pass after the last group flushes the queue, so that drain() has exactly ONE call site
     // and batches are always cut from the top of the queue: a point's arithmetic does not depend on the
     // chunking and results are bit-reproducible across population splits.
-    for (int b = bbeg + warp;; b += PT_WARPS) {
-        const bool live = b < bend;
-        if (live) {
-        const long long base = (long long)b * PT_BLOCK;
-        // ---- classification: can any transit window touch this block? --------------------------
-        bool hit = true;
-        const int lcb = SINGLE_LC ? 0 : P.blc[b];
-        int nz_id = 0;
-        if (LNL) nz_id = P.bnoise ? P.bnoise[b] : 0;
-        if (lcb >= 0 && nz_id != -2) {
-            const double lo = SINGLE_LC ? lo1 : sLo[lcb], hi = SINGLE_LC ? hi1 : sHi[lcb];
-            const double t0 = SINGLE_LC ? t01 : sT0[lcb];
-            const double n1 = ceil(fma(P.bmin[b] - t0 - hi, invp, -PT_EPS));
-            const double n2 = floor(fma(P.bmax[b] - t0 - lo, invp, PT_EPS));
-            hit = !(n1 > n2) || !(p > 0.0);  // NaNs and p <= 0 fall through to the exact per-point path
-        }
-        if (!hit) {
-            if (LNL) {
-                if (lane == 0 && nz_id >= 0) chi = fma(P.bchi[b], isig2[nz_id], chi);
-            } else {
-                double one[VEC];
+    const int ngroups = (nbc + 7) >> 3;
+    for (int g = warp;; g += PT_WARPS) {
+        const bool live = g < ngroups;
+        unsigned bits = live ? (s_hit[g >> 2] >> ((g & 3) * 8)) & 0xffu : 0u;
+        const int b0 = bbeg + g * 8;
+        if (!LNL && live) {
+            // untouched blocks: 64 fluxes of exactly 1.0, one 16-byte streaming store per lane
+            double one[VEC];
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) one[j] = 1.0;
+            for (int j = 0; j < VEC; ++j) one[j] = 1.0;
+            double *fb = frow + (long long)b0 * PT_BLOCK;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (!((bits >> j) & 1u) && b0 + j < bend) {
+#pragma unroll
+                    for (int h = 0; h < 2 / VEC; ++h) VecIO<VEC>::store(fb + j * PT_BLOCK + (h * 32 + lane) * VEC, one);
+                }
+            }
+        }
+        // touched blocks: exact per-point path; the body runs once more on the flush pass (no block)
+        do {
+            if (bits) {
+                const int jb = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const long long base = (long long)(b0 + jb) * PT_BLOCK;
 #pragma unroll
                 for (int h = 0; h < 2 / VEC; ++h) {
                     const long long i0 = base + (long long)(h * 32 + lane) * VEC;
-                    if (i0 < npt) VecIO<VEC>::store(frow + i0, one);
-                }
-            }
-            continue;
-        }
-        // ---- exact per-point path -------------------------------------------------------------------
+                    double tv[VEC], fv[VEC];
+                    const bool inr = i0 < npt;  // VEC == 2 requires an even npt: vectors are all-in or all-out
+                    if (inr) VecIO<VEC>::load(P.time + i0, tv);
 #pragma unroll
-        for (int h = 0; h < 2 / VEC; ++h) {
-            const long long i0 = base + (long long)(h * 32 + lane) * VEC;
-            double tv[VEC], fv[VEC];
-            const bool inr = i0 < npt;  // VEC == 2 requires an even npt: vectors are all-in or all-out
-            if (inr) VecIO<VEC>::load(P.time + i0, tv);
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                bool inbox = false;
-                double tc = 0.0;
-                if (inr) {
-                    double lo = lo1, hi = hi1, t0 = t01;
-                    if (!SINGLE_LC) {
-                        const int lc = P.lcids[i0 + j];
-                        lo = sLo[lc];
-                        hi = sHi[lc];
-                        t0 = sT0[lc];
-                    }
-                    // epoch = floor((t - t0 + p/2)/p); tc = t - (t0 + epoch p)   (model_full.py:88-89)
-                    // The division is a multiplication by 1/p: the two can only disagree half a period
-                    // away from the transit, where the point is outside the box either way.
-                    const double epoch = floor(fma(tv[j] - t0, invp, 0.5));
-                    tc = tv[j] - __dadd_rn(t0, __dmul_rn(epoch, p));
-                    inbox = (lo <= tc) && (tc <= hi);
-                    fv[j] = 1.0;
-                    if (LNL && !inbox) {
-                        const int nb = P.blk ? P.blk[i0 + j] : 0;
-                        if (nb >= 0) {
-                            const double d = P.obs[i0 + j] - 1.0;
-                            chi = fma(d * d, isig2[nb], chi);
+                    for (int j = 0; j < VEC; ++j) {
+                        bool inbox = false;
+                        double tc = 0.0;
+                        if (inr) {
+                            double lo = lo1, hi = hi1, t0 = t01;
+                            if (!SINGLE_LC) {
+                                const int lc = P.lcids[i0 + j];
+                                lo = sLo[lc];
+                                hi = sHi[lc];
+                                t0 = sT0[lc];
+                            }
+                            // epoch = floor((t - t0 + p/2)/p); tc = t - (t0 + epoch p)  (model_full.py:88-89)
+                            // The division is a multiplication by 1/p: the two can only disagree half a
+                            // period away from the transit, where the point is outside the box either way.
+                            const double epoch = floor(fma(tv[j] - t0, invp, 0.5));
+                            tc = tv[j] - __dadd_rn(t0, __dmul_rn(epoch, p));
+                            inbox = (lo <= tc) && (tc <= hi);
+                            fv[j] = 1.0;
+                            if (LNL && !inbox) {
+                                const int nb = P.blk ? P.blk[i0 + j] : 0;
+                                if (nb >= 0) {
+                                    const double d = P.obs[i0 + j] - 1.0;
+                                    chi = fma(d * d, isig2[nb], chi);
+                                }
+                            }
                         }
+                        const unsigned m = __ballot_sync(0xffffffffu, inbox);
+                        if (inbox) {
+                            const int pos = qn + __popc(m & lt_mask);
+                            ws.q_ipt[pos] = (int)(i0 + j);
+                            ws.q_tc[pos] = tc;
+                        }
+                        qn += __popc(m);
                     }
+                    if (!LNL && inr) VecIO<VEC>::store(frow + i0, fv);
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, inbox);
-                if (inbox) {
-                    const int pos = qn + __popc(m & lt_mask);
-                    ws.q_ipt[pos] = (int)(i0 + j);
-                    ws.q_tc[pos] = tc;
-                }
-                qn += __popc(m);
+                __syncwarp();
             }
-            if (!LNL && inr) VecIO<VEC>::store(frow + i0, fv);
-        }
-        __syncwarp();
-        }  // live
-        // drain full batches; the remainder (< PB points) waits for more, except on the flush pass
-        while (qn >= PB || (!live && qn > 0)) {
-            const int n = min(qn, PB);
-            qn -= n;
-            drain(qn, n);
-        }
+            // drain full batches; the remainder (< PB points) waits for more, except on the flush pass
+            while (qn >= PB || (!live && qn > 0)) {
+                const int n = min(qn, PB);
+                qn -= n;
+                drain(qn, n);
+            }
+        } while (bits);
         if (!live) break;
     }
     if (P.stage_ld && !ld_ready) mbar_wait(&bar, 0);  // never exit with the bulk copy in flight
