@@ -106,7 +106,7 @@ struct ptb_model {
 
     // per-vector workspaces
     DevBuf d_orb, d_ldrec, d_ldp, d_istar, d_flux, d_partial, d_isig2, d_lnl, d_xyc;
-    DevBuf d_tsw, d_tsrec;
+    DevBuf d_tsw, d_tsrec, d_sort;
     bool xyc_injected = false;
     int64_t xyc_npv = 0;
     int64_t last_npv = 0, last_npb = 0, last_flux_count = 0;
@@ -364,8 +364,6 @@ int ptb_create(const ptb_config *cfg, ptb_model **out) {
     if (!cu(cudaGetLastError(), "k_weight_table launch")) return bail(PTB_ECUDA);
     if (!cu(cudaDeviceSynchronize(), "k_weight_table")) return bail(PTB_ECUDA);
 
-    const int smem_setup = (int)(2 * (size_t)cfg->ng * nz * 8 + 64 * 1024);
-    cudaFuncSetAttribute(k_rr_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(smem_setup, 227 * 1024));
     *out = h;
     return PTB_OK;
 }
@@ -375,7 +373,7 @@ void ptb_destroy(ptb_model *h) {
     cudaSetDevice(h->cfg.device);
     for (DevBuf *b : {&h->d_tab, &h->d_W, &h->d_time_own, &h->d_meta, &h->d_obs_own, &h->d_blk, &h->d_nblk, &h->d_orb,
                       &h->d_ldrec, &h->d_ldp, &h->d_istar, &h->d_flux, &h->d_partial, &h->d_isig2, &h->d_lnl, &h->d_xyc,
-                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs})
+                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_sort})
         b->release();
     h->h_stage.release();
     if (h->stage_ev) cudaEventDestroy(h->stage_ev);
@@ -651,27 +649,53 @@ int stage_model_args(ptb_model *h, const ModelArgs &A, int64_t npb, int64_t nep,
 
 int launch_rr_setup(ptb_model *h, const ModelArgs &A, const Staged &D, cudaStream_t st) {
     const int64_t npv = A.npv, npb = h->npb;
-    const int ng = h->cfg.ng, nz = h->nz;
+    const int ng = h->cfg.ng, nz = h->nz, nk = h->cfg.nk;
     const int lds = (ng + 4 + 1) & ~1;
     CU(h->d_orb.reserve(npv * ORB_STRIDE * 8));
     CU(h->d_ldrec.reserve((size_t)npv * npb * lds * 8));
     CU(h->d_ldp.reserve((size_t)npv * npb * nz * 8));
     CU(h->d_istar.reserve((size_t)npv * npb * 8));
+    // sort workspace: bin[npv] | perm[npv] | hist[nk+2] | offsets[nk+2] | gstart[nk+2] | cursor[nk+2]
+    const size_t nb4 = ((size_t)nk + 2 + 3) & ~size_t(3);
+    const bool fresh = h->d_sort.cap < (2 * (size_t)npv + 4 * nb4) * 4;
+    CU(h->d_sort.reserve((2 * (size_t)npv + 4 * nb4) * 4));
+    int *bin = h->d_sort.as<int>(), *perm = bin + npv;
+    // the histogram lives at the END of the buffer so that it keeps its place when npv changes
+    int *hist = h->d_sort.as<int>() + h->d_sort.cap / 4 - 4 * nb4;
+    int *offsets = hist + nb4, *gstart = offsets + nb4, *cursor = gstart + nb4;
+    if (fresh) CU(cudaMemsetAsync(hist, 0, 4 * nb4 * 4, st));  // k_bin_scan re-zeroes it after every use
     if (h->xyc_injected && h->xyc_npv != npv)
         return fail(h, PTB_ESHAPE, "injected xyc has npv=%lld but evaluate was called with npv=%lld", (long long)h->xyc_npv, (long long)npv);
-    SetupParams P{};
-    P.k = D.k; P.ld = D.ld; P.istar = D.istar; P.p = D.p; P.a = D.a; P.inc = D.inc; P.e = D.e; P.w = D.w;
-    P.xyc_in = h->xyc_injected ? h->d_xyc.as<double>() : nullptr;
+    if (nk + 2 > 1024) return fail(h, PTB_EINVAL, "nk=%d: at most 1022 table rows are supported", nk);
+
+    OrbitParams O{};
+    O.k = D.k; O.p = D.p; O.a = D.a; O.inc = D.inc; O.e = D.e; O.w = D.w;
+    O.xyc_in = h->xyc_injected ? h->d_xyc.as<double>() : nullptr;
+    O.orb = h->d_orb.as<double>(); O.bin = bin; O.hist = hist;
+    O.npv = (int)npv; O.kcols = (int)A.kcols; O.nk = nk; O.kmin = h->cfg.kmin; O.kmax = h->cfg.kmax; O.dk = h->dk;
+    k_rr_orbit<<<(unsigned)((npv * 8 + 255) / 256), 256, 0, st>>>(O);
+    // group size: as many vectors as fit ~32 KB of profiles, at most RR_GROUP
+    const int grp = (int)std::max<int64_t>(1, std::min<int64_t>(RR_GROUP, (32 * 1024) / (npb * nz * 8)));
+    k_bin_scan<<<1, 256, 0, st>>>(hist, offsets, gstart, cursor, nk + 1, grp);
+    k_bin_scatter<<<(unsigned)((npv + 255) / 256), 256, 0, st>>>(bin, offsets, cursor, perm, (int)npv);
+    h->launches += 3;
+    CU(cudaGetLastError());
+
+    LdmParams P{};
+    P.k = D.k; P.ld = D.ld; P.istar = D.istar;
     P.W = h->d_W.as<double>(); P.ze = h->d_ze; P.mu = h->d_mu; P.gs = h->d_gs; P.ldmu200 = h->d_ldmu; P.ldz200 = h->d_ldz;
+    P.offsets = offsets; P.gstart = gstart; P.perm = perm;
     P.orb = h->d_orb.as<double>(); P.ldrec = h->d_ldrec.as<double>(); P.ldp_out = h->d_ldp.as<double>();
     P.istar_out = h->d_istar.as<double>();
     P.npv = (int)npv; P.kcols = (int)A.kcols; P.npb = (int)npb; P.nld = (int)A.nld; P.law = h->cfg.ldlaw;
-    P.nk = h->cfg.nk; P.ng = ng; P.nz = nz; P.lds = lds;
-    P.kmin = h->cfg.kmin; P.kmax = h->cfg.kmax; P.dk = h->dk;
-    P.check_ldp_nan = 1;
-    const size_t smem = (2 * (size_t)ng * nz + (size_t)npb * nz + npb + 600) * 8 + 16;
-    if (smem > 227 * 1024) return fail(h, PTB_EINVAL, "setup kernel needs %zu bytes of shared memory (> 227 KB)", smem);
-    k_rr_setup<<<(unsigned)npv, 128, smem, st>>>(P);
+    P.nk = nk; P.ng = ng; P.nz = nz; P.lds = lds; P.grp = grp;
+    P.kmin = h->cfg.kmin; P.dk = h->dk;
+    const size_t smem = (2 * (size_t)ng * nz + (size_t)grp * npb * nz + grp * npb + 2 * (size_t)grp * ng + 8 * 200) * 8 + 16;
+    if (smem > 227 * 1024) return fail(h, PTB_EINVAL, "k_rr_ldm needs %zu bytes of shared memory (> 227 KB): too many passbands", smem);
+    CU(cudaFuncSetAttribute(k_rr_ldm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // upper bound on the number of groups: every bin can end with one partial group
+    const unsigned grid = (unsigned)((npv + grp - 1) / grp + nk + 1);
+    k_rr_ldm<<<grid, 256, smem, st>>>(P);
     h->launches++;
     CU(cudaGetLastError());
     h->last_npv = npv;

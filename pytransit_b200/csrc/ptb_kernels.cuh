@@ -1,8 +1,10 @@
 // ptb_kernels.cuh -- sm_100a kernels of the RoadRunner population path.
 //
 //   k_weight_table   W[nk,ng,nz]  (common.py:188-223)                         once per model
-//   k_rr_setup       per-vector state: LD profile, I*, LD means (TMA-staged table rows), Taylor
-//                    orbit coefficients, contact times (model_full.py:39-70)   once per evaluate
+//   k_rr_orbit       per-vector Taylor orbit coefficients + contact times       \
+//   k_bin_scan/scatter  counting sort of the vectors by weight-table row          > once per evaluate
+//   k_rr_ldm         LD profile, I*, LD means (TMA-staged table rows shared      /  (model_full.py:39-70)
+//                    by the vectors of a group)
 //   k_rr_points      the npv x npt pass: phase fold, box test, supersampled flux, optional fused
 //                    chi^2 reduction (model_full.py:76-99, wnloglikelihood.py:22-35)
 //   k_lnl_finish     chi^2 partials -> lnL[npv]
@@ -49,59 +51,136 @@ __global__ void k_weight_table(const double *__restrict__ ks, const double *__re
 }
 
 // ---------------------------------------------------------------------------------------------
-// Per-vector setup.  One CTA (128 threads) per parameter vector:
-//   thread 0      arms an mbarrier and starts two TMA bulk copies of the table rows W[ik], W[ik+1]
-//                 (ng*nz*8 bytes each) into shared memory;
-//   warp 0        meanwhile solves the orbit: lanes 0..6 each do one Kepler solve of the 7-point
-//                 stencil, the coefficients are formed from shuffles, lanes 0/1 bisect T1/T4;
-//   warps 1..3    evaluate the limb-darkening profile at the nz mu nodes and I* per passband;
-//   all           wait on the mbarrier, then contract (ng x nz).(nz) per passband -> ldm.
+// Per-vector setup (model_full.py:39-70), four launches:
+//
+//   k_rr_orbit    8 lanes per vector: validity, the 7 Kepler solves of the Taylor stencil (one per lane),
+//                 coefficients from sub-warp shuffles, T1/T4 bisection on two lanes; also the weight-table
+//                 row `ik` of the vector and a histogram of the rows in use.
+//   k_bin_scan    one CTA: prefix sums of the histogram -> where each table row's vectors and its
+//                 groups of up to RR_GROUP vectors start.
+//   k_bin_scatter counting-sort scatter: vectors ordered by table row.
+//   k_rr_ldm      one CTA per group of vectors that share a table row pair: the two rows W[ik], W[ik+1]
+//                 (ng*nz*8 bytes each) arrive in shared memory through ONE pair of TMA bulk copies per
+//                 group instead of one per vector, overlapped with the limb-darkening profile evaluation;
+//                 then the (ng x nz).(nz) contractions, register-blocked over the group's vectors.
+// Sorting by table row cuts the L2 -> SM traffic of the contraction by the group size and removes the
+// serial orbit solve from the critical path of the table staging.
 // ---------------------------------------------------------------------------------------------
-struct SetupParams {
-    const double *k;      // [npv][kcols]
-    const double *ld;     // ldc[npv][npb][nld] or ldp[npv][npb][nz]
-    const double *istar;  // [npv][npb] (profiles only)
-    const double *p, *a, *inc, *e, *w;
-    const double *xyc_in;  // optional injected coefficients [npv][10]
-    const double *W, *ze, *mu, *gs, *ldmu200, *ldz200;
-    double *orb, *ldrec, *ldp_out, *istar_out;
-    int npv, kcols, npb, nld, law, nk, ng, nz, lds;
-    double kmin, kmax, dk;
-    int check_ldp_nan;  // RoadRunner: 1 (model_full.py:40); TSModel: 0 (model_trspec.py:37)
-};
+constexpr int RR_GROUP = 8;  // vectors per k_rr_ldm CTA (register blocking factor)
 
-__device__ __forceinline__ void solve_orbit_warp(int lane, double p, double a, double inc, double e, double w,
-                                                 double kbox, const double *xyc_in, double *orb_out) {
+template <int WIDTH>
+__device__ __forceinline__ void solve_orbit_lanes(int sl, bool valid, double p, double a, double inc, double e, double w,
+                                                  double kbox, const double *xyc_in, double *orb_out) {
     double cx[5], cy[5];
     if (xyc_in != nullptr) {
 #pragma unroll
         for (int j = 0; j < 5; ++j) { cx[j] = xyc_in[j]; cy[j] = xyc_in[5 + j]; }
     } else {
         double x = 0.0, y = 0.0;
-        const double offset = mean_anomaly_offset(e, w);
-        if (lane < 7) sky_position((lane - 3) * 2e-2, p, a * (1.0 - e * e), cos(inc), e, w, offset, x, y);
+        if (valid && sl < 7) {
+            const double offset = mean_anomaly_offset(e, w);
+            sky_position((sl - 3) * 2e-2, p, a * (1.0 - e * e), cos(inc), e, w, offset, x, y);
+        }
         double vx[7], vy[7];
 #pragma unroll
         for (int j = 0; j < 7; ++j) {
-            vx[j] = __shfl_sync(0xffffffffu, x, j);
-            vy[j] = __shfl_sync(0xffffffffu, y, j);
+            vx[j] = __shfl_sync(0xffffffffu, x, j, WIDTH);
+            vy[j] = __shfl_sync(0xffffffffu, y, j, WIDTH);
         }
         stencil_to_coeffs(vx, cx);
         stencil_to_coeffs(vy, cy);
     }
     double tcon = 0.0;
-    if (lane < 2) tcon = contact_point(kbox, lane == 0 ? -1.0 : 1.0, cx, cy);
-    const double t1 = __shfl_sync(0xffffffffu, tcon, 0);
-    const double t4 = __shfl_sync(0xffffffffu, tcon, 1);
-    if (lane == 0) {
+    if (valid && sl < 2) tcon = contact_point(kbox, sl == 0 ? -1.0 : 1.0, cx, cy);
+    const double t1 = __shfl_sync(0xffffffffu, tcon, 0, WIDTH);
+    const double t4 = __shfl_sync(0xffffffffu, tcon, 1, WIDTH);
+    if (valid && sl == 0) {
 #pragma unroll
         for (int j = 0; j < 5; ++j) { orb_out[j] = cx[j]; orb_out[5 + j] = cy[j]; }
         orb_out[ORB_P] = p;
         orb_out[ORB_INVP] = 1.0 / p;
         orb_out[ORB_T1] = t1;
         orb_out[ORB_T4] = t4;
+        orb_out[ORB_GOOD] = 1.0;
         orb_out[15] = 0.0;
     }
+}
+
+// full-warp form used by the TSModel setup
+__device__ __forceinline__ void solve_orbit_warp(int lane, double p, double a, double inc, double e, double w,
+                                                 double kbox, const double *xyc_in, double *orb_out) {
+    solve_orbit_lanes<32>(lane, true, p, a, inc, e, w, kbox, xyc_in, orb_out);
+}
+
+struct OrbitParams {
+    const double *k;  // [npv][kcols]
+    const double *p, *a, *inc, *e, *w;
+    const double *xyc_in;  // optional injected coefficients [npv][10]
+    double *orb;
+    int *bin;   // [npv]  table row ik, nk = direct weights, nk+1 = invalid vector
+    int *hist;  // [nk+2]
+    int npv, kcols, nk;
+    double kmin, kmax, dk;
+};
+
+__global__ void __launch_bounds__(256) k_rr_orbit(const __grid_constant__ OrbitParams P) {
+    const int lane = threadIdx.x & 31, sl = lane & 7;
+    const int ipv = (blockIdx.x * 256 + threadIdx.x) >> 3;
+    const bool inr = ipv < P.npv;
+    double a = 0, e = 0, k0 = 0, p = 1, inc = 0, w = 0;
+    if (inr) {
+        a = P.a[ipv];
+        e = P.e[ipv];
+        k0 = P.k[(size_t)ipv * P.kcols];
+        p = P.p[ipv];
+        inc = P.inc[ipv];
+        w = P.w[ipv];
+    }
+    const bool good0 = inr && !(isnan(a) || (a <= 1.0) || (e < 0.0));  // model_full.py:40 (ldp checked later)
+    double *orb = P.orb + (size_t)(inr ? ipv : 0) * ORB_STRIDE;
+    solve_orbit_lanes<8>(sl, good0, p, a, inc, e, w, k0, (P.xyc_in && inr) ? P.xyc_in + (size_t)ipv * 10 : nullptr, orb);
+    if (inr && sl == 0) {
+        int bin = P.nk + 1;
+        if (good0) {
+            if ((P.kmin <= k0) && (k0 <= P.kmax)) bin = min((int)floor((k0 - P.kmin) / P.dk), P.nk - 1);
+            else bin = P.nk;
+        } else {
+            for (int j = 0; j < ORB_STRIDE; ++j) orb[j] = (j == ORB_GOOD) ? 0.0 : nan("");
+        }
+        P.bin[ipv] = bin;
+        atomicAdd(&P.hist[bin], 1);
+    }
+}
+
+// offsets[b] = first slot of bin b in `perm`; gstart[b] = first group of bin b; gstart[nk+1] = group count.
+__global__ void __launch_bounds__(256) k_bin_scan(int *hist, int *offsets, int *gstart, int *cursor, int nbins_valid, int grp) {
+    __shared__ int s_cnt[1024 + 8];
+    const int n = nbins_valid;  // nk + 1 bins carry work (table rows + direct); the invalid bin is last
+    for (int i = threadIdx.x; i < n + 1; i += 256) s_cnt[i] = hist[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int off = 0, g = 0;
+        for (int i = 0; i < n; ++i) {
+            offsets[i] = off;
+            gstart[i] = g;
+            off += s_cnt[i];
+            g += (s_cnt[i] + grp - 1) / grp;
+        }
+        offsets[n] = off;  // the invalid bin: listed after all work, never grouped
+        gstart[n] = g;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n + 1; i += 256) {
+        cursor[i] = 0;
+        hist[i] = 0;  // ready for the next call; counts live on in offsets[]
+    }
+}
+
+__global__ void k_bin_scatter(const int *__restrict__ bin, const int *__restrict__ offsets, int *cursor, int *perm, int npv) {
+    const int ipv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ipv >= npv) return;
+    const int b = bin[ipv];
+    perm[offsets[b] + atomicAdd(&cursor[b], 1)] = ipv;
 }
 
 // I* by the reference's numeric fallback, 2 pi trapezoid(z I(mu(z)), z) on 200 nodes
@@ -117,122 +196,163 @@ __device__ __forceinline__ double istar_numeric_warp(int lane, int law, const do
     return 2.0 * kPi * warp_sum(s);
 }
 
-__global__ void __launch_bounds__(128) k_rr_setup(const __grid_constant__ SetupParams P) {
+struct LdmParams {
+    const double *k;      // [npv][kcols]
+    const double *ld;     // ldc[npv][npb][nld] or ldp[npv][npb][nz]
+    const double *istar;  // [npv][npb] (profiles only)
+    const double *W, *ze, *mu, *gs, *ldmu200, *ldz200;
+    const int *offsets, *gstart, *perm;
+    double *orb, *ldrec, *ldp_out, *istar_out;
+    int npv, kcols, npb, nld, law, nk, ng, nz, lds, grp;  // grp <= RR_GROUP vectors per CTA
+    double kmin, dk;
+};
+
+__global__ void __launch_bounds__(256) k_rr_ldm(const __grid_constant__ LdmParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int s_bin, s_first, s_cnt;
+    __shared__ int s_pv[RR_GROUP];
+    __shared__ double s_ak[RR_GROUP];
     const int ng = P.ng, nz = P.nz, npb = P.npb;
     const int rowlen = ng * nz;
-    double *sW0 = reinterpret_cast<double *>(smem_raw);
-    double *sW1 = sW0 + rowlen;
-    double *sLdp = sW1 + rowlen;             // [npb][nz]
-    double *sIstar = sLdp + npb * nz;        // [npb]
-    double *sScr = sIstar + npb;             // [3][200] trapezoid scratch
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sScr + 600);
+    double *sW = reinterpret_cast<double *>(smem_raw);       // [2][ng][nz]
+    double *sLdp = sW + 2 * rowlen;                           // [grp][npb][nz]
+    double *sIstar = sLdp + (size_t)P.grp * npb * nz;         // [grp][npb]
+    double *sOut = sIstar + P.grp * npb;                      // [2][grp][ng] partial contractions
+    double *sScr = sOut + 2 * P.grp * ng;                     // [8][200] trapezoid scratch
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sScr + 8 * 200);
 
-    const int ipv = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double a = P.a[ipv], e = P.e[ipv];
-    const double k0 = P.k[(size_t)ipv * P.kcols];
-    const bool good0 = !(isnan(a) || (a <= 1.0) || (e < 0.0));
-    const bool in_table = (P.kmin <= k0) && (k0 <= P.kmax);
-    int ik = 0, ik1 = 0;
-    double ak = 0.0;
-    if (in_table) {
-        ik = (int)floor((k0 - P.kmin) / P.dk);
-        ak = (k0 - P.kmin - ik * P.dk) / P.dk;
-        ik = min(ik, P.nk - 1);
-        ik1 = min(ik + 1, P.nk - 1);  // the reference reads weights[nk] here
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nbins = P.nk + 1;
+    if (tid == 0) {
+        // which bin does this group belong to?  (binary search over the group starts)
+        const int g = blockIdx.x;
+        int lo = 0, hi = nbins;  // gstart[nbins] = total number of groups
+        if (g >= P.gstart[nbins]) {
+            s_bin = -1;
+        } else {
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (P.gstart[mid] <= g) lo = mid; else hi = mid;
+            }
+            // skip empty bins that share the same start
+            while (lo + 1 < nbins && P.gstart[lo + 1] <= g) ++lo;
+            s_bin = lo;
+            const int j = g - P.gstart[lo];
+            const int cnt = P.offsets[lo + 1] - P.offsets[lo];
+            s_first = P.offsets[lo] + j * P.grp;
+            s_cnt = min(P.grp, cnt - j * P.grp);
+        }
+        mbar_init(bar, 1);
     }
-    const bool use_tma = good0 && in_table;
-
-    if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
-    if (use_tma && tid == 0) {
+    const int bin = s_bin;
+    if (bin < 0) return;
+    const int cnt = s_cnt;
+    const bool in_table = bin < P.nk;
+    if (in_table && tid == 0) {
+        const int ik1 = min(bin + 1, P.nk - 1);  // the reference reads weights[nk] here
         const uint32_t bytes = (uint32_t)rowlen * 8u;
         mbar_expect_tx(bar, 2u * bytes);
-        tma_load_1d(sW0, P.W + (size_t)ik * rowlen, bytes, bar);
-        tma_load_1d(sW1, P.W + (size_t)ik1 * rowlen, bytes, bar);
+        tma_load_1d(sW, P.W + (size_t)bin * rowlen, bytes, bar);
+        tma_load_1d(sW + rowlen, P.W + (size_t)ik1 * rowlen, bytes, bar);
     }
-
-    double *orb = P.orb + (size_t)ipv * ORB_STRIDE;
-    if (warp == 0) {
-        if (good0) {
-            solve_orbit_warp(lane, P.p[ipv], a, P.inc[ipv], e, P.w[ipv], k0,
-                             P.xyc_in ? P.xyc_in + (size_t)ipv * 10 : nullptr, orb);
-        } else if (lane < ORB_STRIDE) {
-            orb[lane] = (lane == ORB_GOOD) ? 0.0 : nan("");
-        }
-    } else {
-        // limb-darkening profile at the mu nodes (evaluate_ld, ldmodels.py:142-157)
-        const int t = tid - 32;
-        for (int idx = t; idx < npb * nz; idx += 96) {
-            const int pb = idx / nz, iz = idx - pb * nz;
-            double v;
-            if (P.law == LD_PROFILES) v = P.ld[((size_t)ipv * npb + pb) * nz + iz];
-            else v = ld_intensity(P.law, P.mu[iz], P.ld + ((size_t)ipv * npb + pb) * P.nld, P.nld);
-            sLdp[idx] = v;
-            if (P.ldp_out) P.ldp_out[((size_t)ipv * npb + pb) * nz + iz] = v;
-        }
-        // disk-integrated intensity (evaluate_ldi, ldmodels.py:160-175; numeric fallback)
-        for (int pb = warp - 1; pb < npb; pb += 3) {
-            double is;
-            if (P.law == LD_PROFILES) {
-                is = P.istar[(size_t)ipv * npb + pb];
-            } else {
-                const double *pv = P.ld + ((size_t)ipv * npb + pb) * P.nld;
-                if (!ld_integral(P.law, pv, is))
-                    is = istar_numeric_warp(lane, P.law, pv, P.nld, P.ldmu200, P.ldz200, sScr + (warp - 1) * 200);
-            }
-            if (lane == 0) {
-                sIstar[pb] = is;
-                if (P.istar_out) P.istar_out[(size_t)ipv * npb + pb] = is;
-            }
-        }
+    if (tid < cnt) {
+        const int ipv = P.perm[s_first + tid];
+        s_pv[tid] = ipv;
+        const double k0 = P.k[(size_t)ipv * P.kcols];
+        const int ikraw = (int)floor((k0 - P.kmin) / P.dk);
+        s_ak[tid] = (k0 - P.kmin - ikraw * P.dk) / P.dk;  // model_full.py:49
     }
     __syncthreads();
 
-    const bool good = good0 && !(P.check_ldp_nan && isnan(sLdp[0]));
-    if (tid == 0 && good0) orb[ORB_GOOD] = good ? 1.0 : 0.0;
-
-    if (use_tma) mbar_wait(bar, 0);  // every thread observes completion before reading / exiting
-    if (!good) return;
-
-    if (!in_table) {
-        // direct weights for this radius ratio (calculate_weights_2d, common.py:152-185)
-        for (int ig = tid; ig < ng; ig += 128) weight_row(k0, P.gs[ig], P.ze, nz, sW0 + (size_t)ig * nz, 1);
-        __syncthreads();
+    // limb-darkening profile at the mu nodes (evaluate_ld, ldmodels.py:142-157) while the TMA is in flight
+    const int nprof = cnt * npb * nz;
+    for (int idx = tid; idx < nprof; idx += 256) {
+        const int q = idx / (npb * nz), r = idx - q * npb * nz;
+        const int pb = r / nz, iz = r - pb * nz;
+        const int ipv = s_pv[q];
+        double v;
+        if (P.law == LD_PROFILES) v = P.ld[((size_t)ipv * npb + pb) * nz + iz];
+        else v = ld_intensity(P.law, P.mu[iz], P.ld + ((size_t)ipv * npb + pb) * P.nld, P.nld);
+        sLdp[idx] = v;
+        if (P.ldp_out) P.ldp_out[((size_t)ipv * npb + pb) * nz + iz] = v;
     }
-
-    double *rec = P.ldrec + (size_t)ipv * npb * P.lds;
-    for (int ig = tid; ig < ng; ig += 128) {
-        const double *w0 = sW0 + (size_t)ig * nz;
-        const double *w1 = sW1 + (size_t)ig * nz;
-        for (int pb = 0; pb < npb; ++pb) {
-            const double *l = sLdp + pb * nz;
-            double d0 = 0.0, d1 = 0.0;
-            int iz = ig % nz;  // rotated start: lanes of a warp hit distinct banks
-            if (in_table) {
-                for (int j = 0; j < nz; ++j) {
-                    d0 = fma(w0[iz], l[iz], d0);
-                    d1 = fma(w1[iz], l[iz], d1);
-                    iz = (iz + 1 == nz) ? 0 : iz + 1;
-                }
-                rec[(size_t)pb * P.lds + ig] = (1.0 - ak) * d0 + ak * d1;
-            } else {
-                for (int j = 0; j < nz; ++j) {
-                    d0 = fma(w0[iz], l[iz], d0);
-                    iz = (iz + 1 == nz) ? 0 : iz + 1;
-                }
-                rec[(size_t)pb * P.lds + ig] = d0;
-            }
+    // disk-integrated intensity (evaluate_ldi, ldmodels.py:160-175; numeric fallback): warp per (vector, pb)
+    for (int r = warp; r < cnt * npb; r += 8) {
+        const int q = r / npb, pb = r - q * npb;
+        const int ipv = s_pv[q];
+        double is;
+        if (P.law == LD_PROFILES) {
+            is = P.istar[(size_t)ipv * npb + pb];
+        } else {
+            const double *pv = P.ld + ((size_t)ipv * npb + pb) * P.nld;
+            if (!ld_integral(P.law, pv, is)) is = istar_numeric_warp(lane, P.law, pv, P.nld, P.ldmu200, P.ldz200, sScr + warp * 200);
+        }
+        if (lane == 0) {
+            sIstar[r] = is;
+            if (P.istar_out) P.istar_out[(size_t)ipv * npb + pb] = is;
         }
     }
-    for (int pb = tid; pb < npb; pb += 128) {
-        const double kk = (P.kcols == npb) ? P.k[(size_t)ipv * P.kcols + pb] : k0;
-        double *tail = rec + (size_t)pb * P.lds + ng;
+    __syncthreads();
+    // isnan(ldp[ipv,0,0]) invalidates the vector (model_full.py:40)
+    if (tid < cnt && isnan(sLdp[(size_t)tid * npb * nz])) P.orb[(size_t)s_pv[tid] * ORB_STRIDE + ORB_GOOD] = 0.0;
+
+    if (in_table) mbar_wait(bar, 0);  // every thread observes the TMA completion
+
+    const int t = tid >> 7, ig0 = tid & 127;  // thread = (table row pair member, g index)
+    for (int q0 = 0; q0 < cnt; q0 += (in_table ? cnt : 1)) {
+        const int nq = in_table ? cnt : 1;
+        if (!in_table) {
+            // direct weights for this radius ratio (calculate_weights_2d, common.py:152-185), one vector at a time
+            __syncthreads();
+            const double k0 = P.k[(size_t)s_pv[q0] * P.kcols];
+            for (int ig = tid; ig < ng; ig += 256) weight_row(k0, P.gs[ig], P.ze, nz, sW + (size_t)ig * nz, 1);
+            __syncthreads();
+        }
+        for (int pb = 0; pb < npb; ++pb) {
+            for (int ig = ig0; ig < ng; ig += 128) {
+                if (t == 0 || in_table) {
+                    const double *wr = sW + (size_t)t * rowlen + (size_t)ig * nz;
+                    double acc[RR_GROUP];
+#pragma unroll
+                    for (int q = 0; q < RR_GROUP; ++q) acc[q] = 0.0;
+                    int iz = ig % nz;  // rotated start: the lanes of a warp hit distinct banks
+                    for (int j = 0; j < nz; ++j) {
+                        const double wv = wr[iz];
+#pragma unroll
+                        for (int q = 0; q < RR_GROUP; ++q)
+                            if (q < nq) acc[q] = fma(wv, sLdp[((size_t)(q0 + q) * npb + pb) * nz + iz], acc[q]);
+                        iz = (iz + 1 == nz) ? 0 : iz + 1;
+                    }
+#pragma unroll
+                    for (int q = 0; q < RR_GROUP; ++q)
+                        if (q < nq) sOut[((size_t)t * P.grp + q) * ng + ig] = acc[q];
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < nq * ng; idx += 256) {
+                const int q = idx / ng, ig = idx - q * ng;
+                const int ipv = s_pv[q0 + q];
+                double v = sOut[(size_t)q * ng + ig];
+                if (in_table) {
+                    const double ak = s_ak[q0 + q];
+                    v = (1.0 - ak) * v + ak * sOut[((size_t)P.grp + q) * ng + ig];
+                }
+                P.ldrec[((size_t)ipv * npb + pb) * P.lds + ig] = v;
+            }
+            __syncthreads();
+        }
+    }
+    for (int r = tid; r < cnt * npb; r += 256) {
+        const int q = r / npb, pb = r - q * npb;
+        const int ipv = s_pv[q];
+        const double kk = P.k[(size_t)ipv * P.kcols + (P.kcols == npb ? pb : 0)];
+        double *tail = P.ldrec + ((size_t)ipv * npb + pb) * P.lds + ng;
         tail[0] = kk;
         tail[1] = 1.0 / (1.0 + kk);
-        tail[2] = 1.0 / sIstar[pb];
+        tail[2] = 1.0 / sIstar[r];
         tail[3] = kk * kk;
-        for (int j = ng + 4; j < P.lds; ++j) rec[(size_t)pb * P.lds + j] = 0.0;
+        for (int j = ng + 4; j < P.lds; ++j) tail[j - ng] = 0.0;
     }
 }
 
