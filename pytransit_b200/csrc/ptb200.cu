@@ -238,17 +238,6 @@ std::vector<double> linspace(double a, double b, int n) {
     return v;
 }
 
-int copy_out(ptb_model *h, double *dst, const double *dsrc, size_t count, cudaStream_t st) {
-    if (!dst || dst == dsrc) return PTB_OK;
-    if (is_device_ptr(dst)) {
-        CU(cudaMemcpyAsync(dst, dsrc, count * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    } else {
-        CU(cudaMemcpyAsync(dst, dsrc, count * sizeof(double), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-    }
-    return PTB_OK;
-}
-
 struct ModelArgs {
     int64_t npv, kcols, nld;
     const double *k, *ld, *istar, *t0, *p, *a, *inc, *e, *w;
@@ -749,9 +738,11 @@ int launch_points(ptb_model *h, int64_t npv, const double *t0, double *flux, con
         P.partial = h->d_partial.as<double>();
     }
     const size_t ldbytes = (size_t)h->npb * lds * 8;
-    P.stage_ld = ldbytes <= 32 * 1024 ? 1 : 0;
-    const size_t smem = sizeof(WarpScratch) * PT_WARPS + (P.stage_ld ? ldbytes : 0) + (single ? 0 : 3 * (size_t)h->nlc * 8) + 16;
-    if (smem > 200 * 1024) return fail(h, PTB_EINVAL, "nlc=%lld light curves need %zu bytes of shared memory", (long long)h->nlc, smem);
+    P.stage_ld = 1;
+    const size_t smem = sizeof(WarpScratch) * PT_WARPS + ldbytes + (single ? 0 : 3 * (size_t)h->nlc * 8) + 16;
+    if (smem > 220 * 1024)
+        return fail(h, PTB_EINVAL, "npb=%lld passbands x nlc=%lld light curves need %zu bytes of shared memory (> 220 KB)",
+                    (long long)h->npb, (long long)h->nlc, smem);
 
 #define PTB_DISPATCH(V, S, L) return launch_points_t<V, S, L>(h, P, smem, st)
     if (vec == 2) {

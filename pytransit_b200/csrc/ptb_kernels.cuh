@@ -396,6 +396,9 @@ struct PointsParams {
     double dg, inv_dg;
 };
 
+#ifndef PT_MINB
+#define PT_MINB 3
+#endif
 constexpr int PT_THREADS = 256;
 constexpr int PT_WARPS = PT_THREADS / 32;
 constexpr int PT_BLOCK = 64;           // points per classification block
@@ -431,8 +434,124 @@ struct VecIO<2> {
     }
 };
 
+// Batched evaluation of `np` queued in-box points starting at queue slot `base` (warp-cooperative;
+// model_full.py:93-99).  Inlined at its single call site (an out-of-line call was measured 15 % slower:
+// the shared-memory address space of the staged record is lost across the call).  Returns the warp
+// lane's chi^2 increment (likelihood mode).
+struct DrainCtx {
+    const PointsParams *P;
+    WarpScratch *ws;
+    const double *orb;
+    const double *ld;  // per-vector record in shared memory: [npb][lds]
+    double *frow;
+    const double *isig2;
+    int lane, S;
+};
+
+template <bool SINGLE_LC, bool LNL>
+__device__ __forceinline__ double drain_batch(const DrainCtx &c, int base, int np) {
+    const PointsParams &P = *c.P;
+    WarpScratch &ws = *c.ws;
+    const int lane = c.lane, S = c.S, ng = P.ng, lds = P.lds;
+    const double dg = P.dg, inv_dg = P.inv_dg;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    double chi = 0.0;
+    double cx[5], cy[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { cx[j] = c.orb[j]; cy[j] = c.orb[5 + j]; }
+    // single light curve: the per-light-curve metadata are block constants
+    const int ns1 = SINGLE_LC ? P.nsamples[0] : 1;
+    const double et1 = SINGLE_LC ? P.exptimes[0] : 0.0;
+    const double *row1 = c.ld + (SINGLE_LC ? (size_t)P.pbids[0] * lds : 0);
+    double bigsum = 0.0;  // S > PT_BATCH only: running sum over sample chunks (np == 1)
+    for (int s0 = 0; s0 < S; s0 += PT_BATCH) {
+        const int SS = min(S - s0, PT_BATCH);  // sample slots in this pass
+        const int nitems = np * SS;
+        // stage A: separation, limb-darkening lerp, cheap area cases; limb samples -> second queue
+        int nl = 0;
+        for (int it0 = 0; it0 < nitems; it0 += 32) {
+            const int it = it0 + lane;
+            bool limb = false;
+            double z = 0.0, ip = 0.0;
+            if (it < nitems) {
+                const int pt = (SS == 1) ? it : it / SS;
+                const int s = s0 + (it - pt * SS);
+                int ns = ns1;
+                double et = et1;
+                const double *row = row1;
+                if (!SINGLE_LC) {
+                    const int lc = P.lcids[ws.q_ipt[base + pt]];
+                    ns = P.nsamples[lc];
+                    et = P.exptimes[lc];
+                    row = c.ld + (size_t)P.pbids[lc] * lds;
+                }
+                double cc = 0.0;
+                if (s < ns) {
+                    // exposure offset exptime*((s+1-0.5)/ns - 0.5) (model_full.py:94); exactly 0 for ns == 1
+                    const double off = (ns == 1) ? 0.0 : et * (((s + 1) - 0.5) / ns - 0.5);
+                    z = sep_poly(ws.q_tc[base + pt] + off, cx, cy);
+                    const double k = row[ng];
+                    ip = ldm_lerp(z * row[ng + 1], dg, inv_dg, row, ng);
+                    if (1.0 + k <= z) cc = 1.0;                                   // no overlap: area 0
+                    else if (fabs(1.0 - k) < z) limb = true;                      // lens: kite formula
+                    else if (z <= 1.0 - k) cc = 1.0 - ip * (kPi * row[ng + 3]) * row[ng + 2];
+                    else if (z <= k - 1.0) cc = 1.0 - ip * kPi * row[ng + 2];    // planet covers the star
+                    else cc = nan("");
+                }
+                ws.contrib[it] = cc;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, limb);
+            if (limb) {
+                const int pos = nl + __popc(m & lt_mask);
+                ws.l_it[pos] = it;
+                ws.l_z[pos] = z;
+                ws.l_ip[pos] = ip;
+            }
+            nl += __popc(m);
+        }
+        __syncwarp();
+        // stage B: lens area on the limb (sqrt + 2 atan2), full warps
+        for (int j = lane; j < nl; j += 32) {
+            const int it = ws.l_it[j];
+            const double *row = row1;
+            if (!SINGLE_LC) {
+                const int pt = (SS == 1) ? it : it / SS;
+                row = c.ld + (size_t)P.pbids[P.lcids[ws.q_ipt[base + pt]]] * lds;
+            }
+            double area, kap;
+            kite_area(row[ng], row[ng + 3], ws.l_z[j], area, kap);
+            ws.contrib[it] = 1.0 - ws.l_ip[j] * area * row[ng + 2];
+        }
+        __syncwarp();
+        // stage C: per-point sum over sub-samples in exposure order (model_full.py:93-99)
+        for (int pt = lane; pt < np; pt += 32) {
+            const int ipt = ws.q_ipt[base + pt];
+            const int ns = SINGLE_LC ? ns1 : P.nsamples[P.lcids[ipt]];
+            const int m = min(SS, ns - s0);
+            double sum = bigsum;
+            for (int j = 0; j < m; ++j) sum += ws.contrib[pt * SS + j];
+            if (s0 + SS >= S) {
+                const double f = sum / ns;
+                if (LNL) {
+                    const int b = P.blk ? P.blk[ipt] : 0;
+                    if (b >= 0) {
+                        const double d = P.obs[ipt] - f;
+                        chi = fma(d * d, c.isig2[b], chi);
+                    }
+                } else {
+                    c.frow[ipt] = f;
+                }
+            } else {
+                bigsum = sum;  // only reached with np == 1 (lane 0)
+            }
+        }
+        __syncwarp();
+    }
+    return chi;
+}
+
 template <int VEC, bool SINGLE_LC, bool LNL>
-__global__ void __launch_bounds__(PT_THREADS, 3) k_rr_points(const __grid_constant__ PointsParams P) {
+__global__ void __launch_bounds__(PT_THREADS, PT_MINB) k_rr_points(const __grid_constant__ PointsParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_red[PT_WARPS];
     __shared__ unsigned s_hit[PT_MAXBLK / 32];
@@ -446,7 +565,7 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_rr_points(const __grid_consta
     // dynamic smem: [WarpScratch x 8] [ldrec copy npb*lds] [lc_lo nlc] [lc_hi nlc] [lc_t0 nlc]
     WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem_raw)[warp];
     double *sLd = reinterpret_cast<double *>(smem_raw + sizeof(WarpScratch) * PT_WARPS);
-    double *sLo = sLd + (P.stage_ld ? (size_t)P.npb * P.lds : 0);
+    double *sLo = sLd + (size_t)P.npb * P.lds;
     double *sHi = sLo + (SINGLE_LC ? 0 : P.nlc);
     double *sT0 = sHi + (SINGLE_LC ? 0 : P.nlc);
 
@@ -472,7 +591,7 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_rr_points(const __grid_consta
         return;
     }
 
-    if (P.stage_ld && tid == 0) {
+    if (tid == 0) {
         mbar_init(&bar, 1);
         const uint32_t bytes = (uint32_t)(P.npb * P.lds * 8);
         mbar_expect_tx(&bar, bytes);
@@ -495,8 +614,8 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_rr_points(const __grid_consta
     }
     __syncthreads();  // mbarrier init + per-light-curve tables visible
 
-    const double *ldrow_base = P.stage_ld ? sLd : ldg;
-    bool ld_ready = !P.stage_ld;
+    bool ld_ready = false;
+    DrainCtx dctx;
 
     const int S = P.ns_max;                        // sub-sample slots per queued point
     const int PB = S >= PT_BATCH ? 1 : PT_BATCH / S;  // points per drain batch
@@ -505,94 +624,8 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_rr_points(const __grid_consta
     const double *isig2 = LNL ? P.isig2 + (size_t)ipv * P.nblocks : nullptr;
     double *frow = LNL ? nullptr : P.flux + (size_t)ipv * npt;
     const unsigned lt_mask = (1u << lane) - 1u;
-
-    // evaluate the `np` queued points starting at queue slot `base` (warp-cooperative)
-    auto drain = [&](int base, int np) {
-        if (!ld_ready) {
-            mbar_wait(&bar, 0);
-            ld_ready = true;
-        }
-        double cx[5], cy[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) { cx[j] = orb[j]; cy[j] = orb[5 + j]; }
-        double bigsum = 0.0;  // S > PT_BATCH only: running sum over sample chunks (np == 1)
-        for (int s0 = 0; s0 < S; s0 += PT_BATCH) {
-            const int SS = min(S - s0, PT_BATCH);  // sample slots in this pass
-            const int nitems = np * SS;
-            // stage A: separation, limb-darkening lerp, cheap area cases; limb samples -> second queue
-            int nl = 0;
-            for (int it0 = 0; it0 < nitems; it0 += 32) {
-                const int it = it0 + lane;
-                bool limb = false;
-                double z = 0.0, ip = 0.0;
-                if (it < nitems) {
-                    const int pt = (SS == 1) ? it : it / SS;
-                    const int s = s0 + (it - pt * SS);
-                    const int ipt = ws.q_ipt[base + pt];
-                    const int lc = SINGLE_LC ? 0 : P.lcids[ipt];
-                    const int ns = P.nsamples[lc];
-                    double c = 0.0;
-                    if (s < ns) {
-                        const double off = P.exptimes[lc] * (((s + 1) - 0.5) / ns - 0.5);
-                        z = sep_poly(ws.q_tc[base + pt] + off, cx, cy);
-                        const double *row = ldrow_base + (size_t)P.pbids[lc] * P.lds;
-                        const double k = row[P.ng];
-                        ip = ldm_lerp(z * row[P.ng + 1], P.dg, P.inv_dg, row, P.ng);
-                        if (1.0 + k <= z) c = 1.0;                                   // no overlap: area 0
-                        else if (fabs(1.0 - k) < z) limb = true;                     // lens: kite formula
-                        else if (z <= 1.0 - k) c = 1.0 - ip * (kPi * row[P.ng + 3]) * row[P.ng + 2];
-                        else if (z <= k - 1.0) c = 1.0 - ip * kPi * row[P.ng + 2];   // planet covers the star
-                        else c = nan("");
-                    }
-                    ws.contrib[it] = c;
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, limb);
-                if (limb) {
-                    const int pos = nl + __popc(m & lt_mask);
-                    ws.l_it[pos] = it;
-                    ws.l_z[pos] = z;
-                    ws.l_ip[pos] = ip;
-                }
-                nl += __popc(m);
-            }
-            __syncwarp();
-            // stage B: lens area on the limb (sqrt + 2 atan2), full warps
-            for (int j = lane; j < nl; j += 32) {
-                const int it = ws.l_it[j];
-                const int pt = (SS == 1) ? it : it / SS;
-                const int lc = SINGLE_LC ? 0 : P.lcids[ws.q_ipt[base + pt]];
-                const double *row = ldrow_base + (size_t)P.pbids[lc] * P.lds;
-                double area, kap;
-                kite_area(row[P.ng], row[P.ng + 3], ws.l_z[j], area, kap);
-                ws.contrib[it] = 1.0 - ws.l_ip[j] * area * row[P.ng + 2];
-            }
-            __syncwarp();
-            // stage C: per-point sum over sub-samples in exposure order (model_full.py:93-99)
-            for (int pt = lane; pt < np; pt += 32) {
-                const int ipt = ws.q_ipt[base + pt];
-                const int lc = SINGLE_LC ? 0 : P.lcids[ipt];
-                const int ns = P.nsamples[lc];
-                const int m = min(SS, ns - s0);
-                double sum = bigsum;
-                for (int j = 0; j < m; ++j) sum += ws.contrib[pt * SS + j];
-                if (s0 + SS >= S) {
-                    const double f = sum / ns;
-                    if (LNL) {
-                        const int b = P.blk ? P.blk[ipt] : 0;
-                        if (b >= 0) {
-                            const double d = P.obs[ipt] - f;
-                            chi = fma(d * d, isig2[b], chi);
-                        }
-                    } else {
-                        frow[ipt] = f;
-                    }
-                } else {
-                    bigsum = sum;  // only reached with np == 1 (lane 0)
-                }
-            }
-            __syncwarp();
-        }
-    };
+    dctx.P = &P; dctx.ws = &ws; dctx.orb = orb; dctx.ld = sLd; dctx.frow = frow; dctx.isig2 = isig2;
+    dctx.lane = lane; dctx.S = S;
 
     // ---- classification of every block of this chunk, in parallel over the CTA -----------------------
     // Can any transit window [t0 + n p + lo, t0 + n p + hi] touch [tmin, tmax] of the block?  If not, the
@@ -636,12 +669,20 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_rr_points(const __grid_consta
             double one[VEC];
 #pragma unroll
             for (int j = 0; j < VEC; ++j) one[j] = 1.0;
-            double *fb = frow + (long long)b0 * PT_BLOCK;
+            double *fb = frow + (long long)b0 * PT_BLOCK + lane * VEC;
+            if (bits == 0u && b0 + 8 <= bend) {  // the common case: eight untouched blocks, no predicates
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (!((bits >> j) & 1u) && b0 + j < bend) {
+                for (int j = 0; j < 8; ++j) {
 #pragma unroll
-                    for (int h = 0; h < 2 / VEC; ++h) VecIO<VEC>::store(fb + j * PT_BLOCK + (h * 32 + lane) * VEC, one);
+                    for (int h = 0; h < 2 / VEC; ++h) VecIO<VEC>::store(fb + j * PT_BLOCK + h * 32 * VEC, one);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (!((bits >> j) & 1u) && b0 + j < bend) {
+#pragma unroll
+                        for (int h = 0; h < 2 / VEC; ++h) VecIO<VEC>::store(fb + j * PT_BLOCK + h * 32 * VEC, one);
+                    }
                 }
             }
         }
@@ -700,12 +741,16 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_rr_points(const __grid_consta
             while (qn >= PB || (!live && qn > 0)) {
                 const int n = min(qn, PB);
                 qn -= n;
-                drain(qn, n);
+                if (!ld_ready) {
+                    mbar_wait(&bar, 0);
+                    ld_ready = true;
+                }
+                chi += drain_batch<SINGLE_LC, LNL>(dctx, qn, n);
             }
         } while (bits);
         if (!live) break;
     }
-    if (P.stage_ld && !ld_ready) mbar_wait(&bar, 0);  // never exit with the bulk copy in flight
+    if (!ld_ready) mbar_wait(&bar, 0);  // never exit with the bulk copy in flight
 
     if (LNL) {
         chi = warp_sum(chi);

@@ -247,7 +247,7 @@ __device__ __forceinline__ TsGeo ts_geometry(double t, const double *cx, const d
 
 template <int VEC, bool MULTI>
 __global__ void __launch_bounds__(256) k_ts_flux(const __grid_constant__ TsFluxParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];  // MULTI: TsGeo[ns][256*VEC]
+    extern __shared__ __align__(128) unsigned char smem_raw[];  // MULTI: TsGeo[ns][256*VEC]
     const int tid = threadIdx.x;
     constexpr int TILE = 256 * VEC;
     int b = blockIdx.x;
