@@ -1,0 +1,84 @@
+"""Population sharding over the GPUs of one box: one process per GPU (torchrun), each rank evaluates a
+contiguous block of parameter vectors, and the only exchange is an all-gather of the per-vector log
+likelihoods (8 bytes per vector) over NCCL / NVLink.  Parameter vectors are independent in the reference
+(models/roadrunner/model_full.py:39-99 has no cross-vector dependence; lpf/loglikelihood/
+wnloglikelihood.py:30-34 reduces over time only), so the flux itself is never exchanged:
+``evaluate`` returns the local shard.
+
+The sharding helpers are pure host logic and run under the gloo backend on CPU (tests/test_distributed.py).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence, Tuple
+
+import numpy as np
+
+__all__ = ['shard_bounds', 'shard_population', 'PopulationSharder']
+
+_POP_ARGS = ('k', 'ldc', 't0', 'p', 'a', 'i', 'e', 'w', 'sigma')
+
+
+def shard_bounds(npv: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced block of the population for `rank`: the first ``npv % world`` ranks get one
+    vector more."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside [0, {world})")
+    base, rem = divmod(int(npv), int(world))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def _leading(x):
+    return x.shape[0] if hasattr(x, 'shape') and len(x.shape) > 0 else None
+
+
+def shard_population(npv: int, world: int, rank: int, **params):
+    """Slice every array whose leading dimension is `npv`; scalars and shared arrays (e.g. ``ldc[npb, nldc]``
+    or a per-passband ``k[npb]``) pass through.  A 2-D/3-D array with leading dimension 1 is shared too."""
+    lo, hi = shard_bounds(npv, world, rank)
+    out = {}
+    for name, v in params.items():
+        n = _leading(v)
+        out[name] = v[lo:hi] if (n == npv and npv > 1) else v
+    return out
+
+
+class PopulationSharder:
+    """Evaluates a population log likelihood data-parallel over the ranks of a ``torch.distributed`` group.
+
+    ``lnl_fn(**shard) -> lnL[n_local]`` is any callable returning a numpy array or a torch tensor for the local
+    shard -- normally ``RoadRunnerModelCUDA.lnlikelihood`` (fused model + likelihood on this rank's GPU).
+    ``lnlikelihood`` returns the full ``lnL[npv]`` on every rank (all-gather; ragged shards are padded)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def bounds(self, npv: int) -> Tuple[int, int]:
+        return shard_bounds(npv, self.world, self.rank)
+
+    def shard(self, npv: int, **params):
+        return shard_population(npv, self.world, self.rank, **params)
+
+    def lnlikelihood(self, lnl_fn: Callable, npv: int, **params):
+        import torch
+        local = lnl_fn(**self.shard(npv, **params))
+        if self.world == 1:
+            return local
+        as_numpy = not isinstance(local, torch.Tensor)
+        loc = torch.as_tensor(np.asarray(local)) if as_numpy else local
+        loc = loc.reshape(-1).to(torch.float64)
+        nmax = -(-npv // self.world)
+        pad = torch.full((nmax,), float('nan'), dtype=torch.float64, device=loc.device)
+        pad[:loc.numel()] = loc
+        out = torch.empty((self.world * nmax,), dtype=torch.float64, device=loc.device)
+        self.dist.all_gather_into_tensor(out, pad, group=self.group)
+        parts = []
+        for r in range(self.world):
+            lo, hi = shard_bounds(npv, self.world, r)
+            parts.append(out[r * nmax:r * nmax + (hi - lo)])
+        full = torch.cat(parts)
+        return full.cpu().numpy() if as_numpy else full
