@@ -107,6 +107,10 @@ struct ptb_model {
     // per-vector workspaces
     DevBuf d_orb, d_ldrec, d_ldp, d_istar, d_flux, d_partial, d_isig2, d_lnl, d_xyc;
     DevBuf d_tsw, d_tsrec, d_sort;
+    DevBuf d_rec, d_work;            // RoadRunner per-vector records; work counters of the persistent kernel
+    int recstride = 0, rec_ld = 0;   // record stride / offset of the ld rows (doubles) of the last setup
+    int pt_occ[16] = {};  // resident CTAs per SM of each k_rr_points instantiation (0 = not queried)
+    size_t pt_occ_smem[16] = {};
     bool xyc_injected = false;
     int64_t xyc_npv = 0;
     int64_t last_npv = 0, last_npb = 0, last_flux_count = 0;
@@ -362,7 +366,7 @@ void ptb_destroy(ptb_model *h) {
     cudaSetDevice(h->cfg.device);
     for (DevBuf *b : {&h->d_tab, &h->d_W, &h->d_time_own, &h->d_meta, &h->d_obs_own, &h->d_blk, &h->d_nblk, &h->d_orb,
                       &h->d_ldrec, &h->d_ldp, &h->d_istar, &h->d_flux, &h->d_partial, &h->d_isig2, &h->d_lnl, &h->d_xyc,
-                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_sort})
+                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_sort, &h->d_rec, &h->d_work})
         b->release();
     h->h_stage.release();
     if (h->stage_ev) cudaEventDestroy(h->stage_ev);
@@ -640,8 +644,15 @@ int launch_rr_setup(ptb_model *h, const ModelArgs &A, const Staged &D, cudaStrea
     const int64_t npv = A.npv, npb = h->npb;
     const int ng = h->cfg.ng, nz = h->nz, nk = h->cfg.nk;
     const int lds = (ng + 4 + 1) & ~1;
-    CU(h->d_orb.reserve(npv * ORB_STRIDE * 8));
-    CU(h->d_ldrec.reserve((size_t)npv * npb * lds * 8));
+    const int nep_pad = (int)((h->nep + 1) & ~int64_t(1));
+    const int rec_ld = ORB_STRIDE + nep_pad;
+    const size_t recstride = (size_t)rec_ld + (size_t)npb * lds;
+    if (recstride * 8 > 96 * 1024)
+        return fail(h, PTB_EINVAL, "per-vector record of %zu bytes (npb=%lld passbands, nep=%lld epochs) exceeds 96 KB", recstride * 8,
+                    (long long)npb, (long long)h->nep);
+    h->recstride = (int)recstride;
+    h->rec_ld = rec_ld;
+    CU(h->d_rec.reserve((size_t)npv * recstride * 8));
     CU(h->d_ldp.reserve((size_t)npv * npb * nz * 8));
     CU(h->d_istar.reserve((size_t)npv * npb * 8));
     // sort workspace: bin[npv] | perm[npv] | hist[nk+2] | offsets[nk+2] | gstart[nk+2] | cursor[nk+2]
@@ -660,8 +671,8 @@ int launch_rr_setup(ptb_model *h, const ModelArgs &A, const Staged &D, cudaStrea
     OrbitParams O{};
     O.k = D.k; O.p = D.p; O.a = D.a; O.inc = D.inc; O.e = D.e; O.w = D.w;
     O.xyc_in = h->xyc_injected ? h->d_xyc.as<double>() : nullptr;
-    O.orb = h->d_orb.as<double>(); O.bin = bin; O.hist = hist;
-    O.npv = (int)npv; O.kcols = (int)A.kcols; O.nk = nk; O.kmin = h->cfg.kmin; O.kmax = h->cfg.kmax; O.dk = h->dk;
+    O.t0 = D.t0; O.rec = h->d_rec.as<double>(); O.bin = bin; O.hist = hist;
+    O.npv = (int)npv; O.kcols = (int)A.kcols; O.nk = nk; O.nep = (int)h->nep; O.recstride = (int)recstride; O.kmin = h->cfg.kmin; O.kmax = h->cfg.kmax; O.dk = h->dk;
     k_rr_orbit<<<(unsigned)((npv * 8 + 255) / 256), 256, 0, st>>>(O);
     // group size: as many vectors as fit ~32 KB of profiles, at most RR_GROUP
     const int grp = (int)std::max<int64_t>(1, std::min<int64_t>(RR_GROUP, (32 * 1024) / (npb * nz * 8)));
@@ -674,7 +685,8 @@ int launch_rr_setup(ptb_model *h, const ModelArgs &A, const Staged &D, cudaStrea
     P.k = D.k; P.ld = D.ld; P.istar = D.istar;
     P.W = h->d_W.as<double>(); P.ze = h->d_ze; P.mu = h->d_mu; P.gs = h->d_gs; P.ldmu200 = h->d_ldmu; P.ldz200 = h->d_ldz;
     P.offsets = offsets; P.gstart = gstart; P.perm = perm;
-    P.orb = h->d_orb.as<double>(); P.ldrec = h->d_ldrec.as<double>(); P.ldp_out = h->d_ldp.as<double>();
+    P.rec = h->d_rec.as<double>(); P.ldp_out = h->d_ldp.as<double>();
+    P.recstride = (int)recstride; P.rec_ld = rec_ld;
     P.istar_out = h->d_istar.as<double>();
     P.npv = (int)npv; P.kcols = (int)A.kcols; P.npb = (int)npb; P.nld = (int)A.nld; P.law = h->cfg.ldlaw;
     P.nk = nk; P.ng = ng; P.nz = nz; P.lds = lds; P.grp = grp;
@@ -692,11 +704,21 @@ int launch_rr_setup(ptb_model *h, const ModelArgs &A, const Staged &D, cudaStrea
     return PTB_OK;
 }
 
-template <int VEC, bool SINGLE, bool LNL>
+template <int VEC, bool SINGLE, bool LNL, bool S1>
 int launch_points_t(ptb_model *h, const PointsParams &P, size_t smem, cudaStream_t st) {
-    auto kern = k_rr_points<VEC, SINGLE, LNL>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long grid = (long long)P.npv * P.nchunks;
+    auto kern = k_rr_points<VEC, SINGLE, LNL, S1>;
+    const int slot = (S1 ? 8 : 0) + (VEC == 2 ? 4 : 0) + (SINGLE ? 2 : 0) + (LNL ? 1 : 0);
+    if (h->pt_occ[slot] == 0 || h->pt_occ_smem[slot] != smem) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PT_THREADS, smem));
+        if (occ < 1) return fail(h, PTB_EINVAL, "k_rr_points does not fit on an SM with %zu bytes of shared memory", smem);
+        h->pt_occ[slot] = occ;
+        h->pt_occ_smem[slot] = smem;
+    }
+    // persistent grid: one wave of CTAs; every warp pulls items from the work counter
+    const long long nitems = (long long)P.npv * P.nchunks;
+    const long long grid = std::min<long long>((nitems + PT_WARPS - 1) / PT_WARPS, (long long)h->sm_count * h->pt_occ[slot]);
     kern<<<(unsigned)grid, PT_THREADS, smem, st>>>(P);
     h->launches++;
     CU(cudaGetLastError());
@@ -704,31 +726,36 @@ int launch_points_t(ptb_model *h, const PointsParams &P, size_t smem, cudaStream
 }
 
 // flux != nullptr -> flux mode; else lnL mode (partials into h->d_partial)
-int launch_points(ptb_model *h, int64_t npv, const double *t0, double *flux, const double *isig2, cudaStream_t st, int *nchunks_out) {
+int launch_points(ptb_model *h, int64_t npv, double *flux, const double *isig2, cudaStream_t st, int *nchunks_out) {
     const int ng = h->cfg.ng;
     const int lds = (ng + 4 + 1) & ~1;
     PointsParams P{};
     P.time = h->d_time; P.lcids = h->d_lcids; P.pbids = h->d_pbids; P.epids = h->d_epids; P.nsamples = h->d_nsamples;
-    P.exptimes = h->d_exptimes; P.orb = h->d_orb.as<double>(); P.t0 = t0; P.ldrec = h->d_ldrec.as<double>();
+    P.exptimes = h->d_exptimes; P.rec = h->d_rec.as<double>(); P.recstride = h->recstride; P.rec_ld = h->rec_ld;
     P.flux = flux; P.obs = h->d_obs; P.blk = h->blk_trivial ? nullptr : h->d_blk.as<int32_t>(); P.isig2 = isig2;
     P.npt = h->npt; P.npv = (int)npv; P.nlc = (int)h->nlc; P.npb = (int)h->npb; P.nep = (int)h->nep; P.ng = ng; P.lds = lds;
     P.nblocks = (int)h->nblocks; P.ns_max = h->ns_max; P.dg = h->dg; P.inv_dg = 1.0 / h->dg;
 
     P.bmin = h->d_bmin; P.bmax = h->d_bmax; P.blc = h->d_blc; P.bchi = h->d_bchi; P.bnoise = h->d_bnoise;
     P.nblk64 = (int)h->nblk64;
+    if (!h->d_work.ptr) {
+        CU(h->d_work.reserve(64));
+        CU(cudaMemsetAsync(h->d_work.ptr, 0, 64, st));  // the kernel re-arms the counters itself afterwards
+    }
+    P.work = h->d_work.as<int>();
     const bool single = (h->nlc == 1);
     const bool lnl = (flux == nullptr);
     const bool aligned = (h->npt % 2 == 0) && ((reinterpret_cast<uintptr_t>(h->d_time) & 15) == 0) &&
                          (lnl || (reinterpret_cast<uintptr_t>(flux) & 15) == 0);
     const int vec = aligned ? 2 : 1;
-    // Enough CTAs to fill the machine ~8 deep, otherwise one CTA walks a whole row; a chunk is a
-    // multiple of 8 blocks (one block per warp and pass).
+    // Items: whole rows when the population alone fills the machine ~8 deep, otherwise rows are cut into
+    // chunks of whole 8-block groups (one group per warp and pass), at most PT_MAXBLK blocks each.
     const long long nb = h->nblk64;
     const long long want = (long long)h->sm_count * 8;
-    long long nchunks = std::min<long long>((nb + 63) / 64, std::max<long long>(1, (want + npv - 1) / npv));
+    long long nchunks = std::min<long long>((nb + 7) / 8, std::max<long long>(1, (want + npv - 1) / npv));
     nchunks = std::max<long long>(nchunks, (nb + PT_MAXBLK - 1) / PT_MAXBLK);
     long long bpc = (nb + nchunks - 1) / nchunks;
-    bpc = std::min<long long>((bpc + 63) / 64 * 64, PT_MAXBLK);  // whole 8-block groups per warp and pass
+    bpc = std::min<long long>((bpc + 7) / 8 * 8, PT_MAXBLK);
     nchunks = (nb + bpc - 1) / bpc;
     P.nchunks = (int)nchunks;
     P.blocks_per_chunk = (int)bpc;
@@ -737,14 +764,21 @@ int launch_points(ptb_model *h, int64_t npv, const double *t0, double *flux, con
         CU(h->d_partial.reserve((size_t)npv * nchunks * 8));
         P.partial = h->d_partial.as<double>();
     }
-    const size_t ldbytes = (size_t)h->npb * lds * 8;
-    P.stage_ld = 1;
-    const size_t smem = sizeof(WarpScratch) * PT_WARPS + ldbytes + (single ? 0 : 3 * (size_t)h->nlc * 8) + 16;
+    P.ssc = std::min(h->ns_max, PT_SSC_MAX);
+    P.frac_tab = ((long long)h->nlc * h->ns_max <= PT_FRAC_MAX) ? 1 : 0;
+    const bool s1 = (h->ns_max == 1);
+    const size_t nfrac = P.frac_tab ? (size_t)h->nlc * h->ns_max : 0;
+    const size_t shared_bytes = (((2 * (size_t)h->nlc + nfrac) * 8 + 3 * (size_t)h->nlc * 4) + 127) & ~size_t(127);
+    const size_t smem = shared_bytes + pt_warp_bytes(s1 ? 0 : P.ssc, h->recstride) * PT_WARPS;
     if (smem > 220 * 1024)
         return fail(h, PTB_EINVAL, "npb=%lld passbands x nlc=%lld light curves need %zu bytes of shared memory (> 220 KB)",
                     (long long)h->npb, (long long)h->nlc, smem);
 
-#define PTB_DISPATCH(V, S, L) return launch_points_t<V, S, L>(h, P, smem, st)
+#define PTB_DISPATCH(V, S, L)                                          \
+    do {                                                               \
+        if (s1) return launch_points_t<V, S, L, true>(h, P, smem, st); \
+        return launch_points_t<V, S, L, false>(h, P, smem, st);        \
+    } while (0)
     if (vec == 2) {
         if (single) { if (lnl) PTB_DISPATCH(2, true, true); else PTB_DISPATCH(2, true, false); }
         else        { if (lnl) PTB_DISPATCH(2, false, true); else PTB_DISPATCH(2, false, false); }
@@ -780,7 +814,7 @@ int ptb_rr_evaluate(ptb_model *h, int64_t npv, const double *k, int64_t kcols, c
         dflux = h->d_flux.as<double>();
     }
     mark(h, 2, st);
-    if (int rc = launch_points(h, npv, D.t0, dflux, nullptr, st, nullptr)) return rc;
+    if (int rc = launch_points(h, npv, dflux, nullptr, st, nullptr)) return rc;
     mark(h, 3, st);
     h->last_flux_count = direct ? 0 : (int64_t)count;
     if (flux && !direct) {
@@ -811,7 +845,7 @@ int ptb_rr_lnlike(ptb_model *h, int64_t npv, const double *k, int64_t kcols, con
     mark(h, 1, st);
     int nchunks = 1;
     mark(h, 2, st);
-    if (int rc = launch_points(h, npv, D.t0, nullptr, h->d_isig2.as<double>(), st, &nchunks)) return rc;
+    if (int rc = launch_points(h, npv, nullptr, h->d_isig2.as<double>(), st, &nchunks)) return rc;
     mark(h, 3, st);
     const bool direct = is_device_ptr(lnl);
     double *dl = lnl;
@@ -876,14 +910,16 @@ int ptb_get_stage(ptb_model *h, int32_t stage, double *out) {
     case PTB_STAGE_LDP: CU(cudaMemcpy(out, h->d_ldp.ptr, (size_t)npv * npb * nz * 8, kind)); break;
     case PTB_STAGE_ISTAR: CU(cudaMemcpy(out, h->d_istar.ptr, (size_t)npv * npb * 8, kind)); break;
     case PTB_STAGE_LDM:
-        CU(cudaMemcpy2D(out, ng * 8, h->d_ldrec.ptr, lds * 8, ng * 8, (size_t)npv * npb, kind));
+        for (int64_t pb = 0; pb < npb; ++pb)  // rows of passband pb: record pitch in, [npv][npb][ng] out
+            CU(cudaMemcpy2D(out + pb * ng, (size_t)npb * ng * 8, h->d_rec.as<double>() + h->rec_ld + pb * lds,
+                            (size_t)h->recstride * 8, ng * 8, npv, kind));
         break;
-    case PTB_STAGE_XYC: CU(cudaMemcpy2D(out, 80, h->d_orb.ptr, ORB_STRIDE * 8, 80, npv, kind)); break;
+    case PTB_STAGE_XYC: CU(cudaMemcpy2D(out, 80, h->d_rec.ptr, (size_t)h->recstride * 8, 80, npv, kind)); break;
     case PTB_STAGE_BBOX:
-        CU(cudaMemcpy2D(out, 16, h->d_orb.as<double>() + ORB_T1, ORB_STRIDE * 8, 16, npv, kind));
+        CU(cudaMemcpy2D(out, 16, h->d_rec.as<double>() + ORB_T1, (size_t)h->recstride * 8, 16, npv, kind));
         break;
     case PTB_STAGE_GOOD:
-        CU(cudaMemcpy2D(out, 8, h->d_orb.as<double>() + ORB_GOOD, ORB_STRIDE * 8, 8, npv, kind));
+        CU(cudaMemcpy2D(out, 8, h->d_rec.as<double>() + ORB_GOOD, (size_t)h->recstride * 8, 8, npv, kind));
         break;
     default: return fail(h, PTB_EINVAL, "get_stage: unknown stage %d", stage);
     }

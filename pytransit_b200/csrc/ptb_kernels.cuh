@@ -11,8 +11,10 @@
 //   k_lnl_model      lnlike_normal on a materialised model flux
 //
 // HBM layout (all fp64 unless noted):
-//   orb  [npv][16]            cx[5] cy[5] p 1/p T1 T4 good -
-//   ldrec[npv][npb][lds]      ldm[ng] | k 1/(1+k) 1/I* k^2 | pad      (lds = ng+4 rounded up to even)
+//   rec  [npv][recstride]     one record per parameter vector, fetched by ONE TMA bulk copy:
+//                               orb[16]         cx[5] cy[5] p 1/p T1 T4 good -
+//                               t0[nep]         transit centres (padded to an even count)
+//                               ld[npb][lds]    ldm[ng] | k 1/(1+k) 1/I* k^2 | pad   (lds = ng+4, even)
 //   flux [npv][npt]           row-major, written with 16-byte stores
 #pragma once
 #include "ptb_math.cuh"
@@ -116,10 +118,11 @@ struct OrbitParams {
     const double *k;  // [npv][kcols]
     const double *p, *a, *inc, *e, *w;
     const double *xyc_in;  // optional injected coefficients [npv][10]
-    double *orb;
+    const double *t0;      // [npv][nep]
+    double *rec;           // per-vector records (orb at offset 0, t0 at ORB_STRIDE)
     int *bin;   // [npv]  table row ik, nk = direct weights, nk+1 = invalid vector
     int *hist;  // [nk+2]
-    int npv, kcols, nk;
+    int npv, kcols, nk, nep, recstride;
     double kmin, kmax, dk;
 };
 
@@ -137,8 +140,12 @@ __global__ void __launch_bounds__(256) k_rr_orbit(const __grid_constant__ OrbitP
         w = P.w[ipv];
     }
     const bool good0 = inr && !(isnan(a) || (a <= 1.0) || (e < 0.0));  // model_full.py:40 (ldp checked later)
-    double *orb = P.orb + (size_t)(inr ? ipv : 0) * ORB_STRIDE;
+    double *orb = P.rec + (size_t)(inr ? ipv : 0) * P.recstride;
     solve_orbit_lanes<8>(sl, good0, p, a, inc, e, w, k0, (P.xyc_in && inr) ? P.xyc_in + (size_t)ipv * 10 : nullptr, orb);
+    if (inr) {  // transit centres travel with the record (one TMA bulk copy per vector in k_rr_points)
+        for (int j = sl; j < P.nep; j += 8) orb[ORB_STRIDE + j] = P.t0[(size_t)ipv * P.nep + j];
+        if (sl == 0 && (P.nep & 1)) orb[ORB_STRIDE + P.nep] = 0.0;
+    }
     if (inr && sl == 0) {
         int bin = P.nk + 1;
         if (good0) {
@@ -202,8 +209,9 @@ struct LdmParams {
     const double *istar;  // [npv][npb] (profiles only)
     const double *W, *ze, *mu, *gs, *ldmu200, *ldz200;
     const int *offsets, *gstart, *perm;
-    double *orb, *ldrec, *ldp_out, *istar_out;
+    double *rec, *ldp_out, *istar_out;
     int npv, kcols, npb, nld, law, nk, ng, nz, lds, grp;  // grp <= RR_GROUP vectors per CTA
+    int recstride, rec_ld;                                // record stride / offset of the ld rows (doubles)
     double kmin, dk;
 };
 
@@ -295,7 +303,7 @@ __global__ void __launch_bounds__(256) k_rr_ldm(const __grid_constant__ LdmParam
     }
     __syncthreads();
     // isnan(ldp[ipv,0,0]) invalidates the vector (model_full.py:40)
-    if (tid < cnt && isnan(sLdp[(size_t)tid * npb * nz])) P.orb[(size_t)s_pv[tid] * ORB_STRIDE + ORB_GOOD] = 0.0;
+    if (tid < cnt && isnan(sLdp[(size_t)tid * npb * nz])) P.rec[(size_t)s_pv[tid] * P.recstride + ORB_GOOD] = 0.0;
 
     if (in_table) mbar_wait(bar, 0);  // every thread observes the TMA completion
 
@@ -338,7 +346,7 @@ __global__ void __launch_bounds__(256) k_rr_ldm(const __grid_constant__ LdmParam
                     const double ak = s_ak[q0 + q];
                     v = (1.0 - ak) * v + ak * sOut[((size_t)P.grp + q) * ng + ig];
                 }
-                P.ldrec[((size_t)ipv * npb + pb) * P.lds + ig] = v;
+                P.rec[(size_t)ipv * P.recstride + P.rec_ld + (size_t)pb * P.lds + ig] = v;
             }
             __syncthreads();
         }
@@ -347,7 +355,7 @@ __global__ void __launch_bounds__(256) k_rr_ldm(const __grid_constant__ LdmParam
         const int q = r / npb, pb = r - q * npb;
         const int ipv = s_pv[q];
         const double kk = P.k[(size_t)ipv * P.kcols + (P.kcols == npb ? pb : 0)];
-        double *tail = P.ldrec + ((size_t)ipv * npb + pb) * P.lds + ng;
+        double *tail = P.rec + (size_t)ipv * P.recstride + P.rec_ld + (size_t)pb * P.lds + ng;
         tail[0] = kk;
         tail[1] = 1.0 / (1.0 + kk);
         tail[2] = 1.0 / sIstar[r];
@@ -359,29 +367,38 @@ __global__ void __launch_bounds__(256) k_rr_ldm(const __grid_constant__ LdmParam
 // ---------------------------------------------------------------------------------------------
 // The npv x npt pass.
 //
-// One CTA = one parameter vector x one chunk of the time axis, 8 warps; the time axis is cut into
-// blocks of 64 consecutive points and each warp walks its own blocks.
+// Persistent kernel, one wave of CTAs (SM count x resident CTAs per SM).  Every WARP is an independent
+// worker: it pulls work items (parameter vector x chunk of the time axis) from a global counter and
+// never synchronises with the other warps of its CTA, so a vector with more transits than its
+// neighbours delays nobody.  The item's per-vector record (orbit coefficients, transit centres, ld
+// rows) is fetched by ONE TMA bulk copy into the warp's double-buffered shared-memory slot while the
+// warp is still working on the previous item: no item starts with a chain of dependent global loads.
 //
-//  * Block classification (warp-uniform, ~10 fp64 ops per 64 points): set_data stores the smallest and
-//    largest time stamp of every block.  A block whose [tmin, tmax] misses every transit window
-//    [t0 + n p + lo, t0 + n p + hi] holds no in-box point, so its 64 fluxes are 1.0: the warp issues
-//    one 16-byte streaming store per lane and moves on (likelihood mode: adds the block's
-//    pre-summed (obs-1)^2).  ~93 % of a TESS sector takes this path at HBM-store speed.
-//  * Other blocks: each point is folded and box-tested in fp64 in the reference's operation order
-//    (model_full.py:88-91); in-box points go to a warp-private queue in shared memory.
-//  * Batched drain: when >= 128 exposure sub-samples are queued the warp evaluates them together --
-//    separation + limb-darkening lerp for every sample, then the samples on the stellar limb (the
-//    ones that need the sqrt + 2 atan2 lens area, ~1/4 of them) are compacted a second time so the
-//    expensive code runs with full warps; per-point sums over sub-samples are taken in exposure order.
-//
-// The per-vector record (ldm rows + k, 1/(1+k), 1/I*, k^2 per passband) is staged into shared memory
-// with one TMA bulk copy per CTA.
+// Per item (the time axis is cut into blocks of 64 consecutive points):
+//  1. Block classification: set_data stores the smallest and largest time stamp of every block.  A
+//     block whose [tmin, tmax] misses every transit window [t0 + n p + lo, t0 + n p + hi] holds no
+//     in-box point.  One ballot per 32 blocks -> a bitmap in shared memory (likelihood mode: the
+//     pre-summed (obs-1)^2 of the untouched blocks is added right here).
+//  2. Untouched blocks (~93 % of a TESS sector): 64 fluxes of exactly 1.0 -- predicate-free 16-byte
+//     streaming stores, eight blocks (4 KB) per step.
+//  3. Touched blocks: each point is folded and box-tested in fp64 in the reference's operation order
+//     (model_full.py:88-91); in-box points go to the warp's queue; the next touched block's time
+//     stamps are already in flight while the current one is folded.
+//  4. Point-major drain: whenever 32 points are queued every lane takes ONE point and walks its
+//     exposure sub-samples in order -- separation (two Horner quartics + sqrt) and ld-mean lerp per
+//     sample, no integer division or per-sample metadata reload.  Samples on the stellar limb (the
+//     ones that need the sqrt + 2 atan2 lens area, ~1/4 of them) are compacted into a second queue
+//     and evaluated 32 at a time with full warps.  With one sample per point (S1) the limb queue is
+//     carried across drains and flushed once per item; with supersampling the per-point sum over
+//     sub-samples is taken in exposure order (model_full.py:93-99) from a per-pass buffer.
+// The drain has a single call site and a point's arithmetic does not depend on batch composition or
+// on which warp runs the item: results are bit-reproducible across launches and population splits.
 // ---------------------------------------------------------------------------------------------
 struct PointsParams {
     const double *time;
     const int32_t *lcids, *pbids, *epids, *nsamples;
     const double *exptimes;
-    const double *orb, *t0, *ldrec;
+    const double *rec;    // [npv][recstride] per-vector records
     double *flux;
     const double *obs;
     const int32_t *blk;
@@ -391,28 +408,54 @@ struct PointsParams {
     const int32_t *blc;         // light curve of the block, -1 when it straddles light curves
     const double *bchi;         // likelihood: sum of (obs-1)^2 over the block's points
     const int32_t *bnoise;      // likelihood: noise id of the block, -1 none, -2 mixed (slow path)
+    int *work;                  // [0] next item, [1] CTAs finished (the last one re-arms both)
     long long npt;
-    int npv, nlc, npb, nep, ng, lds, nblocks, ns_max, nchunks, blocks_per_chunk, nblk64, stage_ld;
+    int npv, nlc, npb, nep, ng, lds, nblocks, ns_max, nchunks, blocks_per_chunk, nblk64;
+    int recstride, rec_ld, ssc, frac_tab;
     double dg, inv_dg;
 };
 
-#ifndef PT_MINB
-#define PT_MINB 3
+// resident CTAs per SM: three for the one-sample kernels (<= 85 registers, no spills), two for the
+// supersampled ones (the sub-sample loop keeps more state live)
+#ifndef PT_MINB_S1
+#define PT_MINB_S1 3
+#endif
+#ifndef PT_MINB_SS
+#define PT_MINB_SS 2
 #endif
 constexpr int PT_THREADS = 256;
 constexpr int PT_WARPS = PT_THREADS / 32;
 constexpr int PT_BLOCK = 64;           // points per classification block
-constexpr int PT_BATCH = 128;          // exposure sub-samples evaluated per drain
-constexpr int PT_QCAP = PT_BATCH + PT_BLOCK;
-constexpr int PT_MAXBLK = 8192;        // blocks per CTA chunk (hit bitmap in shared memory)
+constexpr int PT_MAXBLK = 2048;        // blocks per item (hit bitmap in shared memory)
+constexpr int PT_QCAP = 96;            // in-box point queue: < 32 carried + 64 from one block
+constexpr int PT_LCAP = 64;            // limb sample queue: < 32 carried + 32 from one sub-sample step
+constexpr int PT_SSC_MAX = 12;         // exposure sub-samples buffered per pass
+constexpr int PT_FRAC_MAX = 1024;      // entries of the tabulated sub-sample offsets
 constexpr double PT_EPS = 1e-9;        // classification margin, in periods (>> rounding, << the 0.003 d pad)
 
-struct alignas(16) WarpScratch {
-    double q_tc[PT_QCAP];
-    double contrib[PT_BATCH];
-    double l_z[PT_BATCH], l_ip[PT_BATCH];
-    int q_ipt[PT_QCAP];
-    int l_it[PT_BATCH];
+// Warp-private shared memory: queues, sub-sample buffer (none when every point has one sample),
+// two record slots, the hit bitmap and two mbarriers.
+__host__ __device__ inline size_t pt_warp_bytes(int ssc, int recstride) {
+    return (size_t)(PT_QCAP + 2 * PT_LCAP + 32 * ssc + 2 * recstride) * 8 + (size_t)(2 * PT_QCAP + 2 * PT_LCAP) * 4 +
+           PT_MAXBLK / 8 + 16;
+}
+
+struct WarpScratch {
+    unsigned char *base;
+    __device__ __forceinline__ explicit WarpScratch(unsigned char *b) : base(b) {}
+    __device__ __forceinline__ double *q_tc() const { return reinterpret_cast<double *>(base); }
+    __device__ __forceinline__ double *l_z() const { return q_tc() + PT_QCAP; }
+    __device__ __forceinline__ double *l_ip() const { return l_z() + PT_LCAP; }
+    __device__ __forceinline__ int *q_ipt() const { return reinterpret_cast<int *>(l_ip() + PT_LCAP); }
+    __device__ __forceinline__ int *q_lc() const { return q_ipt() + PT_QCAP; }
+    __device__ __forceinline__ int *l_slot() const { return q_lc() + PT_QCAP; }   // S1: the point index
+    __device__ __forceinline__ int *l_row() const { return l_slot() + PT_LCAP; }
+    __device__ __forceinline__ unsigned *hit() const { return reinterpret_cast<unsigned *>(l_row() + PT_LCAP); }
+    __device__ __forceinline__ uint64_t *bar() const { return reinterpret_cast<uint64_t *>(hit() + PT_MAXBLK / 32); }
+    __device__ __forceinline__ double *rec(int slot, int recstride) const {
+        return reinterpret_cast<double *>(bar() + 2) + (size_t)slot * recstride;
+    }
+    __device__ __forceinline__ double *contrib(int recstride) const { return rec(2, recstride); }
 };
 
 template <int VEC>
@@ -434,289 +477,385 @@ struct VecIO<2> {
     }
 };
 
-// Batched evaluation of `np` queued in-box points starting at queue slot `base` (warp-cooperative;
-// model_full.py:93-99).  Inlined at its single call site (an out-of-line call was measured 15 % slower:
-// the shared-memory address space of the staged record is lost across the call).  Returns the warp
-// lane's chi^2 increment (likelihood mode).
+// Per-CTA constants of the drain (shared-memory tables are item independent).
 struct DrainCtx {
     const PointsParams *P;
-    WarpScratch *ws;
-    const double *orb;
-    const double *ld;  // per-vector record in shared memory: [npb][lds]
-    double *frow;
-    const double *isig2;
-    int lane, S;
+    const double *sEt, *sFrac;     // per light curve: exposure time; tabulated (s+1-0.5)/ns-0.5 or null
+    const int *sNs, *sRow;         // per light curve: nsamples, offset of the passband row in the ld block
+    int ns1, row1;                 // single light curve: the same as scalars
+    double et1;
+    int lane;
 };
 
-template <bool SINGLE_LC, bool LNL>
-__device__ __forceinline__ double drain_batch(const DrainCtx &c, int base, int np) {
-    const PointsParams &P = *c.P;
-    WarpScratch &ws = *c.ws;
-    const int lane = c.lane, S = c.S, ng = P.ng, lds = P.lds;
-    const double dg = P.dg, inv_dg = P.inv_dg;
-    const unsigned lt_mask = (1u << lane) - 1u;
+// Lens-area pass over `take` limb samples at the top of the limb queue (warp-cooperative).
+// S1: writes the flux / accumulates chi^2 directly; otherwise fills the sample's slot of `contrib`.
+template <bool SINGLE_LC, bool LNL, bool S1>
+__device__ __forceinline__ double limb_pass(const PointsParams &P, const WarpScratch &ws, const double *ld, const double *row1,
+                                            double *contrib, double *frow, const double *isig2, int lane, int first,
+                                            int take) {
     double chi = 0.0;
-    double cx[5], cy[5];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) { cx[j] = c.orb[j]; cy[j] = c.orb[5 + j]; }
-    // single light curve: the per-light-curve metadata are block constants
-    const int ns1 = SINGLE_LC ? P.nsamples[0] : 1;
-    const double et1 = SINGLE_LC ? P.exptimes[0] : 0.0;
-    const double *row1 = c.ld + (SINGLE_LC ? (size_t)P.pbids[0] * lds : 0);
-    double bigsum = 0.0;  // S > PT_BATCH only: running sum over sample chunks (np == 1)
-    for (int s0 = 0; s0 < S; s0 += PT_BATCH) {
-        const int SS = min(S - s0, PT_BATCH);  // sample slots in this pass
-        const int nitems = np * SS;
-        // stage A: separation, limb-darkening lerp, cheap area cases; limb samples -> second queue
-        int nl = 0;
-        for (int it0 = 0; it0 < nitems; it0 += 32) {
-            const int it = it0 + lane;
-            bool limb = false;
-            double z = 0.0, ip = 0.0;
-            if (it < nitems) {
-                const int pt = (SS == 1) ? it : it / SS;
-                const int s = s0 + (it - pt * SS);
-                int ns = ns1;
-                double et = et1;
-                const double *row = row1;
-                if (!SINGLE_LC) {
-                    const int lc = P.lcids[ws.q_ipt[base + pt]];
-                    ns = P.nsamples[lc];
-                    et = P.exptimes[lc];
-                    row = c.ld + (size_t)P.pbids[lc] * lds;
-                }
-                double cc = 0.0;
-                if (s < ns) {
-                    // exposure offset exptime*((s+1-0.5)/ns - 0.5) (model_full.py:94); exactly 0 for ns == 1
-                    const double off = (ns == 1) ? 0.0 : et * (((s + 1) - 0.5) / ns - 0.5);
-                    z = sep_poly(ws.q_tc[base + pt] + off, cx, cy);
-                    const double k = row[ng];
-                    ip = ldm_lerp(z * row[ng + 1], dg, inv_dg, row, ng);
-                    if (1.0 + k <= z) cc = 1.0;                                   // no overlap: area 0
-                    else if (fabs(1.0 - k) < z) limb = true;                      // lens: kite formula
-                    else if (z <= 1.0 - k) cc = 1.0 - ip * (kPi * row[ng + 3]) * row[ng + 2];
-                    else if (z <= k - 1.0) cc = 1.0 - ip * kPi * row[ng + 2];    // planet covers the star
-                    else cc = nan("");
-                }
-                ws.contrib[it] = cc;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, limb);
-            if (limb) {
-                const int pos = nl + __popc(m & lt_mask);
-                ws.l_it[pos] = it;
-                ws.l_z[pos] = z;
-                ws.l_ip[pos] = ip;
-            }
-            nl += __popc(m);
-        }
-        __syncwarp();
-        // stage B: lens area on the limb (sqrt + 2 atan2), full warps
-        for (int j = lane; j < nl; j += 32) {
-            const int it = ws.l_it[j];
-            const double *row = row1;
-            if (!SINGLE_LC) {
-                const int pt = (SS == 1) ? it : it / SS;
-                row = c.ld + (size_t)P.pbids[P.lcids[ws.q_ipt[base + pt]]] * lds;
-            }
-            double area, kap;
-            kite_area(row[ng], row[ng + 3], ws.l_z[j], area, kap);
-            ws.contrib[it] = 1.0 - ws.l_ip[j] * area * row[ng + 2];
-        }
-        __syncwarp();
-        // stage C: per-point sum over sub-samples in exposure order (model_full.py:93-99)
-        for (int pt = lane; pt < np; pt += 32) {
-            const int ipt = ws.q_ipt[base + pt];
-            const int ns = SINGLE_LC ? ns1 : P.nsamples[P.lcids[ipt]];
-            const int m = min(SS, ns - s0);
-            double sum = bigsum;
-            for (int j = 0; j < m; ++j) sum += ws.contrib[pt * SS + j];
-            if (s0 + SS >= S) {
-                const double f = sum / ns;
-                if (LNL) {
-                    const int b = P.blk ? P.blk[ipt] : 0;
-                    if (b >= 0) {
-                        const double d = P.obs[ipt] - f;
-                        chi = fma(d * d, c.isig2[b], chi);
-                    }
-                } else {
-                    c.frow[ipt] = f;
+    if (lane < take) {
+        const int q = first + lane, ng = P.ng;
+        const double *r2 = SINGLE_LC ? row1 : ld + ws.l_row()[q];
+        double area, kap;
+        kite_area(r2[ng], r2[ng + 3], ws.l_z()[q], area, kap);
+        const double v = 1.0 - ws.l_ip()[q] * area * r2[ng + 2];
+        if (S1) {
+            const int ipt = ws.l_slot()[q];
+            if (LNL) {
+                const int b = P.blk ? P.blk[ipt] : 0;
+                if (b >= 0) {
+                    const double d = P.obs[ipt] - v;
+                    chi = d * d * isig2[b];
                 }
             } else {
-                bigsum = sum;  // only reached with np == 1 (lane 0)
+                frow[ipt] = v;
             }
+        } else {
+            contrib[ws.l_slot()[q]] = v;
         }
-        __syncwarp();
     }
     return chi;
 }
 
-template <int VEC, bool SINGLE_LC, bool LNL>
-__global__ void __launch_bounds__(PT_THREADS, PT_MINB) k_rr_points(const __grid_constant__ PointsParams P) {
+// Point-major evaluation of `n` (<= 32) queued in-box points starting at queue slot `base`
+// (model_full.py:93-99).  `nl` is the fill of the limb queue (carried across calls when S1; `flush`
+// empties it).  Inlined at its single call site.  Returns the lane's chi^2 increment.
+template <bool SINGLE_LC, bool LNL, bool S1>
+__device__ __forceinline__ double drain_points(const DrainCtx &c, const WarpScratch &ws, const double *rec, double *frow,
+                                               const double *isig2, int base, int n, int &nl, bool flush) {
+    const PointsParams &P = *c.P;
+    const int lane = c.lane, ng = P.ng;
+    const int S = S1 ? 1 : P.ns_max, SSC = S1 ? 1 : P.ssc;
+    const double dg = P.dg, inv_dg = P.inv_dg;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const double *ld = rec + P.rec_ld;
+    double *contrib = ws.contrib(P.recstride);
+    double cx[5], cy[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { cx[j] = rec[j]; cy[j] = rec[5 + j]; }
+
+    const bool valid = lane < n;
+    int ipt = 0, lc = 0, ns = 1, rowoff = c.row1;
+    double tc = 0.0, et = 0.0;
+    if (valid) {
+        ipt = ws.q_ipt()[base + lane];
+        tc = ws.q_tc()[base + lane];
+        if (SINGLE_LC) {
+            ns = c.ns1;
+            et = c.et1;
+        } else {
+            lc = ws.q_lc()[base + lane];
+            ns = c.sNs[lc];
+            et = c.sEt[lc];
+            rowoff = c.sRow[lc];
+        }
+    }
+    const double *row1 = ld + c.row1;
+    const double *row = ld + rowoff;
+    const double k = row[ng], inv1k = row[ng + 1], inv_istar = row[ng + 2], k2 = row[ng + 3];
+    const double *frac = c.sFrac ? c.sFrac + (size_t)lc * S : nullptr;
+
+    double sum = 0.0, chi = 0.0;
+    for (int s0 = 0; s0 < S; s0 += SSC) {
+        const int SS = min(SSC, S - s0);
+        for (int j = 0; j < SS; ++j) {
+            const int s = s0 + j;
+            bool limb = false;
+            double z = 0.0, ip = 0.0;
+            if (valid && s < ns) {
+                // exposure offset exptime*((s+1-0.5)/ns - 0.5) (model_full.py:94); exactly 0 for ns == 1
+                double off = 0.0;
+                if (!S1 && ns != 1) off = et * (frac ? frac[s] : (((s + 1) - 0.5) / ns - 0.5));
+                z = sep_poly(tc + off, cx, cy);
+                ip = ldm_lerp(z * inv1k, dg, inv_dg, row, ng);
+                double cc = 0.0;
+                if (1.0 + k <= z) cc = 1.0;                                   // no overlap: area 0
+                else if (fabs(1.0 - k) < z) limb = true;                      // lens: kite formula
+                else if (z <= 1.0 - k) cc = 1.0 - ip * (kPi * k2) * inv_istar;
+                else if (z <= k - 1.0) cc = 1.0 - ip * kPi * inv_istar;       // planet covers the star
+                else cc = nan("");
+                if (S1) sum = cc;
+                else if (!limb) contrib[j * 32 + lane] = cc;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, limb);
+            if (m) {
+                if (limb) {
+                    const int pos = nl + __popc(m & lt_mask);
+                    ws.l_slot()[pos] = S1 ? ipt : j * 32 + lane;
+                    ws.l_z()[pos] = z;
+                    ws.l_ip()[pos] = ip;
+                    if (!SINGLE_LC) ws.l_row()[pos] = rowoff;
+                }
+                nl += __popc(m);
+                __syncwarp();
+            }
+            if (S1) {
+                // one sample per point: everything that is not on the limb is final
+                if (valid && !limb) {
+                    if (LNL) {
+                        const int b = P.blk ? P.blk[ipt] : 0;
+                        if (b >= 0) {
+                            const double d = P.obs[ipt] - sum;
+                            chi += d * d * isig2[b];
+                        }
+                    } else {
+                        frow[ipt] = sum;
+                    }
+                }
+            }
+            // lens area on the limb (sqrt + 2 atan2): a full warp at a time from the top of the limb
+            // queue (single code copy: one rounding behaviour); leftovers when the pass / item ends
+            const bool last = S1 ? flush : (j + 1 == SS);
+            while (nl >= 32 || (last && nl > 0)) {
+                const int take = min(nl, 32);
+                nl -= take;
+                chi += limb_pass<SINGLE_LC, LNL, S1>(P, ws, ld, row1, contrib, frow, isig2, lane, nl, take);
+                __syncwarp();
+            }
+        }
+        if (!S1) {
+            // per-point sum over this pass's sub-samples, in exposure order
+            if (valid) {
+                const int mm = min(SS, ns - s0);
+                for (int j = 0; j < mm; ++j) sum += contrib[j * 32 + lane];
+            }
+            __syncwarp();
+        }
+    }
+    if (!S1 && valid) {
+        const double f = sum / ns;
+        if (LNL) {
+            const int b = P.blk ? P.blk[ipt] : 0;
+            if (b >= 0) {
+                const double d = P.obs[ipt] - f;
+                chi += d * d * isig2[b];
+            }
+        } else {
+            frow[ipt] = f;
+        }
+    }
+    return chi;
+}
+
+template <int VEC, bool SINGLE_LC, bool LNL, bool S1>
+__global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr_points(const __grid_constant__ PointsParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ double s_red[PT_WARPS];
-    __shared__ unsigned s_hit[PT_MAXBLK / 32];
-    __shared__ __align__(8) uint64_t bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ipv = blockIdx.x / P.nchunks;
-    const int chunk = blockIdx.x - ipv * P.nchunks;
     const long long npt = P.npt;
-
-    // dynamic smem: [WarpScratch x 8] [ldrec copy npb*lds] [lc_lo nlc] [lc_hi nlc] [lc_t0 nlc]
-    WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem_raw)[warp];
-    double *sLd = reinterpret_cast<double *>(smem_raw + sizeof(WarpScratch) * PT_WARPS);
-    double *sLo = sLd + (size_t)P.npb * P.lds;
-    double *sHi = sLo + (SINGLE_LC ? 0 : P.nlc);
-    double *sT0 = sHi + (SINGLE_LC ? 0 : P.nlc);
-
-    const double *orb = P.orb + (size_t)ipv * ORB_STRIDE;
-    const bool good = orb[ORB_GOOD] != 0.0;
-    const double *ldg = P.ldrec + (size_t)ipv * P.npb * P.lds;
-
-    const int bbeg = chunk * P.blocks_per_chunk;
-    const int bend = min(P.nblk64, bbeg + P.blocks_per_chunk);
-
-    if (!good) {  // invalid parameter vector: NaN row (model_full.py:80-82)
-        if (LNL) {
-            if (tid == 0) P.partial[(size_t)ipv * P.nchunks + chunk] = nan("");
-        } else {
-            double *frow = P.flux + (size_t)ipv * npt;
-            double v[VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) v[j] = nan("");
-            const long long cend = min(npt, (long long)bend * PT_BLOCK);
-            for (long long i = (long long)bbeg * PT_BLOCK + (long long)tid * VEC; i < cend; i += PT_THREADS * VEC)
-                VecIO<VEC>::store(frow + i, v);
-        }
-        return;
-    }
-
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        const uint32_t bytes = (uint32_t)(P.npb * P.lds * 8);
-        mbar_expect_tx(&bar, bytes);
-        tma_load_1d(sLd, ldg, bytes, &bar);
-    }
-    const double p = orb[ORB_P], invp = orb[ORB_INVP], T1 = orb[ORB_T1], T4 = orb[ORB_T4];
-    double lo1 = 0, hi1 = 0, t01 = 0;
-    if (SINGLE_LC) {
-        const double pad = 0.003 + P.exptimes[0];
-        lo1 = T1 - pad;
-        hi1 = T4 + pad;
-        t01 = P.t0[(size_t)ipv * P.nep + P.epids[0]];
-    } else {
-        for (int lc = tid; lc < P.nlc; lc += PT_THREADS) {
-            const double pad = 0.003 + P.exptimes[lc];
-            sLo[lc] = T1 - pad;
-            sHi[lc] = T4 + pad;
-            sT0[lc] = P.t0[(size_t)ipv * P.nep + P.epids[lc]];
-        }
-    }
-    __syncthreads();  // mbarrier init + per-light-curve tables visible
-
-    bool ld_ready = false;
-    DrainCtx dctx;
-
-    const int S = P.ns_max;                        // sub-sample slots per queued point
-    const int PB = S >= PT_BATCH ? 1 : PT_BATCH / S;  // points per drain batch
-    int qn = 0;
-    double chi = 0.0;
-    const double *isig2 = LNL ? P.isig2 + (size_t)ipv * P.nblocks : nullptr;
-    double *frow = LNL ? nullptr : P.flux + (size_t)ipv * npt;
+    const int S = P.ns_max, nlc = P.nlc;
+    const long long nitems = (long long)P.npv * P.nchunks;
     const unsigned lt_mask = (1u << lane) - 1u;
-    dctx.P = &P; dctx.ws = &ws; dctx.orb = orb; dctx.ld = sLd; dctx.frow = frow; dctx.isig2 = isig2;
-    dctx.lane = lane; dctx.S = S;
 
-    // ---- classification of every block of this chunk, in parallel over the CTA -----------------------
-    // Can any transit window [t0 + n p + lo, t0 + n p + hi] touch [tmin, tmax] of the block?  If not, the
-    // block holds no in-box point.  One bit per block goes to shared memory; in likelihood mode the
-    // pre-summed (obs-1)^2 of the untouched blocks is added right here.
-    const int nbc = bend - bbeg;
-    for (int bb0 = 0; bb0 < nbc; bb0 += PT_THREADS) {
-        const int bb = bb0 + tid, b = bbeg + bb;
-        bool hit = false;
-        if (bb < nbc) {
-            hit = true;
-            const int lcb = SINGLE_LC ? 0 : P.blc[b];
-            int nz_id = 0;
-            if (LNL) nz_id = P.bnoise ? P.bnoise[b] : 0;
-            const bool partial = (b == P.nblk64 - 1) && (npt % PT_BLOCK != 0);
-            if (lcb >= 0 && nz_id != -2 && !partial) {
-                const double lo = SINGLE_LC ? lo1 : sLo[lcb], hi = SINGLE_LC ? hi1 : sHi[lcb];
-                const double t0 = SINGLE_LC ? t01 : sT0[lcb];
-                const double n1 = ceil(fma(P.bmin[b] - t0 - hi, invp, -PT_EPS));
-                const double n2 = floor(fma(P.bmax[b] - t0 - lo, invp, PT_EPS));
-                hit = !(n1 > n2) || !(p > 0.0);  // NaNs and p <= 0 fall through to the exact per-point path
-            }
-            if (LNL && !hit && nz_id >= 0) chi = fma(P.bchi[b], isig2[nz_id], chi);
+    // dynamic smem: [per-light-curve tables] [sub-sample offsets] [warp-private area x 8]
+    double *sPad = reinterpret_cast<double *>(smem_raw);
+    double *sEt = sPad + nlc;
+    double *sFrac = sEt + nlc;
+    const int nfrac = P.frac_tab ? nlc * S : 0;
+    int *sNs = reinterpret_cast<int *>(sFrac + nfrac);
+    int *sRow = sNs + nlc;
+    int *sEp = sRow + nlc;
+    const size_t shared_bytes = (((2 * (size_t)nlc + nfrac) * 8 + 3 * (size_t)nlc * 4) + 127) & ~size_t(127);
+    const WarpScratch ws(smem_raw + shared_bytes + (size_t)warp * pt_warp_bytes(S1 ? 0 : P.ssc, P.recstride));
+    unsigned *s_hit = ws.hit();
+    uint64_t *bar = ws.bar();
+
+    const uint32_t rec_bytes = (uint32_t)P.recstride * 8u;
+    long long item = 0;
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        item = atomicAdd(&P.work[0], 1);
+        if (item < nitems) {
+            mbar_expect_tx(&bar[0], rec_bytes);
+            tma_load_1d(ws.rec(0, P.recstride), P.rec + (size_t)(item / P.nchunks) * P.recstride, rec_bytes, &bar[0]);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) s_hit[bb >> 5] = m;
     }
-    __syncthreads();
+    item = __shfl_sync(0xffffffffu, item, 0);
+    // item-independent per-light-curve tables
+    for (int lc = tid; lc < nlc; lc += PT_THREADS) {
+        sPad[lc] = 0.003 + P.exptimes[lc];  // model_full.py:69-70
+        sEt[lc] = P.exptimes[lc];
+        sNs[lc] = P.nsamples[lc];
+        sRow[lc] = P.pbids[lc] * P.lds;
+        sEp[lc] = P.epids[lc];
+    }
+    for (int i = tid; i < nfrac; i += PT_THREADS) {
+        const int lc = i / S, s = i - lc * S;
+        sFrac[i] = ((s + 1) - 0.5) / P.nsamples[lc] - 0.5;
+    }
+    __syncthreads();  // the only CTA-wide barrier: from here on the warps are independent workers
 
-    // ---- main loop: a warp takes groups of 8 blocks (512 points) ------------------------------------
-    // One extra pass after the last group flushes the queue, so that drain() has exactly ONE call site
-    // and batches are always cut from the top of the queue: a point's arithmetic does not depend on the
-    // chunking and results are bit-reproducible across population splits.
-    const int ngroups = (nbc + 7) >> 3;
-    for (int g = warp;; g += PT_WARPS) {
-        const bool live = g < ngroups;
-        unsigned bits = live ? (s_hit[g >> 2] >> ((g & 3) * 8)) & 0xffu : 0u;
-        const int b0 = bbeg + g * 8;
-        if (!LNL && live) {
-            // untouched blocks: 64 fluxes of exactly 1.0, one 16-byte streaming store per lane
+    DrainCtx dctx;
+    dctx.P = &P; dctx.sEt = sEt; dctx.sFrac = P.frac_tab ? sFrac : nullptr; dctx.sNs = sNs; dctx.sRow = sRow;
+    dctx.ns1 = sNs[0]; dctx.row1 = sRow[0]; dctx.et1 = sEt[0];
+    dctx.lane = lane;
+    const double pad1 = sPad[0];
+    const int ep1 = sEp[0];
+
+    for (int iter = 0; item < nitems; ++iter) {
+        const int buf = iter & 1;
+        long long next = 0;
+        if (lane == 0) {  // fetch the next item and start its record copy into the other slot
+            next = atomicAdd(&P.work[0], 1);
+            if (next < nitems) {
+                mbar_expect_tx(&bar[buf ^ 1], rec_bytes);
+                tma_load_1d(ws.rec(buf ^ 1, P.recstride), P.rec + (size_t)(next / P.nchunks) * P.recstride, rec_bytes,
+                            &bar[buf ^ 1]);
+            }
+        }
+        next = __shfl_sync(0xffffffffu, next, 0);
+        const int ipv = (int)(item / P.nchunks);
+        const int chunk = (int)(item - (long long)ipv * P.nchunks);
+        item = next;
+        const int bbeg = chunk * P.blocks_per_chunk;
+        const int bend = min(P.nblk64, bbeg + P.blocks_per_chunk);
+        const int nbc = bend - bbeg;
+        const double *rec = ws.rec(buf, P.recstride);
+        double *frow = LNL ? nullptr : P.flux + (size_t)ipv * npt;
+        const double *isig2 = LNL ? P.isig2 + (size_t)ipv * P.nblocks : nullptr;
+        double chi = 0.0;
+
+        mbar_wait(&bar[buf], (iter >> 1) & 1);
+        if (rec[ORB_GOOD] == 0.0) {  // invalid parameter vector: NaN row (model_full.py:80-82)
+            if (LNL) {
+                if (lane == 0) P.partial[(size_t)ipv * P.nchunks + chunk] = nan("");
+            } else {
+                double v[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) v[j] = nan("");
+                const long long cend = min(npt, (long long)bend * PT_BLOCK);
+                for (long long i = (long long)bbeg * PT_BLOCK + (long long)lane * VEC; i < cend; i += 32 * VEC)
+                    VecIO<VEC>::store(frow + i, v);
+            }
+            __syncwarp();
+            continue;
+        }
+
+        const double p = rec[ORB_P], invp = rec[ORB_INVP], T1 = rec[ORB_T1], T4 = rec[ORB_T4];
+        const double *t0v = rec + ORB_STRIDE;
+        const double lo1 = T1 - pad1, hi1 = T4 + pad1, t01 = t0v[ep1];
+
+        // ---- 1. classification of every block of this item --------------------------------------------
+        for (int bb0 = 0; bb0 < nbc; bb0 += 32) {
+            const int bb = bb0 + lane, b = bbeg + bb;
+            bool hit = false;
+            if (bb < nbc) {
+                hit = true;
+                const int lcb = SINGLE_LC ? 0 : P.blc[b];
+                int nz_id = 0;
+                if (LNL) nz_id = P.bnoise ? P.bnoise[b] : 0;
+                const bool partial = (b == P.nblk64 - 1) && (npt % PT_BLOCK != 0);
+                if (lcb >= 0 && nz_id != -2 && !partial) {
+                    const double lo = SINGLE_LC ? lo1 : T1 - sPad[lcb], hi = SINGLE_LC ? hi1 : T4 + sPad[lcb];
+                    const double t0 = SINGLE_LC ? t01 : t0v[sEp[lcb]];
+                    const double n1 = ceil(fma(P.bmin[b] - t0 - hi, invp, -PT_EPS));
+                    const double n2 = floor(fma(P.bmax[b] - t0 - lo, invp, PT_EPS));
+                    hit = !(n1 > n2) || !(p > 0.0);  // NaNs and p <= 0 fall through to the exact per-point path
+                }
+                if (LNL && !hit && nz_id >= 0) chi = fma(P.bchi[b], isig2[nz_id], chi);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_hit[bb0 >> 5] = m;
+        }
+        __syncwarp();
+
+        // ---- 2. untouched blocks: 64 fluxes of exactly 1.0, 16-byte streaming stores ---------------------
+        if (!LNL) {
             double one[VEC];
 #pragma unroll
             for (int j = 0; j < VEC; ++j) one[j] = 1.0;
-            double *fb = frow + (long long)b0 * PT_BLOCK + lane * VEC;
-            if (bits == 0u && b0 + 8 <= bend) {  // the common case: eight untouched blocks, no predicates
+            const int ngroups = (nbc + 7) >> 3;
+            for (int g = 0; g < ngroups; ++g) {
+                const unsigned bits = (s_hit[g >> 2] >> ((g & 3) * 8)) & 0xffu;
+                const int b0 = bbeg + g * 8;
+                double *fb = frow + (long long)b0 * PT_BLOCK + lane * VEC;
+                if (bits == 0u && b0 + 8 <= bend) {  // the common case: eight untouched blocks, no predicates
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-#pragma unroll
-                    for (int h = 0; h < 2 / VEC; ++h) VecIO<VEC>::store(fb + j * PT_BLOCK + h * 32 * VEC, one);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (!((bits >> j) & 1u) && b0 + j < bend) {
+                    for (int j = 0; j < 8; ++j) {
 #pragma unroll
                         for (int h = 0; h < 2 / VEC; ++h) VecIO<VEC>::store(fb + j * PT_BLOCK + h * 32 * VEC, one);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (!((bits >> j) & 1u) && b0 + j < bend) {
+#pragma unroll
+                            for (int h = 0; h < 2 / VEC; ++h) VecIO<VEC>::store(fb + j * PT_BLOCK + h * 32 * VEC, one);
+                        }
                     }
                 }
             }
         }
-        // touched blocks: exact per-point path; the body runs once more on the flush pass (no block)
-        do {
-            if (bits) {
-                const int jb = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const long long base = (long long)(b0 + jb) * PT_BLOCK;
+
+        // ---- 3./4. touched blocks: exact per-point path + drain -----------------------------------------
+        // One extra pass after the last block flushes the queues, so that the drain has exactly ONE call
+        // site and batches are always cut from the top of the queue.
+        int qn = 0, nl = 0;
+        const int nwords = (nbc + 31) >> 5;
+        int wi = 0;
+        unsigned wbits = s_hit[0];
+        // find the first touched block and start loading its time stamps
+        auto next_block = [&]() -> int {
+            while (wbits == 0u) {
+                if (++wi >= nwords) return -1;
+                wbits = s_hit[wi];
+            }
+            const int j = __ffs(wbits) - 1;
+            wbits &= wbits - 1;
+            return wi * 32 + j;
+        };
+        int cur = next_block();
+        double tvn[2 / VEC][VEC];
+        auto load_block = [&](int bb) {
+            const long long base = (long long)(bbeg + bb) * PT_BLOCK;
+#pragma unroll
+            for (int h = 0; h < 2 / VEC; ++h) {
+                const long long i0 = base + (long long)(h * 32 + lane) * VEC;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) tvn[h][j] = 0.0;
+                if (i0 < npt) VecIO<VEC>::load(P.time + i0, tvn[h]);
+            }
+        };
+        if (cur >= 0) load_block(cur);
+        for (;;) {
+            const bool live = cur >= 0;
+            if (live) {
+                const long long base = (long long)(bbeg + cur) * PT_BLOCK;
+                double tv[2 / VEC][VEC];
+#pragma unroll
+                for (int h = 0; h < 2 / VEC; ++h)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) tv[h][j] = tvn[h][j];
+                cur = next_block();
+                if (cur >= 0) load_block(cur);  // in flight while this block is folded
 #pragma unroll
                 for (int h = 0; h < 2 / VEC; ++h) {
                     const long long i0 = base + (long long)(h * 32 + lane) * VEC;
-                    double tv[VEC], fv[VEC];
+                    double fv[VEC];
                     const bool inr = i0 < npt;  // VEC == 2 requires an even npt: vectors are all-in or all-out
-                    if (inr) VecIO<VEC>::load(P.time + i0, tv);
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) {
                         bool inbox = false;
                         double tc = 0.0;
+                        int lc = 0;
+                        fv[j] = 1.0;
                         if (inr) {
                             double lo = lo1, hi = hi1, t0 = t01;
                             if (!SINGLE_LC) {
-                                const int lc = P.lcids[i0 + j];
-                                lo = sLo[lc];
-                                hi = sHi[lc];
-                                t0 = sT0[lc];
+                                lc = P.lcids[i0 + j];
+                                const double pd = sPad[lc];
+                                lo = T1 - pd;
+                                hi = T4 + pd;
+                                t0 = t0v[sEp[lc]];
                             }
                             // epoch = floor((t - t0 + p/2)/p); tc = t - (t0 + epoch p)  (model_full.py:88-89)
                             // The division is a multiplication by 1/p: the two can only disagree half a
                             // period away from the transit, where the point is outside the box either way.
-                            const double epoch = floor(fma(tv[j] - t0, invp, 0.5));
-                            tc = tv[j] - __dadd_rn(t0, __dmul_rn(epoch, p));
+                            const double epoch = floor(fma(tv[h][j] - t0, invp, 0.5));
+                            tc = tv[h][j] - __dadd_rn(t0, __dmul_rn(epoch, p));
                             inbox = (lo <= tc) && (tc <= hi);
-                            fv[j] = 1.0;
                             if (LNL && !inbox) {
                                 const int nb = P.blk ? P.blk[i0 + j] : 0;
                                 if (nb >= 0) {
@@ -728,8 +867,9 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB) k_rr_points(const __grid_
                         const unsigned m = __ballot_sync(0xffffffffu, inbox);
                         if (inbox) {
                             const int pos = qn + __popc(m & lt_mask);
-                            ws.q_ipt[pos] = (int)(i0 + j);
-                            ws.q_tc[pos] = tc;
+                            ws.q_ipt()[pos] = (int)(i0 + j);
+                            ws.q_tc()[pos] = tc;
+                            if (!SINGLE_LC) ws.q_lc()[pos] = lc;
                         }
                         qn += __popc(m);
                     }
@@ -737,29 +877,31 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB) k_rr_points(const __grid_
                 }
                 __syncwarp();
             }
-            // drain full batches; the remainder (< PB points) waits for more, except on the flush pass
-            while (qn >= PB || (!live && qn > 0)) {
-                const int n = min(qn, PB);
+            // drain full warps of points; the remainder (< 32) waits for more, except on the flush pass
+            while (qn >= 32 || (!live && (qn > 0 || nl > 0))) {
+                const int n = min(qn, 32);
                 qn -= n;
-                if (!ld_ready) {
-                    mbar_wait(&bar, 0);
-                    ld_ready = true;
-                }
-                chi += drain_batch<SINGLE_LC, LNL>(dctx, qn, n);
+                chi += drain_points<SINGLE_LC, LNL, S1>(dctx, ws, rec, frow, isig2, qn, n, nl, !live && qn == 0);
             }
-        } while (bits);
-        if (!live) break;
-    }
-    if (!ld_ready) mbar_wait(&bar, 0);  // never exit with the bulk copy in flight
+            if (!live) break;
+        }
 
-    if (LNL) {
-        chi = warp_sum(chi);
-        if (lane == 0) s_red[warp] = chi;
-        __syncthreads();
-        if (tid == 0) {
-            double s = 0.0;
-            for (int wq = 0; wq < PT_WARPS; ++wq) s += s_red[wq];
-            P.partial[(size_t)ipv * P.nchunks + chunk] = s;
+        if (LNL) {
+            chi = warp_sum(chi);
+            if (lane == 0) P.partial[(size_t)ipv * P.nchunks + chunk] = chi;
+        }
+        __syncwarp();  // every lane is done with this record slot before its next refill is issued
+    }
+
+    // the last CTA to leave re-arms the work counters for the next launch
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const int done = atomicAdd(&P.work[1], 1);
+        if (done == (int)gridDim.x - 1) {
+            P.work[0] = 0;
+            P.work[1] = 0;
+            __threadfence();
         }
     }
 }

@@ -1,5 +1,4 @@
-set -x
-ncu --set full --clock-control none --import-source on -k regex:k_rr_points -s 3 -c 1 -o gpurun_out/prof_points_c2_v2 -f python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_rr_points -s 1 -c 1 -o gpurun_out/prof_points_c3_v2 -f python bench.py --steps 1 --warmup 1 --no-cpu --workload c3 > gpurun_out/ncu_full3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_rr_setup -s 3 -c 1 -o gpurun_out/prof_setup_c2_v2 -f python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full_s.log 2>&1
+mkdir -p gpurun_out
+ncu --set full --clock-control none --import-source on -k regex:k_rr_points -s 3 -c 1 -o gpurun_out/prof_points_c2 -f python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_rr_points -s 1 -c 1 -o gpurun_out/prof_points_c3 -f python bench.py --steps 1 --warmup 1 --no-cpu --workload c3 > gpurun_out/ncu_full3.log 2>&1
 ls -la gpurun_out
