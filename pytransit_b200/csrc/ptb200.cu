@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -748,11 +749,20 @@ int launch_points(ptb_model *h, int64_t npv, double *flux, const double *isig2, 
     const bool aligned = (h->npt % 2 == 0) && ((reinterpret_cast<uintptr_t>(h->d_time) & 15) == 0) &&
                          (lnl || (reinterpret_cast<uintptr_t>(flux) & 15) == 0);
     const int vec = aligned ? 2 : 1;
-    // Items: whole rows when the population alone fills the machine ~8 deep, otherwise rows are cut into
-    // chunks of whole 8-block groups (one group per warp and pass), at most PT_MAXBLK blocks each.
+    // Items: rows are cut into chunks of whole 8-block groups so that every warp of the persistent grid
+    // gets ~PT_ITEMS_PER_WARP items (a short tail), at least PT_MIN_ITEM_BLOCKS and at most PT_MAXBLK
+    // blocks each.
     const long long nb = h->nblk64;
-    const long long want = (long long)h->sm_count * 8;
-    long long nchunks = std::min<long long>((nb + 7) / 8, std::max<long long>(1, (want + npv - 1) / npv));
+    static const double items_per_warp = [] {
+        const char *e = getenv("PTB_ITEMS_PER_WARP");
+        return (e && atof(e) > 0) ? atof(e) : 8.0;
+    }();
+    static const long long min_item_blocks = [] {
+        const char *e = getenv("PTB_MIN_ITEM_BLOCKS");
+        return (long long)((e && atoi(e) > 0) ? atoi(e) : 16);
+    }();
+    const long long want = (long long)(h->sm_count * 3 * PT_WARPS * items_per_warp);
+    long long nchunks = std::min<long long>(std::max<long long>(1, nb / min_item_blocks), std::max<long long>(1, (want + npv - 1) / npv));
     nchunks = std::max<long long>(nchunks, (nb + PT_MAXBLK - 1) / PT_MAXBLK);
     long long bpc = (nb + nchunks - 1) / nchunks;
     bpc = std::min<long long>((bpc + 7) / 8 * 8, PT_MAXBLK);
