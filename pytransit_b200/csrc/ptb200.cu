@@ -110,6 +110,10 @@ struct ptb_model {
     DevBuf d_tsw, d_tsrec, d_sort;
     DevBuf d_rec, d_work;            // RoadRunner per-vector records; work counters of the persistent kernel
     int recstride = 0, rec_ld = 0;   // record stride / offset of the ld rows (doubles) of the last setup
+    cudaStream_t side_stream = nullptr;  // the orbit solve runs here, concurrently with the table contraction
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    size_t ldm_smem = 0;
+    bool keep_stages = true;         // write ldp / istar taps (ptb_get_stage); off in throughput runs
     int pt_occ[16] = {};  // resident CTAs per SM of each k_rr_points instantiation (0 = not queried)
     size_t pt_occ_smem[16] = {};
     bool xyc_injected = false;
@@ -371,6 +375,9 @@ void ptb_destroy(ptb_model *h) {
         b->release();
     h->h_stage.release();
     if (h->stage_ev) cudaEventDestroy(h->stage_ev);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
     for (auto &e : h->tev) if (e) cudaEventDestroy(e);
     h->tev.clear();
     delete h;
@@ -656,50 +663,66 @@ int launch_rr_setup(ptb_model *h, const ModelArgs &A, const Staged &D, cudaStrea
     CU(h->d_rec.reserve((size_t)npv * recstride * 8));
     CU(h->d_ldp.reserve((size_t)npv * npb * nz * 8));
     CU(h->d_istar.reserve((size_t)npv * npb * 8));
-    // sort workspace: bin[npv] | perm[npv] | hist[nk+2] | offsets[nk+2] | gstart[nk+2] | cursor[nk+2]
-    const size_t nb4 = ((size_t)nk + 2 + 3) & ~size_t(3);
-    const bool fresh = h->d_sort.cap < (2 * (size_t)npv + 4 * nb4) * 4;
-    CU(h->d_sort.reserve((2 * (size_t)npv + 4 * nb4) * 4));
-    int *bin = h->d_sort.as<int>(), *perm = bin + npv;
-    // the histogram lives at the END of the buffer so that it keeps its place when npv changes
-    int *hist = h->d_sort.as<int>() + h->d_sort.cap / 4 - 4 * nb4;
-    int *offsets = hist + nb4, *gstart = offsets + nb4, *cursor = gstart + nb4;
-    if (fresh) CU(cudaMemsetAsync(hist, 0, 4 * nb4 * 4, st));  // k_bin_scan re-zeroes it after every use
     if (h->xyc_injected && h->xyc_npv != npv)
         return fail(h, PTB_ESHAPE, "injected xyc has npv=%lld but evaluate was called with npv=%lld", (long long)h->xyc_npv, (long long)npv);
-    if (nk + 2 > 1024) return fail(h, PTB_EINVAL, "nk=%d: at most 1022 table rows are supported", nk);
+    if (nk + 2 > SORT_MAXBINS) return fail(h, PTB_EINVAL, "nk=%d: at most %d table rows are supported", nk, SORT_MAXBINS - 2);
 
+    // ---- orbit solve on the side stream (independent of the table contraction) ------------------------
+    if (!h->side_stream) {
+        CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    CU(cudaEventRecord(h->ev_fork, st));
+    CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
     OrbitParams O{};
     O.k = D.k; O.p = D.p; O.a = D.a; O.inc = D.inc; O.e = D.e; O.w = D.w;
     O.xyc_in = h->xyc_injected ? h->d_xyc.as<double>() : nullptr;
-    O.t0 = D.t0; O.rec = h->d_rec.as<double>(); O.bin = bin; O.hist = hist;
-    O.npv = (int)npv; O.kcols = (int)A.kcols; O.nk = nk; O.nep = (int)h->nep; O.recstride = (int)recstride; O.kmin = h->cfg.kmin; O.kmax = h->cfg.kmax; O.dk = h->dk;
-    k_rr_orbit<<<(unsigned)((npv * 8 + 255) / 256), 256, 0, st>>>(O);
+    O.t0 = D.t0; O.rec = h->d_rec.as<double>();
+    O.npv = (int)npv; O.kcols = (int)A.kcols; O.nep = (int)h->nep; O.recstride = (int)recstride;
+    k_rr_orbit<<<(unsigned)((npv * 8 + 255) / 256), 256, 0, h->side_stream>>>(O);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev_join, h->side_stream));
+
+    // ---- counting sort by table row + group descriptors (one cluster) ---------------------------------------
     // group size: as many vectors as fit ~32 KB of profiles, at most RR_GROUP
     const int grp = (int)std::max<int64_t>(1, std::min<int64_t>(RR_GROUP, (32 * 1024) / (npb * nz * 8)));
-    k_bin_scan<<<1, 256, 0, st>>>(hist, offsets, gstart, cursor, nk + 1, grp);
-    k_bin_scatter<<<(unsigned)((npv + 255) / 256), 256, 0, st>>>(bin, offsets, cursor, perm, (int)npv);
-    h->launches += 3;
+    const size_t ngroups_max = (size_t)((npv + grp - 1) / grp + nk + 1);  // every bin can end with a partial group
+    // sort workspace: gdesc[ngroups_max] int4 | perm[npv] | ngroups
+    CU(h->d_sort.reserve(ngroups_max * 16 + ((size_t)npv + 4) * 4));
+    int4 *gdesc = h->d_sort.as<int4>();
+    int *perm = reinterpret_cast<int *>(gdesc + ngroups_max);
+    int *ngroups = perm + npv;
+    SortParams SP{};
+    SP.k = D.k; SP.a = D.a; SP.e = D.e; SP.perm = perm; SP.gdesc = gdesc; SP.ngroups = ngroups;
+    SP.npv = (int)npv; SP.kcols = (int)A.kcols; SP.nk = nk; SP.grp = grp;
+    SP.kmin = h->cfg.kmin; SP.kmax = h->cfg.kmax; SP.dk = h->dk;
+    k_bin_sort<<<SORT_CTAS, SORT_THREADS, 0, st>>>(SP);  // one cluster
+    h->launches += 2;
     CU(cudaGetLastError());
 
     LdmParams P{};
     P.k = D.k; P.ld = D.ld; P.istar = D.istar;
     P.W = h->d_W.as<double>(); P.ze = h->d_ze; P.mu = h->d_mu; P.gs = h->d_gs; P.ldmu200 = h->d_ldmu; P.ldz200 = h->d_ldz;
-    P.offsets = offsets; P.gstart = gstart; P.perm = perm;
-    P.rec = h->d_rec.as<double>(); P.ldp_out = h->d_ldp.as<double>();
+    P.perm = perm; P.ngroups = ngroups; P.gdesc = gdesc;
+    P.rec = h->d_rec.as<double>(); P.ldp_out = h->keep_stages ? h->d_ldp.as<double>() : nullptr;
     P.recstride = (int)recstride; P.rec_ld = rec_ld;
-    P.istar_out = h->d_istar.as<double>();
+    P.istar_out = h->keep_stages ? h->d_istar.as<double>() : nullptr;
     P.npv = (int)npv; P.kcols = (int)A.kcols; P.npb = (int)npb; P.nld = (int)A.nld; P.law = h->cfg.ldlaw;
     P.nk = nk; P.ng = ng; P.nz = nz; P.lds = lds; P.grp = grp;
     P.kmin = h->cfg.kmin; P.dk = h->dk;
-    const size_t smem = (2 * (size_t)ng * nz + (size_t)grp * npb * nz + grp * npb + 2 * (size_t)grp * ng + 8 * 200) * 8 + 16;
+    static const bool analytic[] = {true, true, true, true, false, false, false, false, false, true, false};
+    P.numeric_istar = (h->cfg.ldlaw != PTB_LD_PROFILES && !analytic[h->cfg.ldlaw]) ? 1 : 0;
+    const size_t smem = (2 * (size_t)ng * nz + (size_t)grp * npb * nz + grp * npb + (P.numeric_istar ? 8 * 200 : 0)) * 8 + 16;
     if (smem > 227 * 1024) return fail(h, PTB_EINVAL, "k_rr_ldm needs %zu bytes of shared memory (> 227 KB): too many passbands", smem);
-    CU(cudaFuncSetAttribute(k_rr_ldm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // upper bound on the number of groups: every bin can end with one partial group
-    const unsigned grid = (unsigned)((npv + grp - 1) / grp + nk + 1);
-    k_rr_ldm<<<grid, 256, smem, st>>>(P);
+    if (smem != h->ldm_smem) {
+        CU(cudaFuncSetAttribute(k_rr_ldm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->ldm_smem = smem;
+    }
+    k_rr_ldm<<<(unsigned)ngroups_max, 256, smem, st>>>(P);
     h->launches++;
     CU(cudaGetLastError());
+    CU(cudaStreamWaitEvent(st, h->ev_join, 0));  // records complete: orbit part (side stream) + ld part
     h->last_npv = npv;
     h->last_npb = npb;
     return PTB_OK;
@@ -928,9 +951,14 @@ int ptb_get_stage(ptb_model *h, int32_t stage, double *out) {
     case PTB_STAGE_BBOX:
         CU(cudaMemcpy2D(out, 16, h->d_rec.as<double>() + ORB_T1, (size_t)h->recstride * 8, 16, npv, kind));
         break;
-    case PTB_STAGE_GOOD:
-        CU(cudaMemcpy2D(out, 8, h->d_rec.as<double>() + ORB_GOOD, (size_t)h->recstride * 8, 8, npv, kind));
+    case PTB_STAGE_GOOD: {  // valid orbit/geometry (k_rr_orbit) and a non-NaN limb-darkening profile (k_rr_ldm)
+        std::vector<double> g(npv), l(npv);
+        CU(cudaMemcpy2D(g.data(), 8, h->d_rec.as<double>() + ORB_GOOD, (size_t)h->recstride * 8, 8, npv, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy2D(l.data(), 8, h->d_rec.as<double>() + ORB_LDNAN, (size_t)h->recstride * 8, 8, npv, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < npv; ++i) g[i] = (g[i] != 0.0 && !(l[i] != 0.0)) ? 1.0 : 0.0;
+        CU(cudaMemcpy(out, g.data(), npv * 8, kind));
         break;
+    }
     default: return fail(h, PTB_EINVAL, "get_stage: unknown stage %d", stage);
     }
     return PTB_OK;

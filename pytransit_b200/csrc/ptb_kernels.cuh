@@ -2,7 +2,7 @@
 //
 //   k_weight_table   W[nk,ng,nz]  (common.py:188-223)                         once per model
 //   k_rr_orbit       per-vector Taylor orbit coefficients + contact times       \
-//   k_bin_scan/scatter  counting sort of the vectors by weight-table row          > once per evaluate
+//   k_bin_sort       counting sort of the vectors by weight-table row            > once per evaluate
 //   k_rr_ldm         LD profile, I*, LD means (TMA-staged table rows shared      /  (model_full.py:39-70)
 //                    by the vectors of a group)
 //   k_rr_points      the npv x npt pass: phase fold, box test, supersampled flux, optional fused
@@ -17,6 +17,8 @@
 //                               ld[npb][lds]    ldm[ng] | k 1/(1+k) 1/I* k^2 | pad   (lds = ng+4, even)
 //   flux [npv][npt]           row-major, written with 16-byte stores
 #pragma once
+#include <cooperative_groups.h>
+
 #include "ptb_math.cuh"
 
 namespace ptb {
@@ -53,22 +55,23 @@ __global__ void k_weight_table(const double *__restrict__ ks, const double *__re
 }
 
 // ---------------------------------------------------------------------------------------------
-// Per-vector setup (model_full.py:39-70), four launches:
+// Per-vector setup (model_full.py:39-70), three launches on two streams:
 //
-//   k_rr_orbit    8 lanes per vector: validity, the 7 Kepler solves of the Taylor stencil (one per lane),
-//                 coefficients from sub-warp shuffles, T1/T4 bisection on two lanes; also the weight-table
-//                 row `ik` of the vector and a histogram of the rows in use.
-//   k_bin_scan    one CTA: prefix sums of the histogram -> where each table row's vectors and its
-//                 groups of up to RR_GROUP vectors start.
-//   k_bin_scatter counting-sort scatter: vectors ordered by table row.
-//   k_rr_ldm      one CTA per group of vectors that share a table row pair: the two rows W[ik], W[ik+1]
-//                 (ng*nz*8 bytes each) arrive in shared memory through ONE pair of TMA bulk copies per
-//                 group instead of one per vector, overlapped with the limb-darkening profile evaluation;
-//                 then the (ng x nz).(nz) contractions, register-blocked over the group's vectors.
-// Sorting by table row cuts the L2 -> SM traffic of the contraction by the group size and removes the
-// serial orbit solve from the critical path of the table staging.
+//   k_rr_orbit    (side stream) 8 lanes per vector: validity, the 7 Kepler solves of the Taylor stencil
+//                 (one per lane), coefficients from sub-warp shuffles, T1/T4 bisection on two lanes;
+//                 copies the transit centres into the record.
+//   k_bin_sort    one CTA: weight-table row `ik` of every vector, counting sort of the vectors by row
+//                 (shared-memory histogram, scan, scatter) and one descriptor per group of up to
+//                 RR_GROUP vectors that share a row pair.
+//   k_rr_ldm      one CTA per group: the two rows W[ik], W[ik+1] (ng*nz*8 bytes each) arrive in shared
+//                 memory through ONE pair of TMA bulk copies per group instead of one per vector,
+//                 overlapped with the limb-darkening profile evaluation; then the (ng x nz).(nz)
+//                 contractions, register-blocked over the group's vectors and both table rows.
+// Sorting by table row cuts the L2 -> SM traffic of the contraction by the group size; the orbit solve
+// (latency-bound fp64 chains) runs concurrently with the table staging and the contraction.
 // ---------------------------------------------------------------------------------------------
 constexpr int RR_GROUP = 8;  // vectors per k_rr_ldm CTA (register blocking factor)
+constexpr int ORB_LDNAN = 15;  // record slot: 1.0 when the limb-darkening profile is NaN (model_full.py:40)
 
 template <int WIDTH>
 __device__ __forceinline__ void solve_orbit_lanes(int sl, bool valid, double p, double a, double inc, double e, double w,
@@ -104,7 +107,6 @@ __device__ __forceinline__ void solve_orbit_lanes(int sl, bool valid, double p, 
         orb_out[ORB_T1] = t1;
         orb_out[ORB_T4] = t4;
         orb_out[ORB_GOOD] = 1.0;
-        orb_out[15] = 0.0;
     }
 }
 
@@ -120,10 +122,7 @@ struct OrbitParams {
     const double *xyc_in;  // optional injected coefficients [npv][10]
     const double *t0;      // [npv][nep]
     double *rec;           // per-vector records (orb at offset 0, t0 at ORB_STRIDE)
-    int *bin;   // [npv]  table row ik, nk = direct weights, nk+1 = invalid vector
-    int *hist;  // [nk+2]
-    int npv, kcols, nk, nep, recstride;
-    double kmin, kmax, dk;
+    int npv, kcols, nep, recstride;
 };
 
 __global__ void __launch_bounds__(256) k_rr_orbit(const __grid_constant__ OrbitParams P) {
@@ -139,55 +138,132 @@ __global__ void __launch_bounds__(256) k_rr_orbit(const __grid_constant__ OrbitP
         inc = P.inc[ipv];
         w = P.w[ipv];
     }
-    const bool good0 = inr && !(isnan(a) || (a <= 1.0) || (e < 0.0));  // model_full.py:40 (ldp checked later)
+    const bool good0 = inr && !(isnan(a) || (a <= 1.0) || (e < 0.0));  // model_full.py:40 (ldp checked in k_rr_ldm)
     double *orb = P.rec + (size_t)(inr ? ipv : 0) * P.recstride;
     solve_orbit_lanes<8>(sl, good0, p, a, inc, e, w, k0, (P.xyc_in && inr) ? P.xyc_in + (size_t)ipv * 10 : nullptr, orb);
     if (inr) {  // transit centres travel with the record (one TMA bulk copy per vector in k_rr_points)
         for (int j = sl; j < P.nep; j += 8) orb[ORB_STRIDE + j] = P.t0[(size_t)ipv * P.nep + j];
         if (sl == 0 && (P.nep & 1)) orb[ORB_STRIDE + P.nep] = 0.0;
-    }
-    if (inr && sl == 0) {
-        int bin = P.nk + 1;
-        if (good0) {
-            if ((P.kmin <= k0) && (k0 <= P.kmax)) bin = min((int)floor((k0 - P.kmin) / P.dk), P.nk - 1);
-            else bin = P.nk;
-        } else {
-            for (int j = 0; j < ORB_STRIDE; ++j) orb[j] = (j == ORB_GOOD) ? 0.0 : nan("");
+        if (sl == 0 && !good0) {
+            for (int j = 0; j < ORB_LDNAN; ++j) orb[j] = (j == ORB_GOOD) ? 0.0 : nan("");
         }
-        P.bin[ipv] = bin;
-        atomicAdd(&P.hist[bin], 1);
     }
 }
 
-// offsets[b] = first slot of bin b in `perm`; gstart[b] = first group of bin b; gstart[nk+1] = group count.
-__global__ void __launch_bounds__(256) k_bin_scan(int *hist, int *offsets, int *gstart, int *cursor, int nbins_valid, int grp) {
-    __shared__ int s_cnt[1024 + 8];
-    const int n = nbins_valid;  // nk + 1 bins carry work (table rows + direct); the invalid bin is last
-    for (int i = threadIdx.x; i < n + 1; i += 256) s_cnt[i] = hist[i];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int off = 0, g = 0;
-        for (int i = 0; i < n; ++i) {
-            offsets[i] = off;
-            gstart[i] = g;
-            off += s_cnt[i];
-            g += (s_cnt[i] + grp - 1) / grp;
-        }
-        offsets[n] = off;  // the invalid bin: listed after all work, never grouped
-        gstart[n] = g;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n + 1; i += 256) {
-        cursor[i] = 0;
-        hist[i] = 0;  // ready for the next call; counts live on in offsets[]
-    }
+// Counting sort of the vectors by weight-table row + group descriptors: ONE thread-block cluster of
+// SORT_CTAS CTAs.  Every CTA histograms its share of the vectors in its own shared memory; after a
+// cluster barrier each CTA reads its peers' histograms through distributed shared memory to get the
+// bin totals and its own start slot inside every bin, scans the totals, and scatters its vectors.
+//   bin = table row ik, nk = direct weights (k outside the table), nk+1 = invalid vector (never grouped)
+//   perm[npv]   vectors ordered by bin
+//   gdesc[g]    (bin, first slot in perm, count, -) for every group; *ngroups = number of groups
+struct SortParams {
+    const double *k, *a, *e;
+    int *perm;
+    int4 *gdesc;
+    int *ngroups;
+    int npv, kcols, nk, grp;
+    double kmin, kmax, dk;
+};
+
+constexpr int SORT_THREADS = 1024;
+constexpr int SORT_CTAS = 8;        // cluster size (portable maximum)
+constexpr int SORT_CACHE = 4;       // bins kept in registers per thread (covers npv <= 32768 without recomputation)
+constexpr int SORT_MAXBINS = 1024;  // nk + 2 <= SORT_MAXBINS
+
+__device__ __forceinline__ int table_bin(const SortParams &P, int ipv) {
+    const double a = P.a[ipv], e = P.e[ipv], k0 = P.k[(size_t)ipv * P.kcols];
+    if (isnan(a) || (a <= 1.0) || (e < 0.0)) return P.nk + 1;
+    if ((P.kmin <= k0) && (k0 <= P.kmax)) return min((int)floor((k0 - P.kmin) / P.dk), P.nk - 1);
+    return P.nk;
 }
 
-__global__ void k_bin_scatter(const int *__restrict__ bin, const int *__restrict__ offsets, int *cursor, int *perm, int npv) {
-    const int ipv = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ipv >= npv) return;
-    const int b = bin[ipv];
-    perm[offsets[b] + atomicAdd(&cursor[b], 1)] = ipv;
+__global__ void __cluster_dims__(SORT_CTAS, 1, 1) __launch_bounds__(SORT_THREADS) k_bin_sort(const __grid_constant__ SortParams P) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ int s_cnt[SORT_MAXBINS];      // this CTA's histogram (read by the peers)
+    __shared__ int s_tot[SORT_MAXBINS];      // bin totals over the cluster
+    __shared__ int s_base[SORT_MAXBINS];     // first slot of this CTA's vectors inside each bin
+    __shared__ int s_off[SORT_MAXBINS + 1], s_gst[SORT_MAXBINS + 1], s_cur[SORT_MAXBINS];
+    __shared__ int s_wsum[32], s_wsum_g[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = (int)cluster.block_rank();
+    const int gtid = rank * SORT_THREADS + tid, gthreads = SORT_CTAS * SORT_THREADS;
+    const int nb = P.nk + 1;  // bins that carry work; the invalid bin nk+1 is listed last and never grouped
+    for (int i = tid; i < nb + 1; i += SORT_THREADS) { s_cnt[i] = 0; s_cur[i] = 0; }
+    __syncthreads();
+    int cache[SORT_CACHE];
+#pragma unroll
+    for (int u = 0; u < SORT_CACHE; ++u) {
+        const int i = gtid + u * gthreads;
+        cache[u] = (i < P.npv) ? table_bin(P, i) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < SORT_CACHE; ++u)
+        if (cache[u] >= 0) atomicAdd(&s_cnt[cache[u]], 1);
+    for (int i = gtid + SORT_CACHE * gthreads; i < P.npv; i += gthreads) atomicAdd(&s_cnt[table_bin(P, i)], 1);
+    cluster.sync();
+
+    // bin totals and this CTA's start inside each bin (peers' histograms through DSMEM)
+    int c = 0, mine = 0;
+    if (tid < nb + 1) {
+#pragma unroll
+        for (int r = 0; r < SORT_CTAS; ++r) {
+            const int v = cluster.map_shared_rank(s_cnt, r)[tid];
+            if (r < rank) mine += v;
+            c += v;
+        }
+        s_tot[tid] = c;
+    }
+    // exclusive scans of the totals (slots) and of the group counts; nb + 1 <= 1024 entries, one per thread
+    {
+        const int g = (tid < nb) ? (c + P.grp - 1) / P.grp : 0;
+        int ic = c, ig = g;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, ic, o), u = __shfl_up_sync(0xffffffffu, ig, o);
+            if (lane >= o) { ic += t; ig += u; }
+        }
+        if (lane == 31) { s_wsum[warp] = ic; s_wsum_g[warp] = ig; }
+        __syncthreads();
+        if (warp == 0) {
+            int wc = s_wsum[lane], wg = s_wsum_g[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wc, o), u = __shfl_up_sync(0xffffffffu, wg, o);
+                if (lane >= o) { wc += t; wg += u; }
+            }
+            s_wsum[lane] = wc;
+            s_wsum_g[lane] = wg;
+        }
+        __syncthreads();
+        const int basec = warp ? s_wsum[warp - 1] : 0, baseg = warp ? s_wsum_g[warp - 1] : 0;
+        if (tid < nb + 1) {
+            s_off[tid] = basec + ic - c;
+            s_base[tid] = basec + ic - c + mine;
+            s_gst[tid] = baseg + ig - g;
+        }
+        if (tid == nb && rank == 0) *P.ngroups = baseg + ig - g;  // groups of the bins 0..nb-1
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < SORT_CACHE; ++u)
+        if (cache[u] >= 0) P.perm[s_base[cache[u]] + atomicAdd(&s_cur[cache[u]], 1)] = gtid + u * gthreads;
+    for (int i = gtid + SORT_CACHE * gthreads; i < P.npv; i += gthreads) {
+        const int b = table_bin(P, i);
+        P.perm[s_base[b] + atomicAdd(&s_cur[b], 1)] = i;
+    }
+    const int ngroups = s_gst[nb];
+    for (int g = gtid; g < ngroups; g += gthreads) {
+        int lo = 0, hi = nb;  // last bin with s_gst[bin] <= g (an empty bin shares its successor's start, so
+        while (hi - lo > 1) {  //  the search lands on the non-empty one that owns the group)
+            const int mid = (lo + hi) >> 1;
+            if (s_gst[mid] <= g) lo = mid; else hi = mid;
+        }
+        const int j = g - s_gst[lo];
+        P.gdesc[g] = make_int4(lo, s_off[lo] + j * P.grp, min(P.grp, s_tot[lo] - j * P.grp), 0);
+    }
+    cluster.sync();  // no CTA leaves while a peer may still read its histogram
 }
 
 // I* by the reference's numeric fallback, 2 pi trapezoid(z I(mu(z)), z) on 200 nodes
@@ -203,69 +279,56 @@ __device__ __forceinline__ double istar_numeric_warp(int lane, int law, const do
     return 2.0 * kPi * warp_sum(s);
 }
 
+// fp64 tensor-core MMA (DMMA): D[8x8] += A[8x4] . B[4x8]; lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4)+{0,1}]
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
 struct LdmParams {
     const double *k;      // [npv][kcols]
     const double *ld;     // ldc[npv][npb][nld] or ldp[npv][npb][nz]
     const double *istar;  // [npv][npb] (profiles only)
     const double *W, *ze, *mu, *gs, *ldmu200, *ldz200;
-    const int *offsets, *gstart, *perm;
+    const int *perm, *ngroups;
+    const int4 *gdesc;
     double *rec, *ldp_out, *istar_out;
     int npv, kcols, npb, nld, law, nk, ng, nz, lds, grp;  // grp <= RR_GROUP vectors per CTA
     int recstride, rec_ld;                                // record stride / offset of the ld rows (doubles)
+    int numeric_istar;                                    // the law has no analytic disk integral
     double kmin, dk;
 };
 
 __global__ void __launch_bounds__(256) k_rr_ldm(const __grid_constant__ LdmParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ int s_bin, s_first, s_cnt;
     __shared__ int s_pv[RR_GROUP];
     __shared__ double s_ak[RR_GROUP];
+    __shared__ __align__(8) uint64_t bar;
     const int ng = P.ng, nz = P.nz, npb = P.npb;
     const int rowlen = ng * nz;
     double *sW = reinterpret_cast<double *>(smem_raw);       // [2][ng][nz]
     double *sLdp = sW + 2 * rowlen;                           // [grp][npb][nz]
     double *sIstar = sLdp + (size_t)P.grp * npb * nz;         // [grp][npb]
-    double *sOut = sIstar + P.grp * npb;                      // [2][grp][ng] partial contractions
-    double *sScr = sOut + 2 * P.grp * ng;                     // [8][200] trapezoid scratch
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sScr + 8 * 200);
+    double *sScr = sIstar + P.grp * npb;                      // [8][200] trapezoid scratch (numeric I* only)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nbins = P.nk + 1;
-    if (tid == 0) {
-        // which bin does this group belong to?  (binary search over the group starts)
-        const int g = blockIdx.x;
-        int lo = 0, hi = nbins;  // gstart[nbins] = total number of groups
-        if (g >= P.gstart[nbins]) {
-            s_bin = -1;
-        } else {
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (P.gstart[mid] <= g) lo = mid; else hi = mid;
-            }
-            // skip empty bins that share the same start
-            while (lo + 1 < nbins && P.gstart[lo + 1] <= g) ++lo;
-            s_bin = lo;
-            const int j = g - P.gstart[lo];
-            const int cnt = P.offsets[lo + 1] - P.offsets[lo];
-            s_first = P.offsets[lo] + j * P.grp;
-            s_cnt = min(P.grp, cnt - j * P.grp);
-        }
-        mbar_init(bar, 1);
-    }
-    __syncthreads();
-    const int bin = s_bin;
-    if (bin < 0) return;
-    const int cnt = s_cnt;
+    if ((int)blockIdx.x >= *P.ngroups) return;
+    const int4 gd = P.gdesc[blockIdx.x];
+    const int bin = gd.x, first = gd.y, cnt = gd.z;
     const bool in_table = bin < P.nk;
-    if (in_table && tid == 0) {
-        const int ik1 = min(bin + 1, P.nk - 1);  // the reference reads weights[nk] here
-        const uint32_t bytes = (uint32_t)rowlen * 8u;
-        mbar_expect_tx(bar, 2u * bytes);
-        tma_load_1d(sW, P.W + (size_t)bin * rowlen, bytes, bar);
-        tma_load_1d(sW + rowlen, P.W + (size_t)ik1 * rowlen, bytes, bar);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        if (in_table) {
+            const int ik1 = min(bin + 1, P.nk - 1);  // the reference reads weights[nk] here
+            const uint32_t bytes = (uint32_t)rowlen * 8u;
+            mbar_expect_tx(&bar, 2u * bytes);
+            tma_load_1d(sW, P.W + (size_t)bin * rowlen, bytes, &bar);
+            tma_load_1d(sW + rowlen, P.W + (size_t)ik1 * rowlen, bytes, &bar);
+        }
     }
     if (tid < cnt) {
-        const int ipv = P.perm[s_first + tid];
+        const int ipv = P.perm[first + tid];
         s_pv[tid] = ipv;
         const double k0 = P.k[(size_t)ipv * P.kcols];
         const int ikraw = (int)floor((k0 - P.kmin) / P.dk);
@@ -302,53 +365,57 @@ __global__ void __launch_bounds__(256) k_rr_ldm(const __grid_constant__ LdmParam
         }
     }
     __syncthreads();
-    // isnan(ldp[ipv,0,0]) invalidates the vector (model_full.py:40)
-    if (tid < cnt && isnan(sLdp[(size_t)tid * npb * nz])) P.rec[(size_t)s_pv[tid] * P.recstride + ORB_GOOD] = 0.0;
+    // isnan(ldp[ipv,0,0]) invalidates the vector (model_full.py:40); k_rr_orbit owns ORB_GOOD, this flag is ours
+    if (tid < cnt) P.rec[(size_t)s_pv[tid] * P.recstride + ORB_LDNAN] = isnan(sLdp[(size_t)tid * npb * nz]) ? 1.0 : 0.0;
 
-    if (in_table) mbar_wait(bar, 0);  // every thread observes the TMA completion
-
-    const int t = tid >> 7, ig0 = tid & 127;  // thread = (table row pair member, g index)
-    for (int q0 = 0; q0 < cnt; q0 += (in_table ? cnt : 1)) {
-        const int nq = in_table ? cnt : 1;
-        if (!in_table) {
-            // direct weights for this radius ratio (calculate_weights_2d, common.py:152-185), one vector at a time
-            __syncthreads();
-            const double k0 = P.k[(size_t)s_pv[q0] * P.kcols];
-            for (int ig = tid; ig < ng; ig += 256) weight_row(k0, P.gs[ig], P.ze, nz, sW + (size_t)ig * nz, 1);
-            __syncthreads();
+    // Contraction ldm[q, ig] = sum_iz ldp[q, iz] W[ig, iz] on the fp64 tensor-core path: the group's (up to)
+    // 8 vectors are the M = 8 rows of mma.sync.m8n8k4, a tile of 8 g-nodes the N = 8 columns, the mu nodes K.
+    // A warp takes (passband, g-tile) jobs and accumulates both table rows of the pair.
+    const int fr = lane >> 2, fc = lane & 3;  // fragment row (vector / g-node) and k index of this lane
+    if (in_table) {
+        mbar_wait(&bar, 0);  // every thread observes the TMA completion
+        const int ksteps = (nz + 3) >> 2, ntiles = (ng + 7) >> 3;
+        const int qa = min(fr, P.grp - 1);  // rows beyond the group alias the last one: computed, never stored
+        for (int job = warp; job < npb * ntiles; job += 8) {
+            const int pb = job / ntiles, ig0 = (job - pb * ntiles) * 8;
+            const double *ap = sLdp + ((size_t)qa * npb + pb) * nz + fc;
+            const double *bp = sW + (size_t)min(ig0 + fr, ng - 1) * nz + fc;
+            double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll 5
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const bool inz = ks * 4 + fc < nz;
+                const double av = inz ? ap[ks * 4] : 0.0;
+                const double b0 = inz ? bp[ks * 4] : 0.0, b1 = inz ? bp[rowlen + ks * 4] : 0.0;
+                dmma_m8n8k4(c00, c01, av, b0);
+                dmma_m8n8k4(c10, c11, av, b1);
+            }
+            const int ig = ig0 + fc * 2;
+            if (fr < cnt && ig < ng) {
+                const double ak = s_ak[fr];
+                double *out = P.rec + (size_t)s_pv[fr] * P.recstride + P.rec_ld + (size_t)pb * P.lds + ig;
+                const double v0 = (1.0 - ak) * c00 + ak * c10;
+                if (ig + 1 < ng) *reinterpret_cast<double2 *>(out) = make_double2(v0, (1.0 - ak) * c01 + ak * c11);
+                else out[0] = v0;
+            }
         }
-        for (int pb = 0; pb < npb; ++pb) {
-            for (int ig = ig0; ig < ng; ig += 128) {
-                if (t == 0 || in_table) {
-                    const double *wr = sW + (size_t)t * rowlen + (size_t)ig * nz;
-                    double acc[RR_GROUP];
-#pragma unroll
-                    for (int q = 0; q < RR_GROUP; ++q) acc[q] = 0.0;
-                    int iz = ig % nz;  // rotated start: the lanes of a warp hit distinct banks
-                    for (int j = 0; j < nz; ++j) {
-                        const double wv = wr[iz];
-#pragma unroll
-                        for (int q = 0; q < RR_GROUP; ++q)
-                            if (q < nq) acc[q] = fma(wv, sLdp[((size_t)(q0 + q) * npb + pb) * nz + iz], acc[q]);
-                        iz = (iz + 1 == nz) ? 0 : iz + 1;
-                    }
-#pragma unroll
-                    for (int q = 0; q < RR_GROUP; ++q)
-                        if (q < nq) sOut[((size_t)t * P.grp + q) * ng + ig] = acc[q];
-                }
-            }
+    } else {
+        // direct weights for this radius ratio (calculate_weights_2d, common.py:152-185), one vector at a time
+        for (int q = 0; q < cnt; ++q) {
             __syncthreads();
-            for (int idx = tid; idx < nq * ng; idx += 256) {
-                const int q = idx / ng, ig = idx - q * ng;
-                const int ipv = s_pv[q0 + q];
-                double v = sOut[(size_t)q * ng + ig];
-                if (in_table) {
-                    const double ak = s_ak[q0 + q];
-                    v = (1.0 - ak) * v + ak * sOut[((size_t)P.grp + q) * ng + ig];
-                }
-                P.rec[(size_t)ipv * P.recstride + P.rec_ld + (size_t)pb * P.lds + ig] = v;
-            }
+            const double k0 = P.k[(size_t)s_pv[q] * P.kcols];
+            for (int g = tid; g < ng; g += 256) weight_row(k0, P.gs[g], P.ze, nz, sW + (size_t)g * nz, 1);
             __syncthreads();
+            for (int idx = tid; idx < npb * ng; idx += 256) {
+                const int pb = idx / ng, g = idx - pb * ng;
+                const double *wr = sW + (size_t)g * nz, *lp = sLdp + ((size_t)q * npb + pb) * nz;
+                double acc = 0.0;
+                int iz = g % nz;
+                for (int j = 0; j < nz; ++j) {
+                    acc = fma(wr[iz], lp[iz], acc);
+                    iz = (iz + 1 == nz) ? 0 : iz + 1;
+                }
+                P.rec[(size_t)s_pv[q] * P.recstride + P.rec_ld + (size_t)pb * P.lds + g] = acc;
+            }
         }
     }
     for (int r = tid; r < cnt * npb; r += 256) {
@@ -718,7 +785,7 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
         double chi = 0.0;
 
         mbar_wait(&bar[buf], (iter >> 1) & 1);
-        if (rec[ORB_GOOD] == 0.0) {  // invalid parameter vector: NaN row (model_full.py:80-82)
+        if (rec[ORB_GOOD] == 0.0 || rec[ORB_LDNAN] != 0.0) {  // invalid parameter vector: NaN row (model_full.py:40,80-82)
             if (LNL) {
                 if (lane == 0) P.partial[(size_t)ipv * P.nchunks + chunk] = nan("");
             } else {

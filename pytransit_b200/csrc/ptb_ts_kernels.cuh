@@ -131,12 +131,6 @@ struct TsLdmParams {
 
 constexpr int TSL_PB = 64;
 
-__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
 template <int NT>  // NT = number of 8-wide ig tiles (ldt/8), compile-time for register blocking
 __global__ void __launch_bounds__(256) k_ts_ldm(const __grid_constant__ TsLdmParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
