@@ -531,6 +531,7 @@ template <>
 struct VecIO<1> {
     __device__ static __forceinline__ void load(const double *p, double *v) { v[0] = __ldg(p); }
     __device__ static __forceinline__ void store(double *p, const double *v) { __stcs(p, v[0]); }
+    __device__ static __forceinline__ void store_keep(double *p, const double *v) { *p = v[0]; }
 };
 template <>
 struct VecIO<2> {
@@ -541,6 +542,9 @@ struct VecIO<2> {
     }
     __device__ static __forceinline__ void store(double *p, const double *v) {
         __stcs(reinterpret_cast<double2 *>(p), make_double2(v[0], v[1]));
+    }
+    __device__ static __forceinline__ void store_keep(double *p, const double *v) {
+        *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
     }
 };
 
@@ -829,6 +833,8 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
         __syncwarp();
 
         // ---- 2. untouched blocks: 64 fluxes of exactly 1.0, 16-byte streaming stores ---------------------
+        // (TMA bulk stores out of a constant shared-memory buffer were measured: same kernel time, and the
+        //  16 KB buffer costs the supersampled variants a resident CTA -- DESIGN.md section 3.1)
         if (!LNL) {
             double one[VEC];
 #pragma unroll
@@ -940,7 +946,9 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
                         }
                         qn += __popc(m);
                     }
-                    if (!LNL && inr) VecIO<VEC>::store(frow + i0, fv);
+                    // default cache policy (not evict-first): the line is still in L2 when the drain updates its
+                    // in-box points, so it reaches DRAM once
+                    if (!LNL && inr) VecIO<VEC>::store_keep(frow + i0, fv);
                 }
                 __syncwarp();
             }
