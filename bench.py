@@ -56,6 +56,13 @@ def workload(name: str, rank: int = 0):
     elif name == 'c5':
         c = wl.config5(npv=8192, seed=5 + seed_shift)
         desc = "C5 shard: eccentric 'power-2' npv=8192 x npt=100000 + fused Gaussian lnL"
+    elif name == 'c4':
+        c = wl.config4(seed=4 + seed_shift)
+        desc = "C4: TSModel, tabulated (LDTk-style) profiles, npv=1024 x npb=1000 channels x npt=2000"
+    elif name == 'c1':
+        c = wl.config1()
+        c.npv, c.npt = 1, c.time.size
+        desc = "C1: RoadRunnerModel('quadratic') README example, npv=1 x npt=10000 (latency bound)"
     else:
         raise SystemExit(f'unknown workload {name}')
     return c, desc
@@ -119,6 +126,18 @@ class ClockSampler(threading.Thread):
 def oracle_step(orc, tab, c, rows, lnl: bool):
     sl = slice(0, rows)
     law = c.ldmodel
+    if c.name == 'C4':
+        prof, (x0, dx), (y0, dy), (z0, dz) = c.table
+        ldp, istar = orc.ldtk_profiles(prof, c.teff[sl], c.logg[sl], c.metal[sl], x0, dx, y0, dy, z0, dz, tab.mu)
+        orc.tsmodel(tab, c.time, c.k[sl], c.t0[sl], c.p[sl], c.a[sl], c.i[sl], c.e[sl], c.w[sl], 1, 0.0, ldp, istar)
+        return rows * c.npb * c.npt
+    if c.name == 'C1':
+        ldp, istar = orc.evaluate_ld(law, tab.mu, np.asarray(c.ldc).reshape(1, 1, -1))
+        one = lambda v: np.full(1, float(v))
+        orc.rr_full(tab, c.time, np.full((1, 1), c.k), np.full((1, 1), c.t0), one(c.p), one(c.a), one(c.i), one(c.e), one(c.w),
+                    np.zeros(c.npt, np.int64), np.zeros(1, np.int64), np.zeros(1, np.int64), np.ones(1, np.int64), np.zeros(1),
+                    ldp, istar)
+        return c.npt
     ldp, istar = orc.evaluate_ld(law, tab.mu, c.ldc[sl])
     flux = orc.rr_full(tab, c.time, c.k[sl], c.t0[sl], c.p[sl], c.a[sl], c.i[sl], c.e[sl], c.w[sl], c.lcids, c.pbids,
                        c.epids, c.nsamples, c.exptimes, ldp, istar)
@@ -146,7 +165,7 @@ def cpu_sample_rows(orc, tab, c, lnl, target_s: float):
     dt = max(time.perf_counter() - t, 1e-4)
     rows = int(min(c.npv, max(rows, rows * target_s / dt)))
     # keep the sampled flux array below ~2 GB
-    return max(1, min(rows, int(2e9 // (8 * c.npt))))
+    return max(1, min(rows, int(2e9 // (8 * c.npt * getattr(c, 'npb_out', 1)))))
 
 
 def run_reference(args, rank: int, world: int):
@@ -156,6 +175,8 @@ def run_reference(args, rank: int, world: int):
     orc.lib()
     tab = orc.Tables()
     c, desc = workload(args.workload)
+    if args.workload == 'c4':
+        c.table, c.npb_out = wl.ldtk_style_table(c.npb, tab.mu), c.npb
     lnl = args.workload == 'c5'
     cores = host_threads(orc)
     budget = 120.0 / max(1, args.steps + args.warmup)          # whole run within a few minutes
@@ -168,7 +189,7 @@ def run_reference(args, rank: int, world: int):
         pts += oracle_step(orc, tab, c, rows, lnl)
     dt = time.perf_counter() - t
     value = pts / dt
-    sample = f'{rows} of {c.npv} parameter vectors x {c.npt} points per step (rows 0..{rows - 1} of the same seeded workload)'
+    sample = f'{rows} of {c.npv} parameter vectors x {pts // (rows * args.steps)} points per step (rows 0..{rows - 1} of the same seeded workload)'
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
@@ -195,19 +216,44 @@ def measured_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def run_ours(args, rank: int, world: int, local_rank: int):
+def make_steps(args, c, dev, local_rank, world, dist):
+    """Build the model for the workload and return (model, step_device, step_host, pts_per_step, h2d_bytes, kernel name,
+    algorithmic bytes of the dominant kernel per launch or None)."""
     import torch
-    import torch.distributed as dist
-    from pytransit_b200 import RoadRunnerModelCUDA
+    import pytransit_b200 as pb
+    name = args.workload
+    if name == 'c4':
+        m = pb.TSModelCUDA(pb.TabulatedLDModel(*_table_args(c), device=local_rank), device=local_rank)
+        time_d = torch.as_tensor(c.time, device=dev)
+        m.set_data(time_d)
+        x = np.column_stack([c.teff, c.logg, c.metal])
+        td = {k: torch.as_tensor(np.ascontiguousarray(getattr(c, k)), device=dev) for k in ('k', 't0', 'p', 'a', 'i', 'e', 'w')}
+        pts = c.npv * c.npb * c.npt
 
-    torch.cuda.set_device(local_rank)
-    dev = f'cuda:{local_rank}'
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device(dev))
+        def step_device():
+            return m.evaluate(td['k'], x, td['t0'], td['p'], td['a'], td['i'], td['e'], td['w'], copy=False)
 
-    c, desc = workload(args.workload, rank)
-    lnl = args.workload == 'c5'
-    m = RoadRunnerModelCUDA(c.ldmodel, device=local_rank)
+        def step_host():
+            return m.evaluate(c.k, x, c.t0, c.p, c.a, c.i, c.e, c.w, copy=True)
+
+        h2d = sum(np.asarray(getattr(c, k)).nbytes for k in ('k', 't0', 'p', 'a', 'i', 'e', 'w')) + x.nbytes
+        return m, step_device, step_host, pts, h2d, 'k_ts_flux', 8.0 * pts
+    if name == 'c1':
+        m = pb.RoadRunnerModelCUDA(c.ldmodel, device=local_rank)
+        m.set_data(torch.as_tensor(c.time, device=dev))
+        ldc_d = torch.as_tensor(c.ldc, device=dev)
+
+        def step_device():
+            return m.evaluate(c.k, ldc_d, c.t0, c.p, c.a, c.i, c.e, c.w, copy=False)
+
+        def step_host():
+            return m.evaluate(c.k, c.ldc, c.t0, c.p, c.a, c.i, c.e, c.w, copy=True)
+
+        return m, step_device, step_host, c.npt, 8 * 8 + c.ldc.nbytes, 'k_rr_points', 8.0 * c.npt
+
+    lnl = name == 'c5'
+    m = pb.RoadRunnerModelCUDA(c.ldmodel, device=local_rank, precision=args.precision)
+    esize = 4 if args.precision == 'fp32' else 8
     td = {k: torch.as_tensor(np.ascontiguousarray(getattr(c, k)), device=dev) for k in ('k', 'ldc', 't0', 'p', 'a', 'i', 'e', 'w')}
     time_d = torch.as_tensor(c.time, device=dev)
     if c.nlc > 1:
@@ -217,8 +263,6 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if lnl:
         m.set_obs(torch.as_tensor(c.obs, device=dev))
         sig_d = torch.as_tensor(c.sigma, device=dev)
-    pts_per_step = c.npv * c.npt
-
     gathered = torch.empty((world * c.npv,), dtype=torch.float64, device=dev) if (lnl and world > 1) else None
 
     def step_device():
@@ -234,6 +278,34 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         if lnl:
             return m.lnlikelihood(c.k, c.ldc, c.t0, c.p, c.a, c.i, c.e, c.w, sigma=c.sigma, copy=True)
         return m.evaluate(c.k, c.ldc, c.t0, c.p, c.a, c.i, c.e, c.w, copy=True)
+
+    h2d = sum(np.asarray(getattr(c, k)).nbytes for k in ('k', 'ldc', 't0', 'p', 'a', 'i', 'e', 'w')) + (c.sigma.nbytes if lnl else 0)
+    pts = c.npv * c.npt
+    return m, step_device, step_host, pts, h2d, ('k_rr_points<LNL>' if lnl else 'k_rr_points'), (None if lnl else float(esize) * pts)
+
+
+def _table_args(c):
+    prof, (x0, dx), (y0, dy), (z0, dz) = c.table
+    return prof, x0, dx, y0, dy, z0, dz
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dev = f'cuda:{local_rank}'
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+
+    c, desc = workload(args.workload, rank)
+    lnl = args.workload == 'c5'
+    if args.workload == 'c4':
+        import pytransit_b200 as pb
+        mu = pb.TSModelCUDA('uniform', device=local_rank).mu      # the model's own mu grid (device-built tables)
+        c.table = wl.ldtk_style_table(c.npb, mu)
+        c.npb_out = c.npb
+    m, step_device, step_host, pts_per_step, h2d, kname, alg_bytes = make_steps(args, c, dev, local_rank, world, dist)
 
     def barrier():
         if world > 1:
@@ -271,23 +343,27 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     # ---- end to end through the public API with host buffers ("e2e") ---------------------------------
     m.set_profiling(False)
-    e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(2):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    ev0.record()
-    for _ in range(e2e_steps):
-        r = step_host()
-    ev1.record()
-    barrier()
-    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * pts_per_step * e2e_steps / (float(t.item()) * 1e-3)
-    h2d = sum(np.asarray(getattr(c, k)).nbytes for k in ('k', 'ldc', 't0', 'p', 'a', 'i', 'e', 'w')) + (c.sigma.nbytes if lnl else 0)
-    d2h = int(r.nbytes)
+    e2e_steps = max(1, min(args.steps, 5 if args.workload != 'c4' else 2))
+    e2e = None
+    try:
+        for _ in range(2 if args.workload != 'c4' else 1):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(e2e_steps):
+            r = step_host()
+        ev1.record()
+        barrier()
+        e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {'value': world * pts_per_step * e2e_steps / (float(t.item()) * 1e-3), 'unit': UNIT,
+               'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(r.nbytes), 'steps': e2e_steps}
+        del r
+    except MemoryError as ex:   # page-locked result buffer too large for this host
+        e2e = {'value': None, 'unit': UNIT, 'error': str(ex)[:200]}
 
     if rank != 0:
         if world > 1:
@@ -300,15 +376,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if k_points_ms:
         kp = float(np.mean(k_points_ms))
         ks = float(np.mean(k_setup_ms))
-        if lnl:
-            # nothing is written: the kernel streams time + obs from L2; report the fp64-op rate instead
-            roof = {'bound': 'fp64', 'kernel': 'k_rr_points<LNL>', 'achieved': pts_per_step / (kp * 1e-3) / 1e9,
+        if alg_bytes is None:
+            # nothing is written: the kernel streams time + obs from L2; report the point rate instead
+            roof = {'bound': 'fp64', 'kernel': kname, 'achieved': pts_per_step / (kp * 1e-3) / 1e9,
                     'peak': None, 'unit': 'Gpoints/s', 'frac': None, 'traffic': None,
                     'kernel_ms': kp, 'setup_ms': ks}
         else:
-            alg_bytes = 8.0 * pts_per_step
             ach = alg_bytes / (kp * 1e-3) / 1e9
-            roof = {'bound': 'hbm', 'kernel': 'k_rr_points', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+            roof = {'bound': 'hbm', 'kernel': kname, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
                     'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': kp, 'setup_ms': ks,
                     'kernel_share_of_step': kp / (ms_max / args.steps)}
@@ -327,6 +402,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         ncores = host_threads(orc)
         tab = orc.Tables()
         c0, _ = workload(args.workload, 0)
+        if args.workload == 'c4':
+            c0.table, c0.npb_out = c.table, c.npb
         rows = cpu_sample_rows(orc, tab, c0, lnl, target_s=args.cpu_seconds)
         best = None
         for _ in range(2):
@@ -335,16 +412,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dt = time.perf_counter() - t1
             best = dt if best is None else min(best, dt)
         cpu = {'value': n / best, 'unit': UNIT, 'cores': ncores, 'kind': 'port',
-               'sample': f'{rows} of {c0.npv} parameter vectors x {c0.npt} points, best of 2 passes ({best:.2f} s)'}
+               'sample': f'{rows} of {c0.npv} parameter vectors x {n // rows} points each, best of 2 passes ({best:.2f} s)'}
 
+    out_gb = (4e-9 if args.precision == 'fp32' else 8e-9) * pts_per_step
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': desc, 'per_gpu': f'npv={c.npv} x npt={c.npt}', 'parallelism': f'population sharded over {world} GPU(s), ' + ('NCCL all-gather of lnL[npv] per step' if (lnl and world > 1) else 'no data-path collective'),
-                       'l2': 'each step streams %.2f GB of output through L2 (126 MB): inputs/outputs exceed L2, no explicit flush' % (8e-9 * pts_per_step)
-                       if not lnl else 'time+obs (1.6 MB) are L2 resident by design; nothing is written'},
-            'clocks': clocks,
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': d2h, 'steps': e2e_steps},
+            'dtype': 'f64' if args.precision == 'fp64' else 'f32 (opt-in mode: fp64 phase fold, fp32 samples and output)', 'data': 'synthetic',
+            'config': {'workload': desc, 'per_gpu': f'npv={c.npv} x npt={c.npt}' + (f' x npb={c.npb}' if args.workload == 'c4' else ''),
+                       'parallelism': f'population sharded over {world} GPU(s), ' + ('NCCL all-gather of lnL[npv] per step' if (lnl and world > 1) else 'no data-path collective'),
+                       'l2': ('time+obs (1.6 MB) are L2 resident by design; nothing is written' if lnl else
+                              'each step streams %.2f GB of output through L2 (126 MB): inputs/outputs exceed L2, no explicit flush' % out_gb
+                              if out_gb > 0.2 else
+                              'latency-bound single vector: time axis and output (80 KB each) are L2 resident by design, no flush')},
+            'clocks': clocks, 'e2e': e2e,
             'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu}
     print(json.dumps(line))
     if world > 1:
@@ -357,10 +437,11 @@ def main():
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=['c2', 'c3', 'c5'])
+    ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c3', 'c4', 'c5'])
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-kernel-timing', action='store_true')
+    ap.add_argument('--precision', default='fp64', choices=['fp64', 'fp32'], help="'fp32' = the opt-in single-precision mode (c2/c3/c5 only)")
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

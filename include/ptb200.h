@@ -111,11 +111,14 @@ int ptb_set_data(ptb_model *h, const double *time, int64_t npt, const int64_t *l
  *   k[npv,kcols] (kcols 1 or npb); ld = ldc[npv,npb,nld] for a named law, or ldp[npv,npb,nz] with
  *   istar[npv,npb] for PTB_LD_PROFILES (istar NULL otherwise); t0[npv,nep]; p,a,inc,e,w[npv].
  * flux[npv,npt] may be a device pointer (written in place), a host pointer, or NULL (the flux
- * stays in the handle's device buffer: ptb_flux_device_ptr). */
+ * stays in the handle's device buffer: ptb_flux_device_ptr).  It is a float64 array, or a float32
+ * array when the handle was created with ptb_config.precision = 1 (opt-in fp32 mode: the phase
+ * fold stays fp64, the per-sample geometry / limb-darkening arithmetic and the stored flux are
+ * fp32; <= 1 ppm from the fp64 result). */
 int ptb_rr_evaluate(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld,
                     int64_t nld, const double *istar, const double *t0, const double *p,
                     const double *a, const double *inc, const double *e, const double *w,
-                    double *flux, void *stream);
+                    void *flux, void *stream);
 
 /* Observed fluxes and noise blocks for the fused likelihood: the (o, slices, nids) arguments of
  * lnlike_normal (lpf/loglikelihood/wnloglikelihood.py:22-35,43-55).  obs[npt]; slices[nsl,2]
@@ -166,7 +169,7 @@ int ptb_inject_xyc(ptb_model *h, const double *xyc, int64_t npv);
 
 /* Device pointer / element count of the handle-owned result of the last evaluate call whose
  * output pointer was NULL (the RoadRunnerModelCL `_b_f` analogue, rrmodel_cl.py:365-369). */
-int ptb_flux_device_ptr(ptb_model *h, double **ptr, int64_t *count);
+int ptb_flux_device_ptr(ptb_model *h, void **ptr, int64_t *count);
 
 /* Page-locked host memory for results (so device-to-host copies run at full PCIe rate). */
 int ptb_host_alloc(void **ptr, size_t bytes);

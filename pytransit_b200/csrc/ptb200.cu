@@ -114,8 +114,8 @@ struct ptb_model {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     size_t ldm_smem = 0;
     bool keep_stages = true;         // write ldp / istar taps (ptb_get_stage); off in throughput runs
-    int pt_occ[16] = {};  // resident CTAs per SM of each k_rr_points instantiation (0 = not queried)
-    size_t pt_occ_smem[16] = {};
+    int pt_occ[32] = {};  // resident CTAs per SM of each k_rr_points instantiation (0 = not queried)
+    size_t pt_occ_smem[32] = {};
     bool xyc_injected = false;
     int64_t xyc_npv = 0;
     int64_t last_npv = 0, last_npb = 0, last_flux_count = 0;
@@ -289,7 +289,7 @@ int ptb_create(const ptb_config *cfg, ptb_model **out) {
         !(cfg->zcut > 0 && cfg->zcut < 1))
         return fail(h, PTB_EINVAL, "invalid integration grid (nk=%d ng=%d nzin=%d nzlimb=%d klims=(%g,%g) zcut=%g)",
                     cfg->nk, cfg->ng, cfg->nzin, cfg->nzlimb, cfg->kmin, cfg->kmax, cfg->zcut);
-    if (cfg->precision != 0) return fail(h, PTB_ENOTIMPL, "precision=%d: only fp64 (0) is implemented", cfg->precision);
+    if (cfg->precision != 0 && cfg->precision != 1) return fail(h, PTB_EINVAL, "precision=%d: 0 (fp64) or 1 (opt-in fp32) expected", cfg->precision);
     const int nz = cfg->nzin + cfg->nzlimb;
     if (((size_t)cfg->ng * nz) % 2 != 0 || (size_t)cfg->ng * nz * 16 > 200 * 1024)
         return fail(h, PTB_EINVAL, "ng*nz = %d*%d: two table rows must fit 200 KB of shared memory and be 16-byte multiples",
@@ -728,10 +728,10 @@ int launch_rr_setup(ptb_model *h, const ModelArgs &A, const Staged &D, cudaStrea
     return PTB_OK;
 }
 
-template <int VEC, bool SINGLE, bool LNL, bool S1>
+template <int VEC, bool SINGLE, bool LNL, bool S1, typename T>
 int launch_points_t(ptb_model *h, const PointsParams &P, size_t smem, cudaStream_t st) {
-    auto kern = k_rr_points<VEC, SINGLE, LNL, S1>;
-    const int slot = (S1 ? 8 : 0) + (VEC == 2 ? 4 : 0) + (SINGLE ? 2 : 0) + (LNL ? 1 : 0);
+    auto kern = k_rr_points<VEC, SINGLE, LNL, S1, T>;
+    const int slot = (sizeof(T) == 4 ? 16 : 0) + (S1 ? 8 : 0) + (VEC == 2 ? 4 : 0) + (SINGLE ? 2 : 0) + (LNL ? 1 : 0);
     if (h->pt_occ[slot] == 0 || h->pt_occ_smem[slot] != smem) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
@@ -750,7 +750,7 @@ int launch_points_t(ptb_model *h, const PointsParams &P, size_t smem, cudaStream
 }
 
 // flux != nullptr -> flux mode; else lnL mode (partials into h->d_partial)
-int launch_points(ptb_model *h, int64_t npv, double *flux, const double *isig2, cudaStream_t st, int *nchunks_out) {
+int launch_points(ptb_model *h, int64_t npv, void *flux, const double *isig2, cudaStream_t st, int *nchunks_out) {
     const int ng = h->cfg.ng;
     const int lds = (ng + 4 + 1) & ~1;
     PointsParams P{};
@@ -769,8 +769,10 @@ int launch_points(ptb_model *h, int64_t npv, double *flux, const double *isig2, 
     P.work = h->d_work.as<int>();
     const bool single = (h->nlc == 1);
     const bool lnl = (flux == nullptr);
+    const bool f32 = h->cfg.precision == 1;
+    const int tsize = f32 ? 4 : 8;
     const bool aligned = (h->npt % 2 == 0) && ((reinterpret_cast<uintptr_t>(h->d_time) & 15) == 0) &&
-                         (lnl || (reinterpret_cast<uintptr_t>(flux) & 15) == 0);
+                         (lnl || (reinterpret_cast<uintptr_t>(flux) & (f32 ? 7 : 15)) == 0);
     const int vec = aligned ? 2 : 1;
     // Items: rows are cut into chunks of whole 8-block groups so that every warp of the persistent grid
     // gets ~PT_ITEMS_PER_WARP items (a short tail), at least PT_MIN_ITEM_BLOCKS and at most PT_MAXBLK
@@ -784,11 +786,15 @@ int launch_points(ptb_model *h, int64_t npv, double *flux, const double *isig2, 
         const char *e = getenv("PTB_MIN_ITEM_BLOCKS");
         return (long long)((e && atoi(e) > 0) ? atoi(e) : 16);
     }();
-    const long long want = (long long)(h->sm_count * 3 * PT_WARPS * items_per_warp);
+    const long long workers = (long long)h->sm_count * 3 * PT_WARPS;
+    const long long want = (long long)(workers * items_per_warp);
     long long nchunks = std::min<long long>(std::max<long long>(1, nb / min_item_blocks), std::max<long long>(1, (want + npv - 1) / npv));
+    // a population too small to give every warp an item: cut finer (down to two blocks per item) -- the
+    // single-vector call is latency bound and wants all the parallelism there is
+    if (npv * nchunks < workers) nchunks = std::min<long long>(std::max<long long>(1, nb / 2), (workers + npv - 1) / npv);
     nchunks = std::max<long long>(nchunks, (nb + PT_MAXBLK - 1) / PT_MAXBLK);
     long long bpc = (nb + nchunks - 1) / nchunks;
-    bpc = std::min<long long>((bpc + 7) / 8 * 8, PT_MAXBLK);
+    bpc = std::min<long long>(bpc >= 8 ? (bpc + 7) / 8 * 8 : bpc, PT_MAXBLK);
     nchunks = (nb + bpc - 1) / bpc;
     P.nchunks = (int)nchunks;
     P.blocks_per_chunk = (int)bpc;
@@ -801,16 +807,21 @@ int launch_points(ptb_model *h, int64_t npv, double *flux, const double *isig2, 
     P.frac_tab = ((long long)h->nlc * h->ns_max <= PT_FRAC_MAX) ? 1 : 0;
     const bool s1 = (h->ns_max == 1);
     const size_t nfrac = P.frac_tab ? (size_t)h->nlc * h->ns_max : 0;
-    const size_t shared_bytes = (((2 * (size_t)h->nlc + nfrac) * 8 + 3 * (size_t)h->nlc * 4) + 127) & ~size_t(127);
-    const size_t smem = shared_bytes + pt_warp_bytes(s1 ? 0 : P.ssc, h->recstride) * PT_WARPS;
+    const size_t shared_bytes = ((((size_t)h->nlc) * 8 + ((size_t)h->nlc + nfrac) * tsize + 3 * (size_t)h->nlc * 4) + 127) & ~size_t(127);
+    const size_t smem = shared_bytes + pt_warp_bytes(s1 ? 0 : P.ssc, h->recstride, tsize) * PT_WARPS;
     if (smem > 220 * 1024)
         return fail(h, PTB_EINVAL, "npb=%lld passbands x nlc=%lld light curves need %zu bytes of shared memory (> 220 KB)",
                     (long long)h->npb, (long long)h->nlc, smem);
 
-#define PTB_DISPATCH(V, S, L)                                          \
-    do {                                                               \
-        if (s1) return launch_points_t<V, S, L, true>(h, P, smem, st); \
-        return launch_points_t<V, S, L, false>(h, P, smem, st);        \
+#define PTB_DISPATCH_T(V, S, L, T)                                          \
+    do {                                                                    \
+        if (s1) return launch_points_t<V, S, L, true, T>(h, P, smem, st);  \
+        return launch_points_t<V, S, L, false, T>(h, P, smem, st);         \
+    } while (0)
+#define PTB_DISPATCH(V, S, L)                        \
+    do {                                             \
+        if (f32) PTB_DISPATCH_T(V, S, L, float);     \
+        PTB_DISPATCH_T(V, S, L, double);             \
     } while (0)
     if (vec == 2) {
         if (single) { if (lnl) PTB_DISPATCH(2, true, true); else PTB_DISPATCH(2, true, false); }
@@ -819,6 +830,7 @@ int launch_points(ptb_model *h, int64_t npv, double *flux, const double *isig2, 
         if (single) { if (lnl) PTB_DISPATCH(1, true, true); else PTB_DISPATCH(1, true, false); }
         else        { if (lnl) PTB_DISPATCH(1, false, true); else PTB_DISPATCH(1, false, false); }
     }
+#undef PTB_DISPATCH_T
 #undef PTB_DISPATCH
 }
 
@@ -828,7 +840,7 @@ extern "C" {
 
 int ptb_rr_evaluate(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld, int64_t nld,
                     const double *istar, const double *t0, const double *p, const double *a, const double *inc,
-                    const double *e, const double *w, double *flux, void *stream) {
+                    const double *e, const double *w, void *flux, void *stream) {
     if (!h) return PTB_EINVAL;
     if (int rc = set_device(h)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -840,18 +852,19 @@ int ptb_rr_evaluate(ptb_model *h, int64_t npv, const double *k, int64_t kcols, c
     if (int rc = launch_rr_setup(h, A, D, st)) return rc;
     mark(h, 1, st);
     const size_t count = (size_t)npv * h->npt;
-    double *dflux = flux;
+    const size_t esize = h->cfg.precision == 1 ? 4 : 8;  // fp32 mode: `flux` is a float array
+    void *dflux = flux;
     const bool direct = flux && is_device_ptr(flux);
     if (!direct) {
-        CU(h->d_flux.reserve(count * 8));
-        dflux = h->d_flux.as<double>();
+        CU(h->d_flux.reserve(count * esize));
+        dflux = h->d_flux.ptr;
     }
     mark(h, 2, st);
     if (int rc = launch_points(h, npv, dflux, nullptr, st, nullptr)) return rc;
     mark(h, 3, st);
     h->last_flux_count = direct ? 0 : (int64_t)count;
     if (flux && !direct) {
-        CU(cudaMemcpyAsync(flux, dflux, count * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(flux, dflux, count * esize, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     return PTB_OK;
@@ -980,9 +993,9 @@ int ptb_inject_xyc(ptb_model *h, const double *xyc, int64_t npv) {
     return PTB_OK;
 }
 
-int ptb_flux_device_ptr(ptb_model *h, double **ptr, int64_t *count) {
+int ptb_flux_device_ptr(ptb_model *h, void **ptr, int64_t *count) {
     if (!h || !ptr || !count) return PTB_EINVAL;
-    *ptr = h->d_flux.as<double>();
+    *ptr = h->d_flux.ptr;
     *count = h->last_flux_count;
     return PTB_OK;
 }

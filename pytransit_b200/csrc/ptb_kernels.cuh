@@ -466,7 +466,7 @@ struct PointsParams {
     const int32_t *lcids, *pbids, *epids, *nsamples;
     const double *exptimes;
     const double *rec;    // [npv][recstride] per-vector records
-    double *flux;
+    void *flux;           // [npv][npt] fp64, or fp32 in the opt-in fp32 mode
     const double *obs;
     const int32_t *blk;
     const double *isig2;  // [npv][nblocks]
@@ -500,19 +500,22 @@ constexpr int PT_SSC_MAX = 12;         // exposure sub-samples buffered per pass
 constexpr int PT_FRAC_MAX = 1024;      // entries of the tabulated sub-sample offsets
 constexpr double PT_EPS = 1e-9;        // classification margin, in periods (>> rounding, << the 0.003 d pad)
 
-// Warp-private shared memory: queues, sub-sample buffer (none when every point has one sample),
-// two record slots, the hit bitmap and two mbarriers.
-__host__ __device__ inline size_t pt_warp_bytes(int ssc, int recstride) {
-    return (size_t)(PT_QCAP + 2 * PT_LCAP + 32 * ssc + 2 * recstride) * 8 + (size_t)(2 * PT_QCAP + 2 * PT_LCAP) * 4 +
-           PT_MAXBLK / 8 + 16;
+// Warp-private shared memory: queues, two record slots, the hit bitmap, two mbarriers, the
+// sub-sample buffer (none when every point has one sample) and, in fp32 mode, the record converted to
+// float.  T is the sample arithmetic / output type (double, or float in the opt-in fp32 mode).
+__host__ __device__ inline size_t pt_warp_bytes(int ssc, int recstride, int tsize) {
+    const size_t rec_t = (tsize == 4) ? (((size_t)recstride * 4 + 15) & ~size_t(15)) : 0;
+    return (size_t)(PT_QCAP + 2 * PT_LCAP + 32 * ssc) * tsize + (size_t)(2 * PT_QCAP + 2 * PT_LCAP) * 4 + PT_MAXBLK / 8 + 16 +
+           (size_t)2 * recstride * 8 + rec_t;
 }
 
+template <typename T>
 struct WarpScratch {
     unsigned char *base;
     __device__ __forceinline__ explicit WarpScratch(unsigned char *b) : base(b) {}
-    __device__ __forceinline__ double *q_tc() const { return reinterpret_cast<double *>(base); }
-    __device__ __forceinline__ double *l_z() const { return q_tc() + PT_QCAP; }
-    __device__ __forceinline__ double *l_ip() const { return l_z() + PT_LCAP; }
+    __device__ __forceinline__ T *q_tc() const { return reinterpret_cast<T *>(base); }
+    __device__ __forceinline__ T *l_z() const { return q_tc() + PT_QCAP; }
+    __device__ __forceinline__ T *l_ip() const { return l_z() + PT_LCAP; }
     __device__ __forceinline__ int *q_ipt() const { return reinterpret_cast<int *>(l_ip() + PT_LCAP); }
     __device__ __forceinline__ int *q_lc() const { return q_ipt() + PT_QCAP; }
     __device__ __forceinline__ int *l_slot() const { return q_lc() + PT_QCAP; }   // S1: the point index
@@ -522,19 +525,25 @@ struct WarpScratch {
     __device__ __forceinline__ double *rec(int slot, int recstride) const {
         return reinterpret_cast<double *>(bar() + 2) + (size_t)slot * recstride;
     }
-    __device__ __forceinline__ double *contrib(int recstride) const { return rec(2, recstride); }
+    // fp32 mode: the current record converted to float (16-byte aligned); fp64: unused
+    __device__ __forceinline__ T *rec_t(int recstride) const { return reinterpret_cast<T *>(rec(2, recstride)); }
+    __device__ __forceinline__ T *contrib(int recstride) const {
+        const size_t rt = (sizeof(T) == 4) ? (((size_t)recstride * 4 + 15) & ~size_t(15)) : 0;
+        return reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(rec(2, recstride)) + rt);
+    }
 };
 
-template <int VEC>
+// VEC consecutive points per lane: time stamps are always fp64, fluxes are T.
+template <int VEC, typename T>
 struct VecIO;
-template <>
-struct VecIO<1> {
+template <typename T>
+struct VecIO<1, T> {
     __device__ static __forceinline__ void load(const double *p, double *v) { v[0] = __ldg(p); }
-    __device__ static __forceinline__ void store(double *p, const double *v) { __stcs(p, v[0]); }
-    __device__ static __forceinline__ void store_keep(double *p, const double *v) { *p = v[0]; }
+    __device__ static __forceinline__ void store(T *p, const T *v) { __stcs(p, v[0]); }
+    __device__ static __forceinline__ void store_keep(T *p, const T *v) { *p = v[0]; }
 };
 template <>
-struct VecIO<2> {
+struct VecIO<2, double> {
     __device__ static __forceinline__ void load(const double *p, double *v) {
         const double2 t = __ldg(reinterpret_cast<const double2 *>(p));
         v[0] = t.x;
@@ -547,36 +556,46 @@ struct VecIO<2> {
         *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
     }
 };
+template <>
+struct VecIO<2, float> {
+    __device__ static __forceinline__ void load(const double *p, double *v) { VecIO<2, double>::load(p, v); }
+    __device__ static __forceinline__ void store(float *p, const float *v) {
+        __stcs(reinterpret_cast<float2 *>(p), make_float2(v[0], v[1]));
+    }
+    __device__ static __forceinline__ void store_keep(float *p, const float *v) {
+        *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+    }
+};
 
 // Per-CTA constants of the drain (shared-memory tables are item independent).
+template <typename T>
 struct DrainCtx {
     const PointsParams *P;
-    const double *sEt, *sFrac;     // per light curve: exposure time; tabulated (s+1-0.5)/ns-0.5 or null
+    const T *sEt, *sFrac;          // per light curve: exposure time; tabulated (s+1-0.5)/ns-0.5 or null
     const int *sNs, *sRow;         // per light curve: nsamples, offset of the passband row in the ld block
     int ns1, row1;                 // single light curve: the same as scalars
-    double et1;
+    T et1;
     int lane;
 };
 
 // Lens-area pass over `take` limb samples at the top of the limb queue (warp-cooperative).
 // S1: writes the flux / accumulates chi^2 directly; otherwise fills the sample's slot of `contrib`.
-template <bool SINGLE_LC, bool LNL, bool S1>
-__device__ __forceinline__ double limb_pass(const PointsParams &P, const WarpScratch &ws, const double *ld, const double *row1,
-                                            double *contrib, double *frow, const double *isig2, int lane, int first,
-                                            int take) {
+template <bool SINGLE_LC, bool LNL, bool S1, typename T>
+__device__ __forceinline__ double limb_pass(const PointsParams &P, const WarpScratch<T> &ws, const T *ld, const T *row1,
+                                            T *contrib, T *frow, const double *isig2, int lane, int first, int take) {
     double chi = 0.0;
     if (lane < take) {
         const int q = first + lane, ng = P.ng;
-        const double *r2 = SINGLE_LC ? row1 : ld + ws.l_row()[q];
-        double area, kap;
-        kite_area(r2[ng], r2[ng + 3], ws.l_z()[q], area, kap);
-        const double v = 1.0 - ws.l_ip()[q] * area * r2[ng + 2];
+        const T *r2 = SINGLE_LC ? row1 : ld + ws.l_row()[q];
+        T area, kap;
+        kite_area<T>(r2[ng], r2[ng + 3], ws.l_z()[q], area, kap);
+        const T v = T(1) - ws.l_ip()[q] * area * r2[ng + 2];
         if (S1) {
             const int ipt = ws.l_slot()[q];
             if (LNL) {
                 const int b = P.blk ? P.blk[ipt] : 0;
                 if (b >= 0) {
-                    const double d = P.obs[ipt] - v;
+                    const double d = P.obs[ipt] - (double)v;
                     chi = d * d * isig2[b];
                 }
             } else {
@@ -590,25 +609,26 @@ __device__ __forceinline__ double limb_pass(const PointsParams &P, const WarpScr
 }
 
 // Point-major evaluation of `n` (<= 32) queued in-box points starting at queue slot `base`
-// (model_full.py:93-99).  `nl` is the fill of the limb queue (carried across calls when S1; `flush`
-// empties it).  Inlined at its single call site.  Returns the lane's chi^2 increment.
-template <bool SINGLE_LC, bool LNL, bool S1>
-__device__ __forceinline__ double drain_points(const DrainCtx &c, const WarpScratch &ws, const double *rec, double *frow,
+// (model_full.py:93-99).  `rt` is the record in the arithmetic type.  `nl` is the fill of the limb queue
+// (carried across calls when S1; `flush` empties it).  Inlined at its single call site.  Returns the
+// lane's chi^2 increment.
+template <bool SINGLE_LC, bool LNL, bool S1, typename T>
+__device__ __forceinline__ double drain_points(const DrainCtx<T> &c, const WarpScratch<T> &ws, const T *rt, T *frow,
                                                const double *isig2, int base, int n, int &nl, bool flush) {
     const PointsParams &P = *c.P;
     const int lane = c.lane, ng = P.ng;
     const int S = S1 ? 1 : P.ns_max, SSC = S1 ? 1 : P.ssc;
-    const double dg = P.dg, inv_dg = P.inv_dg;
+    const T dg = (T)P.dg, inv_dg = (T)P.inv_dg, one = T(1), pi = T(kPi);
     const unsigned lt_mask = (1u << lane) - 1u;
-    const double *ld = rec + P.rec_ld;
-    double *contrib = ws.contrib(P.recstride);
-    double cx[5], cy[5];
+    const T *ld = rt + P.rec_ld;
+    T *contrib = ws.contrib(P.recstride);
+    T cx[5], cy[5];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) { cx[j] = rec[j]; cy[j] = rec[5 + j]; }
+    for (int j = 0; j < 5; ++j) { cx[j] = rt[j]; cy[j] = rt[5 + j]; }
 
     const bool valid = lane < n;
     int ipt = 0, lc = 0, ns = 1, rowoff = c.row1;
-    double tc = 0.0, et = 0.0;
+    T tc = T(0), et = T(0);
     if (valid) {
         ipt = ws.q_ipt()[base + lane];
         tc = ws.q_tc()[base + lane];
@@ -622,30 +642,31 @@ __device__ __forceinline__ double drain_points(const DrainCtx &c, const WarpScra
             rowoff = c.sRow[lc];
         }
     }
-    const double *row1 = ld + c.row1;
-    const double *row = ld + rowoff;
-    const double k = row[ng], inv1k = row[ng + 1], inv_istar = row[ng + 2], k2 = row[ng + 3];
-    const double *frac = c.sFrac ? c.sFrac + (size_t)lc * S : nullptr;
+    const T *row1 = ld + c.row1;
+    const T *row = ld + rowoff;
+    const T k = row[ng], inv1k = row[ng + 1], inv_istar = row[ng + 2], k2 = row[ng + 3];
+    const T *frac = c.sFrac ? c.sFrac + (size_t)lc * S : nullptr;
 
-    double sum = 0.0, chi = 0.0;
+    T sum = T(0);
+    double chi = 0.0;
     for (int s0 = 0; s0 < S; s0 += SSC) {
         const int SS = min(SSC, S - s0);
         for (int j = 0; j < SS; ++j) {
             const int s = s0 + j;
             bool limb = false;
-            double z = 0.0, ip = 0.0;
+            T z = T(0), ip = T(0);
             if (valid && s < ns) {
                 // exposure offset exptime*((s+1-0.5)/ns - 0.5) (model_full.py:94); exactly 0 for ns == 1
-                double off = 0.0;
-                if (!S1 && ns != 1) off = et * (frac ? frac[s] : (((s + 1) - 0.5) / ns - 0.5));
-                z = sep_poly(tc + off, cx, cy);
-                ip = ldm_lerp(z * inv1k, dg, inv_dg, row, ng);
-                double cc = 0.0;
-                if (1.0 + k <= z) cc = 1.0;                                   // no overlap: area 0
-                else if (fabs(1.0 - k) < z) limb = true;                      // lens: kite formula
-                else if (z <= 1.0 - k) cc = 1.0 - ip * (kPi * k2) * inv_istar;
-                else if (z <= k - 1.0) cc = 1.0 - ip * kPi * inv_istar;       // planet covers the star
-                else cc = nan("");
+                T off = T(0);
+                if (!S1 && ns != 1) off = et * (frac ? frac[s] : (T)(((s + 1) - 0.5) / ns - 0.5));
+                z = sep_poly<T>(tc + off, cx, cy);
+                ip = ldm_lerp<T>(z * inv1k, dg, inv_dg, row, ng);
+                T cc = T(0);
+                if (one + k <= z) cc = one;                                   // no overlap: area 0
+                else if (fabs(one - k) < z) limb = true;                      // lens: kite formula
+                else if (z <= one - k) cc = one - ip * (pi * k2) * inv_istar;
+                else if (z <= k - one) cc = one - ip * pi * inv_istar;        // planet covers the star
+                else cc = T(nan(""));
                 if (S1) sum = cc;
                 else if (!limb) contrib[j * 32 + lane] = cc;
             }
@@ -667,7 +688,7 @@ __device__ __forceinline__ double drain_points(const DrainCtx &c, const WarpScra
                     if (LNL) {
                         const int b = P.blk ? P.blk[ipt] : 0;
                         if (b >= 0) {
-                            const double d = P.obs[ipt] - sum;
+                            const double d = P.obs[ipt] - (double)sum;
                             chi += d * d * isig2[b];
                         }
                     } else {
@@ -681,7 +702,7 @@ __device__ __forceinline__ double drain_points(const DrainCtx &c, const WarpScra
             while (nl >= 32 || (last && nl > 0)) {
                 const int take = min(nl, 32);
                 nl -= take;
-                chi += limb_pass<SINGLE_LC, LNL, S1>(P, ws, ld, row1, contrib, frow, isig2, lane, nl, take);
+                chi += limb_pass<SINGLE_LC, LNL, S1, T>(P, ws, ld, row1, contrib, frow, isig2, lane, nl, take);
                 __syncwarp();
             }
         }
@@ -695,11 +716,11 @@ __device__ __forceinline__ double drain_points(const DrainCtx &c, const WarpScra
         }
     }
     if (!S1 && valid) {
-        const double f = sum / ns;
+        const T f = sum / ns;
         if (LNL) {
             const int b = P.blk ? P.blk[ipt] : 0;
             if (b >= 0) {
-                const double d = P.obs[ipt] - f;
+                const double d = P.obs[ipt] - (double)f;
                 chi += d * d * isig2[b];
             }
         } else {
@@ -709,9 +730,10 @@ __device__ __forceinline__ double drain_points(const DrainCtx &c, const WarpScra
     return chi;
 }
 
-template <int VEC, bool SINGLE_LC, bool LNL, bool S1>
+template <int VEC, bool SINGLE_LC, bool LNL, bool S1, typename T>
 __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr_points(const __grid_constant__ PointsParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr bool F32 = sizeof(T) == 4;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long npt = P.npt;
@@ -721,14 +743,14 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
 
     // dynamic smem: [per-light-curve tables] [sub-sample offsets] [warp-private area x 8]
     double *sPad = reinterpret_cast<double *>(smem_raw);
-    double *sEt = sPad + nlc;
-    double *sFrac = sEt + nlc;
+    T *sEt = reinterpret_cast<T *>(sPad + nlc);
+    T *sFrac = sEt + nlc;
     const int nfrac = P.frac_tab ? nlc * S : 0;
     int *sNs = reinterpret_cast<int *>(sFrac + nfrac);
     int *sRow = sNs + nlc;
     int *sEp = sRow + nlc;
-    const size_t shared_bytes = (((2 * (size_t)nlc + nfrac) * 8 + 3 * (size_t)nlc * 4) + 127) & ~size_t(127);
-    const WarpScratch ws(smem_raw + shared_bytes + (size_t)warp * pt_warp_bytes(S1 ? 0 : P.ssc, P.recstride));
+    const size_t shared_bytes = ((((size_t)nlc) * 8 + ((size_t)nlc + nfrac) * sizeof(T) + 3 * (size_t)nlc * 4) + 127) & ~size_t(127);
+    const WarpScratch<T> ws(smem_raw + shared_bytes + (size_t)warp * pt_warp_bytes(S1 ? 0 : P.ssc, P.recstride, (int)sizeof(T)));
     unsigned *s_hit = ws.hit();
     uint64_t *bar = ws.bar();
 
@@ -747,23 +769,24 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
     // item-independent per-light-curve tables
     for (int lc = tid; lc < nlc; lc += PT_THREADS) {
         sPad[lc] = 0.003 + P.exptimes[lc];  // model_full.py:69-70
-        sEt[lc] = P.exptimes[lc];
+        sEt[lc] = (T)P.exptimes[lc];
         sNs[lc] = P.nsamples[lc];
         sRow[lc] = P.pbids[lc] * P.lds;
         sEp[lc] = P.epids[lc];
     }
     for (int i = tid; i < nfrac; i += PT_THREADS) {
         const int lc = i / S, s = i - lc * S;
-        sFrac[i] = ((s + 1) - 0.5) / P.nsamples[lc] - 0.5;
+        sFrac[i] = (T)(((s + 1) - 0.5) / P.nsamples[lc] - 0.5);
     }
     __syncthreads();  // the only CTA-wide barrier: from here on the warps are independent workers
 
-    DrainCtx dctx;
+    DrainCtx<T> dctx;
     dctx.P = &P; dctx.sEt = sEt; dctx.sFrac = P.frac_tab ? sFrac : nullptr; dctx.sNs = sNs; dctx.sRow = sRow;
     dctx.ns1 = sNs[0]; dctx.row1 = sRow[0]; dctx.et1 = sEt[0];
     dctx.lane = lane;
     const double pad1 = sPad[0];
     const int ep1 = sEp[0];
+    T *flux = reinterpret_cast<T *>(P.flux);
 
     for (int iter = 0; item < nitems; ++iter) {
         const int buf = iter & 1;
@@ -784,7 +807,7 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
         const int bend = min(P.nblk64, bbeg + P.blocks_per_chunk);
         const int nbc = bend - bbeg;
         const double *rec = ws.rec(buf, P.recstride);
-        double *frow = LNL ? nullptr : P.flux + (size_t)ipv * npt;
+        T *frow = LNL ? nullptr : flux + (size_t)ipv * npt;
         const double *isig2 = LNL ? P.isig2 + (size_t)ipv * P.nblocks : nullptr;
         double chi = 0.0;
 
@@ -793,15 +816,25 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
             if (LNL) {
                 if (lane == 0) P.partial[(size_t)ipv * P.nchunks + chunk] = nan("");
             } else {
-                double v[VEC];
+                T v[VEC];
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) v[j] = nan("");
+                for (int j = 0; j < VEC; ++j) v[j] = T(nan(""));
                 const long long cend = min(npt, (long long)bend * PT_BLOCK);
                 for (long long i = (long long)bbeg * PT_BLOCK + (long long)lane * VEC; i < cend; i += 32 * VEC)
-                    VecIO<VEC>::store(frow + i, v);
+                    VecIO<VEC, T>::store(frow + i, v);
             }
             __syncwarp();
             continue;
+        }
+        // the record in the arithmetic type: fp64 -> the TMA slot itself; fp32 -> converted once per item
+        const T *rt;
+        if (F32) {
+            T *dst = ws.rec_t(P.recstride);
+            for (int i = lane; i < P.recstride; i += 32) dst[i] = (T)rec[i];
+            __syncwarp();
+            rt = dst;
+        } else {
+            rt = reinterpret_cast<const T *>(rec);
         }
 
         const double p = rec[ORB_P], invp = rec[ORB_INVP], T1 = rec[ORB_T1], T4 = rec[ORB_T4];
@@ -832,30 +865,30 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
         }
         __syncwarp();
 
-        // ---- 2. untouched blocks: 64 fluxes of exactly 1.0, 16-byte streaming stores ---------------------
+        // ---- 2. untouched blocks: 64 fluxes of exactly 1.0, vectorised streaming stores -------------------
         // (TMA bulk stores out of a constant shared-memory buffer were measured: same kernel time, and the
         //  16 KB buffer costs the supersampled variants a resident CTA -- DESIGN.md section 3.1)
         if (!LNL) {
-            double one[VEC];
+            T one[VEC];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) one[j] = 1.0;
+            for (int j = 0; j < VEC; ++j) one[j] = T(1);
             const int ngroups = (nbc + 7) >> 3;
             for (int g = 0; g < ngroups; ++g) {
                 const unsigned bits = (s_hit[g >> 2] >> ((g & 3) * 8)) & 0xffu;
                 const int b0 = bbeg + g * 8;
-                double *fb = frow + (long long)b0 * PT_BLOCK + lane * VEC;
+                T *fb = frow + (long long)b0 * PT_BLOCK + lane * VEC;
                 if (bits == 0u && b0 + 8 <= bend) {  // the common case: eight untouched blocks, no predicates
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
 #pragma unroll
-                        for (int h = 0; h < 2 / VEC; ++h) VecIO<VEC>::store(fb + j * PT_BLOCK + h * 32 * VEC, one);
+                        for (int h = 0; h < 2 / VEC; ++h) VecIO<VEC, T>::store(fb + j * PT_BLOCK + h * 32 * VEC, one);
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         if (!((bits >> j) & 1u) && b0 + j < bend) {
 #pragma unroll
-                            for (int h = 0; h < 2 / VEC; ++h) VecIO<VEC>::store(fb + j * PT_BLOCK + h * 32 * VEC, one);
+                            for (int h = 0; h < 2 / VEC; ++h) VecIO<VEC, T>::store(fb + j * PT_BLOCK + h * 32 * VEC, one);
                         }
                     }
                 }
@@ -888,7 +921,7 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
                 const long long i0 = base + (long long)(h * 32 + lane) * VEC;
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) tvn[h][j] = 0.0;
-                if (i0 < npt) VecIO<VEC>::load(P.time + i0, tvn[h]);
+                if (i0 < npt) VecIO<VEC, T>::load(P.time + i0, tvn[h]);
             }
         };
         if (cur >= 0) load_block(cur);
@@ -906,14 +939,14 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
 #pragma unroll
                 for (int h = 0; h < 2 / VEC; ++h) {
                     const long long i0 = base + (long long)(h * 32 + lane) * VEC;
-                    double fv[VEC];
+                    T fv[VEC];
                     const bool inr = i0 < npt;  // VEC == 2 requires an even npt: vectors are all-in or all-out
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) {
                         bool inbox = false;
                         double tc = 0.0;
                         int lc = 0;
-                        fv[j] = 1.0;
+                        fv[j] = T(1);
                         if (inr) {
                             double lo = lo1, hi = hi1, t0 = t01;
                             if (!SINGLE_LC) {
@@ -926,6 +959,7 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
                             // epoch = floor((t - t0 + p/2)/p); tc = t - (t0 + epoch p)  (model_full.py:88-89)
                             // The division is a multiplication by 1/p: the two can only disagree half a
                             // period away from the transit, where the point is outside the box either way.
+                            // Always fp64: time stamps need all their digits; tc itself is small.
                             const double epoch = floor(fma(tv[h][j] - t0, invp, 0.5));
                             tc = tv[h][j] - __dadd_rn(t0, __dmul_rn(epoch, p));
                             inbox = (lo <= tc) && (tc <= hi);
@@ -941,14 +975,14 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
                         if (inbox) {
                             const int pos = qn + __popc(m & lt_mask);
                             ws.q_ipt()[pos] = (int)(i0 + j);
-                            ws.q_tc()[pos] = tc;
+                            ws.q_tc()[pos] = (T)tc;
                             if (!SINGLE_LC) ws.q_lc()[pos] = lc;
                         }
                         qn += __popc(m);
                     }
                     // default cache policy (not evict-first): the line is still in L2 when the drain updates its
                     // in-box points, so it reaches DRAM once
-                    if (!LNL && inr) VecIO<VEC>::store_keep(frow + i0, fv);
+                    if (!LNL && inr) VecIO<VEC, T>::store_keep(frow + i0, fv);
                 }
                 __syncwarp();
             }
@@ -956,7 +990,7 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
             while (qn >= 32 || (!live && (qn > 0 || nl > 0))) {
                 const int n = min(qn, 32);
                 qn -= n;
-                chi += drain_points<SINGLE_LC, LNL, S1>(dctx, ws, rec, frow, isig2, qn, n, nl, !live && qn == 0);
+                chi += drain_points<SINGLE_LC, LNL, S1, T>(dctx, ws, rt, frow, isig2, qn, n, nl, !live && qn == 0);
             }
             if (!live) break;
         }

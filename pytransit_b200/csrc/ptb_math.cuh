@@ -39,44 +39,47 @@ __device__ __forceinline__ double ccia_acos(double r1, double r2, double b) {
 // circle_circle_intersection_area_kite(1, k, z) (common.py:52-73, tsort :5-33): lens area of the
 // unit star and a planet of radius k at separation z, and kappa0.  k2 = k*k is passed in.
 // The Kahan-ordered product keeps the reference's parenthesisation.
-__device__ __forceinline__ void kite_area(double k, double k2, double z, double &area, double &kappa0) {
-    if (1.0 + k <= z) {
-        area = 0.0;
-        kappa0 = 0.0;
-    } else if (fabs(1.0 - k) < z) {
+template <typename T>
+__device__ __forceinline__ void kite_area(T k, T k2, T z, T &area, T &kappa0) {
+    const T one = T(1), two = T(2), half = T(0.5), pi = T(kPi);
+    if (one + k <= z) {
+        area = T(0);
+        kappa0 = T(0);
+    } else if (fabs(one - k) < z) {
         // descending sort of (1, k, z) as a 3-element min/max network (branch free)
-        const double hi = fmax(1.0, k), lo = fmin(1.0, k);
-        const double x = fmax(hi, z), t = fmin(hi, z);
-        const double y = fmax(lo, t), zz = fmin(lo, t);
-        const double akite = 0.5 * sqrt((x + (y + zz)) * (zz - (x - y)) * (zz + (x - y)) * (x + (y - zz)));
-        const double z2 = z * z;
-        const double k0 = atan2(2.0 * akite, (k - 1.0) * (k + 1.0) + z2);
-        const double k1 = atan2(2.0 * akite, (1.0 - k) * (1.0 + k) + z2);
+        const T hi = fmax(one, k), lo = fmin(one, k);
+        const T x = fmax(hi, z), t = fmin(hi, z);
+        const T y = fmax(lo, t), zz = fmin(lo, t);
+        const T akite = half * sqrt((x + (y + zz)) * (zz - (x - y)) * (zz + (x - y)) * (x + (y - zz)));
+        const T z2 = z * z;
+        const T k0 = atan2(two * akite, (k - one) * (k + one) + z2);
+        const T k1 = atan2(two * akite, (one - k) * (one + k) + z2);
         area = k1 + k2 * k0 - akite;
         kappa0 = k0;
-    } else if (z <= 1.0 - k) {
-        area = kPi * k2;
-        kappa0 = kPi;
-    } else if (z <= k - 1.0) {
-        area = kPi;
-        kappa0 = 0.0;
+    } else if (z <= one - k) {
+        area = pi * k2;
+        kappa0 = pi;
+    } else if (z <= k - one) {
+        area = pi;
+        kappa0 = T(0);
     } else {
-        area = nan("");
-        kappa0 = nan("");
+        area = T(nan(""));
+        kappa0 = T(nan(""));
     }
 }
 
 // interpolate_mean_limb_darkening_s (common.py:225-233) with inv_dg = 1/dg hoisted and the upper
 // node clamped to ng-1 (the reference reads lda[ng] for g in (1-1e-7, 1]; that term multiplies a
 // lens area < 1e-10).  `row` may point to shared or global memory.
-__device__ __forceinline__ double ldm_lerp(double g, double dg, double inv_dg, const double *row, int ng) {
-    if (g < 0.0) return nan("");
-    if (g > 1.0) return 0.0;
+template <typename T>
+__device__ __forceinline__ T ldm_lerp(T g, T dg, T inv_dg, const T *row, int ng) {
+    if (g < T(0)) return T(nan(""));
+    if (g > T(1)) return T(0);
     int i = (int)floor(g * inv_dg);
-    const double a = (g - i * dg) * inv_dg;
+    const T a = (g - i * dg) * inv_dg;
     const int i0 = min(i, ng - 1);
     const int i1 = min(i + 1, ng - 1);
-    return (1.0 - a) * row[i0] + a * row[i1];
+    return (T(1) - a) * row[i0] + a * row[i1];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -200,9 +203,10 @@ __device__ __forceinline__ void stencil_to_coeffs(const double *v, double *o) {
 }
 
 // sep_c (taylor_z.py:229-255): projected separation from the two quartics, Horner form.
-__device__ __forceinline__ double sep_poly(double t, const double *cx, const double *cy) {
-    const double px = fma(t, fma(t, fma(t, fma(t, cx[4], cx[3]), cx[2]), cx[1]), cx[0]);
-    const double py = fma(t, fma(t, fma(t, fma(t, cy[4], cy[3]), cy[2]), cy[1]), cy[0]);
+template <typename T>
+__device__ __forceinline__ T sep_poly(T t, const T *cx, const T *cy) {
+    const T px = fma(t, fma(t, fma(t, fma(t, cx[4], cx[3]), cx[2]), cx[1]), cx[0]);
+    const T py = fma(t, fma(t, fma(t, fma(t, cy[4], cy[3]), cy[2]), cy[1]), cy[0]);
     return sqrt(px * px + py * py);
 }
 

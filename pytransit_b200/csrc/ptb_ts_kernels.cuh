@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256) k_ts_flux(const __grid_constant__ TsFluxP
             double v[VEC];
 #pragma unroll
             for (int j = 0; j < VEC; ++j) v[j] = nan("");
-            for (int pb = pb_beg; pb < pb_end; ++pb) VecIO<VEC>::store(fbase + (size_t)pb * npt, v);
+            for (int pb = pb_beg; pb < pb_end; ++pb) VecIO<VEC, double>::store(fbase + (size_t)pb * npt, v);
         }
         return;
     }
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) k_ts_flux(const __grid_constant__ TsFluxP
     TsGeo G[VEC];
     TsGeo *sG = reinterpret_cast<TsGeo *>(smem_raw);
     double tv[VEC];
-    if (inr) VecIO<VEC>::load(P.time + i0, tv);
+    if (inr) VecIO<VEC, double>::load(P.time + i0, tv);
     bool any = false;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(256) k_ts_flux(const __grid_constant__ TsFluxP
         double v[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) v[j] = 1.0;
-        for (int pb = pb_beg; pb < pb_end; ++pb) VecIO<VEC>::store(fbase + (size_t)pb * npt, v);
+        for (int pb = pb_beg; pb < pb_end; ++pb) VecIO<VEC, double>::store(fbase + (size_t)pb * npt, v);
         return;
     }
     for (int pb = pb_beg; pb < pb_end; ++pb) {
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(256) k_ts_flux(const __grid_constant__ TsFluxP
                 }
             }
         }
-        VecIO<VEC>::store(fbase + (size_t)pb * npt, v);
+        VecIO<VEC, double>::store(fbase + (size_t)pb * npt, v);
     }
 }
 

@@ -48,6 +48,11 @@ class RoadRunnerModelCUDA(TransitModel):
     ``[npb,nldc]`` or ``[npv,npb,nldc]``.  With ``copy=True`` the result is a numpy array in
     page-locked memory owned by the model (re-used by the next call, like ``RoadRunnerModelCL.f``);
     with ``copy=False`` it is a ``torch`` CUDA tensor and nothing leaves the device.
+
+    ``precision='fp32'`` opts into the single-precision mode: the phase fold stays fp64, the per-sample
+    geometry / limb-darkening arithmetic and the returned flux are float32 (half the HBM and PCIe
+    traffic; within 1 ppm of the fp64 result).  The fused ``lnlikelihood`` then uses the fp32 model
+    values and accumulates chi^2 in fp64.
     """
 
     ldmodels = tuple(LD_LAWS.keys())
@@ -55,9 +60,13 @@ class RoadRunnerModelCUDA(TransitModel):
     def __init__(self, ldmodel: Union[str, Callable, Tuple[Callable, Callable], LDModel] = 'quadratic',
                  precompute_weights: bool = False, klims: tuple = (0.005, 0.5), nk: int = 256, nzin: int = 20,
                  nzlimb: int = 20, zcut: float = 0.7, ng: int = 100, nthreads: int = 1,
-                 small_planet_limit: float = 0.05, device: Optional[int] = None, **kwargs):
+                 small_planet_limit: float = 0.05, device: Optional[int] = None, precision: str = 'fp64', **kwargs):
         super().__init__()
         self._h = None
+        if precision not in ('fp64', 'fp32'):
+            raise ValueError("precision must be 'fp64' (default) or 'fp32' (opt-in).")
+        self.precision = precision
+        self._fdtype = np.float64 if precision == 'fp64' else np.float32
         self.interpolate = bool(kwargs.get('interpolate', precompute_weights))
         self.nthreads = nthreads
         self.parallel = True
@@ -97,6 +106,7 @@ class RoadRunnerModelCUDA(TransitModel):
         cfg.nk, cfg.nzin, cfg.nzlimb, cfg.ng = nk, nzin, nzlimb, ng
         cfg.kmin, cfg.kmax, cfg.zcut = float(klims[0]), float(klims[1]), float(zcut)
         cfg.precompute_weights = int(self.interpolate)
+        cfg.precision = 0 if precision == 'fp64' else 1
         h = C.c_void_p()
         check(lib().ptb_create(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -287,10 +297,10 @@ class RoadRunnerModelCUDA(TransitModel):
         p, a, i, e, w = (self._vec(v, npv, n) for v, n in ((p, 'p'), (a, 'a'), (i, 'i'), (e, 'e'), (w, 'w')))
         return npv, k, t0, p, a, i, e, w
 
-    def _result_buffer(self, shape, attr='_out'):
+    def _result_buffer(self, shape, attr='_out', dtype=np.float64):
         buf = getattr(self, attr)
-        if buf is None or buf.shape != tuple(shape):
-            buf = _lib.PinnedArray(shape)
+        if buf is None or buf.shape != tuple(shape) or buf.array.dtype != np.dtype(dtype):
+            buf = _lib.PinnedArray(shape, dtype)
             setattr(self, attr, buf)
         return buf.array
 
@@ -304,10 +314,11 @@ class RoadRunnerModelCUDA(TransitModel):
         ld, nld, istar = self._limb_darkening(ldc, npv, self.npb)
         stream = _current_stream(self.device)
         if copy:
-            out = self._result_buffer((npv, self.npt))
+            out = self._result_buffer((npv, self.npt), dtype=self._fdtype)
         else:
             import torch
-            out = torch.empty((npv, self.npt), dtype=torch.float64, device=f'cuda:{self.device}')
+            out = torch.empty((npv, self.npt), dtype=torch.float64 if self.precision == 'fp64' else torch.float32,
+                              device=f'cuda:{self.device}')
         check(lib().ptb_rr_evaluate(self._h, npv, ptr(k), k.shape[1], ptr(ld), nld, ptr(istar), ptr(t0), ptr(p),
                                     ptr(a), ptr(i), ptr(e), ptr(w), ptr(out), stream), self._h)
         return out.squeeze() if not copy else np.squeeze(out)

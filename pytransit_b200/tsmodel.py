@@ -24,6 +24,8 @@ class TSModelCUDA(RoadRunnerModelCUDA):
     def evaluate(self, k, ldc, t0, p, a, i, e=0.0, w=0.0, copy: bool = True):
         if self.time is None:
             raise RuntimeError("set_data must be called before evaluate.")
+        if self.precision != 'fp64':
+            raise NotImplementedError("TSModelCUDA computes in fp64; the opt-in fp32 mode covers RoadRunnerModelCUDA.")
         k = _lib.as_f64(k)
         if k.ndim == 0:
             k = k.reshape(1, 1)

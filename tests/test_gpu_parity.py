@@ -359,3 +359,64 @@ def test_full_size_c2_properties(pb, orc, tab):
     l2 = m.lnlike_normal(f, sigma).copy()
     # different summation orders; lnL is a difference of O(1e5) terms, so compare at 1e-9 relative
     np.testing.assert_allclose(l1, l2, rtol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------
+# opt-in fp32 mode: <= 1 ppm from the reference (north star), float32 output
+# ---------------------------------------------------------------------------------------------
+FP32_TOL = 1e-6       # 1 ppm of the (unit) out-of-transit flux
+
+
+@pytest.mark.parametrize('name,law', [('c2', 'power-2'), ('c3', 'quadratic'), ('c5', 'power-2'), ('edge', 'power-2'),
+                                      ('ttv', 'quadratic')])
+def test_fp32_mode_vs_reference_golden(pb, golden, name, law):
+    d = golden(name)
+    ref = np.atleast_2d(d['flux'])
+    m = pb.RoadRunnerModelCUDA(law, precision='fp32')
+    _set_data(m, d)
+    flux = np.atleast_2d(m.evaluate(*_full_args(d))).copy()
+    assert flux.dtype == np.float32 and flux.shape == ref.shape
+    assert np.array_equal(np.isnan(flux), np.isnan(ref))
+    err = np.nanmax(np.abs(flux.astype(np.float64) - ref))
+    assert err <= FP32_TOL, err
+    assert (flux[~np.isnan(flux)] <= 1.0).all()
+
+
+def test_fp32_mode_population_lnlike_and_device_output(pb, orc, tab):
+    import torch
+    c = wl.config5(npv=96, npt=50_000)
+    ldp, istar = orc.evaluate_ld('power-2', tab.mu, c.ldc)
+    ref = orc.rr_full(tab, c.time, c.k, c.t0, c.p, c.a, c.i, c.e, c.w, c.lcids, c.pbids, c.epids, c.nsamples,
+                      c.exptimes, ldp, istar)
+    m = pb.RoadRunnerModelCUDA('power-2', precision='fp32')
+    m.set_data(c.time)
+    f = m.evaluate(c.k, c.ldc, c.t0, c.p, c.a, c.i, c.e, c.w, copy=False)
+    assert isinstance(f, torch.Tensor) and f.dtype == torch.float32 and f.is_cuda
+    err = np.abs(f.cpu().numpy().astype(np.float64) - ref).max()
+    assert err <= FP32_TOL, err
+    # fused likelihood on the fp32 model values: chi^2 accumulated in fp64
+    m.set_obs(c.obs)
+    lnl = m.lnlikelihood(c.k, c.ldc, c.t0, c.p, c.a, c.i, c.e, c.w, sigma=c.sigma).copy()
+    lref = orc.lnlike_normal(c.obs, ref, c.sigma, c.slices, c.nids)
+    assert lnl.dtype == np.float64
+    # float32 model values are quantised at 6e-8 near 1.0: chi^2 = sum ((o - m) / sigma)^2 over ~2000 in-transit points with
+    # sigma ~ 1e-3 moves by a few 1e-2 (observed <= 0.05), statistically irrelevant but far above the fp64 bar
+    np.testing.assert_allclose(lnl, lref, rtol=0, atol=0.25)
+    # supersampled, several light curves
+    c3 = wl.config3(npv=32, npt_per_lc=2048)
+    m3 = pb.RoadRunnerModelCUDA('quadratic', precision='fp32')
+    m3.set_data(c3.time, c3.lcids, c3.pbids, c3.nsamples, c3.exptimes, c3.epids)
+    f3 = m3.evaluate(c3.k, c3.ldc, c3.t0, c3.p, c3.a, c3.i, c3.e, c3.w).copy()
+    ldp3, istar3 = orc.evaluate_ld('quadratic', tab.mu, c3.ldc)
+    ref3 = orc.rr_full(tab, c3.time, c3.k, c3.t0, c3.p, c3.a, c3.i, c3.e, c3.w, c3.lcids, c3.pbids, c3.epids,
+                       c3.nsamples, c3.exptimes, ldp3, istar3)
+    assert np.abs(f3.astype(np.float64) - ref3).max() <= FP32_TOL
+    # odd npt / misaligned rows take the scalar-store kernels
+    m1 = pb.RoadRunnerModelCUDA('power-2', precision='fp32')
+    m1.set_data(c.time[:4999])
+    f1 = m1.evaluate(c.k[:8], c.ldc[:8], c.t0[:8], c.p[:8], c.a[:8], c.i[:8], c.e[:8], c.w[:8]).copy()
+    assert np.abs(f1.astype(np.float64) - ref[:8, :4999]).max() <= FP32_TOL
+    with pytest.raises(NotImplementedError):
+        mt = pb.TSModelCUDA('power-2', precision='fp32')
+        mt.set_data(c.time[:100])
+        mt.evaluate(np.full((1, 2), 0.1), np.full((1, 2, 2), 0.3), 0.0, 3.0, 9.0, 1.5)
