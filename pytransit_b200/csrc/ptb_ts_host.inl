@@ -120,28 +120,66 @@ int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, con
         CU(h->d_flux.reserve(count * 8));
         dflux = h->d_flux.as<double>();
     }
-    TsFluxParams FP{};
-    FP.time = h->d_time; FP.tsorb = h->d_orb.as<double>(); FP.t0 = D.t0; FP.tsldm = h->d_ldrec.as<double>();
-    FP.tsrec = h->d_tsrec.as<double>(); FP.flux = dflux; FP.npt = h->npt; FP.npv = (int)npv; FP.npb = (int)npb;
-    FP.ng = ng; FP.ldt = ldt; FP.ns = ns; FP.exptime = exptime; FP.dg = h->dg; FP.inv_dg = 1.0 / h->dg;
     const bool multi = ns > 1;
     const bool aligned = !multi && (h->npt % 2 == 0) && ((reinterpret_cast<uintptr_t>(h->d_time) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(dflux) & 15) == 0);
     const int vec = aligned ? 2 : 1;
-    const long long tile = 256LL * vec;
-    FP.ntiles = (int)((h->npt + tile - 1) / tile);
-    const long long base_ctas = (long long)npv * FP.ntiles;
-    const long long want = (long long)h->sm_count * 16;
-    FP.pbsplit = (int)std::min<long long>(std::max<long long>(1, npb / 32), std::max<long long>(1, (want + base_ctas - 1) / base_ctas));
-    const long long grid = base_ctas * FP.pbsplit;
-    if (grid > 0x7fffffffLL) return fail(h, PTB_EINVAL, "ts_evaluate: grid too large");
-    const size_t smem_fl = multi ? (size_t)ns * 256 * sizeof(TsGeo) : 0;
-    mark(h, 2, st);
-    if (vec == 2) rc = launch_ts_flux_t<2, false>(h, FP, smem_fl, (unsigned)grid, st);
-    else if (!multi) rc = launch_ts_flux_t<1, false>(h, FP, smem_fl, (unsigned)grid, st);
-    else rc = launch_ts_flux_t<1, true>(h, FP, smem_fl, (unsigned)grid, st);
-    if (rc) return rc;
-    mark(h, 3, st);
+    const size_t geo_bytes = (size_t)npv * h->npt * 28;
+    if (!multi && geo_bytes <= (size_t)2 << 30) {
+        // ---- one sample per point: geometry pass + channel-chunk flux pass ------------------------------
+        const size_t npts = (size_t)npv * h->npt;
+        CU(h->d_tsgeo.reserve(geo_bytes + 64));
+        double *ga = h->d_tsgeo.as<double>();
+        TsGeoParams GP{};
+        GP.time = h->d_time; GP.tsorb = h->d_orb.as<double>(); GP.t0 = D.t0;
+        GP.galpha = ga; GP.gap0 = ga + npts; GP.gdadk = ga + 2 * npts; GP.gi0 = reinterpret_cast<int *>(ga + 3 * npts);
+        GP.npt = h->npt; GP.npv = (int)npv; GP.ng = ng; GP.exptime = exptime; GP.dg = h->dg; GP.inv_dg = 1.0 / h->dg;
+        const long long gtiles = (h->npt + 256LL * vec - 1) / (256LL * vec);
+        if (npv * gtiles > 0x7fffffffLL) return fail(h, PTB_EINVAL, "ts_evaluate: grid too large");
+        if (vec == 2) k_ts_geo<2><<<(unsigned)(npv * gtiles), 256, 0, st>>>(GP);
+        else k_ts_geo<1><<<(unsigned)(npv * gtiles), 256, 0, st>>>(GP);
+        h->launches++;
+        CU(cudaGetLastError());
+        TsFlux2Params FP{};
+        FP.tsorb = h->d_orb.as<double>(); FP.tsldm = h->d_ldrec.as<double>(); FP.tsrec = h->d_tsrec.as<double>();
+        FP.galpha = GP.galpha; FP.gap0 = GP.gap0; FP.gdadk = GP.gdadk; FP.gi0 = GP.gi0; FP.flux = dflux;
+        FP.npt = h->npt; FP.npv = (int)npv; FP.npb = (int)npb; FP.ng = ng; FP.ldt = ldt;
+        FP.nchunks = (int)((npb + TS_CH - 1) / TS_CH);
+        const long long grid = (long long)npv * FP.nchunks;
+        if (grid > 0x7fffffffLL) return fail(h, PTB_EINVAL, "ts_evaluate: grid too large");
+        const size_t smem_fl = (size_t)TS_CH * (ldt + 4) * 8;
+        mark(h, 2, st);
+        if (vec == 2) {
+            if (smem_fl > 48 * 1024) CU(cudaFuncSetAttribute(k_ts_flux2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fl));
+            k_ts_flux2<2><<<(unsigned)grid, 256, smem_fl, st>>>(FP);
+        } else {
+            if (smem_fl > 48 * 1024) CU(cudaFuncSetAttribute(k_ts_flux2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fl));
+            k_ts_flux2<1><<<(unsigned)grid, 256, smem_fl, st>>>(FP);
+        }
+        h->launches++;
+        CU(cudaGetLastError());
+        mark(h, 3, st);
+    } else {
+        // ---- supersampled (or very large) case: geometry in registers / shared memory per CTA ------------
+        TsFluxParams FP{};
+        FP.time = h->d_time; FP.tsorb = h->d_orb.as<double>(); FP.t0 = D.t0; FP.tsldm = h->d_ldrec.as<double>();
+        FP.tsrec = h->d_tsrec.as<double>(); FP.flux = dflux; FP.npt = h->npt; FP.npv = (int)npv; FP.npb = (int)npb;
+        FP.ng = ng; FP.ldt = ldt; FP.ns = ns; FP.exptime = exptime; FP.dg = h->dg; FP.inv_dg = 1.0 / h->dg;
+        const long long tile = 256LL * vec;
+        FP.ntiles = (int)((h->npt + tile - 1) / tile);
+        const long long base_ctas = (long long)npv * FP.ntiles;
+        const long long want = (long long)h->sm_count * 16;
+        FP.pbsplit = (int)std::min<long long>(std::max<long long>(1, npb / 32), std::max<long long>(1, (want + base_ctas - 1) / base_ctas));
+        const long long grid = base_ctas * FP.pbsplit;
+        if (grid > 0x7fffffffLL) return fail(h, PTB_EINVAL, "ts_evaluate: grid too large");
+        const size_t smem_fl = multi ? (size_t)ns * 256 * sizeof(TsGeo) : 0;
+        mark(h, 2, st);
+        if (vec == 2) rc = launch_ts_flux_t<2, false>(h, FP, smem_fl, (unsigned)grid, st);
+        else if (!multi) rc = launch_ts_flux_t<1, false>(h, FP, smem_fl, (unsigned)grid, st);
+        else rc = launch_ts_flux_t<1, true>(h, FP, smem_fl, (unsigned)grid, st);
+        if (rc) return rc;
+        mark(h, 3, st);
+    }
     h->last_npv = 0;  // RoadRunner stage taps do not describe a TS evaluation
     h->last_flux_count = direct ? 0 : (int64_t)count;
     if (flux && !direct) {

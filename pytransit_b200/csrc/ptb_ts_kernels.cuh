@@ -349,6 +349,158 @@ __global__ void __launch_bounds__(256) k_ts_flux(const __grid_constant__ TsFluxP
 }
 
 // ---------------------------------------------------------------------------------------------
+// Two-pass flux for one sample per point (the common spectroscopy case):
+//   k_ts_geo    geometry per (vector, time): fold, box test, separation, lens area at k-mean, kappa0,
+//               ld-mean node + weight -> geo arrays [npv][npt] (28 bytes per point, L2 resident)
+//   k_ts_flux2  CTA = (vector, chunk of TS_CH channels): the chunk's ld-mean rows and per-channel
+//               records arrive in shared memory by two TMA bulk copies; the CTA then walks the whole
+//               time axis: per point one coalesced geometry load, per channel two shared-memory
+//               gathers, a lerp, the first-order area correction and a 16-byte streaming store.
+// The channel loop reads nothing from global memory but the geometry, so the kernel is bound by the
+// flux write-out (8 B per point).
+// ---------------------------------------------------------------------------------------------
+struct TsGeoParams {
+    const double *time, *tsorb, *t0;
+    double *galpha, *gap0, *gdadk;  // [npv][npt]
+    int *gi0;                       // [npv][npt]: ld-mean node | TS_FULL, or -1 (flux exactly 1)
+    long long npt;
+    int npv, ng;
+    double exptime, dg, inv_dg;
+};
+constexpr int TS_FULL = 1 << 30;
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_ts_geo(const __grid_constant__ TsGeoParams P) {
+    const int ntiles = (int)((P.npt + 256LL * VEC - 1) / (256LL * VEC));
+    const int ipv = blockIdx.x / ntiles, tile = blockIdx.x - ipv * ntiles;
+    const long long i0 = (long long)tile * 256 * VEC + (long long)threadIdx.x * VEC;
+    if (i0 >= P.npt) return;
+    const double *orb = P.tsorb + (size_t)ipv * TSORB_STRIDE;
+    const size_t o = (size_t)ipv * P.npt + i0;
+    double al[VEC], ap[VEC], da[VEC];
+    int id[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { al[j] = 0.0; ap[j] = 0.0; da[j] = 0.0; id[j] = -1; }
+    if (orb[ORB_GOOD] != 0.0) {
+        const double p = orb[ORB_P], invp = orb[ORB_INVP];
+        const double pad = 0.0015 + P.exptime;  // model_trspec.py:67-68
+        const double lo = orb[ORB_T1] - pad, hi = orb[ORB_T4] + pad, t0 = P.t0[ipv];
+        const double kmean = orb[TSORB_KMEAN], kmax = orb[TSORB_KMAX], inv1k = orb[TSORB_INV1K], k2 = orb[TSORB_K2];
+        double cx[5], cy[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { cx[j] = orb[j]; cy[j] = orb[5 + j]; }
+        double tv[VEC];
+        VecIO<VEC, double>::load(P.time + i0, tv);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const double epoch = floor(fma(tv[j] - t0, invp, 0.5));
+            const double tc = tv[j] - __dadd_rn(t0, __dmul_rn(epoch, p));
+            if ((lo <= tc) && (tc <= hi)) {
+                const TsGeo g = ts_geometry(tc, cx, cy, kmean, k2, inv1k, kmax, P.dg, P.inv_dg, P.ng);
+                if (g.i0 >= 0) {
+                    al[j] = g.alpha; ap[j] = g.ap0; da[j] = g.dadk;
+                    id[j] = g.i0 | (g.full ? TS_FULL : 0);
+                }
+            }
+        }
+    }
+    VecIO<VEC, double>::store_keep(P.galpha + o, al);
+    VecIO<VEC, double>::store_keep(P.gap0 + o, ap);
+    VecIO<VEC, double>::store_keep(P.gdadk + o, da);
+    if (VEC == 2) *reinterpret_cast<int2 *>(P.gi0 + o) = make_int2(id[0], id[VEC - 1]);
+    else P.gi0[o] = id[0];
+}
+
+struct TsFlux2Params {
+    const double *tsorb, *tsldm, *tsrec, *galpha, *gap0, *gdadk;
+    const int *gi0;
+    double *flux;
+    long long npt;
+    int npv, npb, ng, ldt, nchunks;
+};
+constexpr int TS_CH = 32;  // channels per CTA
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_ts_flux2(const __grid_constant__ TsFlux2Params P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];  // [TS_CH][ldt] ld means | [TS_CH][4] records
+    __shared__ __align__(8) uint64_t bar;
+    double *sLdm = reinterpret_cast<double *>(smem_raw);
+    double *sRec = sLdm + (size_t)TS_CH * P.ldt;
+    const int tid = threadIdx.x;
+    const int ipv = blockIdx.x / P.nchunks, chunk = blockIdx.x - ipv * P.nchunks;
+    const int pb0 = chunk * TS_CH, nch = min(TS_CH, P.npb - pb0);
+    const long long npt = P.npt;
+    double *fbase = P.flux + ((size_t)ipv * P.npb + pb0) * npt;
+    const bool good = P.tsorb[(size_t)ipv * TSORB_STRIDE + ORB_GOOD] != 0.0;
+    if (good) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            const uint32_t b1 = (uint32_t)nch * P.ldt * 8u, b2 = (uint32_t)nch * 32u;
+            mbar_expect_tx(&bar, b1 + b2);
+            tma_load_1d(sLdm, P.tsldm + ((size_t)ipv * P.npb + pb0) * P.ldt, b1, &bar);
+            tma_load_1d(sRec, P.tsrec + ((size_t)ipv * P.npb + pb0) * 4, b2, &bar);
+        }
+        __syncthreads();
+        mbar_wait(&bar, 0);
+    }
+    const int ngm1 = P.ng - 1;
+    const size_t gbase = (size_t)ipv * npt;
+    for (long long i0 = (long long)tid * VEC; i0 < npt; i0 += 256 * VEC) {
+        double v[VEC];
+        if (!good) {  // flux[ipv, :, :] = nan (model_trspec.py:38)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) v[j] = nan("");
+            for (int c = 0; c < nch; ++c) VecIO<VEC, double>::store(fbase + (size_t)c * npt + i0, v);
+            continue;
+        }
+        double al[VEC], ap[VEC], da[VEC];
+        int id[VEC];
+        if (VEC == 2) {
+            const int2 t = __ldg(reinterpret_cast<const int2 *>(P.gi0 + gbase + i0));
+            id[0] = t.x; id[VEC - 1] = t.y;
+        } else {
+            id[0] = __ldg(P.gi0 + gbase + i0);
+        }
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) any |= id[j] >= 0;
+        if (!__any_sync(__activemask(), any)) {  // the whole warp is out of transit: ones for every channel
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) v[j] = 1.0;
+            for (int c = 0; c < nch; ++c) VecIO<VEC, double>::store(fbase + (size_t)c * npt + i0, v);
+            continue;
+        }
+        VecIO<VEC, double>::load(P.galpha + gbase + i0, al);
+        VecIO<VEC, double>::load(P.gap0 + gbase + i0, ap);
+        VecIO<VEC, double>::load(P.gdadk + gbase + i0, da);
+        int n0[VEC], n1[VEC];
+        bool full[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            full[j] = (id[j] & TS_FULL) != 0 && id[j] >= 0;
+            n0[j] = id[j] >= 0 ? (id[j] & ~TS_FULL) : 0;
+            n1[j] = min(n0[j] + 1, ngm1);
+        }
+#pragma unroll 2
+        for (int c = 0; c < nch; ++c) {
+            const double *row = sLdm + (size_t)c * P.ldt;
+            const double2 r01 = *reinterpret_cast<const double2 *>(sRec + c * 4);  // 1/I*, k^2/kmean^2
+            const double dkk = sRec[c * 4 + 2];                                      // k - kmean
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                v[j] = 1.0;
+                if (id[j] >= 0) {
+                    const double ip = (1.0 - al[j]) * row[n0[j]] + al[j] * row[n1[j]];
+                    const double x = full[j] ? ap[j] * r01.y : ap[j] + dkk * da[j];
+                    v[j] = 1.0 - ip * x * r01.x;
+                }
+            }
+            VecIO<VEC, double>::store(fbase + (size_t)c * npt + i0, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Tabulated-profile limb darkening (models/numba/ldtkldm.py:22-60,77-91): trilinear blend of the
 // 8 surrounding table nodes per vector, then I* = 2 pi trapezoid(z I, z).  One warp per
 // (vector, channel) row; the nmu nodes are contiguous in the table, so loads coalesce.
