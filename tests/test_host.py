@@ -68,8 +68,9 @@ def test_bad_config_rejected(lib):
     cfg.ldlaw, cfg.kmax = 2, 0.001
     assert lib.ptb_create(C.byref(cfg), C.byref(h)) == -1                      # PTB_EINVAL
     assert b'invalid integration grid' in lib.ptb_last_error(None)
-    cfg.kmax, cfg.precision = 0.5, 1
-    assert lib.ptb_create(C.byref(cfg), C.byref(h)) == -6
+    cfg.kmax, cfg.precision = 0.5, 7                                          # 0 (fp64) | 1 (opt-in fp32)
+    assert lib.ptb_create(C.byref(cfg), C.byref(h)) == -1
+    assert b'precision' in lib.ptb_last_error(None)
 
 
 def test_product_never_imports_oracle():
