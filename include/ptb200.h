@@ -175,6 +175,21 @@ int ptb_flux_device_ptr(ptb_model *h, void **ptr, int64_t *count);
 int ptb_host_alloc(void **ptr, size_t bytes);
 int ptb_host_free(void *ptr);
 
+/* Managed host result -- the analogue of RoadRunnerModelCL's persistent host array `f`
+ * (models/roadrunner/rrmodel_cl.py:365-369: `enqueue_copy(queue, self.f, self._b_f); return self.f`).
+ * `buf` is page-locked memory from ptb_host_alloc holding `count` result elements; the caller promises
+ * that between calls nobody but this handle writes to it.  After binding, every ptb_rr_evaluate /
+ * ptb_ts_evaluate whose `flux` argument is `buf` (and whose result has `count` elements) keeps `buf`
+ * up to date by DELTA transfer: a transit model is exactly 1.0 outside the transit windows
+ * (model_full.py:91), so after the first full copy only the 64-element blocks that differ from 1.0
+ * now -- or did after the previous call -- are written, by the GPU, straight into `buf` over PCIe.
+ * The content of `buf` after each call is identical to a full copy.  NULL unbinds.  Any other host
+ * pointer passed as `flux` takes the plain full-copy path. */
+int ptb_bind_host_result(ptb_model *h, void *buf, int64_t count);
+/* Bytes the last managed transfer moved to the host, and how many delta / full transfers ran. */
+int ptb_host_result_stats(const ptb_model *h, int64_t *last_bytes, int64_t *delta_calls,
+                          int64_t *full_calls);
+
 /* Kernels launched by this handle since creation (bench.py's gpu_launches evidence). */
 int64_t ptb_launch_count(const ptb_model *h);
 

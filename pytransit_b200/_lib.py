@@ -45,6 +45,8 @@ SIGNATURES = {
     'ptb_flux_device_ptr': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
     'ptb_host_alloc': (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     'ptb_host_free': (C.c_int, [_vp]),
+    'ptb_bind_host_result': (C.c_int, [_vp, _vp, _i64]),
+    'ptb_host_result_stats': (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     'ptb_launch_count': (_i64, [_vp]),
     'ptb_synchronize': (C.c_int, [_vp, _vp]),
     'ptb_set_profiling': (C.c_int, [_vp, C.c_int32]),

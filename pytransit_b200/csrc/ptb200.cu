@@ -133,6 +133,15 @@ struct ptb_model {
     std::vector<cudaEvent_t> tev;  // TRING x 4 events
     int64_t tcalls = 0;            // timed calls since profiling was enabled
 
+    // managed host result (ptb_bind_host_result): delta transfer of the flux into caller-owned pinned memory
+    void *hr_buf = nullptr, *hr_dev = nullptr;  // host address / its device mapping
+    int64_t hr_count = 0;
+    size_t hr_esize = 0;
+    bool hr_valid = false;           // hr_buf holds the previous result and d_lit its lit-block bitmap
+    DevBuf d_lit;                    // lit bitmap words | 8-byte counter of blocks written
+    PinBuf h_hrstat;                 // the counter, read back with the result
+    int64_t hr_last_bytes = 0, hr_delta_calls = 0, hr_full_calls = 0;
+
     std::string err;
     int64_t launches = 0;
 };
@@ -246,6 +255,50 @@ std::vector<double> linspace(double a, double b, int n) {
         v[n - 1] = b;
     } else if (n == 1) v[0] = a;
     return v;
+}
+
+// Device result -> host.  Plain buffers get one copy-engine transfer.  The bound managed buffer
+// (ptb_bind_host_result) gets a full transfer the first time and k_host_delta afterwards: only blocks
+// that differ from 1.0 now, or did after the previous call, cross PCIe.  Returns after the data has landed.
+int deliver_host(ptb_model *h, void *host, const void *dsrc, size_t count, size_t esize, cudaStream_t st) {
+    const bool managed = host == h->hr_buf && (int64_t)count == h->hr_count && h->hr_buf != nullptr;
+    if (!managed) {
+        CU(cudaMemcpyAsync(host, dsrc, count * esize, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return PTB_OK;
+    }
+    const long long nwords = ((long long)count + 32 * HD_BLOCK - 1) / (32 * HD_BLOCK);
+    const bool delta = h->hr_valid && h->hr_esize == esize;
+    h->hr_valid = false;  // until this transfer has completed
+    const size_t lit_bytes = ((size_t)nwords * 4 + 15) & ~size_t(15);
+    if (lit_bytes + 16 > h->d_lit.cap && delta) return fail(h, PTB_ESTATE, "host result: bitmap lost");
+    CU(h->d_lit.reserve(lit_bytes + 16));
+    CU(h->h_hrstat.reserve(16));
+    unsigned *lit = h->d_lit.as<unsigned>();
+    unsigned long long *nwr = reinterpret_cast<unsigned long long *>(static_cast<char *>(h->d_lit.ptr) + lit_bytes);
+    CU(cudaMemsetAsync(nwr, 0, 8, st));
+    const unsigned grid = (unsigned)std::min<long long>((nwords + 7) / 8, (long long)h->sm_count * 8);
+    if (esize == 8)
+        k_host_delta<double><<<grid, 256, 0, st>>>(static_cast<const double *>(dsrc), static_cast<double *>(h->hr_dev), lit, nwr,
+                                                   (long long)count, nwords, delta ? 0 : 1);
+    else
+        k_host_delta<float><<<grid, 256, 0, st>>>(static_cast<const float *>(dsrc), static_cast<float *>(h->hr_dev), lit, nwr,
+                                                  (long long)count, nwords, delta ? 0 : 1);
+    h->launches++;
+    CU(cudaGetLastError());
+    if (!delta) CU(cudaMemcpyAsync(host, dsrc, count * esize, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_hrstat.ptr, nwr, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    h->hr_esize = esize;
+    h->hr_valid = true;
+    if (delta) {
+        h->hr_last_bytes = (int64_t)(*static_cast<unsigned long long *>(h->h_hrstat.ptr)) * HD_BLOCK * (int64_t)esize;
+        h->hr_delta_calls++;
+    } else {
+        h->hr_last_bytes = (int64_t)(count * esize);
+        h->hr_full_calls++;
+    }
+    return PTB_OK;
 }
 
 struct ModelArgs {
@@ -372,9 +425,10 @@ void ptb_destroy(ptb_model *h) {
     cudaSetDevice(h->cfg.device);
     for (DevBuf *b : {&h->d_tab, &h->d_W, &h->d_time_own, &h->d_meta, &h->d_obs_own, &h->d_blk, &h->d_nblk, &h->d_orb,
                       &h->d_ldrec, &h->d_ldp, &h->d_istar, &h->d_flux, &h->d_partial, &h->d_isig2, &h->d_lnl, &h->d_xyc,
-                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_sort, &h->d_rec, &h->d_work, &h->d_tsgeo})
+                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_sort, &h->d_rec, &h->d_work, &h->d_tsgeo, &h->d_lit})
         b->release();
     h->h_stage.release();
+    h->h_hrstat.release();
     if (h->stage_ev) cudaEventDestroy(h->stage_ev);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -864,10 +918,7 @@ int ptb_rr_evaluate(ptb_model *h, int64_t npv, const double *k, int64_t kcols, c
     if (int rc = launch_points(h, npv, dflux, nullptr, st, nullptr)) return rc;
     mark(h, 3, st);
     h->last_flux_count = direct ? 0 : (int64_t)count;
-    if (flux && !direct) {
-        CU(cudaMemcpyAsync(flux, dflux, count * esize, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-    }
+    if (flux && !direct) return deliver_host(h, flux, dflux, count, esize, st);
     return PTB_OK;
 }
 
@@ -998,6 +1049,34 @@ int ptb_flux_device_ptr(ptb_model *h, void **ptr, int64_t *count) {
     if (!h || !ptr || !count) return PTB_EINVAL;
     *ptr = h->d_flux.ptr;
     *count = h->last_flux_count;
+    return PTB_OK;
+}
+
+int ptb_bind_host_result(ptb_model *h, void *buf, int64_t count) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    h->hr_buf = h->hr_dev = nullptr;
+    h->hr_count = 0;
+    h->hr_valid = false;
+    if (!buf) return PTB_OK;
+    if (count < 1) return fail(h, PTB_ESHAPE, "bind_host_result: count must be >= 1");
+    void *dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, buf, 0) != cudaSuccess || !dp) {
+        cudaGetLastError();
+        return fail(h, PTB_EINVAL, "bind_host_result: the buffer is not page-locked memory mapped into the device "
+                                   "(allocate it with ptb_host_alloc)");
+    }
+    h->hr_buf = buf;
+    h->hr_dev = dp;
+    h->hr_count = count;
+    return PTB_OK;
+}
+
+int ptb_host_result_stats(const ptb_model *h, int64_t *last_bytes, int64_t *delta_calls, int64_t *full_calls) {
+    if (!h) return PTB_EINVAL;
+    if (last_bytes) *last_bytes = h->hr_last_bytes;
+    if (delta_calls) *delta_calls = h->hr_delta_calls;
+    if (full_calls) *full_calls = h->hr_full_calls;
     return PTB_OK;
 }
 

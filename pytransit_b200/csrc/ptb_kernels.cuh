@@ -1061,4 +1061,74 @@ __global__ void __launch_bounds__(256) k_lnl_model(const double *__restrict__ mo
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_host_delta -- keeps a page-locked HOST copy of a device result array up to date by writing only what
+// changed (ptb_bind_host_result).  A transit model flux is exactly 1.0 outside the transit windows
+// (model_full.py:91): the array is cut into blocks of 64 elements; a block is "lit" when any element
+// differs from 1.0 (NaN rows included).  Lit blocks are written straight into the host array through
+// its device mapping (coalesced 16-byte stores, 512 B per block over PCIe); blocks that were lit after
+// the previous call and are not any more are reset to 1.0; everything else already holds 1.0 on the
+// host.  `lit` keeps one bit per block between calls.  mode 0: delta; mode 1: only rebuild `lit`
+// (the caller ships the whole array with the copy engine).
+// One warp per word of 32 blocks, eight 16-byte loads in flight per lane.
+// ---------------------------------------------------------------------------------------------
+constexpr int HD_BLOCK = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_host_delta(const T *__restrict__ src, T *__restrict__ host, unsigned *__restrict__ lit,
+                                                    unsigned long long *__restrict__ nwritten, long long count,
+                                                    long long nwords, int mode) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long w = warp0; w < nwords; w += nwarps) {
+        const unsigned old = mode == 0 ? lit[w] : 0u;
+        unsigned cur = 0u;
+        const long long e0 = w * 32 * HD_BLOCK + lane * 2;
+#pragma unroll
+        for (int j0 = 0; j0 < 32; j0 += 8) {
+            T v[8][2];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const long long e = e0 + (long long)(j0 + j) * HD_BLOCK;
+                v[j][0] = T(1);
+                v[j][1] = T(1);
+                if (e + 1 < count) {
+                    if (sizeof(T) == 8) {
+                        const double2 t = __ldcs(reinterpret_cast<const double2 *>(src + e));
+                        v[j][0] = (T)t.x;
+                        v[j][1] = (T)t.y;
+                    } else {
+                        const float2 t = __ldcs(reinterpret_cast<const float2 *>(src + e));
+                        v[j][0] = (T)t.x;
+                        v[j][1] = (T)t.y;
+                    }
+                } else if (e < count) {
+                    v[j][0] = __ldcs(src + e);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const long long e = e0 + (long long)(j0 + j) * HD_BLOCK;
+                const bool ne = (v[j][0] != T(1)) || (v[j][1] != T(1));
+                const bool is_lit = __any_sync(0xffffffffu, ne);
+                const bool was_lit = (old >> (j0 + j)) & 1u;
+                if (is_lit) cur |= 1u << (j0 + j);
+                if (mode == 0 && (is_lit || was_lit)) {  // a block that went dark holds exactly 1.0 in v
+                    if (e + 1 < count) {
+                        if (sizeof(T) == 8) *reinterpret_cast<double2 *>(host + e) = make_double2((double)v[j][0], (double)v[j][1]);
+                        else *reinterpret_cast<float2 *>(host + e) = make_float2((float)v[j][0], (float)v[j][1]);
+                    } else if (e < count) {
+                        host[e] = v[j][0];
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+            lit[w] = cur;
+            if (mode == 0 && (cur | old)) atomicAdd(nwritten, (unsigned long long)__popc(cur | old));
+        }
+    }
+}
+
 }  // namespace ptb

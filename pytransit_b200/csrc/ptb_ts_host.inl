@@ -182,10 +182,7 @@ int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, con
     }
     h->last_npv = 0;  // RoadRunner stage taps do not describe a TS evaluation
     h->last_flux_count = direct ? 0 : (int64_t)count;
-    if (flux && !direct) {
-        CU(cudaMemcpyAsync(flux, dflux, count * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-    }
+    if (flux && !direct) return deliver_host(h, flux, dflux, count, 8, st);
     return PTB_OK;
 }
 

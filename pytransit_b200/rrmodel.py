@@ -49,6 +49,12 @@ class RoadRunnerModelCUDA(TransitModel):
     page-locked memory owned by the model (re-used by the next call, like ``RoadRunnerModelCL.f``);
     with ``copy=False`` it is a ``torch`` CUDA tensor and nothing leaves the device.
 
+    ``host_result='delta'`` (default): the model's host array is kept current by delta transfer -- after the
+    first full copy only the 64-point blocks that differ from 1.0 now, or did after the previous call, cross
+    PCIe (written by the GPU straight into the page-locked array).  Its content after every call is identical
+    to a full copy; it is handed out as a read-only view because the next call relies on it.  ``'copy'``
+    restores the plain full device-to-host copy into a writable array.
+
     ``precision='fp32'`` opts into the single-precision mode: the phase fold stays fp64, the per-sample
     geometry / limb-darkening arithmetic and the returned flux are float32 (half the HBM and PCIe
     traffic; within 1 ppm of the fp64 result).  The fused ``lnlikelihood`` then uses the fp32 model
@@ -60,9 +66,13 @@ class RoadRunnerModelCUDA(TransitModel):
     def __init__(self, ldmodel: Union[str, Callable, Tuple[Callable, Callable], LDModel] = 'quadratic',
                  precompute_weights: bool = False, klims: tuple = (0.005, 0.5), nk: int = 256, nzin: int = 20,
                  nzlimb: int = 20, zcut: float = 0.7, ng: int = 100, nthreads: int = 1,
-                 small_planet_limit: float = 0.05, device: Optional[int] = None, precision: str = 'fp64', **kwargs):
+                 small_planet_limit: float = 0.05, device: Optional[int] = None, precision: str = 'fp64',
+                 host_result: str = 'delta', **kwargs):
         super().__init__()
         self._h = None
+        if host_result not in ('delta', 'copy'):
+            raise ValueError("host_result must be 'delta' (default) or 'copy'.")
+        self.host_result = host_result
         if precision not in ('fp64', 'fp32'):
             raise ValueError("precision must be 'fp64' (default) or 'fp32' (opt-in).")
         self.precision = precision
@@ -302,7 +312,25 @@ class RoadRunnerModelCUDA(TransitModel):
         if buf is None or buf.shape != tuple(shape) or buf.array.dtype != np.dtype(dtype):
             buf = _lib.PinnedArray(shape, dtype)
             setattr(self, attr, buf)
+            if attr == '_out' and self.host_result == 'delta':
+                # the model's persistent host array (RoadRunnerModelCL.f): kept current by delta transfer
+                check(lib().ptb_bind_host_result(self._h, buf._ptr, buf.array.size), self._h)
         return buf.array
+
+    def _host_view(self, out):
+        """What ``evaluate(copy=True)`` hands out: in delta mode a READ-ONLY view -- the library relies on the
+        array still holding the previous result when the next call updates it."""
+        if self.host_result == 'delta':
+            out = out.view()
+            out.flags.writeable = False
+        return out
+
+    @property
+    def host_result_stats(self):
+        """(bytes moved to the host by the last managed transfer, delta transfers, full transfers)."""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib().ptb_host_result_stats(self._h, C.byref(a), C.byref(b), C.byref(c)), self._h)
+        return a.value, b.value, c.value
 
     # ------------------------------------------------------------------------------------------
     def evaluate(self, k, ldc, t0, p, a, i, e=0.0, w=0.0, copy: bool = True):
@@ -321,7 +349,7 @@ class RoadRunnerModelCUDA(TransitModel):
                               device=f'cuda:{self.device}')
         check(lib().ptb_rr_evaluate(self._h, npv, ptr(k), k.shape[1], ptr(ld), nld, ptr(istar), ptr(t0), ptr(p),
                                     ptr(a), ptr(i), ptr(e), ptr(w), ptr(out), stream), self._h)
-        return out.squeeze() if not copy else np.squeeze(out)
+        return out.squeeze() if not copy else np.squeeze(self._host_view(out))
 
     def __call__(self, k, ldc, t0, p, a, i, e=0.0, w=0.0, copy: bool = True):
         return self.evaluate(k, ldc, t0, p, a, i, e, w, copy)

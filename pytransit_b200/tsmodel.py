@@ -76,7 +76,7 @@ class TSModelCUDA(RoadRunnerModelCUDA):
             out = torch.empty(shape, dtype=torch.float64, device=f'cuda:{self.device}')
         check(lib().ptb_ts_evaluate(self._h, npv, npb, ptr(k), ptr(ld), nld, ptr(istar), ptr(t0), ptr(p), ptr(a),
                                     ptr(i), ptr(e), ptr(w), ptr(out), stream), self._h)
-        return out
+        return self._host_view(out) if copy else out
 
 
 TransmissionSpectroscopyModelCUDA = TSModelCUDA

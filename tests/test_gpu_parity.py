@@ -420,3 +420,54 @@ def test_fp32_mode_population_lnlike_and_device_output(pb, orc, tab):
         mt = pb.TSModelCUDA('power-2', precision='fp32')
         mt.set_data(c.time[:100])
         mt.evaluate(np.full((1, 2), 0.1), np.full((1, 2, 2), 0.3), 0.0, 3.0, 9.0, 1.5)
+
+
+# ---------------------------------------------------------------------------------------------
+# managed host result (ptb_bind_host_result): delta transfer must be indistinguishable from a full copy
+# ---------------------------------------------------------------------------------------------
+def _roll(c, n):
+    return tuple(np.roll(np.asarray(getattr(c, k)), n, axis=0) for k in ('k', 'ldc', 't0', 'p', 'a', 'i', 'e', 'w'))
+
+
+@pytest.mark.parametrize('precision,npt', [('fp64', 20_000), ('fp64', 19_999), ('fp32', 20_000), ('fp32', 4097)])
+def test_host_result_delta_equals_full_copy(pb, precision, npt):
+    """A sequence of different populations through evaluate(copy=True): after every call the model's host
+    array (delta transfer) must be bit-identical to the device result and to the plain full-copy mode --
+    including rows that turn NaN and back, and a change of population size (re-bind)."""
+    c = wl.config2(npv=160, npt=npt)
+    md = pb.RoadRunnerModelCUDA('power-2', precision=precision)                       # host_result='delta'
+    mc = pb.RoadRunnerModelCUDA('power-2', precision=precision, host_result='copy')
+    md.set_data(c.time)
+    mc.set_data(c.time)
+    base = _roll(c, 0)
+    seq = [base, _roll(c, 1), base, _roll(c, 7)]
+    bad = [np.array(x, copy=True) for x in base]
+    bad[4][::3] = 0.5                                # a <= 1: NaN rows (model_full.py:80-82)
+    seq += [tuple(bad), base, tuple(x[:50] for x in base), tuple(x[:50] for x in _roll(c, 3)), base, _roll(c, 2)]
+    for n, args in enumerate(seq):
+        dev = md.evaluate(*args, copy=False).cpu().numpy()
+        host = md.evaluate(*args)
+        full = mc.evaluate(*args)
+        assert not host.flags.writeable and full.flags.writeable
+        assert host.dtype == full.dtype == dev.dtype
+        assert np.array_equal(host, dev, equal_nan=True), n
+        assert np.array_equal(host, full, equal_nan=True), n
+    last, ndelta, nfull = md.host_result_stats
+    assert nfull == 3 and ndelta == len(seq) - 3      # full copies: first call and the two size changes
+    assert 0 < last < 0.5 * host.nbytes
+    with pytest.raises(ValueError):
+        host[0, 0] = 0.0
+
+
+def test_host_result_delta_tsmodel(pb):
+    c = wl.config4(npv=6, npb=40, npt=1500)
+    c.time = np.linspace(-0.5, 0.5, c.npt)            # leave some out-of-transit blocks
+    ldc = np.tile([0.6, 0.5], (c.npv, c.npb, 1))
+    m = pb.TSModelCUDA('power-2')
+    m.set_data(c.time)
+    for shift in (0.0, 0.21, -0.13, 0.0):
+        dev = m.evaluate(c.k, ldc, c.t0 + shift, c.p, c.a, c.i, c.e, c.w, copy=False).cpu().numpy()
+        host = m.evaluate(c.k, ldc, c.t0 + shift, c.p, c.a, c.i, c.e, c.w)
+        assert np.array_equal(host, dev, equal_nan=True)
+        assert (dev < 1).any() and (dev == 1).any()
+    assert m.host_result_stats[1] == 3
