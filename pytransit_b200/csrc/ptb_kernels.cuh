@@ -578,6 +578,31 @@ struct DrainCtx {
     int lane;
 };
 
+// One exposure sub-sample at time `t` from mid-transit, straight-line code (selects only, so that two
+// samples of one lane interleave): separation (taylor_z.py:229-255), LD-mean lerp
+// (common.py:225-233) and the area cases that need no lens formula (common.py:52-73).  `limb` marks a
+// sample on the limb: its contribution comes from limb_pass.
+template <typename T>
+__device__ __forceinline__ void sample_eval(T t, const T *cx, const T *cy, const T *row, int ng, T k, T inv1k, T inv_istar,
+                                            T k2, T dg, T inv_dg, T &z, T &ip, T &cc, bool &limb) {
+    const T one = T(1), pi = T(kPi), qnan = T(nan(""));
+    z = sep_poly<T>(t, cx, cy);
+    const T g = z * inv1k;
+    const T fl = floor(g * inv_dg);
+    const T a = (g - fl * dg) * inv_dg;
+    const int i = (int)fl;  // saturating conversion; NaN -> 0
+    const int i0 = min(max(i, 0), ng - 1), i1 = min(max(i + 1, 0), ng - 1);
+    T v = (one - a) * row[i0] + a * row[i1];
+    v = (g > one) ? T(0) : v;
+    ip = (g < T(0)) ? qnan : v;
+    const bool out = (one + k <= z);
+    limb = !out && (fabs(one - k) < z);
+    T c = qnan;
+    c = (z <= k - one) ? one - ip * pi * inv_istar : c;          // planet covers the star
+    c = (z <= one - k) ? one - ip * (pi * k2) * inv_istar : c;   // planet inside the disk
+    cc = out ? one : c;                                           // no overlap: area 0
+}
+
 // Lens-area pass over `take` limb samples at the top of the limb queue (warp-cooperative).
 // S1: writes the flux / accumulates chi^2 directly; otherwise fills the sample's slot of `contrib`.
 template <bool SINGLE_LC, bool LNL, bool S1, typename T>
@@ -649,61 +674,69 @@ __device__ __forceinline__ double drain_points(const DrainCtx<T> &c, const WarpS
 
     T sum = T(0);
     double chi = 0.0;
+    constexpr int U = S1 ? 1 : 2;  // sub-samples evaluated together per lane (instruction-level parallelism)
     for (int s0 = 0; s0 < S; s0 += SSC) {
         const int SS = min(SSC, S - s0);
-        for (int j = 0; j < SS; ++j) {
-            const int s = s0 + j;
-            bool limb = false;
-            T z = T(0), ip = T(0);
-            if (valid && s < ns) {
-                // exposure offset exptime*((s+1-0.5)/ns - 0.5) (model_full.py:94); exactly 0 for ns == 1
-                T off = T(0);
-                if (!S1 && ns != 1) off = et * (frac ? frac[s] : (T)(((s + 1) - 0.5) / ns - 0.5));
-                z = sep_poly<T>(tc + off, cx, cy);
-                ip = ldm_lerp<T>(z * inv1k, dg, inv_dg, row, ng);
-                T cc = T(0);
-                if (one + k <= z) cc = one;                                   // no overlap: area 0
-                else if (fabs(one - k) < z) limb = true;                      // lens: kite formula
-                else if (z <= one - k) cc = one - ip * (pi * k2) * inv_istar;
-                else if (z <= k - one) cc = one - ip * pi * inv_istar;        // planet covers the star
-                else cc = T(nan(""));
-                if (S1) sum = cc;
-                else if (!limb) contrib[j * 32 + lane] = cc;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, limb);
-            if (m) {
-                if (limb) {
-                    const int pos = nl + __popc(m & lt_mask);
-                    ws.l_slot()[pos] = S1 ? ipt : j * 32 + lane;
-                    ws.l_z()[pos] = z;
-                    ws.l_ip()[pos] = ip;
-                    if (!SINGLE_LC) ws.l_row()[pos] = rowoff;
-                }
-                nl += __popc(m);
-                __syncwarp();
-            }
+        for (int j = 0; j < SS; j += U) {
+            T z[U], ip[U], cc[U], fr[U];
+            bool limb[U], act[U];
+            // exposure offset exptime*((s+1-0.5)/ns - 0.5) (model_full.py:94); exactly 0 for ns == 1
             if (S1) {
-                // one sample per point: everything that is not on the limb is final
-                if (valid && !limb) {
-                    if (LNL) {
-                        const int b = P.blk ? P.blk[ipt] : 0;
-                        if (b >= 0) {
-                            const double d = P.obs[ipt] - (double)sum;
-                            chi += d * d * isig2[b];
+                fr[0] = T(0);
+            } else if (frac) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) fr[u] = frac[min(s0 + j + u, S - 1)];
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) fr[u] = (T)(((s0 + j + u + 1) - 0.5) / ns - 0.5);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                act[u] = valid && (s0 + j + u < ns) && (j + u < SS);
+                const T off = (S1 || ns == 1) ? T(0) : et * fr[u];
+                sample_eval<T>(tc + off, cx, cy, row, ng, k, inv1k, inv_istar, k2, dg, inv_dg, z[u], ip[u], cc[u], limb[u]);
+                limb[u] = limb[u] && act[u];
+                if (S1) sum = cc[u];
+                else if (act[u] && !limb[u]) contrib[(j + u) * 32 + lane] = cc[u];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (U > 1 && j + u >= SS) break;
+                const unsigned m = __ballot_sync(0xffffffffu, limb[u]);
+                if (m) {
+                    if (limb[u]) {
+                        const int pos = nl + __popc(m & lt_mask);
+                        ws.l_slot()[pos] = S1 ? ipt : (j + u) * 32 + lane;
+                        ws.l_z()[pos] = z[u];
+                        ws.l_ip()[pos] = ip[u];
+                        if (!SINGLE_LC) ws.l_row()[pos] = rowoff;
+                    }
+                    nl += __popc(m);
+                    __syncwarp();
+                }
+                if (S1) {
+                    // one sample per point: everything that is not on the limb is final
+                    if (valid && !limb[u]) {
+                        if (LNL) {
+                            const int b = P.blk ? P.blk[ipt] : 0;
+                            if (b >= 0) {
+                                const double d = P.obs[ipt] - (double)sum;
+                                chi += d * d * isig2[b];
+                            }
+                        } else {
+                            frow[ipt] = sum;
                         }
-                    } else {
-                        frow[ipt] = sum;
                     }
                 }
-            }
-            // lens area on the limb (sqrt + 2 atan2): a full warp at a time from the top of the limb
-            // queue (single code copy: one rounding behaviour); leftovers when the pass / item ends
-            const bool last = S1 ? flush : (j + 1 == SS);
-            while (nl >= 32 || (last && nl > 0)) {
-                const int take = min(nl, 32);
-                nl -= take;
-                chi += limb_pass<SINGLE_LC, LNL, S1, T>(P, ws, ld, row1, contrib, frow, isig2, lane, nl, take);
-                __syncwarp();
+                // lens area on the limb (sqrt + 2 atan2): a full warp at a time from the top of the limb
+                // queue (single code copy: one rounding behaviour); leftovers when the pass / item ends
+                const bool last = S1 ? flush : (j + u + 1 == SS);
+                while (nl >= 32 || (last && nl > 0)) {
+                    const int take = min(nl, 32);
+                    nl -= take;
+                    chi += limb_pass<SINGLE_LC, LNL, S1, T>(P, ws, ld, row1, contrib, frow, isig2, lane, nl, take);
+                    __syncwarp();
+                }
             }
         }
         if (!S1) {
@@ -914,8 +947,10 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
         };
         int cur = next_block();
         double tvn[2 / VEC][VEC];
+        int lcbn = 0;  // light curve of the prefetched block (-1: mixed, per-point lookup)
         auto load_block = [&](int bb) {
             const long long base = (long long)(bbeg + bb) * PT_BLOCK;
+            if (!SINGLE_LC) lcbn = __ldg(P.blc + bbeg + bb);
 #pragma unroll
             for (int h = 0; h < 2 / VEC; ++h) {
                 const long long i0 = base + (long long)(h * 32 + lane) * VEC;
@@ -934,6 +969,15 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
                 for (int h = 0; h < 2 / VEC; ++h)
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) tv[h][j] = tvn[h][j];
+                // a block inside one light curve (the rule): window and epoch are block constants
+                const int lcb = SINGLE_LC ? 0 : lcbn;
+                double lob = lo1, hib = hi1, t0b = t01;
+                if (!SINGLE_LC && lcb >= 0) {
+                    const double pd = sPad[lcb];
+                    lob = T1 - pd;
+                    hib = T4 + pd;
+                    t0b = t0v[sEp[lcb]];
+                }
                 cur = next_block();
                 if (cur >= 0) load_block(cur);  // in flight while this block is folded
 #pragma unroll
@@ -948,8 +992,9 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
                         int lc = 0;
                         fv[j] = T(1);
                         if (inr) {
-                            double lo = lo1, hi = hi1, t0 = t01;
-                            if (!SINGLE_LC) {
+                            double lo = lob, hi = hib, t0 = t0b;
+                            if (!SINGLE_LC) lc = lcb;
+                            if (!SINGLE_LC && lcb < 0) {
                                 lc = P.lcids[i0 + j];
                                 const double pd = sPad[lc];
                                 lo = T1 - pd;

@@ -15,6 +15,70 @@ constexpr double kPi = 3.14159265358979323846;
 constexpr double kTwoPi = 6.28318530717958647692;
 constexpr double kHalfPi = 1.57079632679489661923;
 
+
+// ---------------------------------------------------------------------------------------------
+// Branch-free fp64 primitives for the per-sample hot loop.  CUDA's sqrt / division / atan2 carry a
+// slow-path call that ends the basic block, so two independent samples in one lane cannot be interleaved
+// by the scheduler; these straight-line versions can (the loop is bound by dependent-issue latency, not by
+// the fp64 pipe).  Accuracy: <= 1 ulp (sqrt, div), <= 2 ulp (atan2) on the ranges the model produces.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_sqrt(double x) {
+    // operand clamped to the normal range (0 -> 1.5e-154, inf -> 6.7e153: the same side of every comparison
+    // the model makes); NaN passes through
+    const double xs = fmin(fmax(x, 2.2250738585072014e-308), 4.4942328371557893e+307);
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(xs));  // MUFU.RSQ64H, 2^-22 relative
+    double g = xs * r, h = 0.5 * r;
+    const double e = fma(-h, g, 0.5);
+    g = fma(g, e, g);          // sqrt(x)      to ~2^-43
+    h = fma(h, e, h);          // 1/(2 sqrt x) to ~2^-43
+    const double d = fma(-g, g, xs);
+    g = fma(d, h, g);          // residual step: full precision
+    return (x == x) ? g : x;
+}
+__device__ __forceinline__ float fast_sqrt(float x) { return sqrtf(x); }
+
+// n / d for finite, normal d (not 0)
+__device__ __forceinline__ double fast_div(double n, double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));  // MUFU.RCP64H, ~2^-20 relative
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    const double q = n * r;
+    return fma(fma(-q, d, n), r, q);
+}
+
+// atan2(y, x) for y >= 0 (the lens-area kite: y = 2 * kite area).  One division after the argument
+// reduction atan(q) = pi/4 + atan((q-1)/(q+1)) for q > tan(pi/8); odd polynomial of degree 23 in the
+// reduced argument (near-minimax fit, scratch/fit_atan.py: 1.5e-16 relative).
+__device__ __forceinline__ double atan2_pos(double y, double x) {
+    const double ax = fabs(x);
+    const double mx = fmax(ax, y), mn = fmin(ax, y);
+    const bool big = mn > 0.41421356237309503 * mx;
+    const double num = big ? mn - mx : mn;
+    const double den = big ? mn + mx : mx;
+    const double t = (den > 0.0) ? fast_div(num, den) : 0.0;
+    const double u = t * t;
+    double q = -1.78053972054194459e-02;
+    q = fma(q, u, 3.79652574538659332e-02);
+    q = fma(q, u, -5.03510245660155203e-02);
+    q = fma(q, u, 5.84687829733087222e-02);
+    q = fma(q, u, -6.66295181362919070e-02);
+    q = fma(q, u, 7.69204533090222520e-02);
+    q = fma(q, u, -9.09089680906402658e-02);
+    q = fma(q, u, 1.11111107449196583e-01);
+    q = fma(q, u, -1.42857142792502445e-01);
+    q = fma(q, u, 1.99999999999408928e-01);
+    q = fma(q, u, -3.33333333333331205e-01);
+    double r = fma(t * u, q, t);                 // atan(t)
+    r = big ? r + 0.78539816339744830962 : r;    // atan(mn / mx)
+    r = (y > ax) ? kHalfPi - r : r;
+    return (x < 0.0) ? kPi - r : r;
+}
+__device__ __forceinline__ float atan2_pos(float y, float x) { return atan2f(y, x); }
+
 // ---------------------------------------------------------------------------------------------
 // Geometry (models/roadrunner/common.py)
 // ---------------------------------------------------------------------------------------------
@@ -50,10 +114,10 @@ __device__ __forceinline__ void kite_area(T k, T k2, T z, T &area, T &kappa0) {
         const T hi = fmax(one, k), lo = fmin(one, k);
         const T x = fmax(hi, z), t = fmin(hi, z);
         const T y = fmax(lo, t), zz = fmin(lo, t);
-        const T akite = half * sqrt((x + (y + zz)) * (zz - (x - y)) * (zz + (x - y)) * (x + (y - zz)));
+        const T akite = half * fast_sqrt((x + (y + zz)) * (zz - (x - y)) * (zz + (x - y)) * (x + (y - zz)));
         const T z2 = z * z;
-        const T k0 = atan2(two * akite, (k - one) * (k + one) + z2);
-        const T k1 = atan2(two * akite, (one - k) * (one + k) + z2);
+        const T k0 = atan2_pos(two * akite, (k - one) * (k + one) + z2);
+        const T k1 = atan2_pos(two * akite, (one - k) * (one + k) + z2);
         area = k1 + k2 * k0 - akite;
         kappa0 = k0;
     } else if (z <= one - k) {
@@ -207,7 +271,7 @@ template <typename T>
 __device__ __forceinline__ T sep_poly(T t, const T *cx, const T *cy) {
     const T px = fma(t, fma(t, fma(t, fma(t, cx[4], cx[3]), cx[2]), cx[1]), cx[0]);
     const T py = fma(t, fma(t, fma(t, fma(t, cy[4], cy[3]), cy[2]), cy[1]), cy[0]);
-    return sqrt(px * px + py * py);
+    return fast_sqrt(fma(px, px, py * py));
 }
 
 // find_contact_point for points 1 (s=-1) and 4 (s=+1), target z = 1 + k (taylor_z.py:298-328).
