@@ -141,6 +141,35 @@ int ptb_rr_lnlike(ptb_model *h, int64_t npv, const double *k, int64_t kcols, con
 int ptb_lnlike_normal(ptb_model *h, int64_t npv, const double *model, const double *sigma,
                       double *lnl, void *stream);
 
+/* Parameter-vector layout of a log posterior function: where BaseLPF keeps the physical parameters in a
+ * row of the population array pvp[npv, npar] (lpf/lpf.py:328-356: tc, p, rho, b, k2, (q1, q2) per
+ * passband; WNLogLikelihood appends log10 sigma per noise block, wnloglikelihood.py:68-77).  Column
+ * indices are explicit so that TransitAnalysis' per-planet blocks (lpf/transitanalysis.py:72-107) map too. */
+typedef struct ptb_lpf_layout {
+    int32_t npar;               /* columns of pvp                                                    */
+    int32_t i_tc, i_p, i_rho, i_b; /* zero epoch, period [d], stellar density [g/cm^3], impact param. */
+    int32_t i_k2, nk2;          /* area ratio column(s): 1, or npb consecutive (k = sqrt(k2))        */
+    int32_t i_ld, nldc;         /* first limb-darkening column; npb x nldc consecutive                */
+    int32_t ld_map;             /* 1: (q1,q2) -> (u,v) = (2 sqrt(q1) q2, sqrt(q1)(1 - 2 q2)), map_ldc
+                                   (lpf/lpf.py:84-91); 0: coefficients passed through               */
+    int32_t i_secw, i_sesw;     /* sqrt(e) cos w, sqrt(e) sin w columns; -1 = circular orbit         */
+    int32_t inc_mode;           /* 0: i_from_ba (orbits_py.py:674-688); 1: i_from_baew (:654-670)   */
+    int32_t i_loge, nloge;      /* log10 sigma columns, one per noise block (lnlike only)            */
+    double tref;                /* reference time subtracted from tc (lpf/lpf.py:438)                */
+} ptb_lpf_layout;
+
+/* BaseLPF.transit_model (lpf/lpf.py:435-443): k = sqrt(k2), t0 = tc - tref, a = as_from_rhop(rho, p)
+ * (orbits_py.py:604-618, G = scipy.constants.G = 6.67430e-11), i = arccos(b/a), ldc = map_ldc(...), all
+ * computed on the device from pvp (host or device pointer), then the RoadRunner evaluation of
+ * ptb_rr_evaluate.  set_data must describe a single-epoch dataset. */
+int ptb_lpf_transit_model(ptb_model *h, const double *pvp, int64_t npv, const ptb_lpf_layout *lay,
+                          void *flux, void *stream);
+/* BaseLPF.lnlikelihood with one WNLogLikelihood (lpf/lpf.py:454-475, wnloglikelihood.py:79-81): the same
+ * mapping, sigma = 10**pvp[:, i_loge : i_loge + nloge], and the fused model + likelihood of ptb_rr_lnlike.
+ * The population never leaves the device when pvp and lnl are device pointers. */
+int ptb_lpf_lnlike(ptb_model *h, const double *pvp, int64_t npv, const ptb_lpf_layout *lay, double *lnl,
+                   void *stream);
+
 /* TransmissionSpectroscopyModel.evaluate -> tsmodel_serial (models/roadrunner/tsmodel.py:46-130,
  * model_trspec.py:11-93): k[npv,npb]; ld as above with npb = the spectroscopic channel count;
  * t0,p,a,inc,e,w[npv]; flux[npv,npb,npt].  Uses nsamples[0], exptimes[0] of set_data. */

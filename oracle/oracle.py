@@ -229,3 +229,47 @@ def lnlike_normal(o, m, e, slices, nids):
     lib().orc_lnlike_normal(_p(o), _p(m), C.c_int64(npv), C.c_int64(npt), _p(e), C.c_int64(e.shape[1]),
                             _p(slices), _p(nids), C.c_int64(slices.shape[0]), _p(lnl))
     return lnl
+
+
+# ---------------------------------------------------------------------------------------------
+# BaseLPF parameter mapping (numpy restatement; small, vectorised)
+# ---------------------------------------------------------------------------------------------
+G_SI = 6.67430e-11      # scipy.constants.G (CODATA 2018/2022), pytransit/orbits/orbits_py.py:34
+D_S = 86400.0           # orbits_py.py:40-42
+
+
+def as_from_rhop(rho, period):
+    """orbits_py.py:604-618."""
+    return (G_SI / (3 * np.pi)) ** (1 / 3) * ((period * D_S) ** 2 * 1e3 * rho) ** (1 / 3)
+
+
+def i_from_ba(b, a):
+    """orbits_py.py:674-688."""
+    return np.arccos(b / a)
+
+
+def i_from_baew(b, a, e, w):
+    """orbits_py.py:647-670."""
+    return np.arccos(b / (a * ((1.0 - e ** 2) / (1.0 + e * np.sin(w)))))
+
+
+def map_ldc(ldc):
+    """lpf/lpf.py:84-91: triangular (q1, q2) -> quadratic (u, v), interleaved per passband."""
+    ldc = np.atleast_2d(ldc)
+    uv = np.zeros_like(ldc)
+    a, b = np.sqrt(ldc[:, 0::2]), 2. * ldc[:, 1::2]
+    uv[:, 0::2] = a * b
+    uv[:, 1::2] = a * (1. - b)
+    return uv
+
+
+def lpf_map(pvp, npb, tref=0.0, nblocks=1):
+    """BaseLPF.transit_model's mapping (lpf/lpf.py:435-443) for the layout tc, p, rho, b, k2, (q1, q2) x npb,
+    loge x nblocks -> dict of fully expanded RoadRunner arguments + sigma (wnloglikelihood.py:80)."""
+    pv = np.atleast_2d(np.asarray(pvp, np.float64))
+    npv = pv.shape[0]
+    p = pv[:, 1].copy()
+    a = as_from_rhop(pv[:, 2], p)
+    return dict(k=np.sqrt(pv[:, 4:5]), ldc=map_ldc(pv[:, 5:5 + 2 * npb]).reshape(npv, npb, 2), t0=(pv[:, 0] - tref).reshape(npv, 1),
+                p=p, a=a, i=i_from_ba(pv[:, 3], a), e=np.zeros(npv), w=np.zeros(npv),
+                sigma=10 ** pv[:, 5 + 2 * npb:5 + 2 * npb + nblocks])

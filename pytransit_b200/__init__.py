@@ -9,10 +9,11 @@ the package works anywhere, constructing a model needs the built library and a B
 """
 from .ldmodel import LDModel, TabulatedLDModel
 from .loglikelihood import CUDALogLikelihood
+from .lpf import BaseLPFCUDA
 from .rrmodel import RoadRunnerModelCUDA
 from .transitmodel import TransitModel
 from .tsmodel import TSModelCUDA, TransmissionSpectroscopyModelCUDA
 
 __version__ = '0.1.0'
 __all__ = ['TransitModel', 'RoadRunnerModelCUDA', 'TSModelCUDA', 'TransmissionSpectroscopyModelCUDA',
-           'CUDALogLikelihood', 'LDModel', 'TabulatedLDModel']
+           'CUDALogLikelihood', 'BaseLPFCUDA', 'LDModel', 'TabulatedLDModel']

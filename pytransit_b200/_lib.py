@@ -23,6 +23,11 @@ class PtbConfig(C.Structure):
                 ('zcut', C.c_double), ('precompute_weights', C.c_int32), ('precision', C.c_int32)]
 
 
+class PtbLpfLayout(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ('npar', 'i_tc', 'i_p', 'i_rho', 'i_b', 'i_k2', 'nk2', 'i_ld', 'nldc', 'ld_map',
+                                         'i_secw', 'i_sesw', 'inc_mode', 'i_loge', 'nloge')] + [('tref', C.c_double)]
+
+
 _vp, _i64, _dbl = C.c_void_p, C.c_int64, C.c_double
 
 # name -> (restype, argtypes); every symbol include/ptb200.h declares
@@ -38,6 +43,8 @@ SIGNATURES = {
     'ptb_set_obs': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64]),
     'ptb_rr_lnlike': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64] + [_vp] * 10),
     'ptb_lnlike_normal': (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    'ptb_lpf_transit_model': (C.c_int, [_vp, _vp, _i64, C.POINTER(PtbLpfLayout), _vp, _vp]),
+    'ptb_lpf_lnlike': (C.c_int, [_vp, _vp, _i64, C.POINTER(PtbLpfLayout), _vp, _vp]),
     'ptb_ts_evaluate': (C.c_int, [_vp, _i64, _i64, _vp, _vp, _i64] + [_vp] * 9),
     'ptb_ldtk_profiles': (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _i64] + [_dbl] * 6 + [_vp] * 4),
     'ptb_get_stage': (C.c_int, [_vp, C.c_int32, _vp]),

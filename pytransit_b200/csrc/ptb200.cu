@@ -109,6 +109,7 @@ struct ptb_model {
     DevBuf d_orb, d_ldrec, d_ldp, d_istar, d_flux, d_partial, d_isig2, d_lnl, d_xyc;
     DevBuf d_tsw, d_tsrec, d_sort;
     DevBuf d_tsgeo;                  // TSModel geometry pass [npv][npt]
+    DevBuf d_lpf;                    // mapped LPF parameters (k_lpf_map)
     DevBuf d_rec, d_work;            // RoadRunner per-vector records; work counters of the persistent kernel
     int recstride = 0, rec_ld = 0;   // record stride / offset of the ld rows (doubles) of the last setup
     cudaStream_t side_stream = nullptr;  // the orbit solve runs here, concurrently with the table contraction
@@ -425,7 +426,7 @@ void ptb_destroy(ptb_model *h) {
     cudaSetDevice(h->cfg.device);
     for (DevBuf *b : {&h->d_tab, &h->d_W, &h->d_time_own, &h->d_meta, &h->d_obs_own, &h->d_blk, &h->d_nblk, &h->d_orb,
                       &h->d_ldrec, &h->d_ldp, &h->d_istar, &h->d_flux, &h->d_partial, &h->d_isig2, &h->d_lnl, &h->d_xyc,
-                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_sort, &h->d_rec, &h->d_work, &h->d_tsgeo, &h->d_lit})
+                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_sort, &h->d_rec, &h->d_work, &h->d_tsgeo, &h->d_lit, &h->d_lpf})
         b->release();
     h->h_stage.release();
     h->h_hrstat.release();
@@ -1150,6 +1151,85 @@ int ptb_synchronize(ptb_model *h, void *stream) {
     if (int rc = set_device(h)) return rc;
     CU(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     return PTB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+static_assert(sizeof(LpfLayout) == sizeof(ptb_lpf_layout), "LpfLayout must mirror ptb_lpf_layout");
+
+// pvp -> device arrays of the RoadRunner arguments (k_lpf_map); returns device pointers in A / sigma
+int lpf_map(ptb_model *h, const char *who, const double *pvp, int64_t npv, const ptb_lpf_layout *lay, bool want_sigma,
+            cudaStream_t st, ModelArgs &A, const double *&sigma) {
+    if (!h->has_data) return fail(h, PTB_ESTATE, "%s: call set_data first", who);
+    if (!pvp || !lay || npv < 1) return fail(h, PTB_EINVAL, "%s: null argument or npv < 1", who);
+    if (h->nep != 1) return fail(h, PTB_ESTATE, "%s: the LPF mapping needs a single-epoch dataset (nep=%lld)", who, (long long)h->nep);
+    if (h->cfg.ldlaw == PTB_LD_PROFILES) return fail(h, PTB_ESTATE, "%s: needs a named limb-darkening law", who);
+    const int64_t npb = h->npb;
+    const ptb_lpf_layout &L = *lay;
+    auto col = [&](int32_t i, int32_t n) { return i >= 0 && n >= 1 && (int64_t)i + n <= L.npar; };
+    if (L.npar < 5 || !col(L.i_tc, 1) || !col(L.i_p, 1) || !col(L.i_rho, 1) || !col(L.i_b, 1))
+        return fail(h, PTB_ESHAPE, "%s: orbit columns outside the %d-column parameter array", who, L.npar);
+    if (!(L.nk2 == 1 || L.nk2 == npb) || !col(L.i_k2, L.nk2))
+        return fail(h, PTB_ESHAPE, "%s: nk2=%d must be 1 or npb=%lld and lie inside the parameter array", who, L.nk2, (long long)npb);
+    if (L.nldc < 1 || !col(L.i_ld, (int32_t)(npb * L.nldc)) || (L.ld_map && L.nldc != 2))
+        return fail(h, PTB_ESHAPE, "%s: limb-darkening block (npb=%lld x nldc=%d at column %d) invalid", who, (long long)npb, L.nldc, L.i_ld);
+    if ((L.i_secw >= 0) != (L.i_sesw >= 0) || (L.i_secw >= 0 && (!col(L.i_secw, 1) || !col(L.i_sesw, 1))))
+        return fail(h, PTB_ESHAPE, "%s: secw / sesw columns invalid", who);
+    if (want_sigma && (L.nloge != h->nblocks || !col(L.i_loge, L.nloge)))
+        return fail(h, PTB_ESHAPE, "%s: %d log10-sigma columns given, the observations have %lld noise blocks", who, L.nloge, (long long)h->nblocks);
+
+    Stager S(h, st);
+    auto rp = S.add(pvp, (size_t)npv * L.npar * 8);
+    if (int rc = S.commit()) return rc;
+    const size_t n = (size_t)npv;
+    const size_t nsig = want_sigma ? (size_t)L.nloge : 0;
+    const size_t total = n * (L.nk2 + npb * L.nldc + 6 + nsig);
+    CU(h->d_lpf.reserve(total * 8));
+    double *b = h->d_lpf.as<double>();
+    LpfMapParams P{};
+    P.pvp = S.get<double>(rp);
+    P.k = b; b += n * L.nk2;
+    P.ldc = b; b += n * npb * L.nldc;
+    P.t0 = b; b += n;
+    P.p = b; b += n;
+    P.a = b; b += n;
+    P.inc = b; b += n;
+    P.e = b; b += n;
+    P.w = b; b += n;
+    P.sigma = want_sigma ? b : nullptr;
+    P.npv = (int)npv; P.npb = (int)npb;
+    memcpy(&P.L, lay, sizeof(LpfLayout));
+    k_lpf_map<<<(unsigned)((npv + 127) / 128), 128, 0, st>>>(P);
+    h->launches++;
+    CU(cudaGetLastError());
+    A = ModelArgs{npv, L.nk2, L.nldc, P.k, P.ldc, nullptr, P.t0, P.p, P.a, P.inc, P.e, P.w};
+    sigma = P.sigma;
+    return PTB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ptb_lpf_transit_model(ptb_model *h, const double *pvp, int64_t npv, const ptb_lpf_layout *lay, void *flux, void *stream) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    ModelArgs A{};
+    const double *sigma = nullptr;
+    if (int rc = lpf_map(h, "lpf_transit_model", pvp, npv, lay, false, static_cast<cudaStream_t>(stream), A, sigma)) return rc;
+    return ptb_rr_evaluate(h, npv, A.k, A.kcols, A.ld, A.nld, nullptr, A.t0, A.p, A.a, A.inc, A.e, A.w, flux, stream);
+}
+
+int ptb_lpf_lnlike(ptb_model *h, const double *pvp, int64_t npv, const ptb_lpf_layout *lay, double *lnl, void *stream) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    if (!h->has_obs) return fail(h, PTB_ESTATE, "lpf_lnlike: call set_obs first");
+    ModelArgs A{};
+    const double *sigma = nullptr;
+    if (int rc = lpf_map(h, "lpf_lnlike", pvp, npv, lay, true, static_cast<cudaStream_t>(stream), A, sigma)) return rc;
+    return ptb_rr_lnlike(h, npv, A.k, A.kcols, A.ld, A.nld, nullptr, A.t0, A.p, A.a, A.inc, A.e, A.w, sigma, lnl, stream);
 }
 
 }  // extern "C"

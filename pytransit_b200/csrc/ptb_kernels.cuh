@@ -1176,4 +1176,59 @@ __global__ void __launch_bounds__(256) k_host_delta(const T *__restrict__ src, T
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_lpf_map -- BaseLPF.transit_model's parameter mapping (lpf/lpf.py:435-443) on the device: one thread
+// per parameter vector turns a row of pvp[npv, npar] into the arguments of the RoadRunner evaluation.
+// as_from_rhop: orbits_py.py:604-618 with D_S = 86400 and G = scipy.constants.G; map_ldc: lpf.py:84-91;
+// sigma = 10**pv (wnloglikelihood.py:80).
+// ---------------------------------------------------------------------------------------------
+struct LpfLayout {  // mirror of ptb_lpf_layout (include/ptb200.h)
+    int32_t npar, i_tc, i_p, i_rho, i_b, i_k2, nk2, i_ld, nldc, ld_map, i_secw, i_sesw, inc_mode, i_loge, nloge;
+    double tref;
+};
+
+struct LpfMapParams {
+    const double *pvp;
+    double *k, *ldc, *t0, *p, *a, *inc, *e, *w, *sigma;
+    int npv, npb;
+    LpfLayout L;
+};
+
+__global__ void k_lpf_map(const __grid_constant__ LpfMapParams P) {
+    const int ipv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ipv >= P.npv) return;
+    const LpfLayout &L = P.L;
+    const double *pv = P.pvp + (size_t)ipv * L.npar;
+    const double per = pv[L.i_p], rho = pv[L.i_rho], b = pv[L.i_b];
+    const double ps = per * 86400.0;
+    const double a = pow(6.67430e-11 / (3.0 * kPi), 1.0 / 3.0) * pow(ps * ps * 1e3 * rho, 1.0 / 3.0);
+    double e = 0.0, w = 0.0;
+    if (L.i_secw >= 0) {
+        const double c = pv[L.i_secw], s = pv[L.i_sesw];
+        e = c * c + s * s;
+        w = atan2(s, c);
+    }
+    const double inc = (L.inc_mode == 1) ? acos(b / (a * ((1.0 - e * e) / (1.0 + e * sin(w))))) : acos(b / a);
+    P.t0[ipv] = pv[L.i_tc] - L.tref;
+    P.p[ipv] = per;
+    P.a[ipv] = a;
+    P.inc[ipv] = inc;
+    P.e[ipv] = e;
+    P.w[ipv] = w;
+    for (int j = 0; j < L.nk2; ++j) P.k[(size_t)ipv * L.nk2 + j] = sqrt(pv[L.i_k2 + j]);
+    double *ld = P.ldc + (size_t)ipv * P.npb * L.nldc;
+    const double *q = pv + L.i_ld;
+    if (L.ld_map) {
+        for (int pb = 0; pb < P.npb; ++pb) {
+            const double sa = sqrt(q[2 * pb]), tb = 2.0 * q[2 * pb + 1];
+            ld[2 * pb] = sa * tb;
+            ld[2 * pb + 1] = sa * (1.0 - tb);
+        }
+    } else {
+        for (int j = 0; j < P.npb * L.nldc; ++j) ld[j] = q[j];
+    }
+    if (P.sigma)
+        for (int j = 0; j < L.nloge; ++j) P.sigma[(size_t)ipv * L.nloge + j] = pow(10.0, pv[L.i_loge + j]);
+}
+
 }  // namespace ptb

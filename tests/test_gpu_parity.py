@@ -471,3 +471,38 @@ def test_host_result_delta_tsmodel(pb):
         assert np.array_equal(host, dev, equal_nan=True)
         assert (dev < 1).any() and (dev == 1).any()
     assert m.host_result_stats[1] == 3
+
+
+# ---------------------------------------------------------------------------------------------
+# BaseLPF glue on the device
+# ---------------------------------------------------------------------------------------------
+def test_base_lpf_on_device_vs_reference_golden(pb, golden):
+    """BaseLPFCUDA.transit_model / lnlikelihood against the fixture produced by the reference's own
+    map_ldc / as_from_rhop / i_from_ba / RoadRunnerModel / lnlike_normal (tests/golden/make_golden_lpf.py)."""
+    import torch
+    g = golden('lpf')
+    times = [g[f'time{i}'] for i in range(3)]
+    fluxes = [g[f'flux{i}'] for i in range(3)]
+    lpf = pb.BaseLPFCUDA('golden', ['g', 'r'], times, fluxes, pbids=g['pbids'], wnids=g['wnids'], nsamples=g['nsamples'],
+                         exptimes=g['exptimes'], tref=float(g['tref']))
+    assert lpf.npar == 11 and lpf.parameter_names[:5] == ['tc', 'p', 'rho', 'b', 'k2'] and lpf._sl_ld == slice(5, 9)
+    pvp = g['pvp']
+    flux = lpf.transit_model(pvp)
+    assert np.array_equal(np.isnan(flux), np.isnan(g['flux'])) and np.isnan(flux[7]).all()
+    ok = ~np.isnan(g['flux'])
+    err = np.abs(flux[ok] - g['flux'][ok]).max()
+    assert err <= FLUX_TOL, err
+    assert (g['flux'][ok] < 1).mean() > 0.05
+    lnl = lpf.lnlikelihood(pvp).copy()
+    fin = np.isfinite(g['lnl'])
+    assert np.array_equal(np.isfinite(lnl), fin)
+    np.testing.assert_allclose(lnl[fin], g['lnl'][fin], rtol=LNL_RTOL)
+    np.testing.assert_allclose(lpf.residuals(pvp[3]), np.concatenate(fluxes) - g['flux'][3], rtol=0, atol=FLUX_TOL)
+    # the population as a CUDA tensor: nothing touches the host
+    pv_d = torch.as_tensor(pvp, device='cuda')
+    lnl_d = lpf.lnlikelihood(pv_d, copy=False)
+    assert lnl_d.is_cuda and np.array_equal(lnl_d.cpu().numpy(), lnl, equal_nan=True)
+    f_d = lpf.transit_model(pv_d, copy=False)
+    assert f_d.is_cuda and np.array_equal(f_d.cpu().numpy(), flux, equal_nan=True)
+    with pytest.raises(ValueError):
+        lpf.lnlikelihood(pvp[:, :10])

@@ -123,3 +123,35 @@ def test_tsmodel_matches_reference(orc, tab, golden):
     ldpn, istarn = orc.evaluate_ld('power-2', tab.mu, d['ldc_named'])
     f = orc.tsmodel(tab, d['time'], d['k'], d['t0'], d['p'], d['a'], d['i'], d['e'], d['w'], 1, 0.0, ldpn, istarn)
     assert np.nanmax(np.abs(f - d['flux_named'])) <= 5e-15
+
+
+def _lpf_dataset(g):
+    times = [g[f'time{i}'] for i in range(3)]
+    fluxes = [g[f'flux{i}'] for i in range(3)]
+    return times, fluxes
+
+
+def test_lpf_mapping_and_likelihood_match_reference(orc, tab, golden):
+    """BaseLPF.transit_model / lnlikelihood (lpf/lpf.py:435-475): the oracle's mapping + rr_full + lnlike_normal
+    against the fixture produced by the reference's own map_ldc / as_from_rhop / i_from_ba / RoadRunnerModel."""
+    g = golden('lpf')
+    tref = float(g['tref'])
+    times, fluxes = _lpf_dataset(g)
+    m = orc.lpf_map(g['pvp'], npb=2, tref=tref, nblocks=2)
+    assert np.array_equal(m['ldc'].reshape(40, 4), g['ldc'])
+    np.testing.assert_allclose(m['a'], g['a'], rtol=2e-16)
+    np.testing.assert_allclose(m['i'], g['i'], rtol=2e-16)
+    assert np.array_equal(m['k'], g['k']) and np.array_equal(m['sigma'], g['sigma'])
+    timea = np.concatenate(times) - tref
+    lcids = np.concatenate([np.full(t.size, i) for i, t in enumerate(times)]).astype(np.int64)
+    ldp, istar = orc.evaluate_ld('quadratic', tab.mu, m['ldc'])
+    flux = orc.rr_full(tab, timea, m['k'], m['t0'], m['p'], m['a'], m['i'], m['e'], m['w'], lcids, g['pbids'].astype(np.int64),
+                       np.zeros(3, np.int64), g['nsamples'].astype(np.int64), g['exptimes'], ldp, istar)
+    assert np.array_equal(np.isnan(flux), np.isnan(g['flux'])) and np.isnan(flux[7]).all()
+    np.testing.assert_allclose(flux, g['flux'], rtol=0, atol=FLUX_TOL)
+    starts = np.cumsum([0] + [t.size for t in times])
+    slices = np.array([[starts[i], starts[i + 1]] for i in range(3)], np.int64)
+    lnl = orc.lnlike_normal(np.concatenate(fluxes), flux, m['sigma'], slices, g['wnids'].astype(np.int64))
+    ok = np.isfinite(g['lnl'])
+    assert ok.sum() == 39
+    np.testing.assert_allclose(lnl[ok], g['lnl'][ok], rtol=1e-13)
