@@ -110,6 +110,7 @@ struct ptb_model {
     DevBuf d_tsw, d_tsrec, d_sort;
     DevBuf d_tsgeo;                  // TSModel geometry pass [npv][npt]
     DevBuf d_lpf;                    // mapped LPF parameters (k_lpf_map)
+    DevBuf d_cells;                  // per-vector table cells of the tabulated-profile interpolation
     DevBuf d_rec, d_work;            // RoadRunner per-vector records; work counters of the persistent kernel
     int recstride = 0, rec_ld = 0;   // record stride / offset of the ld rows (doubles) of the last setup
     cudaStream_t side_stream = nullptr;  // the orbit solve runs here, concurrently with the table contraction
@@ -426,7 +427,7 @@ void ptb_destroy(ptb_model *h) {
     cudaSetDevice(h->cfg.device);
     for (DevBuf *b : {&h->d_tab, &h->d_W, &h->d_time_own, &h->d_meta, &h->d_obs_own, &h->d_blk, &h->d_nblk, &h->d_orb,
                       &h->d_ldrec, &h->d_ldp, &h->d_istar, &h->d_flux, &h->d_partial, &h->d_isig2, &h->d_lnl, &h->d_xyc,
-                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_sort, &h->d_rec, &h->d_work, &h->d_tsgeo, &h->d_lit, &h->d_lpf})
+                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_sort, &h->d_rec, &h->d_work, &h->d_tsgeo, &h->d_lit, &h->d_lpf, &h->d_cells})
         b->release();
     h->h_stage.release();
     h->h_hrstat.release();

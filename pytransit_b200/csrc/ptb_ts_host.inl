@@ -56,7 +56,7 @@ int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, con
     const int rs = ((nz + 3) / 4) * 4 + 4;
 
     CU(h->d_orb.reserve((size_t)npv * TSORB_STRIDE * 8));
-    CU(h->d_tsw.reserve((size_t)npv * ng * nz * 8));
+    CU(h->d_tsw.reserve((size_t)npv * ng * rs * 8));
     CU(h->d_ldrec.reserve((size_t)npv * npb * ldt * 8));
     CU(h->d_tsrec.reserve((size_t)npv * npb * 4 * 8));
 
@@ -68,9 +68,12 @@ int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, con
     SP.tsorb = h->d_orb.as<double>(); SP.tsw = h->d_tsw.as<double>();
     SP.npv = (int)npv; SP.npb = (int)npb; SP.nk = h->cfg.nk; SP.ng = ng; SP.nz = nz;
     SP.use_table = h->cfg.precompute_weights ? 1 : 0;
+    SP.rs = rs;
     SP.kmin = h->cfg.kmin; SP.dk = h->dk;
     mark(h, 0, st);
-    k_ts_setup<<<(unsigned)npv, 128, 0, st>>>(SP);
+    const size_t smem_setup = SP.use_table ? 0 : (size_t)ng * (nz + 1) * 8;   // direct weights are built in shared memory
+    if (smem_setup > 48 * 1024) CU(cudaFuncSetAttribute(k_ts_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_setup));
+    k_ts_setup<<<(unsigned)npv, TSS_THREADS, smem_setup, st>>>(SP);
     h->launches++;
     CU(cudaGetLastError());
 
@@ -100,8 +103,10 @@ int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, con
     MP.tsw = h->d_tsw.as<double>(); MP.ldp = ldp; MP.istar = ist; MP.k = D.k; MP.tsorb = h->d_orb.as<double>();
     MP.tsldm = h->d_ldrec.as<double>(); MP.tsrec = h->d_tsrec.as<double>();
     MP.npv = (int)npv; MP.npb = (int)npb; MP.ng = ng; MP.nz = nz; MP.ldt = ldt; MP.rs = rs;
-    const size_t smem_ldm = (size_t)(nt * 8 + TSL_PB) * rs * 8;
-    const unsigned grid_ldm = (unsigned)(npv * ((npb + TSL_PB - 1) / TSL_PB));
+    const size_t smem_ldm = (size_t)(nt * 8 + 2 * TSL_PB) * rs * 8;
+    const long long ntile_ldm = (npb + TSL_PB - 1) / TSL_PB;
+    MP.tpc = (int)std::min<long long>(4, ntile_ldm);
+    const unsigned grid_ldm = (unsigned)(npv * ((ntile_ldm + MP.tpc - 1) / MP.tpc));
     int rc;
     switch (nt) {
     case 4: rc = launch_ts_ldm_t<4>(h, MP, smem_ldm, grid_ldm, st); break;
@@ -213,9 +218,27 @@ int ptb_ldtk_profiles(ptb_model *h, const double *profiles, int64_t nx, int64_t 
     P.profiles = S.get<double>(rp); P.xs = S.get<double>(rx); P.ys = S.get<double>(ry); P.zs = S.get<double>(rz);
     P.mu = S.get<double>(rm); P.ldp = dldp; P.istar = dis; P.npv = npv; P.nx = (int)nx; P.ny = (int)ny; P.nz3 = (int)nz3;
     P.npb = (int)npb; P.nmu = (int)nmu; P.x0 = x0; P.dx = dx; P.y0 = y0; P.dy = dy; P.z0 = z0; P.dz = dz;
-    const long long rows = (long long)npv * npb;
-    k_ldtk_profiles<<<(unsigned)((rows + 3) / 4), 128, 0, st>>>(P);
-    h->launches++;
+    // Slab kernel when a few channels of the whole table fit in shared memory (chunk <= 32 channels, <= 96 KB
+    // so that two CTAs share an SM) and the population is large enough to amortise staging the table;
+    // otherwise one warp per (vector, channel) row reading the 8 nodes from L2.
+    const size_t node_bytes = (size_t)nmu * 8, nodes = (size_t)nx * ny * nz3;
+    const int chunk = (int)std::min<size_t>({(size_t)32, (size_t)npb, (96 * 1024) / std::max<size_t>(1, nodes * node_bytes)});
+    if (chunk >= 1 && npv >= 64 && nodes * nmu < ((size_t)1 << 30)) {
+        CU(h->d_cells.reserve((size_t)npv * sizeof(LdtkCell)));
+        LdtkCell *cells = h->d_cells.as<LdtkCell>();
+        k_ldtk_cells<<<(unsigned)((npv + 127) / 128), 128, 0, st>>>(P, cells);
+        const int nchunks = (int)((npb + chunk - 1) / chunk);
+        const long long want = (long long)h->sm_count * 4;
+        const int vsplit = (int)std::max<long long>(1, std::min<long long>((npv + 63) / 64, (want + nchunks - 1) / nchunks));
+        const size_t smem = (nodes * chunk * nmu + ((nmu + 1) & ~(size_t)1) + (size_t)LDS_WARPS * chunk * nmu) * 8;
+        CU(cudaFuncSetAttribute(k_ldtk_profiles_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ldtk_profiles_slab<<<(unsigned)(nchunks * vsplit), LDS_THREADS, smem, st>>>(P, cells, chunk, vsplit);
+        h->launches += 2;
+    } else {
+        const long long rows = (long long)npv * npb;
+        k_ldtk_profiles<<<(unsigned)((rows + 3) / 4), 128, 0, st>>>(P);
+        h->launches++;
+    }
     CU(cudaGetLastError());
     if (!ldp_dev) CU(cudaMemcpyAsync(ldp, dldp, (size_t)npv * npb * nmu * 8, cudaMemcpyDeviceToHost, st));
     if (!is_dev) CU(cudaMemcpyAsync(istar, dis, (size_t)npv * npb * 8, cudaMemcpyDeviceToHost, st));

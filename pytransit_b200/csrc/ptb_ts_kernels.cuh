@@ -12,7 +12,7 @@
 //
 // HBM layout:
 //   tsorb [npv][24]        cx[5] cy[5] p 1/p T1 T4 good - | kmean kmax 1/(1+kmean) kmean^2 ...
-//   tsw   [npv][ng][nz]    weight matrix at kmean
+//   tsw   [npv][ng][rs]    weight matrix at kmean, rows padded to rs = nz rounded up to 4, + 4 (pad = 0)
 //   tsldm [npv][npb][ldt]  limb-darkening means, ldt = ng rounded up to a multiple of 8
 //   tsrec [npv][npb][4]    1/I*, k^2/kmean^2, k - kmean, -
 //   flux  [npv][npb][npt]
@@ -29,13 +29,15 @@ struct TsSetupParams {
     const double *p, *a, *inc, *e, *w;
     const double *xyc_in;
     const double *W, *ze, *gs;
-    double *tsorb, *tsw;
-    int npv, npb, nk, ng, nz, use_table;
+    double *tsorb, *tsw;   // tsw[npv][ng][rs]: rows padded to rs doubles (pad columns zero) so that k_ts_ldm can
+    int npv, npb, nk, ng, nz, use_table, rs;  // stage the whole matrix with ONE bulk copy, bank-conflict free
     double kmin, dk;
 };
 
-__global__ void __launch_bounds__(128) k_ts_setup(const __grid_constant__ TsSetupParams P) {
-    __shared__ double s_sum[4], s_max[4];
+constexpr int TSS_THREADS = 256;
+
+__global__ void __launch_bounds__(TSS_THREADS) k_ts_setup(const __grid_constant__ TsSetupParams P) {
+    __shared__ double s_sum[TSS_THREADS / 32], s_max[TSS_THREADS / 32];
     const int ipv = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double a = P.a[ipv], e = P.e[ipv];
     double *orb = P.tsorb + (size_t)ipv * TSORB_STRIDE;
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(128) k_ts_setup(const __grid_constant__ TsSetu
     const double *kv = P.k + (size_t)ipv * P.npb;
     double s = 0.0, m = -INFINITY;
     bool anynan = false;
-    for (int i = tid; i < P.npb; i += 128) {
+    for (int i = tid; i < P.npb; i += TSS_THREADS) {
         const double v = kv[i];
         s += v;
         m = fmax(m, v);
@@ -63,9 +65,13 @@ __global__ void __launch_bounds__(128) k_ts_setup(const __grid_constant__ TsSetu
     }
     if (lane == 0) { s_sum[warp] = s; s_max[warp] = m; }
     __syncthreads();
-    const double kmean = (s_sum[0] + s_sum[1] + s_sum[2] + s_sum[3]) / P.npb;
+    double ksum = s_sum[0];
     double kmax = s_max[0];
-    for (int i = 1; i < 4; ++i) kmax = (isnan(kmax) || isnan(s_max[i])) ? nan("") : fmax(kmax, s_max[i]);
+    for (int i = 1; i < TSS_THREADS / 32; ++i) {
+        ksum += s_sum[i];
+        kmax = (isnan(kmax) || isnan(s_max[i])) ? nan("") : fmax(kmax, s_max[i]);
+    }
+    const double kmean = ksum / P.npb;
 
     if (warp == 0) {
         solve_orbit_warp(lane, P.p[ipv], a, P.inc[ipv], e, P.w[ipv], kmean,
@@ -81,17 +87,47 @@ __global__ void __launch_bounds__(128) k_ts_setup(const __grid_constant__ TsSetu
     }
     // weight matrix at kmean: table blend when precompute_weights and kmin <= kmean <= max(k)
     // (the reference's kmax argument is shadowed by max(k[ipv])), else direct.
-    double *wout = P.tsw + (size_t)ipv * P.ng * P.nz;
-    const int rowlen = P.ng * P.nz;
+    const int rs = P.rs, nz = P.nz;
+    double *wout = P.tsw + (size_t)ipv * P.ng * rs;
+    const int rowlen = P.ng * nz;
     if (P.use_table && P.kmin <= kmean && kmean <= kmax) {
         int ik = (int)floor((kmean - P.kmin) / P.dk);
         const double ak = (kmean - P.kmin - ik * P.dk) / P.dk;
         const int ik1 = min(ik + 1, P.nk - 1);
         ik = min(ik, P.nk - 1);
         const double *w0 = P.W + (size_t)ik * rowlen, *w1 = P.W + (size_t)ik1 * rowlen;
-        for (int i = tid; i < rowlen; i += 128) wout[i] = (1.0 - ak) * w0[i] + ak * w1[i];
+        for (int i = tid; i < P.ng * rs; i += TSS_THREADS) {
+            const int g = i / rs, c = i - g * rs;
+            wout[i] = c < nz ? (1.0 - ak) * w0[g * nz + c] + ak * w1[g * nz + c] : 0.0;
+        }
     } else {
-        for (int ig = tid; ig < P.ng; ig += 128) weight_row(kmean, P.gs[ig], P.ze, P.nz, wout + (size_t)ig * P.nz, 1);
+        // calculate_weights_2d (common.py:152-185) in shared memory: the ng x nz annulus areas in parallel, the
+        // running difference and running-sum normalisation of each row in index order (as weight_row does), then
+        // one coalesced write of the padded matrix
+        extern __shared__ __align__(16) double s_w[];   // [ng][nz + 1]  (odd stride: conflict-free row walks)
+        const int ws = nz + 1;
+        for (int i = tid; i < P.ng * nz; i += TSS_THREADS) {
+            const int g = i / nz, c = i - g * nz;
+            s_w[g * ws + c] = ccia_acos(P.ze[c], kmean, P.gs[g] * (1.0 + kmean));
+        }
+        __syncthreads();
+        for (int g = tid; g < P.ng; g += TSS_THREADS) {
+            double *w = s_w + (size_t)g * ws;
+            double a0 = w[0], sum = a0;
+            for (int i = 1; i < nz; ++i) {
+                const double a1 = w[i];
+                const double d = a1 - a0;
+                w[i] = d;
+                a0 = a1;
+                sum += d;
+            }
+            for (int i = 0; i < nz; ++i) w[i] /= sum;
+        }
+        __syncthreads();
+        for (int i = tid; i < P.ng * rs; i += TSS_THREADS) {
+            const int g = i / rs, c = i - g * rs;
+            wout[i] = c < nz ? s_w[g * ws + c] : 0.0;
+        }
     }
 }
 
@@ -118,7 +154,9 @@ __global__ void __launch_bounds__(128) k_ts_ld(const __grid_constant__ TsLdParam
 
 // ---------------------------------------------------------------------------------------------
 // LD contraction on the fp64 tensor cores.
-// CTA = (vector, tile of 64 channels), 8 warps; warp w owns channels [8w, 8w+8) x all ng.
+// CTA = (vector, run of `tpc` tiles of 64 channels), 8 warps; warp w owns channels [8w, 8w+8) x all ng of a tile.
+// The vector's weight matrix is staged once per CTA; profile tiles are double buffered (tile t+1 is in flight
+// while tile t is contracted).
 // A = ldp tile [64][nz] (row-major, K = nz), B = W [ng][nz] ("col-major" K x N), both staged in
 // shared memory with per-row TMA bulk copies into rows padded to nz+4 doubles (bank-conflict-free
 // fragment loads).  D[pb][ig] accumulates over nz/4 DMMA k-steps.
@@ -127,6 +165,7 @@ struct TsLdmParams {
     const double *tsw, *ldp, *istar, *k, *tsorb;
     double *tsldm, *tsrec;
     int npv, npb, ng, nz, ldt, rs;  // rs: padded shared-memory row stride (doubles), >= nz rounded up to 4
+    int tpc;                        // channel tiles per CTA (the weight matrix is staged once per CTA)
 };
 
 constexpr int TSL_PB = 64;
@@ -135,67 +174,92 @@ template <int NT>  // NT = number of 8-wide ig tiles (ldt/8), compile-time for r
 __global__ void __launch_bounds__(256) k_ts_ldm(const __grid_constant__ TsLdmParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int TSL_RS = P.rs;
-    double *sB = reinterpret_cast<double *>(smem_raw);   // [NT*8][rs]
-    double *sA = sB + NT * 8 * TSL_RS;                    // [TSL_PB][rs]
-    __shared__ __align__(8) uint64_t bar;
+    double *sB = reinterpret_cast<double *>(smem_raw);   // [NT*8][rs]  weight matrix, rows padded in global memory too
+    double *sA0 = sB + NT * 8 * TSL_RS;                   // 2 x [TSL_PB][ars] profile tiles; ars = nz (bulk) or rs (per-row)
+    __shared__ __align__(8) uint64_t bar[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ntile = (P.npb + TSL_PB - 1) / TSL_PB;
-    const int ipv = blockIdx.x / ntile;
-    const int pb0 = (blockIdx.x - ipv * ntile) * TSL_PB;
+    const int ngrp = (ntile + P.tpc - 1) / P.tpc;         // CTAs per vector
+    const int ipv = blockIdx.x / ngrp;
+    const int tile0 = (blockIdx.x - ipv * ngrp) * P.tpc, tile1 = min(ntile, tile0 + P.tpc);
     const double *orb = P.tsorb + (size_t)ipv * TSORB_STRIDE;
     if (orb[ORB_GOOD] == 0.0) return;
     const int nz = P.nz, ng = P.ng;
-    const int nrowsA = min(TSL_PB, P.npb - pb0);
+    // nz a multiple of 4: the k-steps never run past a row, so a profile tile needs no padding and arrives
+    // as ONE bulk copy (its rows are contiguous in ldp); otherwise rows are staged one by one into padded rows
+    const bool bulkA = (nz & 3) == 0;
+    const int ars = bulkA ? nz : TSL_RS;
+    const size_t atile = (size_t)TSL_PB * ars;
 
-    // zero the padding (rows beyond ng / npb, columns beyond nz) so it contributes nothing
-    for (int i = tid; i < (NT * 8 + TSL_PB) * TSL_RS; i += 256) {
-        const int r = i / TSL_RS, c = i - r * TSL_RS;
-        const bool isB = r < NT * 8;
-        const bool live = isB ? (r < ng && c < nz) : ((r - NT * 8) < nrowsA && c < nz);
-        if (!live) sB[i] = 0.0;
+    // zero what the copies never write: B rows beyond ng; A pad columns (per-row staging only)
+    for (int i = tid; i < (NT * 8 - ng) * TSL_RS; i += 256) sB[ng * TSL_RS + i] = 0.0;
+    if (!bulkA)
+        for (int i = tid; i < 2 * TSL_PB * ars; i += 256)
+            if (i % ars >= nz) sA0[i] = 0.0;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
     }
-    if (tid == 0) mbar_init(&bar, 1);
     __syncthreads();
-    if (warp == 0) {
-        const uint32_t rb = (uint32_t)nz * 8u;
-        if (lane == 0) mbar_expect_tx(&bar, rb * (uint32_t)(ng + nrowsA));
-        __syncwarp();
-        const double *wsrc = P.tsw + (size_t)ipv * ng * nz;
-        const double *asrc = P.ldp + ((size_t)ipv * P.npb + pb0) * nz;
-        for (int r = lane; r < ng; r += 32) tma_load_1d(sB + r * TSL_RS, wsrc + (size_t)r * nz, rb, &bar);
-        for (int r = lane; r < nrowsA; r += 32) tma_load_1d(sA + r * TSL_RS, asrc + (size_t)r * nz, rb, &bar);
-    }
-    mbar_wait(&bar, 0);
 
-    double acc[NT][2];
-#pragma unroll
-    for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = 0.0;
+    // stage tile `t` into buffer `b` (warp 0); the weight matrix rides on the first tile's barrier
+    auto stage = [&](int t, int b, bool with_w) {
+        const int pb0 = t * TSL_PB, nrows = min(TSL_PB, P.npb - pb0);
+        const uint32_t rb = (uint32_t)nz * 8u, wb = (uint32_t)ng * TSL_RS * 8u;
+        const double *asrc = P.ldp + ((size_t)ipv * P.npb + pb0) * nz;
+        double *dst = sA0 + (size_t)b * atile;
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&bar[b], (with_w ? wb : 0u) + rb * (uint32_t)nrows);
+            if (with_w) tma_load_1d(sB, P.tsw + (size_t)ipv * ng * TSL_RS, wb, &bar[b]);
+            if (bulkA) tma_load_1d(dst, asrc, rb * (uint32_t)nrows, &bar[b]);
+        }
+        __syncwarp();
+        if (!bulkA)
+            for (int r = lane; r < nrows; r += 32) tma_load_1d(dst + r * ars, asrc + (size_t)r * nz, rb, &bar[b]);
+    };
+    if (warp == 0) stage(tile0, 0, true);
+
     const int fr = lane >> 2, fc = lane & 3;
-    const double *arow = sA + (warp * 8 + fr) * TSL_RS + fc;
-    const double *brow = sB + fr * TSL_RS + fc;
     const int ksteps = (nz + 3) / 4;
-    for (int ks = 0; ks < ksteps; ++ks) {
-        const double av = arow[ks * 4];
+    const double kmean = orb[TSORB_KMEAN];
+    for (int t = tile0; t < tile1; ++t) {
+        const int it = t - tile0, b = it & 1;
+        const int pb0 = t * TSL_PB, nrowsA = min(TSL_PB, P.npb - pb0);
+        // every warp has finished reading buffer b^1 (tile t-1): refill it with tile t+1
+        __syncthreads();
+        if (warp == 0 && t + 1 < tile1) stage(t + 1, b ^ 1, false);
+        mbar_wait(&bar[b], (it >> 1) & 1);
+        double *sA = sA0 + (size_t)b * atile;
+        // rows beyond the last tile's channels hold stale data: finite garbage times computed-never-stored is
+        // fine, NaN is not a problem either (those accumulators are discarded)
+        double acc[NT][2];
 #pragma unroll
-        for (int n = 0; n < NT; ++n) dmma_m8n8k4(acc[n][0], acc[n][1], av, brow[n * 8 * TSL_RS + ks * 4]);
-    }
-    const int pb = pb0 + warp * 8 + fr;
-    if (pb < P.npb) {
-        double *out = P.tsldm + ((size_t)ipv * P.npb + pb) * P.ldt + fc * 2;
+        for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = 0.0;
+        const double *arow = sA + (warp * 8 + fr) * ars + fc;
+        const double *brow = sB + fr * TSL_RS + fc;
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const double av = arow[ks * 4];
 #pragma unroll
-        for (int n = 0; n < NT; ++n) *reinterpret_cast<double2 *>(out + n * 8) = make_double2(acc[n][0], acc[n][1]);
-    }
-    // per-channel record (model_trspec.py:43,87,91)
-    if (tid < nrowsA) {
-        const int q = pb0 + tid;
-        const double kmean = orb[TSORB_KMEAN];
-        const double kk = P.k[(size_t)ipv * P.npb + q];
-        double *rec = P.tsrec + ((size_t)ipv * P.npb + q) * 4;
-        rec[0] = 1.0 / P.istar[(size_t)ipv * P.npb + q];
-        rec[1] = (kk * kk) / (kmean * kmean);
-        rec[2] = kk - kmean;
-        rec[3] = 0.0;
+            for (int n = 0; n < NT; ++n) dmma_m8n8k4(acc[n][0], acc[n][1], av, brow[n * 8 * TSL_RS + ks * 4]);
+        }
+        const int pb = pb0 + warp * 8 + fr;
+        if (pb < P.npb) {
+            double *out = P.tsldm + ((size_t)ipv * P.npb + pb) * P.ldt + fc * 2;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) *reinterpret_cast<double2 *>(out + n * 8) = make_double2(acc[n][0], acc[n][1]);
+        }
+        // per-channel record (model_trspec.py:43,87,91)
+        if (tid < nrowsA) {
+            const int q = pb0 + tid;
+            const double kk = P.k[(size_t)ipv * P.npb + q];
+            double *rec = P.tsrec + ((size_t)ipv * P.npb + q) * 4;
+            rec[0] = 1.0 / P.istar[(size_t)ipv * P.npb + q];
+            rec[1] = (kk * kk) / (kmean * kmean);
+            rec[2] = kk - kmean;
+            rec[3] = 0.0;
+        }
     }
 }
 
@@ -558,6 +622,118 @@ __global__ void __launch_bounds__(128) k_ldtk_profiles(const __grid_constant__ L
     }
     s = warp_sum(s);
     if (lane == 0) P.istar[row] = 2.0 * kPi * s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same interpolation with the table slab of a few channels resident in shared memory.
+// k_ldtk_profiles reads 8 table rows from L2 for every (vector, channel) row it writes (C4: 2.6 GB of L2
+// reads for 0.33 GB of output).  Here a CTA owns `chunk` channels: the slab profiles[:, :, :, pb0:pb0+chunk, :]
+// (nodes x chunk x nmu doubles) is staged ONCE with one TMA bulk copy per table node, and the CTA then
+// walks the vectors, one warp per vector: L2 traffic drops to the table size and the kernel is bound by
+// its coalesced output stream.  k_ldtk_cells precomputes each vector's cell (8 node ids + 8 weights,
+// ldtkldm.py:22-50) so the per-element work is 8 shared-memory loads and 8 FMAs.
+// ---------------------------------------------------------------------------------------------
+struct LdtkCell {
+    double w[8];
+    int node[8];
+};
+
+__global__ void k_ldtk_cells(const __grid_constant__ LdtkParams P, LdtkCell *__restrict__ cells) {
+    const long long ipv = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ipv >= P.npv) return;
+    const double x = fmin(fmax(P.xs[ipv], P.x0), P.x0 + P.nx * P.dx);
+    const double y = fmin(fmax(P.ys[ipv], P.y0), P.y0 + P.ny * P.dy);
+    const double z = fmin(fmax(P.zs[ipv], P.z0), P.z0 + P.nz3 * P.dz);
+    int ix = (int)floor((x - P.x0) / P.dx), iy = (int)floor((y - P.y0) / P.dy), iz = (int)floor((z - P.z0) / P.dz);
+    const double ax = (x - P.x0 - ix * P.dx) / P.dx, ay = (y - P.y0 - iy * P.dy) / P.dy, az = (z - P.z0 - iz * P.dz) / P.dz;
+    const double rx = 1.0 - ax, ry = 1.0 - ay, rz = 1.0 - az;
+    const int ix1 = min(ix + 1, P.nx - 1), iy1 = min(iy + 1, P.ny - 1), iz1 = min(iz + 1, P.nz3 - 1);
+    ix = min(ix, P.nx - 1); iy = min(iy, P.ny - 1); iz = min(iz, P.nz3 - 1);
+    auto nd = [&](int jx, int jy, int jz) { return (jx * P.ny + jy) * P.nz3 + jz; };
+    LdtkCell c;
+    // the term order of trilinear_interpolation (ldtkldm.py:45-50)
+    c.w[0] = rx * ry * rz; c.node[0] = nd(ix, iy, iz);
+    c.w[1] = ax * ry * rz; c.node[1] = nd(ix1, iy, iz);
+    c.w[2] = rx * ay * rz; c.node[2] = nd(ix, iy1, iz);
+    c.w[3] = rx * ry * az; c.node[3] = nd(ix, iy, iz1);
+    c.w[4] = ax * ry * az; c.node[4] = nd(ix1, iy, iz1);
+    c.w[5] = rx * ay * az; c.node[5] = nd(ix, iy1, iz1);
+    c.w[6] = ax * ay * rz; c.node[6] = nd(ix1, iy1, iz);
+    c.w[7] = ax * ay * az; c.node[7] = nd(ix1, iy1, iz1);
+    cells[ipv] = c;
+}
+
+constexpr int LDS_THREADS = 512, LDS_WARPS = LDS_THREADS / 32;
+
+__global__ void __launch_bounds__(LDS_THREADS, 2) k_ldtk_profiles_slab(const __grid_constant__ LdtkParams P, const LdtkCell *__restrict__ cells,
+                                                           int chunk, int vsplit) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nmu = P.nmu, nodes = P.nx * P.ny * P.nz3;
+    const int nchunks = (P.npb + chunk - 1) / chunk;
+    const int ichunk = blockIdx.x % nchunks, isplit = blockIdx.x / nchunks;
+    const int pb0 = ichunk * chunk, nch = min(chunk, P.npb - pb0);
+    const int slab = chunk * nmu;        // doubles per node in shared memory
+    const int ne = nch * nmu;            // live elements per node / per vector
+    double *sT = reinterpret_cast<double *>(smem_raw);   // [nodes][chunk][nmu]
+    double *sZ = sT + (size_t)nodes * slab;               // [nmu]  z = sqrt(1 - mu^2)
+    double *sTerm = sZ + ((nmu + 1) & ~1);                // [LDS_WARPS][slab] trapezoid terms
+
+    const bool tma_ok = ((nmu & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.profiles) & 15) == 0);
+    if (tma_ok) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            mbar_expect_tx(&bar, (uint32_t)nodes * (uint32_t)ne * 8u);
+        }
+        __syncthreads();
+        for (int n = tid; n < nodes; n += LDS_THREADS)
+            tma_load_1d(sT + (size_t)n * slab, P.profiles + ((size_t)n * P.npb + pb0) * nmu, (uint32_t)ne * 8u, &bar);
+    } else {
+        for (int idx = tid; idx < nodes * ne; idx += LDS_THREADS) {
+            const int n = idx / ne, r = idx - n * ne;
+            sT[(size_t)n * slab + r] = __ldg(P.profiles + ((size_t)n * P.npb + pb0) * nmu + r);
+        }
+    }
+    for (int i = tid; i < nmu; i += LDS_THREADS) sZ[i] = sqrt(1.0 - P.mu[i] * P.mu[i]);
+    __syncthreads();
+    if (tma_ok) mbar_wait(&bar, 0);
+
+    double *term = sTerm + (size_t)warp * slab;
+    const int i_first = lane % nmu;   // mu node of this lane's first element; advanced by 32 (mod nmu) per pass
+    for (long long ipv = (long long)isplit * LDS_WARPS + warp; ipv < P.npv; ipv += (long long)LDS_WARPS * vsplit) {
+        const LdtkCell c = cells[ipv];   // uniform across the warp
+        const double *t0 = sT + (size_t)c.node[0] * slab, *t1 = sT + (size_t)c.node[1] * slab, *t2 = sT + (size_t)c.node[2] * slab,
+                     *t3 = sT + (size_t)c.node[3] * slab, *t4 = sT + (size_t)c.node[4] * slab, *t5 = sT + (size_t)c.node[5] * slab,
+                     *t6 = sT + (size_t)c.node[6] * slab, *t7 = sT + (size_t)c.node[7] * slab;
+        double *out = P.ldp + ((size_t)ipv * P.npb + pb0) * nmu;
+        double carry = 0.0;  // value of the element before this pass's first
+        int i = i_first;
+        for (int e0 = 0; e0 < ne; e0 += 32) {
+            const int e = e0 + lane;
+            double v = 0.0;
+            if (e < ne) {
+                v = t0[e] * c.w[0] + t1[e] * c.w[1] + t2[e] * c.w[2] + t3[e] * c.w[3] + t4[e] * c.w[4] + t5[e] * c.w[5] +
+                    t6[e] * c.w[6] + t7[e] * c.w[7];
+                out[e] = v;
+            }
+            double vp = __shfl_up_sync(0xffffffffu, v, 1);
+            if (lane == 0) vp = carry;
+            carry = __shfl_sync(0xffffffffu, v, 31);
+            // trapezoid term between nodes i-1 and i (integrate_profiles_set, ldtkldm.py:86-89)
+            if (e < ne) term[e] = i > 0 ? (sZ[i] - sZ[i - 1]) * 0.5 * (sZ[i] * v + sZ[i - 1] * vp) : 0.0;
+            i += 32;
+            while (i >= nmu) i -= nmu;
+        }
+        __syncwarp();
+        for (int ch = 0; ch < nch; ++ch) {   // the warp sums one channel's terms at a time
+            double sum = 0.0;
+            for (int j = lane; j < nmu; j += 32) sum += term[ch * nmu + j];
+            sum = warp_sum(sum);
+            if (lane == 0) P.istar[(size_t)ipv * P.npb + pb0 + ch] = 2.0 * kPi * sum;
+        }
+        __syncwarp();
+    }
 }
 
 }  // namespace ptb
