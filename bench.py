@@ -267,10 +267,18 @@ def make_steps(args, c, dev, local_rank, world, dist):
     if lnl:
         m.set_obs(torch.as_tensor(c.obs, device=dev))
         sig_d = torch.as_tensor(c.sigma, device=dev)
-    gathered = torch.empty((world * c.npv,), dtype=torch.float64, device=dev) if (lnl and world > 1) else None
+    gathered = peer = None
+    if lnl and world > 1:
+        if args.gather == 'peer':     # fused: the finishing kernel stores the shard into every rank's gathered array
+            from pytransit_b200.distributed import PeerLnLGather
+            peer = PeerLnLGather(m, c.npv)
+        else:
+            gathered = torch.empty((world * c.npv,), dtype=torch.float64, device=dev)
 
     def step_device():
         if lnl:
+            if peer is not None:
+                return peer.lnlikelihood(td['k'], td['ldc'], td['t0'], td['p'], td['a'], td['i'], td['e'], td['w'], sigma=sig_d)
             loc = m.lnlikelihood(td['k'], td['ldc'], td['t0'], td['p'], td['a'], td['i'], td['e'], td['w'], sigma=sig_d, copy=False)
             if gathered is not None:      # the one collective of the path: all-gather of lnL over NCCL/NVLink
                 dist.all_gather_into_tensor(gathered, loc)
@@ -444,7 +452,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64' if args.precision == 'fp64' else 'f32 (opt-in mode: fp64 phase fold, fp32 samples and output)', 'data': 'synthetic',
             'config': {'workload': desc, 'per_gpu': f'npv={c.npv} x npt={c.npt}' + (f' x npb={c.npb}' if args.workload == 'c4' else ''),
-                       'parallelism': f'population sharded over {world} GPU(s), ' + ('NCCL all-gather of lnL[npv] per step' if (lnl and world > 1) else 'no data-path collective'),
+                       'parallelism': f'population sharded over {world} GPU(s), ' + (('lnL[npv] all-gathered by peer stores from the finishing kernel into symmetric memory over NVLink + one barrier per step' if args.gather == 'peer' else 'NCCL all-gather of lnL[npv] per step') if (lnl and world > 1) else 'no data-path collective'),
                        'l2': ('time+obs (1.6 MB) are L2 resident by design; nothing is written' if lnl else
                               'each step streams %.2f GB of output through L2 (126 MB): inputs/outputs exceed L2, no explicit flush' % out_gb
                               if out_gb > 0.2 else
@@ -466,6 +474,7 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-kernel-timing', action='store_true')
+    ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'], help='N>1 lnL workloads: fused peer-memory all-gather (default) or NCCL all_gather')
     ap.add_argument('--host-result', default='delta', choices=['delta', 'copy'], help='e2e: delta transfer (default) or plain full copy')
     ap.add_argument('--precision', default='fp64', choices=['fp64', 'fp32'], help="'fp32' = the opt-in single-precision mode (c2/c3/c5 only)")
     args = ap.parse_args()

@@ -136,6 +136,18 @@ int ptb_rr_lnlike(ptb_model *h, int64_t npv, const double *k, int64_t kcols, con
                   const double *a, const double *inc, const double *e, const double *w,
                   const double *sigma, double *lnl, void *stream);
 
+/* The same, for a population sharded over the GPUs of one box: the likelihood and its
+ * all-gather in one pass.  peer_bufs[r] (r < world <= 16) is rank r's gathered array lnl_all[world * npv]
+ * as a device pointer valid in THIS process (symmetric / CUDA-IPC peer memory over NVLink); the finishing
+ * kernel stores this rank's lnl[npv] into slot `rank` of every one of them.  The caller orders the ranks
+ * afterwards (one symmetric-memory barrier) before anyone reads its gathered array.  Every rank must pass
+ * the same npv. */
+int ptb_rr_lnlike_allgather(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld,
+                            int64_t nld, const double *istar, const double *t0, const double *p,
+                            const double *a, const double *inc, const double *e, const double *w,
+                            const double *sigma, double *const *peer_bufs, int32_t world, int32_t rank,
+                            void *stream);
+
 /* lnlike_normal (wnloglikelihood.py:22-35) on an existing model flux m[npv,npt] (device or host),
  * e.g. baseline-multiplied flux produced by the caller (lpf/lpf.py:445-449). */
 int ptb_lnlike_normal(ptb_model *h, int64_t npv, const double *model, const double *sigma,

@@ -924,14 +924,21 @@ int ptb_rr_evaluate(ptb_model *h, int64_t npv, const double *k, int64_t kcols, c
     return PTB_OK;
 }
 
-int ptb_rr_lnlike(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld, int64_t nld,
-                  const double *istar, const double *t0, const double *p, const double *a, const double *inc,
-                  const double *e, const double *w, const double *sigma, double *lnl, void *stream) {
+static int rr_lnlike_impl(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld, int64_t nld,
+                          const double *istar, const double *t0, const double *p, const double *a, const double *inc,
+                          const double *e, const double *w, const double *sigma, double *lnl, double *const *peers,
+                          int world, int rank, void *stream) {
     if (!h) return PTB_EINVAL;
     if (int rc = set_device(h)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!h->has_obs) return fail(h, PTB_ESTATE, "rr_lnlike: call set_obs first");
-    if (!sigma || !lnl) return fail(h, PTB_EINVAL, "rr_lnlike: sigma / lnl is null");
+    if (!sigma || (!lnl && !peers)) return fail(h, PTB_EINVAL, "rr_lnlike: sigma / lnl is null");
+    if (peers) {
+        if (world < 1 || world > LNL_MAXPEERS || rank < 0 || rank >= world)
+            return fail(h, PTB_EINVAL, "rr_lnlike_allgather: world=%d (max %d), rank=%d", world, LNL_MAXPEERS, rank);
+        for (int r = 0; r < world; ++r)
+            if (!peers[r]) return fail(h, PTB_EINVAL, "rr_lnlike_allgather: peer buffer %d is null", r);
+    }
     ModelArgs A{npv, kcols, nld, k, ld, istar, t0, p, a, inc, e, w};
     if (int rc = check_model_args(h, "rr_lnlike", A, h->npb)) return rc;
     Staged D{};
@@ -947,21 +954,42 @@ int ptb_rr_lnlike(ptb_model *h, int64_t npv, const double *k, int64_t kcols, con
     mark(h, 2, st);
     if (int rc = launch_points(h, npv, nullptr, h->d_isig2.as<double>(), st, &nchunks)) return rc;
     mark(h, 3, st);
-    const bool direct = is_device_ptr(lnl);
-    double *dl = lnl;
-    if (!direct) {
-        CU(h->d_lnl.reserve(npv * 8));
-        dl = h->d_lnl.as<double>();
+    LnlOut out{};
+    const bool direct = peers || is_device_ptr(lnl);
+    if (peers) {
+        out.nout = world;
+        for (int r = 0; r < world; ++r) out.ptr[r] = peers[r] + (size_t)rank * npv;
+    } else {
+        out.nout = 1;
+        out.ptr[0] = lnl;
+        if (!direct) {
+            CU(h->d_lnl.reserve(npv * 8));
+            out.ptr[0] = h->d_lnl.as<double>();
+        }
     }
     k_lnl_finish<<<(unsigned)((npv + 127) / 128), 128, 0, st>>>(h->d_partial.as<double>(), nchunks, D.sigma,
-                                                                 h->d_nblk.as<double>(), (int)h->nblocks, (int)npv, dl);
+                                                                 h->d_nblk.as<double>(), (int)h->nblocks, (int)npv, out);
     h->launches++;
     CU(cudaGetLastError());
     if (!direct) {
-        CU(cudaMemcpyAsync(lnl, dl, npv * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(lnl, out.ptr[0], npv * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     return PTB_OK;
+}
+
+int ptb_rr_lnlike(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld, int64_t nld,
+                  const double *istar, const double *t0, const double *p, const double *a, const double *inc,
+                  const double *e, const double *w, const double *sigma, double *lnl, void *stream) {
+    return rr_lnlike_impl(h, npv, k, kcols, ld, nld, istar, t0, p, a, inc, e, w, sigma, lnl, nullptr, 1, 0, stream);
+}
+
+int ptb_rr_lnlike_allgather(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld, int64_t nld,
+                            const double *istar, const double *t0, const double *p, const double *a, const double *inc,
+                            const double *e, const double *w, const double *sigma, double *const *peer_bufs,
+                            int32_t world, int32_t rank, void *stream) {
+    if (!peer_bufs) return h ? fail(h, PTB_EINVAL, "rr_lnlike_allgather: peer_bufs is null") : PTB_EINVAL;
+    return rr_lnlike_impl(h, npv, k, kcols, ld, nld, istar, t0, p, a, inc, e, w, sigma, nullptr, peer_bufs, world, rank, stream);
 }
 
 int ptb_lnlike_normal(ptb_model *h, int64_t npv, const double *model, const double *sigma, double *lnl, void *stream) {
@@ -987,8 +1015,11 @@ int ptb_lnlike_normal(ptb_model *h, int64_t npv, const double *model, const doub
         CU(h->d_lnl.reserve(npv * 8));
         dl = h->d_lnl.as<double>();
     }
+    LnlOut out{};
+    out.nout = 1;
+    out.ptr[0] = dl;
     k_lnl_finish<<<(unsigned)((npv + 127) / 128), 128, 0, st>>>(h->d_partial.as<double>(), 1, ds, h->d_nblk.as<double>(),
-                                                                 (int)h->nblocks, (int)npv, dl);
+                                                                 (int)h->nblocks, (int)npv, out);
     h->launches += 3;
     CU(cudaGetLastError());
     if (!direct) {

@@ -1060,16 +1060,26 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
     }
 }
 
-// chi^2 partials -> lnL (wnloglikelihood.py:34): lnL = sum_b n_b (-log s_b - log(2 pi)/2) - chi^2/2
+// chi^2 partials -> lnL (wnloglikelihood.py:34): lnL = sum_b n_b (-log s_b - log(2 pi)/2) - chi^2/2.
+// The result goes to `nout` destinations: one (the caller's buffer), or -- the fused all-gather of a sharded
+// population -- slot `rank` of the gathered array on EVERY GPU of the box, written through NVLink peer
+// mappings (each rank's buffer is symmetric memory mapped into this process).
+constexpr int LNL_MAXPEERS = 16;
+struct LnlOut {
+    double *ptr[LNL_MAXPEERS];
+    int nout;
+};
+
 __global__ void k_lnl_finish(const double *__restrict__ partial, int nchunks, const double *__restrict__ sigma,
-                             const double *__restrict__ nblk, int nblocks, int npv, double *__restrict__ lnl) {
+                             const double *__restrict__ nblk, int nblocks, int npv, const __grid_constant__ LnlOut out) {
     const int ipv = blockIdx.x * blockDim.x + threadIdx.x;
     if (ipv >= npv) return;
     double chi = 0.0;
     for (int c = 0; c < nchunks; ++c) chi += partial[(size_t)ipv * nchunks + c];
     double cst = 0.0;
     for (int b = 0; b < nblocks; ++b) cst += nblk[b] * (-log(sigma[(size_t)ipv * nblocks + b]) - 0.5 * log(kTwoPi));
-    lnl[ipv] = cst - 0.5 * chi;
+    const double v = cst - 0.5 * chi;
+    for (int r = 0; r < out.nout; ++r) out.ptr[r][ipv] = v;
 }
 
 __global__ void k_inv_sigma2(const double *__restrict__ sigma, long long n, double *__restrict__ out) {

@@ -13,7 +13,7 @@ from typing import Callable, Optional, Sequence, Tuple
 
 import numpy as np
 
-__all__ = ['shard_bounds', 'shard_population', 'PopulationSharder']
+__all__ = ['shard_bounds', 'shard_population', 'PopulationSharder', 'PeerLnLGather']
 
 _POP_ARGS = ('k', 'ldc', 't0', 'p', 'a', 'i', 'e', 'w', 'sigma')
 
@@ -82,3 +82,39 @@ class PopulationSharder:
             parts.append(out[r * nmax:r * nmax + (hi - lo)])
         full = torch.cat(parts)
         return full.cpu().numpy() if as_numpy else full
+
+
+class PeerLnLGather:
+    """Fused likelihood + all-gather over NVLink peer memory (one box, one process per GPU).
+
+    Every rank owns a gathered array ``lnL[world * npv]`` in symmetric memory
+    (``torch.distributed._symmetric_memory``) that all peers map into their address space.  The likelihood's
+    finishing kernel stores the local shard straight into slot ``rank`` of EVERY rank's array
+    (``ptb_rr_lnlike_allgather``), so the exchange is part of the kernel instead of a separate NCCL
+    collective; one symmetric-memory barrier then orders the ranks.  Shards must have equal size
+    (``npv`` vectors per rank, SURVEY.md section 8e: 8192 per GPU at C5)."""
+
+    def __init__(self, model, npv_local: int, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.model = model
+        self.npv = int(npv_local)
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        dev = torch.device(f'cuda:{model.device}')
+        self.gathered = symm_mem.empty(self.world * self.npv, dtype=torch.float64, device=dev)
+        self.handle = symm_mem.rendezvous(self.gathered, self.group)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(self.peer_ptrs) != self.world:
+            raise RuntimeError("symmetric-memory rendezvous returned %d peer buffers for a world of %d"
+                               % (len(self.peer_ptrs), self.world))
+
+    def lnlikelihood(self, k, ldc, t0, p, a, i, e=0.0, w=0.0, sigma=1e-3):
+        """``lnL[world * npv]`` of the whole population on every rank (a CUDA tensor view of the symmetric
+        buffer, valid until the next call)."""
+        self.handle.barrier(channel=0)   # nobody is still reading the previous result
+        self.model.lnlikelihood_allgather(k, ldc, t0, p, a, i, e, w, sigma, self.peer_ptrs, self.rank)
+        self.handle.barrier(channel=1)   # every shard has landed everywhere
+        return self.gathered

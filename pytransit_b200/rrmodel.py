@@ -422,6 +422,21 @@ class RoadRunnerModelCUDA(TransitModel):
                                   ptr(a), ptr(i), ptr(e), ptr(w), ptr(sigma), ptr(out), stream), self._h)
         return out
 
+    def lnlikelihood_allgather(self, k, ldc, t0, p, a, i, e, w, sigma, peer_ptrs, rank: int) -> None:
+        """The fused likelihood with its all-gather (``ptb_rr_lnlike_allgather``): this rank's ``lnL[npv]`` is
+        stored into slot ``rank`` of every peer's gathered array (device pointers ``peer_ptrs``, mapped into
+        this process -- see ``pytransit_b200.distributed.PeerLnLGather``).  Asynchronous on the current stream."""
+        if not getattr(self, '_has_obs', False):
+            raise RuntimeError("set_obs must be called before lnlikelihood.")
+        npv, k, t0, p, a, i, e, w = self._expand(k, t0, p, a, i, e, w)
+        self._lastnpv = npv
+        ld, nld, istar = self._limb_darkening(ldc, npv, self.npb)
+        sigma = self._sigma(sigma, npv)
+        ptrs = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
+        check(lib().ptb_rr_lnlike_allgather(self._h, npv, ptr(k), k.shape[1], ptr(ld), nld, ptr(istar), ptr(t0), ptr(p),
+                                            ptr(a), ptr(i), ptr(e), ptr(w), ptr(sigma), ptrs, len(peer_ptrs), int(rank),
+                                            _current_stream(self.device)), self._h)
+
     def lnlike_normal(self, model, sigma, copy: bool = True):
         """``lnlike_normal(o, m, e, slices, nids)`` (wnloglikelihood.py:22-35) on a materialised model flux
         ``m[npv, npt]`` (numpy or CUDA tensor), using the observations registered with ``set_obs``."""

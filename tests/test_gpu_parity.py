@@ -506,3 +506,23 @@ def test_base_lpf_on_device_vs_reference_golden(pb, golden):
     assert f_d.is_cuda and np.array_equal(f_d.cpu().numpy(), flux, equal_nan=True)
     with pytest.raises(ValueError):
         lpf.lnlikelihood(pvp[:, :10])
+
+
+# ---------------------------------------------------------------------------------------------
+# fused likelihood + NVLink peer-memory all-gather (needs >= 2 GPUs; skipped on a single-GPU box)
+# ---------------------------------------------------------------------------------------------
+def test_peer_memory_allgather_two_gpus(pb):
+    import socket
+    import subprocess
+    import sys
+    import torch
+    from pathlib import Path
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    script = Path(__file__).resolve().parent / 'mgpu_peer_gather_check.py'
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+                        '127.0.0.1', '--master-port', str(port), str(script)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'peer gather ok' in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
