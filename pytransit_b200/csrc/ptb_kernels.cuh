@@ -490,6 +490,9 @@ struct PointsParams {
 #ifndef PT_MINB_SS
 #define PT_MINB_SS 2
 #endif
+#ifndef PT_SS_UNROLL
+#define PT_SS_UNROLL 1
+#endif
 constexpr int PT_THREADS = 256;
 constexpr int PT_WARPS = PT_THREADS / 32;
 constexpr int PT_BLOCK = 64;           // points per classification block
@@ -674,7 +677,7 @@ __device__ __forceinline__ double drain_points(const DrainCtx<T> &c, const WarpS
 
     T sum = T(0);
     double chi = 0.0;
-    constexpr int U = S1 ? 1 : 2;  // sub-samples evaluated together per lane (instruction-level parallelism)
+    constexpr int U = S1 ? 1 : PT_SS_UNROLL;  // sub-samples evaluated together per lane (instruction-level parallelism)
     for (int s0 = 0; s0 < S; s0 += SSC) {
         const int SS = min(SSC, S - s0);
         for (int j = 0; j < SS; j += U) {

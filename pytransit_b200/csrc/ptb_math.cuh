@@ -23,18 +23,18 @@ constexpr double kHalfPi = 1.57079632679489661923;
 // the fp64 pipe).  Accuracy: <= 1 ulp (sqrt, div), <= 2 ulp (atan2) on the ranges the model produces.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double fast_sqrt(double x) {
-    // operand clamped to the normal range (0 -> 1.5e-154, inf -> 6.7e153: the same side of every comparison
-    // the model makes); NaN passes through
-    const double xs = fmin(fmax(x, 2.2250738585072014e-308), 4.4942328371557893e+307);
     double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(xs));  // MUFU.RSQ64H, 2^-22 relative
-    double g = xs * r, h = 0.5 * r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));  // MUFU.RSQ64H, 2^-22 relative
+    double g = x * r, h = 0.5 * r;
     const double e = fma(-h, g, 0.5);
     g = fma(g, e, g);          // sqrt(x)      to ~2^-43
     h = fma(h, e, h);          // 1/(2 sqrt x) to ~2^-43
-    const double d = fma(-g, g, xs);
+    const double d = fma(-g, g, x);
     g = fma(d, h, g);          // residual step: full precision
-    return (x == x) ? g : x;
+    // 0 and subnormal operands (flushed by the approximation) give 0; inf and NaN pass through.
+    // (fp64 min/max are multi-instruction on this pipe: compares and selects only.)
+    g = (x >= 2.2250738585072014e-308) ? g : 0.0;
+    return (x < __longlong_as_double(0x7ff0000000000000LL)) ? g : x;
 }
 __device__ __forceinline__ float fast_sqrt(float x) { return sqrtf(x); }
 
@@ -55,7 +55,8 @@ __device__ __forceinline__ double fast_div(double n, double d) {
 // reduced argument (near-minimax fit, scratch/fit_atan.py: 1.5e-16 relative).
 __device__ __forceinline__ double atan2_pos(double y, double x) {
     const double ax = fabs(x);
-    const double mx = fmax(ax, y), mn = fmin(ax, y);
+    const bool ygt = y > ax;
+    const double mx = ygt ? y : ax, mn = ygt ? ax : y;
     const bool big = mn > 0.41421356237309503 * mx;
     const double num = big ? mn - mx : mn;
     const double den = big ? mn + mx : mx;
@@ -74,7 +75,7 @@ __device__ __forceinline__ double atan2_pos(double y, double x) {
     q = fma(q, u, -3.33333333333331205e-01);
     double r = fma(t * u, q, t);                 // atan(t)
     r = big ? r + 0.78539816339744830962 : r;    // atan(mn / mx)
-    r = (y > ax) ? kHalfPi - r : r;
+    r = ygt ? kHalfPi - r : r;
     return (x < 0.0) ? kPi - r : r;
 }
 __device__ __forceinline__ float atan2_pos(float y, float x) { return atan2f(y, x); }
@@ -110,10 +111,13 @@ __device__ __forceinline__ void kite_area(T k, T k2, T z, T &area, T &kappa0) {
         area = T(0);
         kappa0 = T(0);
     } else if (fabs(one - k) < z) {
-        // descending sort of (1, k, z) as a 3-element min/max network (branch free)
-        const T hi = fmax(one, k), lo = fmin(one, k);
-        const T x = fmax(hi, z), t = fmin(hi, z);
-        const T y = fmax(lo, t), zz = fmin(lo, t);
+        // descending sort of (1, k, z), compares and selects only (tsort, common.py:5-33)
+        const bool kg = k > one;
+        const T hi = kg ? k : one, lo = kg ? one : k;
+        const bool c1 = z > hi, c2 = z > lo;
+        const T x = c1 ? z : hi;
+        const T y = c1 ? hi : (c2 ? z : lo);
+        const T zz = c2 ? lo : z;
         const T akite = half * fast_sqrt((x + (y + zz)) * (zz - (x - y)) * (zz + (x - y)) * (x + (y - zz)));
         const T z2 = z * z;
         const T k0 = atan2_pos(two * akite, (k - one) * (k + one) + z2);

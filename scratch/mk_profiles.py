@@ -1,11 +1,18 @@
 """Copy the measurements of the last gpurun calls from gpurun_out/ (scratch) into profiles/ (tracked):
-bench lines, the ncu launch list, and per-kernel summaries of the `ncu --set full` captures
-(key raw metrics + hottest CUDA source lines).  Usage: python scratch/mk_profiles.py [tag]"""
+bench lines, the ncu launch lists, and per-kernel summaries of the `ncu --set full` captures
+(key raw metrics + hottest CUDA source lines).
+
+    python scratch/mk_profiles.py [tag]                      assemble profiles/ from gpurun_out/
+    python scratch/mk_profiles.py --summarise REP OUT [KEY]  (on the GPU box) one .ncu-rep -> text summary OUT;
+                                                             KEY: record the dominant kernel's DRAM traffic in
+                                                             gpurun_out/summ/traffic.json under that workload key
+"""
 import csv, io, json, shutil, subprocess, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 G, P = ROOT / 'gpurun_out', ROOT / 'profiles'
-tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'
+SUMM = len(sys.argv) > 1 and sys.argv[1] == '--summarise'
+tag = sys.argv[1] if (len(sys.argv) > 1 and not SUMM) else 'r01'
 P.mkdir(exist_ok=True)
 
 def num(x):
@@ -38,7 +45,7 @@ def summarise(rep, out, traffic_key=None, traffic=None):
         st = sorted(((num(d[h]), h) for h in hdr if h.startswith('smsp__average_warps_issue_stalled') and h.endswith('_per_issue_active.ratio')), reverse=True)[:8]
         for v, h in st:
             lines.append(f'  stall {h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]:30s} {v:.2f}')
-        if traffic_key and traffic is not None and 'k_rr_points' in name:
+        if traffic_key and traffic is not None and ('k_rr_points' in name or 'k_ts_flux2' in name):
             mult = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}
             traffic[traffic_key] = num(d['dram__bytes_read.sum']) * mult.get(u['dram__bytes_read.sum'], 1) + \
                                    num(d['dram__bytes_write.sum']) * mult.get(u['dram__bytes_write.sum'], 1)
@@ -60,19 +67,31 @@ def summarise(rep, out, traffic_key=None, traffic=None):
         lines.append('')
     out.write_text('\n'.join(lines))
 
+if SUMM:
+    rep, out = Path(sys.argv[2]), Path(sys.argv[3])
+    key = sys.argv[4] if len(sys.argv) > 4 else None
+    out.parent.mkdir(parents=True, exist_ok=True)
+    tf = out.parent / 'traffic.json'
+    traffic = json.loads(tf.read_text()) if tf.exists() else {}
+    summarise(rep, out, key, traffic)
+    tf.write_text(json.dumps(traffic, indent=1) + '\n')
+    sys.exit(0)
+
 traffic = {}
 tf = P / 'traffic.json'
 if tf.exists():
     traffic = json.loads(tf.read_text())
-for w in ('c2', 'c3', 'c4', 'c5', 'c1', 'ref'):
-    f = G / f'bench_{w}.json'
-    if f.exists() and f.read_text().strip():
-        (P / f'{tag}_bench_{w}.json').write_text(f.read_text().strip().splitlines()[-1] + '\n')
-if (G / 'launches_c2.csv').exists():
-    shutil.copy(G / 'launches_c2.csv', P / f'{tag}_launches_c2.csv')
-for name, key in (('prof_points_c2', 'c2'), ('prof_points_c3', 'c3'), ('prof_points_c5', 'c5'), ('prof_setup_c2', None), ('prof_ts_c4', 'c4')):
-    rep = G / f'{name}.ncu-rep'
-    if rep.exists():
-        summarise(rep, P / f'{tag}_ncu_{name[5:]}.txt', key, traffic)
+for f in sorted(G.glob('bench_*.json')):
+    lines = [l for l in f.read_text().splitlines() if l.startswith('{')]
+    if lines:
+        (P / f'{tag}_{f.name}').write_text(lines[-1] + '\n')
+for f in sorted(G.glob('launches_*.csv')):
+    shutil.copy(f, P / f'{tag}_{f.name}')
+S = G / 'summ'
+if S.exists():
+    for f in sorted(S.glob('*.txt')):
+        shutil.copy(f, P / f'{tag}_ncu_{f.name}')
+    if (S / 'traffic.json').exists():
+        traffic.update(json.loads((S / 'traffic.json').read_text()))
 tf.write_text(json.dumps(traffic, indent=1) + '\n')
 print(sorted(p.name for p in P.iterdir()))
