@@ -418,16 +418,22 @@ __global__ void __launch_bounds__(256) k_rr_ldm(const __grid_constant__ LdmParam
             }
         }
     }
+    __syncthreads();  // the contraction's stores precede the (rare) NaN overwrite below
     for (int r = tid; r < cnt * npb; r += 256) {
         const int q = r / npb, pb = r - q * npb;
         const int ipv = s_pv[q];
         const double kk = P.k[(size_t)ipv * P.kcols + (P.kcols == npb ? pb : 0)];
-        double *tail = P.rec + (size_t)ipv * P.recstride + P.rec_ld + (size_t)pb * P.lds + ng;
+        double *rowp = P.rec + (size_t)ipv * P.recstride + P.rec_ld + (size_t)pb * P.lds;
+        double *tail = rowp + ng;
         tail[0] = kk;
         tail[1] = 1.0 / (1.0 + kk);
         tail[2] = 1.0 / sIstar[r];
         tail[3] = kk * kk;
         for (int j = ng + 4; j < P.lds; ++j) tail[j - ng] = 0.0;
+        // k < -1 makes g = z / (1 + k) negative, for which interpolate_mean_limb_darkening_s returns NaN
+        // (common.py:227): the row itself carries the NaN, so the per-sample code needs no sign test
+        if (1.0 + kk < 0.0)
+            for (int g = 0; g < ng; ++g) rowp[g] = nan("");
     }
 }
 
@@ -590,20 +596,19 @@ __device__ __forceinline__ void sample_eval(T t, const T *cx, const T *cy, const
                                             T k2, T dg, T inv_dg, T &z, T &ip, T &cc, bool &limb) {
     const T one = T(1), pi = T(kPi), qnan = T(nan(""));
     z = sep_poly<T>(t, cx, cy);
-    const T g = z * inv1k;
+    const T g = z * inv1k;       // >= 0, or NaN; a negative g needs k < -1: k_rr_ldm stores NaN rows for that
     const T fl = floor(g * inv_dg);
     const T a = (g - fl * dg) * inv_dg;
     const int i = (int)fl;  // saturating conversion; NaN -> 0
     const int i0 = min(max(i, 0), ng - 1), i1 = min(max(i + 1, 0), ng - 1);
-    T v = (one - a) * row[i0] + a * row[i1];
-    v = (g > one) ? T(0) : v;
-    ip = (g < T(0)) ? qnan : v;
+    const T v = (one - a) * row[i0] + a * row[i1];
+    ip = (g > one) ? T(0) : v;
     const bool out = (one + k <= z);
     limb = !out && (fabs(one - k) < z);
-    T c = qnan;
-    c = (z <= k - one) ? one - ip * pi * inv_istar : c;          // planet covers the star
-    c = (z <= one - k) ? one - ip * (pi * k2) * inv_istar : c;   // planet inside the disk
-    cc = out ? one : c;                                           // no overlap: area 0
+    const bool covers = (z <= k - one);                       // planet covers the star: area pi; else pi k^2
+    const bool inside = covers || (z <= one - k);
+    const T c = one - ip * (covers ? pi : pi * k2) * inv_istar;
+    cc = out ? one : (inside ? c : qnan);                     // no overlap: area 0
 }
 
 // Lens-area pass over `take` limb samples at the top of the limb queue (warp-cooperative).
@@ -688,15 +693,16 @@ __device__ __forceinline__ double drain_points(const DrainCtx<T> &c, const WarpS
                 fr[0] = T(0);
             } else if (frac) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) fr[u] = frac[min(s0 + j + u, S - 1)];
+                for (int u = 0; u < U; ++u) fr[u] = frac[U == 1 ? s0 + j : min(s0 + j + u, S - 1)];
             } else {
 #pragma unroll
                 for (int u = 0; u < U; ++u) fr[u] = (T)(((s0 + j + u + 1) - 0.5) / ns - 0.5);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                act[u] = valid && (s0 + j + u < ns) && (j + u < SS);
-                const T off = (S1 || ns == 1) ? T(0) : et * fr[u];
+                act[u] = valid && (s0 + j + u < ns) && (U == 1 || j + u < SS);
+                // exptime * frac is exactly 0 for ns == 1 (frac = 0), as the reference's own product is
+                const T off = S1 ? T(0) : et * fr[u];
                 sample_eval<T>(tc + off, cx, cy, row, ng, k, inv1k, inv_istar, k2, dg, inv_dg, z[u], ip[u], cc[u], limb[u]);
                 limb[u] = limb[u] && act[u];
                 if (S1) sum = cc[u];
