@@ -361,6 +361,87 @@ def test_full_size_c2_properties(pb, orc, tab):
     np.testing.assert_allclose(l1, l2, rtol=1e-9)
 
 
+def test_full_size_c3_properties(pb, orc, tab):
+    """BASELINE configs[2] at full size (16384 vectors x 4 light curves x 16384 points, nsamples = 10): device-side
+    properties on all 1.07e9 points, subset evaluation bit-identical, the oracle on a strided sample of rows."""
+    import torch
+    c = wl.config3()
+    m = pb.RoadRunnerModelCUDA('quadratic')
+    m.set_data(c.time, c.lcids, c.pbids, c.nsamples, c.exptimes, c.epids)
+    f = m.evaluate(c.k, c.ldc, c.t0, c.p, c.a, c.i, c.e, c.w, copy=False)
+    assert f.shape == (16384, 65536)
+    assert bool(torch.isfinite(f).all()) and float(f.max()) == 1.0 and float(f.min()) > 0.96
+    frac = float((f < 1).double().mean())
+    assert 0.025 < frac < 0.06
+    # the four light curves share the time axis but not k / limb darkening: same transit windows, different depths
+    lc = f.view(16384, 4, 16384)
+    assert bool(((lc[:, 0] < 1) == (lc[:, 1] < 1)).double().mean() > 0.99)
+    assert not bool(torch.equal(lc[:, 0], lc[:, 1]))
+    rows = np.arange(3, 16384, 1489)
+    fs = m.evaluate(c.k[rows], c.ldc[rows], c.t0[rows], c.p[rows], c.a[rows], c.i[rows], c.e[rows], c.w[rows]).copy()
+    assert np.array_equal(fs, f[torch.as_tensor(rows, device=f.device)].cpu().numpy())
+    ldp, istar = orc.evaluate_ld('quadratic', tab.mu, c.ldc[rows])
+    ref = orc.rr_full(tab, c.time, c.k[rows], c.t0[rows], c.p[rows], c.a[rows], c.i[rows], c.e[rows], c.w[rows],
+                      c.lcids, c.pbids, c.epids, c.nsamples, c.exptimes, ldp, istar)
+    err = np.abs(fs - ref).max()
+    assert err <= FLUX_TOL, err
+    del f, lc
+    torch.cuda.empty_cache()
+
+
+def test_full_size_c5_shard_properties(pb, orc, tab):
+    """One GPU's shard of BASELINE configs[4] (8192 eccentric vectors x 100000 points, fused Gaussian lnL): the
+    fused likelihood against lnlike_normal on the materialised flux for every vector, and against the oracle on
+    a strided sample of vectors."""
+    import torch
+    c = wl.config5(npv=8192)
+    m = pb.RoadRunnerModelCUDA('power-2')
+    m.set_data(c.time)
+    m.set_obs(c.obs)
+    lnl = m.lnlikelihood(c.k, c.ldc, c.t0, c.p, c.a, c.i, c.e, c.w, sigma=c.sigma).copy()
+    assert lnl.shape == (8192,) and np.isfinite(lnl).all()
+    f = m.evaluate(c.k, c.ldc, c.t0, c.p, c.a, c.i, c.e, c.w, copy=False)
+    l2 = m.lnlike_normal(f, c.sigma).copy()
+    np.testing.assert_allclose(lnl, l2, rtol=1e-9)
+    del f
+    torch.cuda.empty_cache()
+    rows = np.arange(5, 8192, 431)
+    ldp, istar = orc.evaluate_ld('power-2', tab.mu, c.ldc[rows])
+    flux = orc.rr_full(tab, c.time, c.k[rows], c.t0[rows], c.p[rows], c.a[rows], c.i[rows], c.e[rows], c.w[rows],
+                       c.lcids, c.pbids, c.epids, c.nsamples, c.exptimes, ldp, istar)
+    ref = orc.lnlike_normal(c.obs, flux, c.sigma[rows], c.slices, c.nids)
+    np.testing.assert_allclose(lnl[rows], ref, rtol=LNL_RTOL)
+
+
+def test_full_size_c4_properties(pb, orc, tab):
+    """BASELINE configs[3] at full size (1024 vectors x 1000 channels x 2000 points, tabulated profiles): device-side
+    properties on all 2.05e9 points and the oracle (tsmodel_serial restatement) on two vectors."""
+    import torch
+    c = wl.config4()
+    prof, (x0, dx), (y0, dy), (z0, dz) = wl.ldtk_style_table(c.npb, tab.mu)
+    m = pb.TSModelCUDA(pb.TabulatedLDModel(prof, x0, dx, y0, dy, z0, dz))
+    m.set_data(c.time)
+    x = np.column_stack([c.teff, c.logg, c.metal])
+    f = m.evaluate(c.k, x, c.t0, c.p, c.a, c.i, c.e, c.w, copy=False)
+    assert f.shape == (1024, 1000, 2000)
+    # the first-order area correction (k - kmean) dA/dk (model_trspec.py:91) overshoots 1 by ~1e-5 at the contacts
+    assert bool(torch.isfinite(f).all()) and 1.0 <= float(f.max()) < 1.0001 and float(f.min()) > 0.97
+    frac = float((f < 1).double().mean())
+    assert 0.25 < frac < 0.5
+    # all channels of a vector share the geometry (one z per time stamp): identical touched-point masks, depth
+    # growing with k along the channels
+    assert bool(((f[:, 0] != 1) == (f[:, -1] != 1)).all())
+    assert bool((f[:, -1].min(dim=1).values < f[:, 0].min(dim=1).values).all())
+    rows = np.array([7, 801])
+    ldp, istar = orc.ldtk_profiles(prof, c.teff[rows], c.logg[rows], c.metal[rows], x0, dx, y0, dy, z0, dz, tab.mu)
+    ref = orc.tsmodel(tab, c.time, c.k[rows], c.t0[rows], c.p[rows], c.a[rows], c.i[rows], c.e[rows], c.w[rows], 1, 0.0, ldp, istar)
+    got = f[torch.as_tensor(rows, device=f.device)].cpu().numpy()
+    err = np.abs(got - ref).max()
+    assert err <= FLUX_TOL, err
+    del f
+    torch.cuda.empty_cache()
+
+
 # ---------------------------------------------------------------------------------------------
 # opt-in fp32 mode: <= 1 ppm from the reference (north star), float32 output
 # ---------------------------------------------------------------------------------------------
