@@ -104,17 +104,25 @@ class PeerLnLGather:
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         dev = torch.device(f'cuda:{model.device}')
-        self.gathered = symm_mem.empty(self.world * self.npv, dtype=torch.float64, device=dev)
-        self.handle = symm_mem.rendezvous(self.gathered, self.group)
-        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        if len(self.peer_ptrs) != self.world:
+        # two gathered arrays used alternately: a peer can only overwrite the array of step i at its step i+2,
+        # i.e. after it has passed the barrier of step i+1 -- which this rank joins only once it is done with
+        # result i.  One barrier per step is then enough.
+        n = self.world * self.npv
+        self._buf = symm_mem.empty(2 * n, dtype=torch.float64, device=dev)
+        self.handle = symm_mem.rendezvous(self._buf, self.group)
+        base = [int(p) for p in self.handle.buffer_ptrs]
+        if len(base) != self.world:
             raise RuntimeError("symmetric-memory rendezvous returned %d peer buffers for a world of %d"
-                               % (len(self.peer_ptrs), self.world))
+                               % (len(base), self.world))
+        self.peer_ptrs = [base, [p + 8 * n for p in base]]
+        self.gathered = [self._buf[:n], self._buf[n:]]
+        self._step = 0
 
     def lnlikelihood(self, k, ldc, t0, p, a, i, e=0.0, w=0.0, sigma=1e-3):
-        """``lnL[world * npv]`` of the whole population on every rank (a CUDA tensor view of the symmetric
-        buffer, valid until the next call)."""
-        self.handle.barrier(channel=0)   # nobody is still reading the previous result
-        self.model.lnlikelihood_allgather(k, ldc, t0, p, a, i, e, w, sigma, self.peer_ptrs, self.rank)
-        self.handle.barrier(channel=1)   # every shard has landed everywhere
-        return self.gathered
+        """``lnL[world * npv]`` of the whole population on every rank: a CUDA tensor view of the symmetric
+        buffer, valid until the call after the next one."""
+        b = self._step & 1
+        self._step += 1
+        self.model.lnlikelihood_allgather(k, ldc, t0, p, a, i, e, w, sigma, self.peer_ptrs[b], self.rank)
+        self.handle.barrier(channel=b)   # every shard has landed everywhere
+        return self.gathered[b]
