@@ -120,6 +120,16 @@ int ptb_rr_evaluate(ptb_model *h, int64_t npv, const double *k, int64_t kcols, c
                     const double *a, const double *inc, const double *e, const double *w,
                     void *flux, void *stream);
 
+/* EclipseModel.evaluate -> eclipse_model (models/new_eclipse_model.py:33-70, models/roadrunner/model_eclipse.py:11-81):
+ * the secondary-eclipse sibling of the RoadRunner model.  k[npv]; t0[npv,nep]; p,a,inc,e,w[npv]; rstar [R_sun].
+ * flux[npv,npt] = pi k^2 - (planet area occulted by the star), averaged over the exposure sub-samples: the
+ * orbit is expanded about mid-eclipse (eclipse_time_offset = the reference's eclipse_phase,
+ * orbits/orbits_py.py:544-555) and the eclipse centre is shifted by the light travel time.  The handle must
+ * have been created with PTB_LD_UNIFORM; light-curve / epoch ids, nsamples and exptimes come from ptb_set_data. */
+int ptb_eclipse_evaluate(ptb_model *h, int64_t npv, const double *k, const double *t0, const double *p,
+                         const double *a, const double *inc, const double *e, const double *w, double rstar,
+                         double *flux, void *stream);
+
 /* Observed fluxes and noise blocks for the fused likelihood: the (o, slices, nids) arguments of
  * lnlike_normal (lpf/loglikelihood/wnloglikelihood.py:22-35,43-55).  obs[npt]; slices[nsl,2]
  * half-open point ranges; nids[nsl] in [0,nblocks).  Points outside every slice do not contribute.

@@ -147,6 +147,31 @@ def bounding_box(k, c):
     return t1.value, t4.value
 
 
+def eclipse_time_offset(p, i, e, w) -> float:
+    f = lib().orc_eclipse_time_offset
+    f.restype = C.c_double
+    return float(f(*(C.c_double(float(v)) for v in (p, i, e, w))))
+
+
+def eclipse_light_travel_time(p, a, i, e, w, rstar) -> float:
+    f = lib().orc_eclipse_light_travel_time
+    f.restype = C.c_double
+    return float(f(*(C.c_double(float(v)) for v in (p, a, i, e, w, rstar))))
+
+
+def eclipse_model(times, k, t0, p, a, i, e, w, rstar, lcids, epids, nsamples, exptimes):
+    """model_eclipse.py:11-81 on fully expanded arrays: k[npv], t0[npv, nep], p, a, i, e, w[npv]."""
+    times, k, t0 = _d(times), _d(k).reshape(-1), _d(np.atleast_2d(t0))
+    npv, nep = t0.shape
+    p, a, i, e, w = (_d(v).reshape(-1) for v in (p, a, i, e, w))
+    lcids, epids, nsamples, exptimes = _i(lcids), _i(epids), _i(nsamples), _d(exptimes)
+    flux = np.zeros((npv, times.size))
+    lib().orc_eclipse_model(_p(times), C.c_int64(times.size), _p(k), _p(t0), _p(p), _p(a), _p(i), _p(e), _p(w),
+                            C.c_double(float(rstar)), C.c_int64(npv), C.c_int64(nsamples.size), C.c_int64(nep),
+                            _p(lcids), _p(epids), _p(nsamples), _p(exptimes), _p(flux))
+    return flux
+
+
 class Tables:
     """z-grid + weight table of RoadRunnerModel.init_integration (rrmodel.py:165-173)."""
 

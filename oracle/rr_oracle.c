@@ -426,10 +426,78 @@ static double orc_find_contact_point(double k, int point, const double *c) {
     return t1;
 }
 
-/* bounding_box(k, c): orbits/taylor_z.py:391-394. */
+/* bounding_box(k, c): orbits/taylor_z.py:391-394.  The two contact times are returned in ascending
+ * order: around a secondary eclipse the sky-plane x velocity c[0][1] is negative, which swaps the roles of
+ * the "first" and "fourth" contact searches (for a transit the order is unchanged). */
 void orc_bounding_box(double k, const double *c, double *t1, double *t4) {
-    *t1 = orc_find_contact_point(k, 1, c);
-    *t4 = orc_find_contact_point(k, 4, c);
+    double a = orc_find_contact_point(k, 1, c);
+    double b = orc_find_contact_point(k, 4, c);
+    *t1 = a < b ? a : b;
+    *t4 = a < b ? b : a;
+}
+
+/* eclipse_time_offset (meepmeep.backends.numba.utils; absent) restated from its in-tree ancestor
+ * eclipse_phase, orbits/orbits_py.py:544-555: time from mid-transit to mid-eclipse. */
+double orc_eclipse_time_offset(double p, double i, double e, double w) {
+    (void)i;
+    double etr = atan2(sqrt(1. - e * e) * sin(ORC_HALF_PI - w), e + cos(ORC_HALF_PI - w));
+    double eec = atan2(sqrt(1. - e * e) * sin(ORC_HALF_PI + ORC_PI - w), e + cos(ORC_HALF_PI + ORC_PI - w));
+    double mtr = etr - e * sin(etr);
+    double mec = eec - e * sin(eec);
+    double phase = (mec - mtr) * p / ORC_TWO_PI;
+    return phase > 0. ? phase : p + phase;
+}
+
+/* eclipse_light_travel_time (meepmeep.backends.numba.newton; absent, no in-tree ancestor -- PARITY
+ * UNPINNED): light travel time across the line-of-sight distance between the planet's positions at
+ * mid-transit and mid-eclipse, (r_tr + r_ec) sin(i) stellar radii, in days.  R_sun as orbits_py.py:46. */
+double orc_eclipse_light_travel_time(double p, double a, double i, double e, double w, double rstar) {
+    (void)p;
+    const double rsun = 0.5 * 1.392684e9, c_light = 299792458.0, d_s = 86400.0;
+    double ae = a * (1. - e * e);
+    double r_tr = ae / (1. + e * sin(w)), r_ec = ae / (1. - e * sin(w));
+    return (r_tr + r_ec) * sin(i) * rstar * rsun / c_light / d_s;
+}
+
+/* eclipse_model: pytransit/models/roadrunner/model_eclipse.py:11-81.  k[npv]; t0[npv,nep]; flux[npv,npt] =
+ * pi k^2 minus the occulted planet area, averaged over the exposure sub-samples. */
+void orc_eclipse_model(const double *times, int64_t npt, const double *k, const double *t0, const double *p,
+                       const double *a, const double *inc, const double *e, const double *w, double rstar,
+                       int64_t npv, int64_t nlc, int64_t nep, const int64_t *lcids, const int64_t *epids,
+                       const int64_t *nsamples, const double *exptimes, double *flux) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t ipv = 0; ipv < npv; ++ipv) {
+        double *f = flux + ipv * npt;
+        if (isnan(a[ipv]) || a[ipv] <= 1.0 || e[ipv] < 0.0) {
+            for (int64_t j = 0; j < npt; ++j) f[j] = NAN;
+            continue;
+        }
+        double xyc[10], bt1, bt4;
+        double shift = orc_eclipse_time_offset(p[ipv], inc[ipv], e[ipv], w[ipv]);
+        orc_solve2d(shift, p[ipv], a[ipv], inc[ipv], e[ipv], w[ipv], xyc);
+        double ltt = orc_eclipse_light_travel_time(p[ipv], a[ipv], inc[ipv], e[ipv], w[ipv], rstar);
+        orc_bounding_box(k[ipv], xyc, &bt1, &bt4);
+        const double pk2 = ORC_PI * k[ipv] * k[ipv];
+        for (int64_t ipt = 0; ipt < npt; ++ipt) {
+            int64_t ilc = lcids[ipt], iep = epids[ilc];
+            double lo = bt1 - (0.003 + exptimes[ilc]), hi = bt4 + (0.003 + exptimes[ilc]);
+            double te = t0[ipv * nep + iep] + shift + ltt;
+            double epoch = floor((times[ipt] - te + 0.5 * p[ipv]) / p[ipv]);
+            double tc = times[ipt] - (te + epoch * p[ipv]);
+            if (!(lo <= tc && tc <= hi)) {
+                f[ipt] = pk2;
+            } else {
+                double acc = 0.0;
+                for (int64_t s = 1; s <= nsamples[ilc]; ++s) {
+                    double off = exptimes[ilc] * ((s - 0.5) / nsamples[ilc] - 0.5);
+                    double z = orc_sep_c(tc + off, xyc), area, kap;
+                    orc_ccia_kite(1.0, k[ipv], z, &area, &kap);
+                    acc += pk2 - area;
+                }
+                f[ipt] = acc / nsamples[ilc];
+            }
+        }
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ */

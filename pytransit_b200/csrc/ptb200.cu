@@ -111,6 +111,9 @@ struct ptb_model {
     DevBuf d_tsgeo;                  // TSModel geometry pass [npv][npt]
     DevBuf d_lpf;                    // mapped LPF parameters (k_lpf_map)
     DevBuf d_cells;                  // per-vector table cells of the tabulated-profile interpolation
+    DevBuf d_dummy;                  // zero limb-darkening coefficients of the eclipse model (uniform disk)
+    bool ecl_mode = false;           // the next launch_rr_setup expands about mid-eclipse (ptb_eclipse_evaluate)
+    double ecl_rstar = 1.0;
     DevBuf d_rec, d_work;            // RoadRunner per-vector records; work counters of the persistent kernel
     int recstride = 0, rec_ld = 0;   // record stride / offset of the ld rows (doubles) of the last setup
     cudaStream_t side_stream = nullptr;  // the orbit solve runs here, concurrently with the table contraction
@@ -427,7 +430,7 @@ void ptb_destroy(ptb_model *h) {
     cudaSetDevice(h->cfg.device);
     for (DevBuf *b : {&h->d_tab, &h->d_W, &h->d_time_own, &h->d_meta, &h->d_obs_own, &h->d_blk, &h->d_nblk, &h->d_orb,
                       &h->d_ldrec, &h->d_ldp, &h->d_istar, &h->d_flux, &h->d_partial, &h->d_isig2, &h->d_lnl, &h->d_xyc,
-                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_sort, &h->d_rec, &h->d_work, &h->d_tsgeo, &h->d_lit, &h->d_lpf, &h->d_cells})
+                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_sort, &h->d_rec, &h->d_work, &h->d_tsgeo, &h->d_lit, &h->d_lpf, &h->d_cells, &h->d_dummy})
         b->release();
     h->h_stage.release();
     h->h_hrstat.release();
@@ -737,6 +740,7 @@ int launch_rr_setup(ptb_model *h, const ModelArgs &A, const Staged &D, cudaStrea
     O.xyc_in = h->xyc_injected ? h->d_xyc.as<double>() : nullptr;
     O.t0 = D.t0; O.rec = h->d_rec.as<double>();
     O.npv = (int)npv; O.kcols = (int)A.kcols; O.nep = (int)h->nep; O.recstride = (int)recstride;
+    O.eclipse = h->ecl_mode ? 1 : 0; O.rstar = h->ecl_rstar;
     k_rr_orbit<<<(unsigned)((npv * 8 + 255) / 256), 256, 0, h->side_stream>>>(O);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev_join, h->side_stream));
@@ -895,14 +899,14 @@ int launch_points(ptb_model *h, int64_t npv, void *flux, const double *isig2, cu
 
 extern "C" {
 
-int ptb_rr_evaluate(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld, int64_t nld,
-                    const double *istar, const double *t0, const double *p, const double *a, const double *inc,
-                    const double *e, const double *w, void *flux, void *stream) {
+static int rr_evaluate_impl(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld, int64_t nld,
+                            const double *istar, const double *t0, const double *p, const double *a, const double *inc,
+                            const double *e, const double *w, void *flux, void *stream, bool eclipse) {
     if (!h) return PTB_EINVAL;
     if (int rc = set_device(h)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ModelArgs A{npv, kcols, nld, k, ld, istar, t0, p, a, inc, e, w};
-    if (int rc = check_model_args(h, "rr_evaluate", A, h->npb)) return rc;
+    if (int rc = check_model_args(h, eclipse ? "eclipse_evaluate" : "rr_evaluate", A, h->npb)) return rc;
     Staged D{};
     if (int rc = stage_model_args(h, A, h->npb, h->nep, nullptr, 0, st, D)) return rc;
     mark(h, 0, st);
@@ -918,10 +922,41 @@ int ptb_rr_evaluate(ptb_model *h, int64_t npv, const double *k, int64_t kcols, c
     }
     mark(h, 2, st);
     if (int rc = launch_points(h, npv, dflux, nullptr, st, nullptr)) return rc;
+    if (eclipse) {  // pi k^2 - A from the uniform-disk transit shape (model_eclipse.py:72-80)
+        k_ecl_finish<<<(unsigned)((count / 2 + 256) / 256), 256, 0, st>>>(static_cast<double *>(dflux), D.k, h->npt, (long long)count);
+        h->launches++;
+        CU(cudaGetLastError());
+    }
     mark(h, 3, st);
     h->last_flux_count = direct ? 0 : (int64_t)count;
     if (flux && !direct) return deliver_host(h, flux, dflux, count, esize, st);
     return PTB_OK;
+}
+
+int ptb_rr_evaluate(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld, int64_t nld,
+                    const double *istar, const double *t0, const double *p, const double *a, const double *inc,
+                    const double *e, const double *w, void *flux, void *stream) {
+    return rr_evaluate_impl(h, npv, k, kcols, ld, nld, istar, t0, p, a, inc, e, w, flux, stream, false);
+}
+
+int ptb_eclipse_evaluate(ptb_model *h, int64_t npv, const double *k, const double *t0, const double *p, const double *a,
+                         const double *inc, const double *e, const double *w, double rstar, double *flux, void *stream) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    if (h->cfg.ldlaw != PTB_LD_UNIFORM || h->cfg.precision != 0)
+        return fail(h, PTB_ESTATE, "eclipse_evaluate: the handle must be created with PTB_LD_UNIFORM in fp64 (no stellar limb darkening in an eclipse)");
+    if (npv < 1) return fail(h, PTB_ESHAPE, "eclipse_evaluate: npv must be >= 1");
+    // a uniform disk has no coefficients: one zero per (vector, passband) keeps the shared argument checks happy
+    const size_t nz = (size_t)npv * h->npb;
+    if (nz * 8 > h->d_dummy.cap) {
+        CU(h->d_dummy.reserve(nz * 8));
+        CU(cudaMemset(h->d_dummy.ptr, 0, h->d_dummy.cap));
+    }
+    h->ecl_mode = true;
+    h->ecl_rstar = rstar;
+    const int rc = rr_evaluate_impl(h, npv, k, 1, h->d_dummy.as<double>(), 1, nullptr, t0, p, a, inc, e, w, flux, stream, true);
+    h->ecl_mode = false;
+    return rc;
 }
 
 static int rr_lnlike_impl(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld, int64_t nld,

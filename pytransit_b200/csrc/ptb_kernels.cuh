@@ -75,7 +75,7 @@ constexpr int ORB_LDNAN = 15;  // record slot: 1.0 when the limb-darkening profi
 
 template <int WIDTH>
 __device__ __forceinline__ void solve_orbit_lanes(int sl, bool valid, double p, double a, double inc, double e, double w,
-                                                  double kbox, const double *xyc_in, double *orb_out) {
+                                                  double kbox, const double *xyc_in, double *orb_out, double t_centre = 0.0) {
     double cx[5], cy[5];
     if (xyc_in != nullptr) {
 #pragma unroll
@@ -84,7 +84,7 @@ __device__ __forceinline__ void solve_orbit_lanes(int sl, bool valid, double p, 
         double x = 0.0, y = 0.0;
         if (valid && sl < 7) {
             const double offset = mean_anomaly_offset(e, w);
-            sky_position((sl - 3) * 2e-2, p, a * (1.0 - e * e), cos(inc), e, w, offset, x, y);
+            sky_position(t_centre + (sl - 3) * 2e-2, p, a * (1.0 - e * e), cos(inc), e, w, offset, x, y);
         }
         double vx[7], vy[7];
 #pragma unroll
@@ -97,8 +97,10 @@ __device__ __forceinline__ void solve_orbit_lanes(int sl, bool valid, double p, 
     }
     double tcon = 0.0;
     if (valid && sl < 2) tcon = contact_point(kbox, sl == 0 ? -1.0 : 1.0, cx, cy);
-    const double t1 = __shfl_sync(0xffffffffu, tcon, 0, WIDTH);
-    const double t4 = __shfl_sync(0xffffffffu, tcon, 1, WIDTH);
+    // ascending order: around a secondary eclipse the x velocity is negative and the two searches swap roles
+    const double ta = __shfl_sync(0xffffffffu, tcon, 0, WIDTH);
+    const double tb = __shfl_sync(0xffffffffu, tcon, 1, WIDTH);
+    const double t1 = (tb < ta) ? tb : ta, t4 = (tb < ta) ? ta : tb;
     if (valid && sl == 0) {
 #pragma unroll
         for (int j = 0; j < 5; ++j) { orb_out[j] = cx[j]; orb_out[5 + j] = cy[j]; }
@@ -123,7 +125,29 @@ struct OrbitParams {
     const double *t0;      // [npv][nep]
     double *rec;           // per-vector records (orb at offset 0, t0 at ORB_STRIDE)
     int npv, kcols, nep, recstride;
+    int eclipse;           // secondary-eclipse geometry (model_eclipse.py:38-44): expansion about mid-eclipse
+    double rstar;          // stellar radius [R_sun] for the light-travel-time shift
 };
+
+// eclipse_time_offset: time from mid-transit to mid-eclipse (the reference's eclipse_phase, orbits_py.py:544-555)
+__device__ __forceinline__ double eclipse_time_offset(double p, double e, double w) {
+    double s, c;
+    sincos(kHalfPi - w, &s, &c);
+    const double q = sqrt(1.0 - e * e);
+    const double etr = atan2(q * s, e + c);
+    sincos(kHalfPi + kPi - w, &s, &c);
+    const double eec = atan2(q * s, e + c);
+    const double mtr = etr - e * sin(etr), mec = eec - e * sin(eec);
+    const double phase = (mec - mtr) * p / kTwoPi;
+    return phase > 0.0 ? phase : p + phase;
+}
+
+// eclipse_light_travel_time [d]: light crossing the line-of-sight distance between the mid-transit and
+// mid-eclipse positions, (r_tr + r_ec) sin i stellar radii (meepmeep function, restated; R_sun as orbits_py.py:46)
+__device__ __forceinline__ double eclipse_light_travel_time(double a, double inc, double e, double w, double rstar) {
+    const double ae = a * (1.0 - e * e), sw = sin(w);
+    return (ae / (1.0 + e * sw) + ae / (1.0 - e * sw)) * sin(inc) * rstar * (0.5 * 1.392684e9) / 299792458.0 / 86400.0;
+}
 
 __global__ void __launch_bounds__(256) k_rr_orbit(const __grid_constant__ OrbitParams P) {
     const int lane = threadIdx.x & 31, sl = lane & 7;
@@ -140,9 +164,14 @@ __global__ void __launch_bounds__(256) k_rr_orbit(const __grid_constant__ OrbitP
     }
     const bool good0 = inr && !(isnan(a) || (a <= 1.0) || (e < 0.0));  // model_full.py:40 (ldp checked in k_rr_ldm)
     double *orb = P.rec + (size_t)(inr ? ipv : 0) * P.recstride;
-    solve_orbit_lanes<8>(sl, good0, p, a, inc, e, w, k0, (P.xyc_in && inr) ? P.xyc_in + (size_t)ipv * 10 : nullptr, orb);
+    double shift = 0.0, tadd = 0.0;
+    if (P.eclipse && good0) {
+        shift = eclipse_time_offset(p, e, w);
+        tadd = shift + eclipse_light_travel_time(a, inc, e, w, P.rstar);  // te = t0 + shift + ltt (model_eclipse.py:71)
+    }
+    solve_orbit_lanes<8>(sl, good0, p, a, inc, e, w, k0, (P.xyc_in && inr) ? P.xyc_in + (size_t)ipv * 10 : nullptr, orb, shift);
     if (inr) {  // transit centres travel with the record (one TMA bulk copy per vector in k_rr_points)
-        for (int j = sl; j < P.nep; j += 8) orb[ORB_STRIDE + j] = P.t0[(size_t)ipv * P.nep + j];
+        for (int j = sl; j < P.nep; j += 8) orb[ORB_STRIDE + j] = P.eclipse ? P.t0[(size_t)ipv * P.nep + j] + tadd : P.t0[(size_t)ipv * P.nep + j];
         if (sl == 0 && (P.nep & 1)) orb[ORB_STRIDE + P.nep] = 0.0;
         if (sl == 0 && !good0) {
             for (int j = 0; j < ORB_LDNAN; ++j) orb[j] = (j == ORB_GOOD) ? 0.0 : nan("");
@@ -1248,6 +1277,29 @@ __global__ void k_lpf_map(const __grid_constant__ LpfMapParams P) {
     }
     if (P.sigma)
         for (int j = 0; j < L.nloge; ++j) P.sigma[(size_t)ipv * L.nloge + j] = pow(10.0, pv[L.i_loge + j]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Secondary eclipse (model_eclipse.py:72-80): flux = pi k^2 - A(1, k, z), averaged over the sub-samples.
+// The points kernel has just produced F = 1 - A / pi for a uniform stellar disk at the eclipse geometry
+// (ldm = 1, I* = pi), so E = pi (k^2 - 1 + F): one in-place pass.  Out of eclipse F = 1 exactly -> pi k^2.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_ecl_finish(double *__restrict__ flux, const double *__restrict__ k, long long npt, long long total) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i >= total) return;
+    const double k0 = k[i / npt];
+    if (i + 1 < total && (i + 1) / npt == i / npt && ((reinterpret_cast<uintptr_t>(flux + i) & 15) == 0)) {
+        double2 f = *reinterpret_cast<double2 *>(flux + i);
+        f.x = kPi * ((k0 * k0 - 1.0) + f.x);
+        f.y = kPi * ((k0 * k0 - 1.0) + f.y);
+        *reinterpret_cast<double2 *>(flux + i) = f;
+    } else {
+        flux[i] = kPi * ((k0 * k0 - 1.0) + flux[i]);
+        if (i + 1 < total) {
+            const double k1 = k[(i + 1) / npt];
+            flux[i + 1] = kPi * ((k1 * k1 - 1.0) + flux[i + 1]);
+        }
+    }
 }
 
 }  // namespace ptb

@@ -86,4 +86,7 @@ def find_contact_point(k, point, c):
 
 @njit
 def bounding_box(k, c):
-    return find_contact_point(k, 1, c), find_contact_point(k, 4, c)
+    # ascending order: around a secondary eclipse c[0, 1] < 0 swaps the two searches (model_eclipse.py:49-55 compares
+    # bbs[..., 0] <= tc <= bbs[..., 1]); unchanged for transits
+    a, b = find_contact_point(k, 1, c), find_contact_point(k, 4, c)
+    return min(a, b), max(a, b)

@@ -155,3 +155,28 @@ def test_lpf_mapping_and_likelihood_match_reference(orc, tab, golden):
     ok = np.isfinite(g['lnl'])
     assert ok.sum() == 39
     np.testing.assert_allclose(lnl[ok], g['lnl'][ok], rtol=1e-13)
+
+
+def test_eclipse_model_matches_reference(orc, golden):
+    """model_eclipse.py:11-81 (executed unmodified for the fixture, third-party meepmeep functions from the stand-ins)
+    against the oracle's restatement; plus the assertions of the reference's own tests/test_roadrunner_eclipse.py."""
+    g = golden('eclipse')
+    # the reference's test case: circular, k = 0.1, p = 2, a = 8, edge-on, times 0..2
+    t = g['ref_times']
+    one = lambda v: np.full(1, float(v))
+    f = orc.eclipse_model(t, one(0.1), np.zeros((1, 1)), one(2.0), one(8.0), one(0.5 * np.pi), one(0.0), one(0.0), 1.0,
+                          np.zeros(t.size, np.int64), np.zeros(1, np.int64), np.ones(1, np.int64), np.zeros(1))
+    assert f.shape == (1, t.size)
+    baseline = np.pi * 0.1 ** 2
+    assert abs(f.max() - baseline) < 1e-6                       # out of eclipse: the full planet area
+    assert f[0, np.argmin(np.abs(t - 1.0))] < baseline - 1e-4   # eclipse near t = p/2
+    assert f.min() < 1e-3                                       # a non-grazing eclipse is total
+    np.testing.assert_allclose(f, g['ref_flux'], rtol=0, atol=1e-15)
+    # seeded eccentric population, 3 light curves / 2 epochs / supersampling, NaN rows
+    f = orc.eclipse_model(g['times'], g['k'], g['t0'], g['p'], g['a'], g['i'], g['e'], g['w'], float(g['rstar']), g['lcids'],
+                          g['epids'], g['nsamples'], g['exptimes'])
+    assert np.array_equal(np.isnan(f), np.isnan(g['flux'])) and np.isnan(f[5]).all() and np.isnan(f[9]).all()
+    np.testing.assert_allclose(f, g['flux'], rtol=0, atol=1e-15)
+    ok = np.isfinite(g['shifts'])
+    sh = np.array([orc.eclipse_time_offset(g['p'][j], g['i'][j], g['e'][j], g['w'][j]) for j in np.flatnonzero(ok)])
+    np.testing.assert_allclose(sh, g['shifts'][ok], rtol=1e-15)
