@@ -241,8 +241,18 @@ int ptb_bind_host_result(ptb_model *h, void *buf, int64_t count);
 int ptb_host_result_stats(const ptb_model *h, int64_t *last_bytes, int64_t *delta_calls,
                           int64_t *full_calls);
 
-/* Kernels launched by this handle since creation (bench.py's gpu_launches evidence). */
+/* Kernels launched by this handle since creation (bench.py's gpu_launches evidence; kernels inside a replayed
+ * CUDA graph are counted). */
 int64_t ptb_launch_count(const ptb_model *h);
+
+/* CUDA-graph replay of launch-bound calls.  For populations of up to 2048 vectors the kernel sequence of
+ * ptb_rr_evaluate / ptb_rr_lnlike / ptb_eclipse_evaluate (argument copy, orbit solve on its side stream,
+ * sort, limb-darkening contraction, points kernel, likelihood finish) is captured the second time a call
+ * signature (sizes, which arguments are host or device pointers, output pointer) is seen, and replayed with
+ * one cudaGraphLaunch afterwards.  Results are identical to the eager path.  Enabled by default
+ * (environment PTB_GRAPHS=0 disables it process-wide); never used while ptb_set_profiling is on. */
+int ptb_set_graphs(ptb_model *h, int32_t enabled);
+int ptb_graph_stats(const ptb_model *h, int64_t *replays, int64_t *captures);
 
 /* Per-kernel device timing for bench.py's roofline: when enabled, CUDA events are recorded on the
  * launching stream around the per-vector setup kernel(s) and around the dominant npv x npt kernel of

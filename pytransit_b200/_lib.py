@@ -57,6 +57,8 @@ SIGNATURES = {
     'ptb_bind_host_result': (C.c_int, [_vp, _vp, _i64]),
     'ptb_host_result_stats': (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     'ptb_launch_count': (_i64, [_vp]),
+    'ptb_set_graphs': (C.c_int, [_vp, C.c_int32]),
+    'ptb_graph_stats': (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     'ptb_synchronize': (C.c_int, [_vp, _vp]),
     'ptb_set_profiling': (C.c_int, [_vp, C.c_int32]),
     'ptb_last_timing': (C.c_int, [_vp, C.POINTER(_dbl), C.POINTER(_dbl)]),

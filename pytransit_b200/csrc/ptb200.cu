@@ -25,6 +25,7 @@ using namespace ptb;
 namespace {
 
 thread_local std::string g_create_error;
+unsigned long long g_alloc_gen = 1;  // bumped whenever a device buffer moves: captured graphs hold raw pointers
 
 struct DevBuf {  // grow-only device buffer
     void *ptr = nullptr;
@@ -37,6 +38,7 @@ struct DevBuf {  // grow-only device buffer
         const size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&ptr, want);
         if (e == cudaSuccess) cap = want;
+        ++g_alloc_gen;
         return e;
     }
     void release() {
@@ -147,6 +149,23 @@ struct ptb_model {
     PinBuf h_hrstat;                 // the counter, read back with the result
     int64_t hr_last_bytes = 0, hr_delta_calls = 0, hr_full_calls = 0;
 
+    // CUDA-graph replay of launch-bound calls (small populations): the per-call kernel sequence is captured once
+    // per argument signature and relaunched with ONE API call; host arguments travel through the same pinned block
+    struct GraphEntry {
+        std::vector<unsigned long long> key;
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches = 0;
+        int nchunks = 1;
+        unsigned long long used = 0;
+    };
+    std::vector<GraphEntry> graphs;
+    std::vector<std::vector<unsigned long long>> seen_keys;  // signatures that have run once (buffers are sized)
+    cudaStream_t cap_stream = nullptr;
+    bool capturing = false;
+    bool graphs_enabled = true;
+    unsigned long long data_gen = 1, graph_clock = 0;
+    int64_t graph_replays = 0, graph_captures = 0;
+
     std::string err;
     int64_t launches = 0;
 };
@@ -172,14 +191,29 @@ int fail(ptb_model *h, int code, const char *fmt, ...) {
                         #call, cudaGetErrorString(_e));                                               \
     } while (0)
 
+// A call classifies each argument pointer once: the graph key and the stager ask about the same pointers.
+struct PtrMemo {
+    const void *p[16];
+    bool dev[16];
+    int n = 0;
+};
+thread_local PtrMemo g_ptr_memo;
+
 bool is_device_ptr(const void *p) {
     if (!p) return false;
+    PtrMemo &m = g_ptr_memo;
+    for (int i = 0; i < m.n; ++i)
+        if (m.p[i] == p) return m.dev[i];
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
+    bool dev = false;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) cudaGetLastError();
+    else dev = at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+    if (m.n < 16) {
+        m.p[m.n] = p;
+        m.dev[m.n] = dev;
+        m.n++;
     }
-    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+    return dev;
 }
 
 // Stager: host arrays are packed into the pinned block and shipped with ONE async copy;
@@ -201,7 +235,8 @@ struct Stager {
         total += (bytes + 255) & ~size_t(255);
         return {nullptr, off, true};
     }
-    int commit() {
+    // pack the host arrays into the pinned block (after the previous copy out of it has finished)
+    int pack() {
         if (total == 0) return PTB_OK;
         if (h->stage_pending) {  // the previous call's copy must have left the pinned block
             CU(cudaEventSynchronize(h->stage_ev));
@@ -210,11 +245,22 @@ struct Stager {
         CU(h->h_stage.reserve(total));
         CU(h->d_stage.reserve(total));
         for (auto &it : items) memcpy(static_cast<char *>(h->h_stage.ptr) + it.off, it.src, it.bytes);
-        CU(cudaMemcpyAsync(h->d_stage.ptr, h->h_stage.ptr, total, cudaMemcpyHostToDevice, st));
+        return PTB_OK;
+    }
+    // mark the pinned block busy until the work just queued on `s` has consumed it
+    int fence(cudaStream_t s) {
+        if (total == 0) return PTB_OK;
         if (!h->stage_ev) CU(cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming));
-        CU(cudaEventRecord(h->stage_ev, st));
+        CU(cudaEventRecord(h->stage_ev, s));
         h->stage_pending = true;
         return PTB_OK;
+    }
+    int commit() {
+        if (total == 0) return PTB_OK;
+        if (int rc = pack()) return rc;
+        CU(cudaMemcpyAsync(h->d_stage.ptr, h->h_stage.ptr, total, cudaMemcpyHostToDevice, st));
+        if (h->capturing) return PTB_OK;  // the event is recorded on the launching stream after the graph launch
+        return fence(st);
     }
     template <class T>
     const T *get(const Ref &r) const {
@@ -224,6 +270,7 @@ struct Stager {
 };
 
 int set_device(ptb_model *h) {
+    g_ptr_memo.n = 0;  // every entry point starts here: pointer classifications do not outlive a call
     CU(cudaSetDevice(h->cfg.device));
     return PTB_OK;
 }
@@ -434,6 +481,9 @@ void ptb_destroy(ptb_model *h) {
         b->release();
     h->h_stage.release();
     h->h_hrstat.release();
+    for (auto &g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     if (h->stage_ev) cudaEventDestroy(h->stage_ev);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -572,6 +622,7 @@ int ptb_set_data(ptb_model *h, const double *time, int64_t npt, const int64_t *l
     h->h_exptimes = het;
     h->has_data = true;
     h->has_obs = false;  // observations are tied to the time axis
+    h->data_gen++;
     return PTB_OK;
 }
 
@@ -654,6 +705,7 @@ int ptb_set_obs(ptb_model *h, const double *obs, const int64_t *slices, const in
     h->blk_trivial = trivial;
     h->nblocks = nblocks;
     h->has_obs = true;
+    h->data_gen++;
     return PTB_OK;
 }
 
@@ -679,12 +731,113 @@ int check_model_args(ptb_model *h, const char *who, const ModelArgs &A, int64_t 
     return PTB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-graph replay.  A call is eligible when the population is small enough to be launch bound and nothing
+// is being timed.  The first call with a given signature runs normally (it sizes every buffer), the second
+// is captured on a private stream while it is enqueued, and from then on the call is: refill the pinned
+// argument block, ONE cudaGraphLaunch into the caller's stream, one event record.
+// ---------------------------------------------------------------------------------------------
+using GKey = std::vector<unsigned long long>;
+constexpr int64_t GRAPH_MAX_NPV = 2048;
+constexpr size_t GRAPH_CACHE = 6;
+
+inline unsigned long long pkey(const void *p) {  // device pointers are baked into the graph, host ones are staged
+    if (!p) return 0ull;
+    return is_device_ptr(p) ? (unsigned long long)reinterpret_cast<uintptr_t>(p) : 1ull;
+}
+
+bool graph_eligible(const ptb_model *h, int64_t npv) {
+    static const bool env_on = [] {
+        const char *e = getenv("PTB_GRAPHS");
+        return !(e && atoi(e) == 0);
+    }();
+    return env_on && h->graphs_enabled && !h->profiling && npv <= GRAPH_MAX_NPV;
+}
+
+ptb_model::GraphEntry *graph_find(ptb_model *h, const GKey &key) {
+    for (auto &g : h->graphs)
+        if (g.key == key) {
+            g.used = ++h->graph_clock;
+            return &g;
+        }
+    return nullptr;
+}
+
+// true when this signature has already run once; otherwise remembers it (a few recent ones: output tensors of
+// the caller typically alternate between two or three addresses)
+bool graph_seen(ptb_model *h, const GKey &key) {
+    for (auto &k : h->seen_keys)
+        if (k == key) return true;
+    if (h->seen_keys.size() >= 8) h->seen_keys.erase(h->seen_keys.begin());
+    h->seen_keys.push_back(key);
+    return false;
+}
+
+int graph_fence(ptb_model *h, cudaStream_t st) {
+    if (!h->stage_ev) CU(cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(h->stage_ev, st));
+    h->stage_pending = true;
+    return PTB_OK;
+}
+
+int graph_begin(ptb_model *h) {
+    if (!h->cap_stream) CU(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    if (h->stage_pending) {
+        CU(cudaEventSynchronize(h->stage_ev));
+        h->stage_pending = false;
+    }
+    CU(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed));
+    h->capturing = true;
+    return PTB_OK;
+}
+
+// Ends the capture; on success instantiates, stores and launches the graph on `st`.  `*launched` tells the caller
+// whether the work has been queued (otherwise it must enqueue normally).
+int graph_end(ptb_model *h, const GKey &key, cudaStream_t st, int rc_enqueue, int64_t nlaunches, int nchunks,
+              unsigned long long gen0, bool *launched) {
+    *launched = false;
+    h->capturing = false;
+    cudaGraph_t gr = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &gr);
+    if (ce != cudaSuccess || !gr || rc_enqueue != PTB_OK || gen0 != g_alloc_gen) {
+        cudaGetLastError();
+        if (gr) cudaGraphDestroy(gr);
+        return rc_enqueue;   // nothing queued: the caller falls back to a normal enqueue (or reports the error)
+    }
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, gr, 0);
+    cudaGraphDestroy(gr);
+    if (ce != cudaSuccess || !exec) {
+        cudaGetLastError();
+        return PTB_OK;
+    }
+    if (h->graphs.size() >= GRAPH_CACHE) {  // evict the least recently used entry
+        size_t lru = 0;
+        for (size_t i = 1; i < h->graphs.size(); ++i)
+            if (h->graphs[i].used < h->graphs[lru].used) lru = i;
+        cudaGraphExecDestroy(h->graphs[lru].exec);
+        h->graphs.erase(h->graphs.begin() + lru);
+    }
+    ptb_model::GraphEntry g;
+    g.key = key;
+    g.exec = exec;
+    g.launches = nlaunches;
+    g.nchunks = nchunks;
+    g.used = ++h->graph_clock;
+    h->graphs.push_back(g);
+    h->graph_captures++;
+    CU(cudaGraphLaunch(exec, st));
+    *launched = true;
+    return graph_fence(h, st);
+}
+
 struct Staged {
     const double *k, *ld, *istar, *t0, *p, *a, *inc, *e, *w, *sigma;
 };
 
 int stage_model_args(ptb_model *h, const ModelArgs &A, int64_t npb, int64_t nep, const double *sigma, int64_t nsig,
-                     cudaStream_t st, Staged &D) {
+                     cudaStream_t st, Staged &D, bool pack_only = false) {
     Stager S(h, st);
     const size_t npv = A.npv;
     auto rk = S.add(A.k, npv * A.kcols * 8);
@@ -694,6 +847,7 @@ int stage_model_args(ptb_model *h, const ModelArgs &A, int64_t npb, int64_t nep,
     auto rp = S.add(A.p, npv * 8), ra = S.add(A.a, npv * 8), ri = S.add(A.inc, npv * 8), re = S.add(A.e, npv * 8),
          rw = S.add(A.w, npv * 8);
     auto rs = S.add(sigma, npv * nsig * 8);
+    if (pack_only) return S.pack();  // graph replay: the captured copy node ships the block
     if (int rc = S.commit()) return rc;
     D.k = S.get<double>(rk);
     D.ld = S.get<double>(rld);
@@ -899,6 +1053,24 @@ int launch_points(ptb_model *h, int64_t npv, void *flux, const double *isig2, cu
 
 extern "C" {
 
+// stage + per-vector setup + points kernel (+ eclipse finish) on `st`
+static int rr_evaluate_enqueue(ptb_model *h, const ModelArgs &A, void *dflux, size_t count, cudaStream_t st, bool eclipse) {
+    Staged D{};
+    if (int rc = stage_model_args(h, A, h->npb, h->nep, nullptr, 0, st, D)) return rc;
+    mark(h, 0, st);
+    if (int rc = launch_rr_setup(h, A, D, st)) return rc;
+    mark(h, 1, st);
+    mark(h, 2, st);
+    if (int rc = launch_points(h, A.npv, dflux, nullptr, st, nullptr)) return rc;
+    if (eclipse) {  // pi k^2 - A from the uniform-disk transit shape (model_eclipse.py:72-80)
+        k_ecl_finish<<<(unsigned)((count / 2 + 256) / 256), 256, 0, st>>>(static_cast<double *>(dflux), D.k, h->npt, (long long)count);
+        h->launches++;
+        CU(cudaGetLastError());
+    }
+    mark(h, 3, st);
+    return PTB_OK;
+}
+
 static int rr_evaluate_impl(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld, int64_t nld,
                             const double *istar, const double *t0, const double *p, const double *a, const double *inc,
                             const double *e, const double *w, void *flux, void *stream, bool eclipse) {
@@ -907,11 +1079,6 @@ static int rr_evaluate_impl(ptb_model *h, int64_t npv, const double *k, int64_t 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ModelArgs A{npv, kcols, nld, k, ld, istar, t0, p, a, inc, e, w};
     if (int rc = check_model_args(h, eclipse ? "eclipse_evaluate" : "rr_evaluate", A, h->npb)) return rc;
-    Staged D{};
-    if (int rc = stage_model_args(h, A, h->npb, h->nep, nullptr, 0, st, D)) return rc;
-    mark(h, 0, st);
-    if (int rc = launch_rr_setup(h, A, D, st)) return rc;
-    mark(h, 1, st);
     const size_t count = (size_t)npv * h->npt;
     const size_t esize = h->cfg.precision == 1 ? 4 : 8;  // fp32 mode: `flux` is a float array
     void *dflux = flux;
@@ -920,14 +1087,44 @@ static int rr_evaluate_impl(ptb_model *h, int64_t npv, const double *k, int64_t 
         CU(h->d_flux.reserve(count * esize));
         dflux = h->d_flux.ptr;
     }
-    mark(h, 2, st);
-    if (int rc = launch_points(h, npv, dflux, nullptr, st, nullptr)) return rc;
-    if (eclipse) {  // pi k^2 - A from the uniform-disk transit shape (model_eclipse.py:72-80)
-        k_ecl_finish<<<(unsigned)((count / 2 + 256) / 256), 256, 0, st>>>(static_cast<double *>(dflux), D.k, h->npt, (long long)count);
-        h->launches++;
-        CU(cudaGetLastError());
+    bool queued = false;
+    if (graph_eligible(h, npv)) {
+        // the graph always writes the handle-owned flux buffer, so that one graph serves every output tensor the
+        // caller comes with (a small device-to-device copy follows); the eager path writes in place
+        void *gflux = dflux;
+        if (direct) {
+            CU(h->d_flux.reserve(count * esize));
+            gflux = h->d_flux.ptr;
+        }
+        double rs = h->ecl_rstar;
+        unsigned long long rsbits;
+        memcpy(&rsbits, &rs, 8);
+        const GKey key{eclipse ? 2ull : 0ull, (unsigned long long)npv, (unsigned long long)kcols, (unsigned long long)nld, pkey(k),
+                       pkey(ld), pkey(istar), pkey(t0), pkey(p), pkey(a), pkey(inc), pkey(e), pkey(w),
+                       (unsigned long long)reinterpret_cast<uintptr_t>(gflux), eclipse ? rsbits : 0ull,
+                       h->xyc_injected ? 1ull : 0ull, g_alloc_gen, h->data_gen};
+        if (auto *g = graph_find(h, key)) {
+            Staged D{};
+            if (int rc = stage_model_args(h, A, h->npb, h->nep, nullptr, 0, st, D, true)) return rc;
+            CU(cudaGraphLaunch(g->exec, st));
+            if (int rc = graph_fence(h, st)) return rc;
+            h->launches += g->launches;
+            h->graph_replays++;
+            h->last_npv = npv;
+            h->last_npb = h->npb;
+            queued = true;
+        } else if (graph_seen(h, key)) {  // second call with this signature: capture while enqueueing
+            const unsigned long long gen0 = g_alloc_gen;
+            const int64_t l0 = h->launches;
+            if (graph_begin(h) == PTB_OK) {
+                const int rc = rr_evaluate_enqueue(h, A, gflux, count, h->cap_stream, eclipse);
+                if (int rc2 = graph_end(h, key, st, rc, h->launches - l0, 1, gen0, &queued)) return rc2;
+            }
+        }
+        if (queued && direct) CU(cudaMemcpyAsync(flux, gflux, count * esize, cudaMemcpyDeviceToDevice, st));
     }
-    mark(h, 3, st);
+    if (!queued)
+        if (int rc = rr_evaluate_enqueue(h, A, dflux, count, st, eclipse)) return rc;
     h->last_flux_count = direct ? 0 : (int64_t)count;
     if (flux && !direct) return deliver_host(h, flux, dflux, count, esize, st);
     return PTB_OK;
@@ -959,6 +1156,29 @@ int ptb_eclipse_evaluate(ptb_model *h, int64_t npv, const double *k, const doubl
     return rc;
 }
 
+// stage + per-vector setup + fused likelihood kernels on `st`
+static int rr_lnlike_enqueue(ptb_model *h, const ModelArgs &A, const double *sigma, const LnlOut &out, cudaStream_t st) {
+    const int64_t npv = A.npv;
+    Staged D{};
+    if (int rc = stage_model_args(h, A, h->npb, h->nep, sigma, h->nblocks, st, D)) return rc;
+    mark(h, 0, st);
+    if (int rc = launch_rr_setup(h, A, D, st)) return rc;
+    const long long nsig = (long long)npv * h->nblocks;
+    CU(h->d_isig2.reserve(nsig * 8));
+    k_inv_sigma2<<<(unsigned)((nsig + 255) / 256), 256, 0, st>>>(D.sigma, nsig, h->d_isig2.as<double>());
+    h->launches++;
+    mark(h, 1, st);
+    int nchunks = 1;
+    mark(h, 2, st);
+    if (int rc = launch_points(h, npv, nullptr, h->d_isig2.as<double>(), st, &nchunks)) return rc;
+    mark(h, 3, st);
+    k_lnl_finish<<<(unsigned)((npv + 127) / 128), 128, 0, st>>>(h->d_partial.as<double>(), nchunks, D.sigma,
+                                                                 h->d_nblk.as<double>(), (int)h->nblocks, (int)npv, out);
+    h->launches++;
+    CU(cudaGetLastError());
+    return PTB_OK;
+}
+
 static int rr_lnlike_impl(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld, int64_t nld,
                           const double *istar, const double *t0, const double *p, const double *a, const double *inc,
                           const double *e, const double *w, const double *sigma, double *lnl, double *const *peers,
@@ -976,39 +1196,53 @@ static int rr_lnlike_impl(ptb_model *h, int64_t npv, const double *k, int64_t kc
     }
     ModelArgs A{npv, kcols, nld, k, ld, istar, t0, p, a, inc, e, w};
     if (int rc = check_model_args(h, "rr_lnlike", A, h->npb)) return rc;
-    Staged D{};
-    if (int rc = stage_model_args(h, A, h->npb, h->nep, sigma, h->nblocks, st, D)) return rc;
-    mark(h, 0, st);
-    if (int rc = launch_rr_setup(h, A, D, st)) return rc;
-    const long long nsig = (long long)npv * h->nblocks;
-    CU(h->d_isig2.reserve(nsig * 8));
-    k_inv_sigma2<<<(unsigned)((nsig + 255) / 256), 256, 0, st>>>(D.sigma, nsig, h->d_isig2.as<double>());
-    h->launches++;
-    mark(h, 1, st);
-    int nchunks = 1;
-    mark(h, 2, st);
-    if (int rc = launch_points(h, npv, nullptr, h->d_isig2.as<double>(), st, &nchunks)) return rc;
-    mark(h, 3, st);
     LnlOut out{};
     const bool direct = peers || is_device_ptr(lnl);
+    const bool use_graph = graph_eligible(h, npv);
+    bool via_own = false;   // the result lands in the handle's buffer first (host output, or graph mode: one graph
+                            // for every output tensor) and is copied out afterwards
     if (peers) {
         out.nout = world;
         for (int r = 0; r < world; ++r) out.ptr[r] = peers[r] + (size_t)rank * npv;
     } else {
         out.nout = 1;
         out.ptr[0] = lnl;
-        if (!direct) {
+        if (!direct || use_graph) {
             CU(h->d_lnl.reserve(npv * 8));
             out.ptr[0] = h->d_lnl.as<double>();
+            via_own = true;
         }
     }
-    k_lnl_finish<<<(unsigned)((npv + 127) / 128), 128, 0, st>>>(h->d_partial.as<double>(), nchunks, D.sigma,
-                                                                 h->d_nblk.as<double>(), (int)h->nblocks, (int)npv, out);
-    h->launches++;
-    CU(cudaGetLastError());
-    if (!direct) {
-        CU(cudaMemcpyAsync(lnl, out.ptr[0], npv * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+    bool queued = false;
+    if (use_graph) {
+        GKey key{1ull, (unsigned long long)npv, (unsigned long long)kcols, (unsigned long long)nld, pkey(k), pkey(ld), pkey(istar),
+                 pkey(t0), pkey(p), pkey(a), pkey(inc), pkey(e), pkey(w), pkey(sigma), h->xyc_injected ? 1ull : 0ull, g_alloc_gen,
+                 h->data_gen, (unsigned long long)out.nout};
+        for (int r = 0; r < out.nout; ++r) key.push_back((unsigned long long)reinterpret_cast<uintptr_t>(out.ptr[r]));
+        if (auto *g = graph_find(h, key)) {
+            Staged D{};
+            if (int rc = stage_model_args(h, A, h->npb, h->nep, sigma, h->nblocks, st, D, true)) return rc;
+            CU(cudaGraphLaunch(g->exec, st));
+            if (int rc = graph_fence(h, st)) return rc;
+            h->launches += g->launches;
+            h->graph_replays++;
+            h->last_npv = npv;
+            h->last_npb = h->npb;
+            queued = true;
+        } else if (graph_seen(h, key)) {
+            const unsigned long long gen0 = g_alloc_gen;
+            const int64_t l0 = h->launches;
+            if (graph_begin(h) == PTB_OK) {
+                const int rc = rr_lnlike_enqueue(h, A, sigma, out, h->cap_stream);
+                if (int rc2 = graph_end(h, key, st, rc, h->launches - l0, 1, gen0, &queued)) return rc2;
+            }
+        }
+    }
+    if (!queued)
+        if (int rc = rr_lnlike_enqueue(h, A, sigma, out, st)) return rc;
+    if (via_own) {
+        CU(cudaMemcpyAsync(lnl, out.ptr[0], npv * 8, direct ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        if (!direct) CU(cudaStreamSynchronize(st));
     }
     return PTB_OK;
 }
@@ -1100,6 +1334,7 @@ int ptb_get_stage(ptb_model *h, int32_t stage, double *out) {
 int ptb_inject_xyc(ptb_model *h, const double *xyc, int64_t npv) {
     if (!h) return PTB_EINVAL;
     if (int rc = set_device(h)) return rc;
+    h->data_gen++;
     if (!xyc) {
         h->xyc_injected = false;
         h->xyc_npv = 0;
@@ -1165,6 +1400,19 @@ int ptb_host_free(void *ptr) {
 }
 
 int64_t ptb_launch_count(const ptb_model *h) { return h ? h->launches : 0; }
+
+int ptb_set_graphs(ptb_model *h, int32_t enabled) {
+    if (!h) return PTB_EINVAL;
+    h->graphs_enabled = enabled != 0;
+    return PTB_OK;
+}
+
+int ptb_graph_stats(const ptb_model *h, int64_t *replays, int64_t *captures) {
+    if (!h) return PTB_EINVAL;
+    if (replays) *replays = h->graph_replays;
+    if (captures) *captures = h->graph_captures;
+    return PTB_OK;
+}
 
 int ptb_set_profiling(ptb_model *h, int32_t enabled) {
     if (!h) return PTB_EINVAL;

@@ -157,6 +157,17 @@ class RoadRunnerModelCUDA(TransitModel):
     def launch_count(self) -> int:
         return int(lib().ptb_launch_count(self._h))
 
+    def set_graphs(self, enabled: bool = True) -> None:
+        """CUDA-graph replay of launch-bound (small-population) calls; on by default."""
+        check(lib().ptb_set_graphs(self._h, int(enabled)), self._h)
+
+    @property
+    def graph_stats(self):
+        """(graph replays, graph captures) of this model."""
+        a, b = C.c_int64(), C.c_int64()
+        check(lib().ptb_graph_stats(self._h, C.byref(a), C.byref(b)), self._h)
+        return a.value, b.value
+
     def set_profiling(self, enabled: bool = True) -> None:
         """Record CUDA events around the setup kernel(s) and the dominant kernel of every call."""
         check(lib().ptb_set_profiling(self._h, int(enabled)), self._h)

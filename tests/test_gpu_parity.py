@@ -650,3 +650,53 @@ def test_eclipse_model_vs_reference_golden(pb, orc, golden):
     got = fd.cpu().numpy()
     assert isinstance(fd, torch.Tensor) and np.array_equal(np.isnan(got), np.isnan(ro))
     assert np.nanmax(np.abs(got - ro)) <= 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+# CUDA-graph replay of launch-bound calls must be indistinguishable from the eager path
+# ---------------------------------------------------------------------------------------------
+def test_graph_replay_equals_eager(pb, golden):
+    import torch
+    d = golden('ttv')                                    # 3 light curves, 2 passbands, 2 epochs, supersampling
+    mg = pb.RoadRunnerModelCUDA('quadratic', host_result='copy')
+    me = pb.RoadRunnerModelCUDA('quadratic', host_result='copy')
+    me.set_graphs(False)
+    for m in (mg, me):
+        _set_data(m, d)
+    rng = np.random.default_rng(3)
+    obs = 1 + rng.normal(0, 1e-3, d['time'].size)
+    mg.set_obs(obs)
+    me.set_obs(obs)
+    base = _full_args(d)
+    npv = d['p'].size
+    sigma = np.full((npv, 1), 1e-3)
+    for it in range(6):                                  # new parameter VALUES every call, same signature
+        args = list(np.array(x, copy=True) for x in base)
+        args[2] = args[2] + 0.001 * it                   # t0
+        args[0] = args[0] * (1 + 0.01 * it)              # k
+        fg, fe = mg.evaluate(*args).copy(), me.evaluate(*args).copy()
+        assert np.array_equal(fg, fe, equal_nan=True), it
+        lg, le = mg.lnlikelihood(*args, sigma=sigma).copy(), me.lnlikelihood(*args, sigma=sigma).copy()
+        assert np.array_equal(lg, le, equal_nan=True), it
+        # device-resident arguments and output
+        dargs = [torch.as_tensor(x, device='cuda') for x in args]
+        fd = mg.evaluate(*dargs, copy=False)
+        assert np.array_equal(fd.cpu().numpy(), fe, equal_nan=True), it
+    replays, captures = mg.graph_stats
+    assert captures >= 2 and replays >= 6, (replays, captures)
+    assert me.graph_stats == (0, 0)
+    np.testing.assert_allclose(mg.evaluate(*base), d['flux'], rtol=0, atol=FLUX_TOL)
+    # a new dataset invalidates the captured graphs
+    mg.set_data(d['time'][:500], d['lcids'][:500], d['pbids'], d['nsamples'], d['exptimes'], d['epids'])
+    me.set_data(d['time'][:500], d['lcids'][:500], d['pbids'], d['nsamples'], d['exptimes'], d['epids'])
+    for it in range(3):
+        assert np.array_equal(mg.evaluate(*base), me.evaluate(*base), equal_nan=True)
+    # eclipse sibling through the same machinery
+    g = golden('eclipse')
+    ec = pb.EclipseModelCUDA()
+    ec.set_data(g['times'], g['lcids'], np.zeros(3, np.int64), g['nsamples'], g['exptimes'], g['epids'])
+    ok = ~np.isnan(g['flux'])
+    for it in range(5):
+        f = ec.evaluate(g['k'], g['t0'], g['p'], g['a'], g['i'], g['e'], g['w'], rstar=float(g['rstar'])).copy()
+        assert np.abs(f[ok] - g['flux'][ok]).max() <= 1e-12
+    assert ec.graph_stats[0] >= 1                       # call 1 sizes the buffers, 2 runs eagerly, 3 captures, 4 replays
