@@ -17,6 +17,9 @@
  * is NOT in the reference tree and not installable here: they are restated from the in-tree
  * ancestor pytransit/orbits/taylor_z.py + orbits/orbits_py.py with the (2,5) monomial layout
  * evidenced by pytransit/models/numba/gdmodel.py:441-442.  For those three: PARITY UNPINNED.
+ * The eclipse sibling (model_eclipse.py) calls two more absent meepmeep functions: eclipse_time_offset
+ * (restated from the in-tree eclipse_phase, orbits/orbits_py.py:544-555) and eclipse_light_travel_time
+ * (no in-tree ancestor; restated from its physical definition): PARITY UNPINNED for both as well.
  *
  * Build: see oracle/Makefile (gcc -O2 -fopenmp -shared; no -ffast-math).
  */
