@@ -37,7 +37,8 @@ def up_to_date() -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and up_to_date():
         return SO
-    cmd = [find_nvcc(), *NVCC_FLAGS, *(['-Xptxas', '-v'] if verbose else []), '-o', str(SO), *map(str, SOURCES)]
+    extra = os.environ.get('PTB_NVCC_EXTRA', '').split()      # e.g. -DPT_MINB_SS=3 for tuning experiments
+    cmd = [find_nvcc(), *NVCC_FLAGS, *extra, *(['-Xptxas', '-v'] if verbose else []), '-o', str(SO), *map(str, SOURCES)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + res.stdout + res.stderr)

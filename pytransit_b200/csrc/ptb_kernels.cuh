@@ -525,6 +525,12 @@ struct PointsParams {
 #ifndef PT_MINB_SS
 #define PT_MINB_SS 2
 #endif
+// record slots per warp of the supersampled kernels: 2 = the next item's record is prefetched, 1 = fetched at the
+// start of the item (their items are tens of thousands of points long, the fetch is noise) -- saves 3.4 KB per
+// warp of shared memory, which is what a third resident CTA needs
+#ifndef PT_NREC_SS
+#define PT_NREC_SS 2
+#endif
 #ifndef PT_SS_UNROLL
 #define PT_SS_UNROLL 1
 #endif
@@ -541,16 +547,18 @@ constexpr double PT_EPS = 1e-9;        // classification margin, in periods (>> 
 // Warp-private shared memory: queues, two record slots, the hit bitmap, two mbarriers, the
 // sub-sample buffer (none when every point has one sample) and, in fp32 mode, the record converted to
 // float.  T is the sample arithmetic / output type (double, or float in the opt-in fp32 mode).
+__host__ __device__ inline int pt_nrec(int ssc) { return ssc == 0 ? 2 : PT_NREC_SS; }
 __host__ __device__ inline size_t pt_warp_bytes(int ssc, int recstride, int tsize) {
     const size_t rec_t = (tsize == 4) ? (((size_t)recstride * 4 + 15) & ~size_t(15)) : 0;
     return (size_t)(PT_QCAP + 2 * PT_LCAP + 32 * ssc) * tsize + (size_t)(2 * PT_QCAP + 2 * PT_LCAP) * 4 + PT_MAXBLK / 8 + 16 +
-           (size_t)2 * recstride * 8 + rec_t;
+           (size_t)pt_nrec(ssc) * recstride * 8 + rec_t;
 }
 
 template <typename T>
 struct WarpScratch {
     unsigned char *base;
-    __device__ __forceinline__ explicit WarpScratch(unsigned char *b) : base(b) {}
+    int nrec;  // record slots (2: double buffered)
+    __device__ __forceinline__ WarpScratch(unsigned char *b, int nrec_) : base(b), nrec(nrec_) {}
     __device__ __forceinline__ T *q_tc() const { return reinterpret_cast<T *>(base); }
     __device__ __forceinline__ T *l_z() const { return q_tc() + PT_QCAP; }
     __device__ __forceinline__ T *l_ip() const { return l_z() + PT_LCAP; }
@@ -564,10 +572,10 @@ struct WarpScratch {
         return reinterpret_cast<double *>(bar() + 2) + (size_t)slot * recstride;
     }
     // fp32 mode: the current record converted to float (16-byte aligned); fp64: unused
-    __device__ __forceinline__ T *rec_t(int recstride) const { return reinterpret_cast<T *>(rec(2, recstride)); }
+    __device__ __forceinline__ T *rec_t(int recstride) const { return reinterpret_cast<T *>(rec(nrec, recstride)); }
     __device__ __forceinline__ T *contrib(int recstride) const {
         const size_t rt = (sizeof(T) == 4) ? (((size_t)recstride * 4 + 15) & ~size_t(15)) : 0;
-        return reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(rec(2, recstride)) + rt);
+        return reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(rec(nrec, recstride)) + rt);
     }
 };
 
@@ -821,7 +829,8 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
     int *sRow = sNs + nlc;
     int *sEp = sRow + nlc;
     const size_t shared_bytes = ((((size_t)nlc) * 8 + ((size_t)nlc + nfrac) * sizeof(T) + 3 * (size_t)nlc * 4) + 127) & ~size_t(127);
-    const WarpScratch<T> ws(smem_raw + shared_bytes + (size_t)warp * pt_warp_bytes(S1 ? 0 : P.ssc, P.recstride, (int)sizeof(T)));
+    constexpr int NREC = S1 ? 2 : PT_NREC_SS;
+    const WarpScratch<T> ws(smem_raw + shared_bytes + (size_t)warp * pt_warp_bytes(S1 ? 0 : P.ssc, P.recstride, (int)sizeof(T)), NREC);
     unsigned *s_hit = ws.hit();
     uint64_t *bar = ws.bar();
 
@@ -831,7 +840,7 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         item = atomicAdd(&P.work[0], 1);
-        if (item < nitems) {
+        if (NREC == 2 && item < nitems) {
             mbar_expect_tx(&bar[0], rec_bytes);
             tma_load_1d(ws.rec(0, P.recstride), P.rec + (size_t)(item / P.nchunks) * P.recstride, rec_bytes, &bar[0]);
         }
@@ -860,11 +869,15 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
     T *flux = reinterpret_cast<T *>(P.flux);
 
     for (int iter = 0; item < nitems; ++iter) {
-        const int buf = iter & 1;
+        const int buf = (NREC == 2) ? (iter & 1) : 0;
         long long next = 0;
         if (lane == 0) {  // fetch the next item and start its record copy into the other slot
+            if (NREC == 1) {  // single slot: this item's record (every lane left the slot at the end of the last item)
+                mbar_expect_tx(&bar[0], rec_bytes);
+                tma_load_1d(ws.rec(0, P.recstride), P.rec + (size_t)(item / P.nchunks) * P.recstride, rec_bytes, &bar[0]);
+            }
             next = atomicAdd(&P.work[0], 1);
-            if (next < nitems) {
+            if (NREC == 2 && next < nitems) {
                 mbar_expect_tx(&bar[buf ^ 1], rec_bytes);
                 tma_load_1d(ws.rec(buf ^ 1, P.recstride), P.rec + (size_t)(next / P.nchunks) * P.recstride, rec_bytes,
                             &bar[buf ^ 1]);
@@ -882,7 +895,7 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
         const double *isig2 = LNL ? P.isig2 + (size_t)ipv * P.nblocks : nullptr;
         double chi = 0.0;
 
-        mbar_wait(&bar[buf], (iter >> 1) & 1);
+        mbar_wait(&bar[buf], (NREC == 2) ? ((iter >> 1) & 1) : (iter & 1));
         if (rec[ORB_GOOD] == 0.0 || rec[ORB_LDNAN] != 0.0) {  // invalid parameter vector: NaN row (model_full.py:40,80-82)
             if (LNL) {
                 if (lane == 0) P.partial[(size_t)ipv * P.nchunks + chunk] = nan("");
