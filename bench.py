@@ -393,7 +393,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             last, ndelta, nfull = m.host_result_stats
             d2h = int(last)
             how = ('delta transfer into the model-owned page-locked host array: the full [npv, npt] result (%d bytes) is '
-                   'current on the host after every step, but only the 64-point blocks that differ from 1.0 now or did '
+                   'current on the host after every step, but only the 16-point blocks that differ from 1.0 now or did '
                    'after the previous step cross PCIe (written by the GPU); the timed steps alternate between two '
                    'different populations; %d delta / %d full transfers so far' % (r.nbytes, ndelta, nfull))
         e2e = {'value': world * pts_per_step * e2e_steps / (float(t.item()) * 1e-3), 'unit': UNIT,

@@ -232,7 +232,7 @@ int ptb_host_free(void *ptr);
  * that between calls nobody but this handle writes to it.  After binding, every ptb_rr_evaluate /
  * ptb_ts_evaluate whose `flux` argument is `buf` (and whose result has `count` elements) keeps `buf`
  * up to date by DELTA transfer: a transit model is exactly 1.0 outside the transit windows
- * (model_full.py:91), so after the first full copy only the 64-element blocks that differ from 1.0
+ * (model_full.py:91), so after the first full copy only the 16-element blocks (128 B) that differ from 1.0
  * now -- or did after the previous call -- are written, by the GPU, straight into `buf` over PCIe.
  * The content of `buf` after each call is identical to a full copy.  NULL unbinds.  Any other host
  * pointer passed as `flux` takes the plain full-copy path. */

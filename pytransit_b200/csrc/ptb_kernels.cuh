@@ -1170,21 +1170,27 @@ __global__ void __launch_bounds__(256) k_lnl_model(const double *__restrict__ mo
 // ---------------------------------------------------------------------------------------------
 // k_host_delta -- keeps a page-locked HOST copy of a device result array up to date by writing only what
 // changed (ptb_bind_host_result).  A transit model flux is exactly 1.0 outside the transit windows
-// (model_full.py:91): the array is cut into blocks of 64 elements; a block is "lit" when any element
+// (model_full.py:91): the array is cut into blocks of HD_BLOCK elements; a block is "lit" when any element
 // differs from 1.0 (NaN rows included).  Lit blocks are written straight into the host array through
-// its device mapping (coalesced 16-byte stores, 512 B per block over PCIe); blocks that were lit after
+// its device mapping (coalesced 16-byte stores, HD_BLOCK * 8 B per block over PCIe); blocks that were lit after
 // the previous call and are not any more are reset to 1.0; everything else already holds 1.0 on the
 // host.  `lit` keeps one bit per block between calls.  mode 0: delta; mode 1: only rebuild `lit`
 // (the caller ships the whole array with the copy engine).
-// One warp per word of 32 blocks, eight 16-byte loads in flight per lane.
+// One warp per word of 32 blocks, eight 16-byte loads in flight per lane; a warp-wide load covers 64 elements,
+// i.e. HD_BPI blocks, told apart by sub-masks of one ballot.
 // ---------------------------------------------------------------------------------------------
-constexpr int HD_BLOCK = 64;
+constexpr int HD_BLOCK = 16;                 // elements per block: one 128-byte line (fp64) per PCIe write burst (measured: 64 -> 7.8e10, 32 -> 9.2e10, 16 -> 9.9e10, 8 -> 9.9e10 pts/s e2e on C2)
+constexpr int HD_LPB = HD_BLOCK / 2;         // lanes per block (two elements per lane)
+constexpr int HD_BPI = 32 / HD_LPB;          // blocks covered by one warp-wide load
+constexpr int HD_UNR = (32 / HD_BPI < 8) ? 32 / HD_BPI : 8;   // loads in flight per lane
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_host_delta(const T *__restrict__ src, T *__restrict__ host, unsigned *__restrict__ lit,
                                                     unsigned long long *__restrict__ nwritten, long long count,
                                                     long long nwords, int mode) {
     const int lane = threadIdx.x & 31;
+    const int sub = lane / HD_LPB;                                   // which of the HD_BPI blocks of a load is mine
+    const unsigned submask = (HD_LPB == 32 ? 0xffffffffu : ((1u << HD_LPB) - 1u)) << (sub * HD_LPB);
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long w = warp0; w < nwords; w += nwarps) {
@@ -1192,11 +1198,11 @@ __global__ void __launch_bounds__(256) k_host_delta(const T *__restrict__ src, T
         unsigned cur = 0u;
         const long long e0 = w * 32 * HD_BLOCK + lane * 2;
 #pragma unroll
-        for (int j0 = 0; j0 < 32; j0 += 8) {
-            T v[8][2];
+        for (int j0 = 0; j0 < 32 / HD_BPI; j0 += HD_UNR) {   // 32 / HD_BPI warp-wide loads cover the word's 32 blocks
+            T v[HD_UNR][2];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const long long e = e0 + (long long)(j0 + j) * HD_BLOCK;
+            for (int j = 0; j < HD_UNR; ++j) {
+                const long long e = e0 + (long long)(j0 + j) * 64;
                 v[j][0] = T(1);
                 v[j][1] = T(1);
                 if (e + 1 < count) {
@@ -1214,12 +1220,18 @@ __global__ void __launch_bounds__(256) k_host_delta(const T *__restrict__ src, T
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const long long e = e0 + (long long)(j0 + j) * HD_BLOCK;
+            for (int j = 0; j < HD_UNR; ++j) {
+                const long long e = e0 + (long long)(j0 + j) * 64;
                 const bool ne = (v[j][0] != T(1)) || (v[j][1] != T(1));
-                const bool is_lit = __any_sync(0xffffffffu, ne);
-                const bool was_lit = (old >> (j0 + j)) & 1u;
-                if (is_lit) cur |= 1u << (j0 + j);
+                const unsigned m = __ballot_sync(0xffffffffu, ne);
+                const int b0 = (j0 + j) * HD_BPI;                 // first block of this load inside the word
+#pragma unroll
+                for (int q = 0; q < HD_BPI; ++q) {
+                    const unsigned qm = (HD_LPB == 32 ? 0xffffffffu : ((1u << HD_LPB) - 1u)) << (q * HD_LPB);
+                    if (m & qm) cur |= 1u << (b0 + q);
+                }
+                const bool is_lit = (m & submask) != 0u;
+                const bool was_lit = (old >> (b0 + sub)) & 1u;
                 if (mode == 0 && (is_lit || was_lit)) {  // a block that went dark holds exactly 1.0 in v
                     if (e + 1 < count) {
                         if (sizeof(T) == 8) *reinterpret_cast<double2 *>(host + e) = make_double2((double)v[j][0], (double)v[j][1]);

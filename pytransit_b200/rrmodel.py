@@ -50,7 +50,7 @@ class RoadRunnerModelCUDA(TransitModel):
     with ``copy=False`` it is a ``torch`` CUDA tensor and nothing leaves the device.
 
     ``host_result='delta'`` (default): the model's host array is kept current by delta transfer -- after the
-    first full copy only the 64-point blocks that differ from 1.0 now, or did after the previous call, cross
+    first full copy only the 16-point blocks that differ from 1.0 now, or did after the previous call, cross
     PCIe (written by the GPU straight into the page-locked array).  Its content after every call is identical
     to a full copy; it is handed out as a read-only view because the next call relies on it.  ``'copy'``
     restores the plain full device-to-host copy into a writable array.
