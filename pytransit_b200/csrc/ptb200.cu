@@ -147,6 +147,7 @@ struct ptb_model {
     bool hr_valid = false;           // hr_buf holds the previous result and d_lit its lit-block bitmap
     DevBuf d_lit;                    // lit bitmap words | 8-byte counter of blocks written
     PinBuf h_hrstat;                 // the counter, read back with the result
+    std::vector<cudaEvent_t> ev_part;  // pipelined host delivery: points kernel of part i done / all deltas done
     int64_t hr_last_bytes = 0, hr_delta_calls = 0, hr_full_calls = 0;
 
     // CUDA-graph replay of launch-bound calls (small populations): the per-call kernel sequence is captured once
@@ -332,10 +333,10 @@ int deliver_host(ptb_model *h, void *host, const void *dsrc, size_t count, size_
     const unsigned grid = (unsigned)std::min<long long>((nwords + 7) / 8, (long long)h->sm_count * 8);
     if (esize == 8)
         k_host_delta<double><<<grid, 256, 0, st>>>(static_cast<const double *>(dsrc), static_cast<double *>(h->hr_dev), lit, nwr,
-                                                   (long long)count, nwords, delta ? 0 : 1);
+                                                   (long long)count, 0, nwords, delta ? 0 : 1);
     else
         k_host_delta<float><<<grid, 256, 0, st>>>(static_cast<const float *>(dsrc), static_cast<float *>(h->hr_dev), lit, nwr,
-                                                  (long long)count, nwords, delta ? 0 : 1);
+                                                  (long long)count, 0, nwords, delta ? 0 : 1);
     h->launches++;
     CU(cudaGetLastError());
     if (!delta) CU(cudaMemcpyAsync(host, dsrc, count * esize, cudaMemcpyDeviceToHost, st));
@@ -481,6 +482,7 @@ void ptb_destroy(ptb_model *h) {
         b->release();
     h->h_stage.release();
     h->h_hrstat.release();
+    for (auto &ev : h->ev_part) if (ev) cudaEventDestroy(ev);
     for (auto &g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     h->graphs.clear();
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
@@ -965,12 +967,13 @@ int launch_points_t(ptb_model *h, const PointsParams &P, size_t smem, cudaStream
 }
 
 // flux != nullptr -> flux mode; else lnL mode (partials into h->d_partial)
-int launch_points(ptb_model *h, int64_t npv, void *flux, const double *isig2, cudaStream_t st, int *nchunks_out) {
+int launch_points(ptb_model *h, int64_t npv, void *flux, const double *isig2, cudaStream_t st, int *nchunks_out,
+                  int64_t row0 = 0) {   // rows [row0, row0 + npv) of the records; `flux` points at row row0
     const int ng = h->cfg.ng;
     const int lds = (ng + 4 + 1) & ~1;
     PointsParams P{};
     P.time = h->d_time; P.lcids = h->d_lcids; P.pbids = h->d_pbids; P.epids = h->d_epids; P.nsamples = h->d_nsamples;
-    P.exptimes = h->d_exptimes; P.rec = h->d_rec.as<double>(); P.recstride = h->recstride; P.rec_ld = h->rec_ld;
+    P.exptimes = h->d_exptimes; P.rec = h->d_rec.as<double>() + (size_t)row0 * h->recstride; P.recstride = h->recstride; P.rec_ld = h->rec_ld;
     P.flux = flux; P.obs = h->d_obs; P.blk = h->blk_trivial ? nullptr : h->d_blk.as<int32_t>(); P.isig2 = isig2;
     P.npt = h->npt; P.npv = (int)npv; P.nlc = (int)h->nlc; P.npb = (int)h->npb; P.nep = (int)h->nep; P.ng = ng; P.lds = lds;
     P.nblocks = (int)h->nblocks; P.ns_max = h->ns_max; P.dg = h->dg; P.inv_dg = 1.0 / h->dg;
@@ -1122,6 +1125,62 @@ static int rr_evaluate_impl(ptb_model *h, int64_t npv, const double *k, int64_t 
             }
         }
         if (queued && direct) CU(cudaMemcpyAsync(flux, gflux, count * esize, cudaMemcpyDeviceToDevice, st));
+    }
+    // Large managed host result in its steady state: the population is cut into parts and the delta transfer of
+    // part i (PCIe bound, on the side stream) runs under the points kernel of part i+1 (HBM bound).
+    if (!queued && flux && !direct && !eclipse && flux == h->hr_buf && (int64_t)count == h->hr_count && h->hr_valid &&
+        h->hr_esize == esize && count * esize >= ((size_t)64 << 20) && !h->profiling) {
+        const long long wordlen = 32LL * HD_BLOCK;                          // elements per bitmap word
+        long long g = h->npt, b = wordlen;                                  // rows per part must keep parts word aligned
+        while (b) { const long long t = g % b; g = b; b = t; }
+        const long long rowstep = wordlen / g;
+        const int nparts = 4;
+        long long rows_per = ((npv + nparts - 1) / nparts + rowstep - 1) / rowstep * rowstep;
+        if (rows_per > 0 && rows_per < npv) {
+            Staged D{};
+            if (int rc = stage_model_args(h, A, h->npb, h->nep, nullptr, 0, st, D)) return rc;
+            if (int rc = launch_rr_setup(h, A, D, st)) return rc;
+            const long long nwords = ((long long)count + wordlen - 1) / wordlen;
+            const size_t lit_bytes = ((size_t)nwords * 4 + 15) & ~size_t(15);
+            if (lit_bytes + 16 > h->d_lit.cap) return fail(h, PTB_ESTATE, "host result: bitmap lost");
+            unsigned *lit = h->d_lit.as<unsigned>();
+            unsigned long long *nwr = reinterpret_cast<unsigned long long *>(static_cast<char *>(h->d_lit.ptr) + lit_bytes);
+            const int np = (int)((npv + rows_per - 1) / rows_per);
+            while ((int)h->ev_part.size() < np + 1) {
+                cudaEvent_t ev;
+                CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                h->ev_part.push_back(ev);
+            }
+            h->hr_valid = false;
+            CU(cudaMemsetAsync(nwr, 0, 8, st));
+            for (int ip = 0; ip < np; ++ip) {
+                const long long r0 = ip * rows_per, r1 = std::min<long long>(npv, r0 + rows_per);
+                if (int rc = launch_points(h, r1 - r0, static_cast<char *>(dflux) + (size_t)r0 * h->npt * esize, nullptr, st, nullptr, r0)) return rc;
+                CU(cudaEventRecord(h->ev_part[ip], st));
+                CU(cudaStreamWaitEvent(h->side_stream, h->ev_part[ip], 0));
+                const long long w0 = r0 * h->npt / wordlen;
+                const long long w1 = (r1 == npv) ? nwords : r1 * h->npt / wordlen;
+                const unsigned grid = (unsigned)std::min<long long>((w1 - w0 + 7) / 8, (long long)h->sm_count * 4);
+                if (esize == 8)
+                    k_host_delta<double><<<grid, 256, 0, h->side_stream>>>(static_cast<const double *>(dflux), static_cast<double *>(h->hr_dev),
+                                                                            lit, nwr, (long long)count, w0, w1, 0);
+                else
+                    k_host_delta<float><<<grid, 256, 0, h->side_stream>>>(static_cast<const float *>(dflux), static_cast<float *>(h->hr_dev),
+                                                                           lit, nwr, (long long)count, w0, w1, 0);
+                h->launches++;
+                CU(cudaGetLastError());
+            }
+            CU(cudaEventRecord(h->ev_part[np], h->side_stream));
+            CU(cudaStreamWaitEvent(st, h->ev_part[np], 0));
+            CU(h->h_hrstat.reserve(16));
+            CU(cudaMemcpyAsync(h->h_hrstat.ptr, nwr, 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            h->hr_valid = true;
+            h->hr_last_bytes = (int64_t)(*static_cast<unsigned long long *>(h->h_hrstat.ptr)) * HD_BLOCK * (int64_t)esize;
+            h->hr_delta_calls++;
+            h->last_flux_count = (int64_t)count;
+            return PTB_OK;
+        }
     }
     if (!queued)
         if (int rc = rr_evaluate_enqueue(h, A, dflux, count, st, eclipse)) return rc;

@@ -1187,13 +1187,13 @@ constexpr int HD_UNR = (32 / HD_BPI < 8) ? 32 / HD_BPI : 8;   // loads in flight
 template <typename T>
 __global__ void __launch_bounds__(256) k_host_delta(const T *__restrict__ src, T *__restrict__ host, unsigned *__restrict__ lit,
                                                     unsigned long long *__restrict__ nwritten, long long count,
-                                                    long long nwords, int mode) {
+                                                    long long word0, long long nwords, int mode) {
     const int lane = threadIdx.x & 31;
     const int sub = lane / HD_LPB;                                   // which of the HD_BPI blocks of a load is mine
     const unsigned submask = (HD_LPB == 32 ? 0xffffffffu : ((1u << HD_LPB) - 1u)) << (sub * HD_LPB);
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long w = warp0; w < nwords; w += nwarps) {
+    for (long long w = word0 + warp0; w < nwords; w += nwarps) {   // words [word0, nwords)
         const unsigned old = mode == 0 ? lit[w] : 0u;
         unsigned cur = 0u;
         const long long e0 = w * 32 * HD_BLOCK + lane * 2;

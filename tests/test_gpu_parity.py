@@ -700,3 +700,21 @@ def test_graph_replay_equals_eager(pb, golden):
         f = ec.evaluate(g['k'], g['t0'], g['p'], g['a'], g['i'], g['e'], g['w'], rstar=float(g['rstar'])).copy()
         assert np.abs(f[ok] - g['flux'][ok]).max() <= 1e-12
     assert ec.graph_stats[0] >= 1                       # call 1 sizes the buffers, 2 runs eagerly, 3 captures, 4 replays
+
+
+def test_host_result_delta_pipelined_full_size(pb):
+    """Results of 64 MB and more take the pipelined delivery (delta transfer of one part of the population under the
+    points kernel of the next): at the full C2 size the host array must equal the device result for a sequence of
+    different populations, in fp64 and fp32, with a population size that does not divide evenly into parts."""
+    for precision, npv in (('fp64', 8192), ('fp32', 8192), ('fp64', 5003)):
+        c = wl.config2(npv=npv)
+        m = pb.RoadRunnerModelCUDA('power-2', precision=precision)
+        m.set_data(c.time)
+        for shift in (0, 1, 5, 0):
+            args = _roll(c, shift)
+            host = m.evaluate(*args)
+            dev = m.evaluate(*args, copy=False).cpu().numpy()
+            assert np.array_equal(host, dev), (precision, npv, shift)
+        last, ndelta, nfull = m.host_result_stats
+        assert (ndelta, nfull) == (3, 1) and 0 < last < 0.2 * host.nbytes
+        del m
