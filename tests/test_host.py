@@ -182,3 +182,45 @@ def test_ldmodel_protocol():
     ldp, istar = Quad()(np.linspace(1, 0.1, 40), x)
     assert ldp.shape == (1, 1, 40) and istar.shape == (1, 1)
     assert abs(istar[0, 0] - np.pi * (1 - 0.3 / 3 - 0.2 / 6)) < 1e-3      # trapezoid on 200 nodes in z
+
+
+def test_base_lpf_host_logic_with_a_stub_model():
+    """BaseLPFCUDA's data model and parameter layout (lpf/lpf.py:234-356, wnloglikelihood.py:49-77) are host logic:
+    checked here against the reference's conventions with a stub in place of the CUDA transit model."""
+    from pytransit_b200.lpf import BaseLPFCUDA
+
+    class StubTM:
+        ldmodel, device, npb = 'quadratic', 0, None
+
+        def set_data(self, time, lcids, pbids, nsamples, exptimes):
+            self.args = (time, lcids, pbids, nsamples, exptimes)
+            self.npb = int(np.unique(pbids).size)
+
+        def set_obs(self, obs, slices, nids, nblocks):
+            self.obs = (obs, slices, nids, nblocks)
+
+    rng = np.random.default_rng(0)
+    times = [np.linspace(0, 1, 30), np.linspace(2, 3, 20), np.linspace(5, 6, 10)]
+    fluxes = [1 + rng.normal(0, 1e-3, t.size) for t in times]
+    tm = StubTM()
+    lpf = BaseLPFCUDA('t', ['g', 'r'], times, fluxes, pbids=[0, 1, 0], wnids=[0, 1, 1], nsamples=[1, 1, 5],
+                      exptimes=[0., 0., 0.02], tref=0.5, tm=tm)
+    assert lpf.parameter_names == ['tc', 'p', 'rho', 'b', 'k2', 'q1_g', 'q2_g', 'q1_r', 'q2_r', 'wn_loge_0', 'wn_loge_1']
+    assert (lpf._sl_k2, lpf._sl_ld, lpf._sl_wn) == (slice(4, 5), slice(5, 9), slice(9, 11)) and len(lpf) == 11
+    assert lpf._start_ld == 5 and np.array_equal(lpf._pid_k2, [4, 4])
+    time, lcids, pbids, nsamples, exptimes = tm.args
+    assert np.array_equal(time, np.concatenate(times) - 0.5)                       # tm.set_data(timea - tref, ...)
+    assert np.array_equal(lcids, np.repeat([0, 1, 2], [30, 20, 10])) and np.array_equal(pbids, [0, 1, 0])
+    assert np.array_equal(nsamples, [1, 1, 5]) and np.array_equal(exptimes, [0., 0., 0.02])
+    obs, slices, nids, nblocks = tm.obs
+    assert np.array_equal(slices, [[0, 30], [30, 50], [50, 60]]) and np.array_equal(nids, [0, 1, 1]) and nblocks == 2
+    assert [s.start for s in lpf.lcslices] == [0, 30, 50] and lpf.n_noise_blocks == 2
+    L = lpf._layout
+    assert (L.npar, L.i_tc, L.i_p, L.i_rho, L.i_b, L.i_k2, L.nk2, L.i_ld, L.nldc, L.ld_map, L.i_loge, L.nloge, L.tref) == \
+           (11, 0, 1, 2, 3, 4, 1, 5, 2, 1, 9, 2, 0.5)
+    with pytest.raises(ValueError):
+        lpf._pvp(np.zeros((3, 10)))
+    with pytest.raises(ValueError):
+        BaseLPFCUDA('t', ['g'], times, fluxes, pbids=[0, 1, 0], tm=StubTM())        # two passbands used, one named
+    with pytest.raises(NotImplementedError):
+        BaseLPFCUDA('t', ['g', 'r'], times, fluxes, pbids=[0, 1, 0], tm=StubTM(), lnlikelihood='celerite')
