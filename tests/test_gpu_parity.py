@@ -718,3 +718,37 @@ def test_host_result_delta_pipelined_full_size(pb):
         last, ndelta, nfull = m.host_result_stats
         assert (ndelta, nfull) == (3, 1) and 0 < last < 0.2 * host.nbytes
         del m
+
+
+def test_lpf_layout_eccentric_mapping_vs_oracle(pb, orc, tab):
+    """ptb_lpf_layout with explicit columns: the per-planet block of TransitAnalysis (lpf/transitanalysis.py:72-107:
+    rho first, then tc, p, b, k2, secw, sesw; i_from_ba) and the i_from_baew variant, against the oracle's numpy
+    restatement of the same mapping + rr_full."""
+    import ctypes as C
+    from pytransit_b200 import _lib
+    rng = np.random.default_rng(17)
+    npv, npt = 40, 6000
+    time = np.arange(npt) * (2.0 / 1440.0)
+    pvp = np.column_stack([rng.uniform(1.0, 2.5, npv), rng.normal(1.0, 0.01, npv), rng.normal(3.5, 0.01, npv),
+                           rng.uniform(0.0, 0.8, npv), rng.uniform(0.05, 0.15, npv) ** 2, rng.uniform(-0.4, 0.4, npv),
+                           rng.uniform(-0.4, 0.4, npv), rng.uniform(0.1, 0.9, npv), rng.uniform(0.1, 0.9, npv)])
+    m = pb.RoadRunnerModelCUDA('quadratic', host_result='copy')
+    m.set_data(time)
+    e = pvp[:, 5] ** 2 + pvp[:, 6] ** 2
+    w = np.arctan2(pvp[:, 6], pvp[:, 5])
+    a = orc.as_from_rhop(pvp[:, 0], pvp[:, 2])
+    ldc = orc.map_ldc(pvp[:, 7:9]).reshape(npv, 1, 2)
+    ldp, istar = orc.evaluate_ld('quadratic', tab.mu, ldc)
+    for inc_mode, inc in ((0, orc.i_from_ba(pvp[:, 3], a)), (1, orc.i_from_baew(pvp[:, 3], a, e, w))):
+        lay = _lib.PtbLpfLayout(npar=9, i_tc=1, i_p=2, i_rho=0, i_b=3, i_k2=4, nk2=1, i_ld=7, nldc=2, ld_map=1, i_secw=5,
+                                i_sesw=6, inc_mode=inc_mode, i_loge=0, nloge=0, tref=0.25)
+        out = np.zeros((npv, npt))
+        _lib.check(_lib.lib().ptb_lpf_transit_model(m._h, _lib.ptr(pvp), npv, C.byref(lay), _lib.ptr(out), 0), m._h)
+        ref = orc.rr_full(tab, time, np.sqrt(pvp[:, 4:5]), (pvp[:, 1] - 0.25).reshape(npv, 1), pvp[:, 2].copy(), a, inc, e, w,
+                          np.zeros(npt, np.int64), np.zeros(1, np.int64), np.zeros(1, np.int64), np.ones(1, np.int64),
+                          np.zeros(1), ldp, istar)
+        assert np.array_equal(np.isnan(out), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        assert np.abs(out[ok] - ref[ok]).max() <= FLUX_TOL and (ref[ok] < 1).mean() > 0.01
+    bad = _lib.PtbLpfLayout(npar=9, i_tc=1, i_p=2, i_rho=0, i_b=3, i_k2=4, nk2=1, i_ld=8, nldc=2, ld_map=1, i_secw=5, i_sesw=6)
+    assert _lib.lib().ptb_lpf_transit_model(m._h, _lib.ptr(pvp), npv, C.byref(bad), _lib.ptr(out), 0) == -2   # PTB_ESHAPE
