@@ -990,7 +990,7 @@ int launch_points(ptb_model *h, int64_t npv, void *flux, const double *isig2, cu
     const bool f32 = h->cfg.precision == 1;
     const int tsize = f32 ? 4 : 8;
     const bool aligned = (h->npt % 2 == 0) && ((reinterpret_cast<uintptr_t>(h->d_time) & 15) == 0) &&
-                         (lnl || (reinterpret_cast<uintptr_t>(flux) & (f32 ? 7 : 15)) == 0);
+                         (lnl ? (reinterpret_cast<uintptr_t>(h->d_obs) & 15) == 0 : (reinterpret_cast<uintptr_t>(flux) & (f32 ? 7 : 15)) == 0);
     const int vec = aligned ? 2 : 1;
     // Items: rows are cut into chunks of whole 8-block groups so that every warp of the persistent grid
     // gets ~PT_ITEMS_PER_WARP items (a short tail), at least PT_MIN_ITEM_BLOCKS and at most PT_MAXBLK

@@ -925,6 +925,8 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
         const double *t0v = rec + ORB_STRIDE;
         const double lo1 = T1 - pad1, hi1 = T4 + pad1, t01 = t0v[ep1];
 
+        const double w_one = (LNL && !P.blk) ? isig2[0] : 0.0;  // single noise block: its weight is an item constant
+
         // ---- 1. classification of every block of this item --------------------------------------------
         for (int bb0 = 0; bb0 < nbc; bb0 += 32) {
             const int bb = bb0 + lane, b = bbeg + bb;
@@ -933,7 +935,7 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
                 hit = true;
                 const int lcb = SINGLE_LC ? 0 : P.blc[b];
                 int nz_id = 0;
-                if (LNL) nz_id = P.bnoise ? P.bnoise[b] : 0;
+                if (LNL && P.blk) nz_id = P.bnoise ? P.bnoise[b] : 0;  // one block over all points: id 0 everywhere
                 const bool partial = (b == P.nblk64 - 1) && (npt % PT_BLOCK != 0);
                 if (lcb >= 0 && nz_id != -2 && !partial) {
                     const double lo = SINGLE_LC ? lo1 : T1 - sPad[lcb], hi = SINGLE_LC ? hi1 : T4 + sPad[lcb];
@@ -942,7 +944,7 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
                     const double n2 = floor(fma(P.bmax[b] - t0 - lo, invp, PT_EPS));
                     hit = !(n1 > n2) || !(p > 0.0);  // NaNs and p <= 0 fall through to the exact per-point path
                 }
-                if (LNL && !hit && nz_id >= 0) chi = fma(P.bchi[b], isig2[nz_id], chi);
+                if (LNL && !hit && nz_id >= 0) chi = fma(P.bchi[b], P.blk ? isig2[nz_id] : w_one, chi);
             }
             const unsigned m = __ballot_sync(0xffffffffu, hit);
             if (lane == 0) s_hit[bb0 >> 5] = m;
@@ -998,6 +1000,7 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
         };
         int cur = next_block();
         double tvn[2 / VEC][VEC];
+        double obn[2 / VEC][VEC];  // likelihood: the observed fluxes of the prefetched block travel with its time stamps
         int lcbn = 0;  // light curve of the prefetched block (-1: mixed, per-point lookup)
         auto load_block = [&](int bb) {
             const long long base = (long long)(bbeg + bb) * PT_BLOCK;
@@ -1008,6 +1011,11 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) tvn[h][j] = 0.0;
                 if (i0 < npt) VecIO<VEC, T>::load(P.time + i0, tvn[h]);
+                if (LNL) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) obn[h][j] = 1.0;
+                    if (i0 < npt) VecIO<VEC, T>::load(P.obs + i0, obn[h]);
+                }
             }
         };
         if (cur >= 0) load_block(cur);
@@ -1020,6 +1028,13 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
                 for (int h = 0; h < 2 / VEC; ++h)
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) tv[h][j] = tvn[h][j];
+                double ob[2 / VEC][VEC];
+                if (LNL) {
+#pragma unroll
+                    for (int h = 0; h < 2 / VEC; ++h)
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) ob[h][j] = obn[h][j];
+                }
                 // a block inside one light curve (the rule): window and epoch are block constants
                 const int lcb = SINGLE_LC ? 0 : lcbn;
                 double lob = lo1, hib = hi1, t0b = t01;
@@ -1060,10 +1075,12 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
                             tc = tv[h][j] - __dadd_rn(t0, __dmul_rn(epoch, p));
                             inbox = (lo <= tc) && (tc <= hi);
                             if (LNL && !inbox) {
-                                const int nb = P.blk ? P.blk[i0 + j] : 0;
-                                if (nb >= 0) {
-                                    const double d = P.obs[i0 + j] - 1.0;
-                                    chi = fma(d * d, isig2[nb], chi);
+                                const double d = ob[h][j] - 1.0;
+                                if (!P.blk) {
+                                    chi = fma(d * d, w_one, chi);
+                                } else {
+                                    const int nb = P.blk[i0 + j];
+                                    if (nb >= 0) chi = fma(d * d, isig2[nb], chi);
                                 }
                             }
                         }
