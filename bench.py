@@ -199,7 +199,7 @@ def run_reference(args, rank: int, world: int):
                                      'itself needs the absent meepmeep package'},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -476,12 +476,32 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                               'the timed loop replays the call as a CUDA graph, per-kernel durations are taken in a separate loop')},
             'clocks': clocks, 'e2e': e2e,
             'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Everything except the result line goes to stderr: libraries (NCCL's version banner, torchrun notices) write to
+    file descriptor 1 behind Python's back, and the contract is ONE JSON line on stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)
