@@ -130,6 +130,14 @@ int ptb_eclipse_evaluate(ptb_model *h, int64_t npv, const double *k, const doubl
                          const double *a, const double *inc, const double *e, const double *w, double rstar,
                          double *flux, void *stream);
 
+/* EclipseSpectroscopyModel.evaluate -> esmodel (models/roadrunner/esmodel.py:46-89, model_ecspec.py:13-63): the
+ * secondary eclipse in npb spectroscopic channels.  fratio[npv,npb] planet-to-star flux ratios; k,t0,p,a,inc,e,w,
+ * rstar[npv].  flux[npv,npb,npt] = 1 - (f A / pi) / (1 + f k^2), averaged over the exposure sub-samples
+ * (nsamples[0], exptimes[0] of ptb_set_data; one light curve, one epoch).  Handle created with PTB_LD_UNIFORM. */
+int ptb_es_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *fratio, const double *k, const double *t0,
+                    const double *p, const double *a, const double *inc, const double *e, const double *w,
+                    const double *rstar, double *flux, void *stream);
+
 /* Observed fluxes and noise blocks for the fused likelihood: the (o, slices, nids) arguments of
  * lnlike_normal (lpf/loglikelihood/wnloglikelihood.py:22-35,43-55).  obs[npt]; slices[nsl,2]
  * half-open point ranges; nids[nsl] in [0,nblocks).  Points outside every slice do not contribute.

@@ -172,6 +172,17 @@ def eclipse_model(times, k, t0, p, a, i, e, w, rstar, lcids, epids, nsamples, ex
     return flux
 
 
+def esmodel(times, k, t0, p, a, i, e, w, rstar, fratio, nsamples, exptime):
+    """model_ecspec.py:13-63 on fully expanded arrays: k, t0, p, a, i, e, w, rstar[npv]; fratio[npv, npb]."""
+    times, fratio = _d(times), _d(np.atleast_2d(fratio))
+    npv, npb = fratio.shape
+    k, t0, p, a, i, e, w, rstar = (_d(np.broadcast_to(np.asarray(v, float).reshape(-1), (npv,))) for v in (k, t0, p, a, i, e, w, rstar))
+    flux = np.zeros((npv, npb, times.size))
+    lib().orc_esmodel(_p(times), C.c_int64(times.size), _p(k), _p(t0), _p(p), _p(a), _p(i), _p(e), _p(w), _p(rstar), _p(fratio),
+                      C.c_int64(npv), C.c_int64(npb), C.c_int64(int(nsamples)), C.c_double(float(exptime)), _p(flux))
+    return flux
+
+
 class Tables:
     """z-grid + weight table of RoadRunnerModel.init_integration (rrmodel.py:165-173)."""
 

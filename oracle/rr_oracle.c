@@ -503,6 +503,49 @@ void orc_eclipse_model(const double *times, int64_t npt, const double *k, const 
     }
 }
 
+
+/* esmodel: pytransit/models/roadrunner/model_ecspec.py:13-63 (eclipse spectroscopy).  k, t0, p, a, inc, e, w,
+ * rstar[npv]; fratio[npv,npb]; flux[npv,npb,npt] = 1 - (f A / pi) / (1 + f k^2), averaged over the sub-samples. */
+void orc_esmodel(const double *times, int64_t npt, const double *k, const double *t0, const double *p, const double *a,
+                 const double *inc, const double *e, const double *w, const double *rstar, const double *fratio,
+                 int64_t npv, int64_t npb, int64_t nsamples, double exptime, double *flux) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t ipv = 0; ipv < npv; ++ipv) {
+        double *f = flux + ipv * npb * npt;
+        if (isnan(a[ipv]) || a[ipv] <= 1.0 || e[ipv] < 0.0) {
+            for (int64_t j = 0; j < npb * npt; ++j) f[j] = NAN;
+            continue;
+        }
+        double xyc[10], bt1, bt4;
+        double shift = orc_eclipse_time_offset(p[ipv], inc[ipv], e[ipv], w[ipv]);
+        orc_solve2d(shift, p[ipv], a[ipv], inc[ipv], e[ipv], w[ipv], xyc);
+        double ltt = orc_eclipse_light_travel_time(p[ipv], a[ipv], inc[ipv], e[ipv], w[ipv], rstar[ipv]);
+        double te = t0[ipv] + shift + ltt;
+        orc_bounding_box(k[ipv], xyc, &bt1, &bt4);
+        bt1 -= 0.0015 + exptime;
+        bt4 += 0.0015 + exptime;
+        for (int64_t ipt = 0; ipt < npt; ++ipt) {
+            double epoch = floor((times[ipt] - te + 0.5 * p[ipv]) / p[ipv]);
+            double tc = times[ipt] - (te + epoch * p[ipv]);
+            if (!(bt1 <= tc && tc <= bt4)) {
+                for (int64_t pb = 0; pb < npb; ++pb) f[pb * npt + ipt] = 1.0;
+            } else {
+                for (int64_t pb = 0; pb < npb; ++pb) f[pb * npt + ipt] = 0.0;
+                for (int64_t s = 1; s <= nsamples; ++s) {
+                    double off = exptime * ((s - 0.5) / nsamples - 0.5);
+                    double z = orc_sep_c(tc + off, xyc), area, kap;
+                    orc_ccia_kite(1.0, k[ipv], z, &area, &kap);
+                    for (int64_t pb = 0; pb < npb; ++pb) {
+                        double fr = fratio[ipv * npb + pb];
+                        f[pb * npt + ipt] += 1.0 - (fr * area / ORC_PI) / (1.0 + fr * (k[ipv] * k[ipv]));
+                    }
+                }
+                for (int64_t pb = 0; pb < npb; ++pb) f[pb * npt + ipt] /= nsamples;
+            }
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* RoadRunner population model: pytransit/models/roadrunner/model_full.py:9-100 (rr_full)      */
 /* ------------------------------------------------------------------------------------------ */

@@ -7,7 +7,7 @@ The classes keep the reference's TransitModel API (set_data / evaluate) and call
 kernels through the C ABI of libptb200.so (include/ptb200.h).  There is no CPU fallback: importing
 the package works anywhere, constructing a model needs the built library and a Blackwell GPU.
 """
-from .eclipsemodel import EclipseModelCUDA
+from .eclipsemodel import EclipseModelCUDA, EclipseSpectroscopyModelCUDA, ESModelCUDA
 from .ldmodel import LDModel, TabulatedLDModel
 from .loglikelihood import CUDALogLikelihood
 from .lpf import BaseLPFCUDA
@@ -17,4 +17,4 @@ from .tsmodel import TSModelCUDA, TransmissionSpectroscopyModelCUDA
 
 __version__ = '0.1.0'
 __all__ = ['TransitModel', 'RoadRunnerModelCUDA', 'TSModelCUDA', 'TransmissionSpectroscopyModelCUDA',
-           'CUDALogLikelihood', 'BaseLPFCUDA', 'EclipseModelCUDA', 'LDModel', 'TabulatedLDModel']
+           'CUDALogLikelihood', 'BaseLPFCUDA', 'EclipseModelCUDA', 'ESModelCUDA', 'EclipseSpectroscopyModelCUDA', 'LDModel', 'TabulatedLDModel']

@@ -41,6 +41,7 @@ SIGNATURES = {
     'ptb_set_data': (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
     'ptb_rr_evaluate': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64] + [_vp] * 9),
     'ptb_eclipse_evaluate': (C.c_int, [_vp, _i64] + [_vp] * 7 + [_dbl, _vp, _vp]),
+    'ptb_es_evaluate': (C.c_int, [_vp, _i64, _i64] + [_vp] * 11),
     'ptb_set_obs': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64]),
     'ptb_rr_lnlike': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64] + [_vp] * 10),
     'ptb_rr_lnlike_allgather': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64] + [_vp] * 8 + [C.POINTER(_vp), C.c_int32, C.c_int32, _vp]),

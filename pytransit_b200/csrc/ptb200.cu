@@ -116,6 +116,7 @@ struct ptb_model {
     DevBuf d_dummy;                  // zero limb-darkening coefficients of the eclipse model (uniform disk)
     bool ecl_mode = false;           // the next launch_rr_setup expands about mid-eclipse (ptb_eclipse_evaluate)
     double ecl_rstar = 1.0;
+    const double *ecl_rstar_v = nullptr;  // per-vector stellar radii (device) for ptb_es_evaluate
     DevBuf d_rec, d_work;            // RoadRunner per-vector records; work counters of the persistent kernel
     int recstride = 0, rec_ld = 0;   // record stride / offset of the ld rows (doubles) of the last setup
     cudaStream_t side_stream = nullptr;  // the orbit solve runs here, concurrently with the table contraction
@@ -896,7 +897,7 @@ int launch_rr_setup(ptb_model *h, const ModelArgs &A, const Staged &D, cudaStrea
     O.xyc_in = h->xyc_injected ? h->d_xyc.as<double>() : nullptr;
     O.t0 = D.t0; O.rec = h->d_rec.as<double>();
     O.npv = (int)npv; O.kcols = (int)A.kcols; O.nep = (int)h->nep; O.recstride = (int)recstride;
-    O.eclipse = h->ecl_mode ? 1 : 0; O.rstar = h->ecl_rstar;
+    O.eclipse = h->ecl_mode ? 1 : 0; O.rstar = h->ecl_rstar; O.rstar_v = h->ecl_mode ? h->ecl_rstar_v : nullptr;
     k_rr_orbit<<<(unsigned)((npv * 8 + 255) / 256), 256, 0, h->side_stream>>>(O);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev_join, h->side_stream));
@@ -1213,6 +1214,71 @@ int ptb_eclipse_evaluate(ptb_model *h, int64_t npv, const double *k, const doubl
     const int rc = rr_evaluate_impl(h, npv, k, 1, h->d_dummy.as<double>(), 1, nullptr, t0, p, a, inc, e, w, flux, stream, true);
     h->ecl_mode = false;
     return rc;
+}
+
+
+int ptb_es_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *fratio, const double *k, const double *t0,
+                    const double *p, const double *a, const double *inc, const double *e, const double *w,
+                    const double *rstar, double *flux, void *stream) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (h->cfg.ldlaw != PTB_LD_UNIFORM || h->cfg.precision != 0)
+        return fail(h, PTB_ESTATE, "es_evaluate: the handle must be created with PTB_LD_UNIFORM in fp64");
+    if (!h->has_data) return fail(h, PTB_ESTATE, "es_evaluate: call set_data first");
+    if (h->nlc != 1 || h->nep != 1)
+        return fail(h, PTB_ESTATE, "es_evaluate: eclipse spectroscopy uses one light curve and one epoch (model_ecspec.py:13-14), got nlc=%lld nep=%lld",
+                    (long long)h->nlc, (long long)h->nep);
+    if (npv < 1 || npb < 1) return fail(h, PTB_ESHAPE, "es_evaluate: npv and npb must be >= 1");
+    if (!fratio || !k || !t0 || !p || !a || !inc || !e || !w || !rstar) return fail(h, PTB_EINVAL, "es_evaluate: null parameter array");
+    if ((double)npv * (double)npb * (double)h->npt >= 9.0e18 || npv * ((npb + ES_CH - 1) / ES_CH) > 0x7fffffffLL)
+        return fail(h, PTB_EINVAL, "es_evaluate: output too large");
+    // a uniform disk has no coefficients: one zero per vector keeps the shared argument checks happy
+    if ((size_t)npv * h->npb * 8 > h->d_dummy.cap) {
+        CU(h->d_dummy.reserve((size_t)npv * h->npb * 8));
+        CU(cudaMemset(h->d_dummy.ptr, 0, h->d_dummy.cap));
+    }
+    ModelArgs A{npv, 1, 1, k, h->d_dummy.as<double>(), nullptr, t0, p, a, inc, e, w};
+    if (int rc = check_model_args(h, "es_evaluate", A, h->npb)) return rc;
+    // every host argument of this call in ONE pinned block: the model arguments, the stellar radii and the flux ratios
+    Stager S(h, st);
+    const size_t n = (size_t)npv;
+    auto rk = S.add(k, n * 8), rt0 = S.add(t0, n * 8), rp = S.add(p, n * 8), ra = S.add(a, n * 8), ri = S.add(inc, n * 8),
+         re = S.add(e, n * 8), rw = S.add(w, n * 8), rr = S.add(rstar, n * 8), rf = S.add(fratio, n * npb * 8);
+    if (int rc = S.commit()) return rc;
+    Staged D{};
+    D.k = S.get<double>(rk); D.ld = h->d_dummy.as<double>(); D.istar = nullptr; D.t0 = S.get<double>(rt0); D.p = S.get<double>(rp);
+    D.a = S.get<double>(ra); D.inc = S.get<double>(ri); D.e = S.get<double>(re); D.w = S.get<double>(rw); D.sigma = nullptr;
+    const double *d_rstar = S.get<double>(rr), *d_fratio = S.get<double>(rf);
+    h->ecl_mode = true;
+    h->ecl_rstar_v = d_rstar;
+    mark(h, 0, st);
+    int rc = launch_rr_setup(h, A, D, st);
+    h->ecl_mode = false;
+    h->ecl_rstar_v = nullptr;
+    if (rc) return rc;
+    mark(h, 1, st);
+    // uniform-disk eclipse shape F[npv, npt], then the per-channel expansion
+    CU(h->d_tsgeo.reserve(n * h->npt * 8 + 64));
+    double *shape = h->d_tsgeo.as<double>();
+    if (int rc2 = launch_points(h, npv, shape, nullptr, st, nullptr)) return rc2;
+    const size_t count = n * npb * h->npt;
+    double *dflux = flux;
+    const bool direct = flux && is_device_ptr(flux);
+    if (!direct) {
+        CU(h->d_flux.reserve(count * 8));
+        dflux = h->d_flux.as<double>();
+    }
+    const int nchunks = (int)((npb + ES_CH - 1) / ES_CH);
+    mark(h, 2, st);
+    k_es_expand<<<(unsigned)(npv * nchunks), 256, 0, st>>>(shape, d_fratio, D.k, dflux, h->npt, (int)npb, nchunks);
+    h->launches++;
+    CU(cudaGetLastError());
+    mark(h, 3, st);
+    h->last_npv = 0;  // RoadRunner stage taps do not describe this evaluation
+    h->last_flux_count = direct ? 0 : (int64_t)count;
+    if (flux && !direct) return deliver_host(h, flux, dflux, count, 8, st);
+    return PTB_OK;
 }
 
 // stage + per-vector setup + fused likelihood kernels on `st`

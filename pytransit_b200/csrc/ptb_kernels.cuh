@@ -127,6 +127,7 @@ struct OrbitParams {
     int npv, kcols, nep, recstride;
     int eclipse;           // secondary-eclipse geometry (model_eclipse.py:38-44): expansion about mid-eclipse
     double rstar;          // stellar radius [R_sun] for the light-travel-time shift
+    const double *rstar_v; // per-vector stellar radii (eclipse spectroscopy, model_ecspec.py:41); overrides rstar
 };
 
 // eclipse_time_offset: time from mid-transit to mid-eclipse (the reference's eclipse_phase, orbits_py.py:544-555)
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(256) k_rr_orbit(const __grid_constant__ OrbitP
     double shift = 0.0, tadd = 0.0;
     if (P.eclipse && good0) {
         shift = eclipse_time_offset(p, e, w);
-        tadd = shift + eclipse_light_travel_time(a, inc, e, w, P.rstar);  // te = t0 + shift + ltt (model_eclipse.py:71)
+        tadd = shift + eclipse_light_travel_time(a, inc, e, w, P.rstar_v ? P.rstar_v[ipv] : P.rstar);  // te = t0 + shift + ltt (model_eclipse.py:71)
     }
     solve_orbit_lanes<8>(sl, good0, p, a, inc, e, w, k0, (P.xyc_in && inr) ? P.xyc_in + (size_t)ipv * 10 : nullptr, orb, shift);
     if (inr) {  // transit centres travel with the record (one TMA bulk copy per vector in k_rr_points)
@@ -1340,6 +1341,43 @@ __global__ void k_ecl_finish(double *__restrict__ flux, const double *__restrict
         if (i + 1 < total) {
             const double k1 = k[(i + 1) / npt];
             flux[i + 1] = kPi * ((k1 * k1 - 1.0) + flux[i + 1]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Eclipse spectroscopy (model_ecspec.py:55-62): flux[ipv, pb, t] = mean_s [1 - (f_pb A_s / pi) / (1 + f_pb k^2)]
+// = 1 - c_pb (1 - F[ipv, t]) with c = f / (1 + f k^2) and F the uniform-disk shape 1 - mean_s(A_s) / pi that the
+// points kernel has just written.  A streaming expansion: F (one row per vector, L2 resident) is read once per
+// channel, the output is written with 16-byte stores.  One CTA per (vector, channel chunk).
+// ---------------------------------------------------------------------------------------------
+constexpr int ES_CH = 16;
+__global__ void __launch_bounds__(256) k_es_expand(const double *__restrict__ shape, const double *__restrict__ fratio,
+                                                   const double *__restrict__ k, double *__restrict__ flux, long long npt,
+                                                   int npb, int nchunks) {
+    const int ipv = blockIdx.x / nchunks, chunk = blockIdx.x - ipv * nchunks;
+    const int pb0 = chunk * ES_CH, nch = min(ES_CH, npb - pb0);
+    __shared__ double s_c[ES_CH];
+    const double k0 = k[ipv];
+    if (threadIdx.x < nch) {
+        const double f = fratio[(size_t)ipv * npb + pb0 + threadIdx.x];
+        s_c[threadIdx.x] = f / (1.0 + f * (k0 * k0));
+    }
+    __syncthreads();
+    const double *F = shape + (size_t)ipv * npt;
+    double *out = flux + ((size_t)ipv * npb + pb0) * npt;
+    const bool vec = ((npt & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((reinterpret_cast<uintptr_t>(F) & 15) == 0);
+    if (vec) {
+        for (long long i = (long long)threadIdx.x * 2; i < npt; i += 512) {
+            const double2 f = *reinterpret_cast<const double2 *>(F + i);
+            const double d0 = 1.0 - f.x, d1 = 1.0 - f.y;
+            for (int c = 0; c < nch; ++c)
+                __stcs(reinterpret_cast<double2 *>(out + (size_t)c * npt + i), make_double2(1.0 - s_c[c] * d0, 1.0 - s_c[c] * d1));
+        }
+    } else {
+        for (long long i = threadIdx.x; i < npt; i += 256) {
+            const double d0 = 1.0 - F[i];
+            for (int c = 0; c < nch; ++c) out[(size_t)c * npt + i] = 1.0 - s_c[c] * d0;
         }
     }
 }

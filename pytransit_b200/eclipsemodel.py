@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import check, lib, ptr
 from .rrmodel import RoadRunnerModelCUDA, _current_stream
 
-__all__ = ['EclipseModelCUDA']
+__all__ = ['EclipseModelCUDA', 'ESModelCUDA', 'EclipseSpectroscopyModelCUDA']
 
 
 class EclipseModelCUDA(RoadRunnerModelCUDA):
@@ -49,3 +49,41 @@ class EclipseModelCUDA(RoadRunnerModelCUDA):
 
     def __call__(self, k, t0, p, a, i, e=None, w=None, rstar: float = 1.0, copy: bool = True):
         return self.evaluate(k, t0, p, a, i, e, w, rstar, copy)
+
+
+class ESModelCUDA(RoadRunnerModelCUDA):
+    """Drop-in for ``EclipseSpectroscopyModel`` (pytransit/models/roadrunner/esmodel.py:40-93 ->
+    model_ecspec.py:13-63): ``evaluate(f[npv, npb], k, t0, p, a, i, e=0, w=0, rstar=1.0)`` returns the eclipse in
+    ``npb`` spectroscopic channels, ``flux[npv, npb, npt] = 1 - (f A / pi) / (1 + f k^2)``.  One geometry pass per
+    (vector, time) on the shared eclipse machinery, then a streaming expansion over the channels."""
+
+    def __init__(self, parallel: bool = False, device=None, **kwargs):
+        super().__init__('uniform', device=device, host_result='copy', **kwargs)
+        self.parallel = parallel
+
+    def evaluate(self, f, k, t0, p, a, i, e=0.0, w=0.0, rstar=1.0, copy: bool = True):
+        if self.time is None:
+            raise RuntimeError("set_data must be called before evaluate.")
+        f = _lib.as_f64(f)
+        if f.ndim == 1:
+            f = f.reshape(1, -1)
+        if f.ndim != 2:
+            raise ValueError(" The flux ratio must be given as a 2D array with shape (npv, npb)")
+        npv, npb = int(f.shape[0]), int(f.shape[1])
+        k, t0, p, a, i, e, w, rstar = (self._vec(v, npv, n) for v, n in
+                                       ((k, 'k'), (t0, 't0'), (p, 'p'), (a, 'a'), (i, 'i'), (e, 'e'), (w, 'w'), (rstar, 'rstar')))
+        shape = (npv, npb, self.npt)
+        if copy:
+            out = self._result_buffer(shape)
+        else:
+            import torch
+            out = torch.empty(shape, dtype=torch.float64, device=f'cuda:{self.device}')
+        check(lib().ptb_es_evaluate(self._h, npv, npb, ptr(f), ptr(k), ptr(t0), ptr(p), ptr(a), ptr(i), ptr(e), ptr(w),
+                                    ptr(rstar), ptr(out), _current_stream(self.device)), self._h)
+        return out
+
+    def __call__(self, f, k, t0, p, a, i, e=0.0, w=0.0, rstar=1.0, copy: bool = True):
+        return self.evaluate(f, k, t0, p, a, i, e, w, rstar, copy)
+
+
+EclipseSpectroscopyModelCUDA = ESModelCUDA

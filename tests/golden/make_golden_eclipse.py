@@ -67,3 +67,36 @@ def main():
 
 if __name__ == '__main__':
     main()
+
+
+def make_es():
+    """Eclipse spectroscopy (model_ecspec.py:13-63): the reference's esmodel, a plain Python function, jitted as
+    EclipseSpectroscopyModel does (esmodel.py:44) and run unmodified -> tests/golden/ecspec.npz."""
+    mg.load_reference()
+    from numba import njit
+    from pytransit.models.roadrunner.model_ecspec import esmodel
+    model = njit(fastmath=False)(esmodel)
+    rng = np.random.default_rng(71)
+    npv, npb = 10, 7
+    k = rng.uniform(0.05, 0.15, npv)
+    p = rng.normal(3.5, 0.01, npv)
+    a = rng.normal(10.0, 0.5, npv)
+    b = rng.uniform(0.0, 0.8, npv)
+    e = rng.uniform(0.0, 0.3, npv)
+    w = rng.uniform(0.0, 2 * np.pi, npv)
+    inc = np.arccos(np.clip(b / a * (1 - e * np.sin(w)) / (1 - e ** 2), 0.0, 1.0))
+    t0 = rng.normal(1.0, 0.01, npv)
+    rstar = rng.uniform(0.7, 1.5, npv)
+    fratio = rng.uniform(1e-4, 5e-3, (npv, npb))
+    a[3] = 0.9        # invalid vector -> NaN block
+    times = np.arange(3000) * (2.0 / 1440.0) + 1.5
+    out = dict(times=times, k=k, t0=t0, p=p, a=a, i=inc, e=e, w=w, rstar=rstar, fratio=fratio)
+    out['flux_ns1'] = model(times, k, t0, p, a, inc, e, w, rstar, fratio, 1, 0.0)
+    out['flux_ns5'] = model(times, k, t0, p, a, inc, e, w, rstar, fratio, 5, 0.02)
+    np.savez_compressed(HERE / 'ecspec.npz', **out)
+    f = out['flux_ns1']
+    print('ecspec: shape', f.shape, 'nan blocks', np.isnan(f).all((1, 2)).sum(), 'eclipsed fraction', np.nanmean(f < 1), 'min', np.nanmin(f))
+
+
+if __name__ == '__main__':
+    make_es()

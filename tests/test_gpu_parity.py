@@ -755,3 +755,28 @@ def test_lpf_layout_eccentric_mapping_vs_oracle(pb, orc, tab):
         assert np.abs(out[ok] - ref[ok]).max() <= FLUX_TOL and (ref[ok] < 1).mean() > 0.01
     bad = _lib.PtbLpfLayout(npar=9, i_tc=1, i_p=2, i_rho=0, i_b=3, i_k2=4, nk2=1, i_ld=8, nldc=2, ld_map=1, i_secw=5, i_sesw=6)
     assert _lib.lib().ptb_lpf_transit_model(m._h, _lib.ptr(pvp), npv, C.byref(bad), _lib.ptr(out), 0) == -2   # PTB_ESHAPE
+
+
+def test_eclipse_spectroscopy_vs_reference_golden(pb, orc, golden):
+    """ESModelCUDA against the fixture produced by the reference's esmodel (model_ecspec.py:13-63), with and without
+    supersampling, host and device output, plus the oracle on fresh flux ratios."""
+    g = golden('ecspec')
+    m = pb.ESModelCUDA()
+    args = (g['k'], g['t0'], g['p'], g['a'], g['i'], g['e'], g['w'], g['rstar'])
+    for ns, et, key in ((1, 0.0, 'flux_ns1'), (5, 0.02, 'flux_ns5')):
+        m.set_data(g['times'], nsamples=[ns], exptimes=[et])
+        f = m.evaluate(g['fratio'], *args).copy()
+        ref = g[key]
+        assert f.shape == ref.shape
+        assert np.array_equal(np.isnan(f), np.isnan(ref)) and np.isnan(f[3]).all()
+        ok = ~np.isnan(ref)
+        err = np.abs(f[ok] - ref[ok]).max()
+        assert err <= 1e-13, err                       # eclipse depths are O(1e-4): far inside the 1e-9 bar
+        fd = m.evaluate(g['fratio'], *args, copy=False)
+        assert np.array_equal(fd.cpu().numpy(), f, equal_nan=True)
+    fr = np.random.default_rng(9).uniform(1e-4, 1e-2, (10, 33))
+    f = m.evaluate(fr, *args).copy()
+    ro = orc.esmodel(g['times'], *args, fr, 5, 0.02)
+    assert np.array_equal(np.isnan(f), np.isnan(ro)) and np.nanmax(np.abs(f - ro)) <= 1e-13
+    with pytest.raises(ValueError):
+        m.evaluate(np.zeros((2, 3, 4)), *args)

@@ -180,3 +180,16 @@ def test_eclipse_model_matches_reference(orc, golden):
     ok = np.isfinite(g['shifts'])
     sh = np.array([orc.eclipse_time_offset(g['p'][j], g['i'][j], g['e'][j], g['w'][j]) for j in np.flatnonzero(ok)])
     np.testing.assert_allclose(sh, g['shifts'][ok], rtol=1e-15)
+
+
+def test_eclipse_spectroscopy_matches_reference(orc, golden):
+    """model_ecspec.py:13-63 (the reference's esmodel, run unmodified for the fixture) against the oracle."""
+    g = golden('ecspec')
+    for ns, et, key in ((1, 0.0, 'flux_ns1'), (5, 0.02, 'flux_ns5')):
+        f = orc.esmodel(g['times'], g['k'], g['t0'], g['p'], g['a'], g['i'], g['e'], g['w'], g['rstar'], g['fratio'], ns, et)
+        ref = g[key]
+        assert f.shape == ref.shape == (10, 7, 3000)
+        assert np.array_equal(np.isnan(f), np.isnan(ref)) and np.isnan(f[3]).all()
+        np.testing.assert_allclose(f, ref, rtol=0, atol=1e-15)
+        ok = ~np.isnan(ref)
+        assert ref[ok].max() == 1.0 and (ref[ok] < 1).mean() > 0.01
