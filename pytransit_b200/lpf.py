@@ -56,47 +56,54 @@ class BaseLPFCUDA:
         self._init_parameters()
 
     # ---- data (lpf.py:234-305) -----------------------------------------------------------------
+    @staticmethod
+    def _as_curve_list(x, what: str):
+        """One float ndarray -> a single light curve; a list / tuple of ndarrays -> one light curve each."""
+        if isinstance(x, np.ndarray) and x.ndim == 1 and x.dtype == float:
+            return [x]
+        if isinstance(x, (list, tuple)):
+            return list(x)
+        raise ValueError(f'The {what} must be given either as an ndarray or a list of ndarrays.')
+
     def _init_data(self, times, fluxes, pbids=None, covariates=None, errors=None, wnids=None, nsamples=1, exptimes=0.):
-        if isinstance(times, np.ndarray) and times.ndim == 1 and times.dtype == float:
-            times = [times]
-        elif not isinstance(times, (list, tuple)):
-            raise ValueError('The times must be given either as an ndarray or a list of ndarrays.')
-        if isinstance(fluxes, np.ndarray) and fluxes.ndim == 1 and fluxes.dtype == float:
-            fluxes = [fluxes]
-        elif not isinstance(fluxes, (list, tuple)):
-            raise ValueError('The fluxes must be given either as an ndarray or a list of ndarrays.')
-        self.pbids = np.zeros(len(fluxes), int) if pbids is None else np.atleast_1d(pbids).astype('int')
-        self.nlc = len(times)
-        self.times, self.fluxes = times, fluxes
-        self.timea = np.concatenate(times)
-        self.ofluxa = np.concatenate(fluxes)
-        self.lcids = np.concatenate([np.full(t.size, i) for i, t in enumerate(times)])
+        """Concatenated data arrays and per-light-curve metadata with the reference's attribute names, then
+        ``tm.set_data(timea - tref, lcids, pbids, nsamples, exptimes)`` (lpf.py:286) and the observations / noise
+        blocks for the fused likelihood (wnloglikelihood.py:49-60)."""
+        self.times = self._as_curve_list(times, 'times')
+        self.fluxes = self._as_curve_list(fluxes, 'fluxes')
+        sizes = np.array([t.size for t in self.times], dtype=np.int64)
+        self.nlc = sizes.size
+        self.pbids = np.zeros(len(self.fluxes), int) if pbids is None else np.atleast_1d(pbids).astype('int')
+        self.timea, self.ofluxa = np.concatenate(self.times), np.concatenate(self.fluxes)
+        self.lcids = np.repeat(np.arange(self.nlc), sizes)
+
         if wnids is None:
-            self.noise_ids = np.zeros(self.nlc, int)
-            self.n_noise_blocks = 1
+            self.noise_ids, self.n_noise_blocks = np.zeros(self.nlc, int), 1
         else:
             self.noise_ids = np.asarray(wnids)
-            self.n_noise_blocks = len(np.unique(self.noise_ids))
-            assert self.noise_ids.size == self.nlc, "Need one noise block id per light curve."
-            assert self.noise_ids.max() == self.n_noise_blocks - 1, "Error initialising noise block ids."
-        if np.isscalar(nsamples):
-            self.nsamples = np.full(self.nlc, nsamples)
-            self.exptimes = np.full(self.nlc, exptimes)
+            self.n_noise_blocks = int(np.unique(self.noise_ids).size)
+            if self.noise_ids.size != self.nlc:
+                raise AssertionError("Need one noise block id per light curve.")
+            if self.noise_ids.max() != self.n_noise_blocks - 1:
+                raise AssertionError("Error initialising noise block ids.")
+
+        if np.isscalar(nsamples):                        # one setting for every light curve
+            self.nsamples, self.exptimes = np.full(self.nlc, nsamples), np.full(self.nlc, exptimes)
         else:
-            assert (len(nsamples) == self.nlc) and (len(exptimes) == self.nlc)
-            self.nsamples = np.asarray(nsamples, 'int')
-            self.exptimes = np.asarray(exptimes)
+            if len(nsamples) != self.nlc or len(exptimes) != self.nlc:
+                raise AssertionError("nsamples and exptimes need one entry per light curve.")
+            self.nsamples, self.exptimes = np.asarray(nsamples, 'int'), np.asarray(exptimes)
+
         self.tm.set_data(self.timea - self._tref, self.lcids, self.pbids, self.nsamples, self.exptimes)
         if self.tm.npb != self.npb:
             raise ValueError(f"{self.npb} passbands were named but pbids refers to {self.tm.npb}.")
-        self.errors = [np.full(t.size, np.nan) for t in times] if errors is None else errors
-        self.lcslices, sstart = [], 0
-        for t in times:
-            self.lcslices.append(np.s_[sstart:sstart + t.size])
-            sstart += t.size
-        # WNLogLikelihood.__init__ (wnloglikelihood.py:49-60): slices and local noise ids
-        sl = np.array([[s.start, s.stop] for s in self.lcslices], np.int64)
-        self.tm.set_obs(self.ofluxa, sl, np.asarray(self.noise_ids, np.int64), self.n_noise_blocks)
+        self.errors = [np.full(n, np.nan) for n in sizes] if errors is None else errors
+
+        stops = np.cumsum(sizes)
+        starts = stops - sizes
+        self.lcslices = [np.s_[int(a):int(b)] for a, b in zip(starts, stops)]
+        self.tm.set_obs(self.ofluxa, np.column_stack([starts, stops]).astype(np.int64),
+                        np.asarray(self.noise_ids, np.int64), self.n_noise_blocks)
 
     # ---- parameters (lpf.py:320-356, wnloglikelihood.py:68-77) -------------------------------------
     def _init_parameters(self):
