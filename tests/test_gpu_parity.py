@@ -780,3 +780,46 @@ def test_eclipse_spectroscopy_vs_reference_golden(pb, orc, golden):
     assert np.array_equal(np.isnan(f), np.isnan(ro)) and np.nanmax(np.abs(f - ro)) <= 1e-13
     with pytest.raises(ValueError):
         m.evaluate(np.zeros((2, 3, 4)), *args)
+
+
+def test_supersampling_and_layout_corner_cases_vs_oracle(pb, orc, tab):
+    """Paths no fixture reaches: more sub-samples than the drain buffers in one pass (nsamples > 12: several passes),
+    very different nsamples per light curve, and a dataset too large for the tabulated sub-sample offsets
+    (nlc * max(nsamples) > 1024: offsets computed on the fly) with many passbands and epochs -- against the oracle."""
+    rng = np.random.default_rng(77)
+
+    def run(time, lcids, pbids, epids, nsamples, exptimes, npv, law='quadratic'):
+        nlc, npb, nep = len(nsamples), int(np.max(pbids)) + 1, int(np.max(epids)) + 1
+        k = rng.uniform(0.05, 0.15, size=(npv, npb))
+        t0 = rng.normal(1.0, 0.01, size=(npv, 1)) + rng.normal(0, 0.002, size=(npv, nep))
+        p = rng.normal(3.5, 0.01, npv)
+        a = rng.normal(10.0, 0.5, npv)
+        b = rng.uniform(0.0, 0.9, npv)
+        e = rng.uniform(0.0, 0.2, npv)
+        w = rng.uniform(0.0, 2 * np.pi, npv)
+        i = np.arccos(np.clip(b / a * (1 + e * np.sin(w)) / (1 - e ** 2), 0.0, 1.0))
+        ldc = rng.uniform(0.1, 0.5, size=(npv, npb, 2))
+        m = pb.RoadRunnerModelCUDA(law, host_result='copy')
+        m.set_data(time, lcids, pbids, nsamples, exptimes, epids)
+        f = np.atleast_2d(m.evaluate(k, ldc, t0, p, a, i, e, w)).copy()
+        ldp, istar = orc.evaluate_ld(law, tab.mu, ldc)
+        ref = orc.rr_full(tab, time, k, t0, p, a, i, e, w, np.asarray(lcids, np.int64), np.asarray(pbids, np.int64),
+                          np.asarray(epids, np.int64), np.asarray(nsamples, np.int64), np.asarray(exptimes, float), ldp, istar)
+        err = np.abs(f - ref).max()
+        assert err <= FLUX_TOL, err
+        assert (ref < 1).mean() > 0.01
+        return err
+
+    # (1) one light curve, 15 and 30 sub-samples (two and three passes of the 12-deep buffer)
+    t = np.arange(6000) * 0.0204
+    for ns in (15, 30):
+        run(t, np.zeros(t.size, np.int64), [0], [0], [ns], [0.0204], npv=24)
+    # (2) two light curves with 1 and 30 sub-samples
+    t2 = np.concatenate([np.arange(4000) * (2.0 / 1440.0), 10.0 + np.arange(2000) * 0.0204])
+    run(t2, np.repeat([0, 1], [4000, 2000]), [0, 1], [0, 0], [1, 30], [0.0, 0.0204], npv=16)
+    # (3) 40 light curves x 30 sub-samples (1200 offsets > 1024: no table), 8 passbands, 5 epochs, interleaved order
+    nlc = 40
+    t3 = np.concatenate([j * 0.37 + np.arange(150) * 0.0204 for j in range(nlc)])
+    lc3 = np.repeat(np.arange(nlc), 150)
+    perm = rng.permutation(t3.size)
+    run(t3[perm], lc3[perm], np.arange(nlc) % 8, np.arange(nlc) % 5, np.full(nlc, 30), np.full(nlc, 0.0204), npv=12)
