@@ -808,6 +808,21 @@ def test_supersampling_and_layout_corner_cases_vs_oracle(pb, orc, tab):
         err = np.abs(f - ref).max()
         assert err <= FLUX_TOL, err
         assert (ref < 1).mean() > 0.01
+        # fused likelihood on the same dataset: two noise blocks assigned by light curve parity
+        lcids = np.asarray(lcids)
+        order = np.argsort(lcids, kind='stable')
+        if np.array_equal(order, np.arange(lcids.size)):          # slices need contiguous light curves
+            edges = np.flatnonzero(np.diff(lcids)) + 1
+            starts = np.concatenate([[0], edges])
+            stops = np.concatenate([edges, [lcids.size]])
+            slices = np.column_stack([starts, stops]).astype(np.int64)
+            nids = (np.arange(starts.size) % 2).astype(np.int64) if starts.size > 1 else np.zeros(1, np.int64)
+            nblocks = int(nids.max()) + 1
+            obs = 1 + rng.normal(0, 1e-3, lcids.size)
+            sigma = 10 ** rng.uniform(-3.2, -2.8, size=(npv, nblocks))
+            m.set_obs(obs, slices, nids, nblocks)
+            lnl = m.lnlikelihood(k, ldc, t0, p, a, i, e, w, sigma=sigma).copy()
+            np.testing.assert_allclose(lnl, orc.lnlike_normal(obs, ref, sigma, slices, nids), rtol=LNL_RTOL)
         return err
 
     # (1) one light curve, 15 and 30 sub-samples (two and three passes of the 12-deep buffer)
@@ -815,11 +830,13 @@ def test_supersampling_and_layout_corner_cases_vs_oracle(pb, orc, tab):
     for ns in (15, 30):
         run(t, np.zeros(t.size, np.int64), [0], [0], [ns], [0.0204], npv=24)
     # (2) two light curves with 1 and 30 sub-samples
-    t2 = np.concatenate([np.arange(4000) * (2.0 / 1440.0), 10.0 + np.arange(2000) * 0.0204])
-    run(t2, np.repeat([0, 1], [4000, 2000]), [0, 1], [0, 0], [1, 30], [0.0, 0.0204], npv=16)
+    # (an odd number of points: the scalar-load variants of the supersampled multi-light-curve kernels)
+    t2 = np.concatenate([np.arange(4001) * (2.0 / 1440.0), 10.0 + np.arange(2000) * 0.0204])
+    run(t2, np.repeat([0, 1], [4001, 2000]), [0, 1], [0, 0], [1, 30], [0.0, 0.0204], npv=16)
     # (3) 40 light curves x 30 sub-samples (1200 offsets > 1024: no table), 8 passbands, 5 epochs, interleaved order
     nlc = 40
     t3 = np.concatenate([j * 0.37 + np.arange(150) * 0.0204 for j in range(nlc)])
     lc3 = np.repeat(np.arange(nlc), 150)
     perm = rng.permutation(t3.size)
     run(t3[perm], lc3[perm], np.arange(nlc) % 8, np.arange(nlc) % 5, np.full(nlc, 30), np.full(nlc, 0.0204), npv=12)
+    run(t3, lc3, np.arange(nlc) % 8, np.arange(nlc) % 5, np.full(nlc, 30), np.full(nlc, 0.0204), npv=12)   # + likelihood
