@@ -457,7 +457,9 @@ __global__ void __launch_bounds__(256) k_rr_ldm(const __grid_constant__ LdmParam
         double *tail = rowp + ng;
         tail[0] = kk;
         tail[1] = 1.0 / (1.0 + kk);
-        tail[2] = 1.0 / sIstar[r];
+        // a disk integral that is not finite (the reference's numeric fallback gives NaN for 'logarithmic', -inf for
+        // 'exponential': mu = 0 is a node) turns every in-box point into NaN there: (I* - x) / I*  (model_full.py:97)
+        tail[2] = isfinite(sIstar[r]) ? 1.0 / sIstar[r] : nan("");
         tail[3] = kk * kk;
         for (int j = ng + 4; j < P.lds; ++j) tail[j - ng] = 0.0;
         // k < -1 makes g = z / (1 + k) negative, for which interpolate_mean_limb_darkening_s returns NaN
@@ -646,7 +648,8 @@ __device__ __forceinline__ void sample_eval(T t, const T *cx, const T *cy, const
     const bool covers = (z <= k - one);                       // planet covers the star: area pi; else pi k^2
     const bool inside = covers || (z <= one - k);
     const T c = one - ip * (covers ? pi : pi * k2) * inv_istar;
-    cc = out ? one : (inside ? c : qnan);                     // no overlap: area 0
+    // no overlap: area 0 -> (I* - 0) / I* = 1, or NaN when 1/I* is NaN (non-finite disk integral, see k_rr_ldm)
+    cc = out ? fma(T(0), inv_istar, one) : (inside ? c : qnan);
 }
 
 // Lens-area pass over `take` limb samples at the top of the limb queue (warp-cooperative).

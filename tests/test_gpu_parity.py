@@ -840,3 +840,19 @@ def test_supersampling_and_layout_corner_cases_vs_oracle(pb, orc, tab):
     perm = rng.permutation(t3.size)
     run(t3[perm], lc3[perm], np.arange(nlc) % 8, np.arange(nlc) % 5, np.full(nlc, 30), np.full(nlc, 0.0204), npv=12)
     run(t3, lc3, np.arange(nlc) % 8, np.arange(nlc) % 5, np.full(nlc, 30), np.full(nlc, 0.0204), npv=12)   # + likelihood
+
+
+@pytest.mark.parametrize('law', ['uniform', 'linear', 'quadratic', 'quadratic-tri', 'nonlinear', 'general', 'square_root',
+                                 'logarithmic', 'exponential', 'power-2', 'power-2-pm'])
+def test_full_flux_path_for_every_ld_law(pb, golden, law):
+    """The whole flux path for each named law against the reference's own output (tests/golden/make_golden_laws.py),
+    including the two laws whose numeric disk integral is not finite as coded -- the reference returns NaN for every
+    in-box point there, and so must we."""
+    g = golden('lawsflux')
+    m = pb.RoadRunnerModelCUDA(law, host_result='copy')
+    m.set_data(g['time'], g['lcids'], g['pbids'], g['nsamples'], g['exptimes'], g['epids'])
+    f = m.evaluate(g['k'], g[f'{law}__ldc'], g['t0'], g['p'], g['a'], g['i'], g['e'], g['w'])
+    ref = g[f'{law}__flux']
+    assert np.array_equal(np.isnan(f), np.isnan(ref)), (np.isnan(f).sum(), np.isnan(ref).sum())
+    ok = ~np.isnan(ref)
+    assert np.abs(f[ok] - ref[ok]).max() <= FLUX_TOL

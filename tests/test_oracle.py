@@ -193,3 +193,27 @@ def test_eclipse_spectroscopy_matches_reference(orc, golden):
         np.testing.assert_allclose(f, ref, rtol=0, atol=1e-15)
         ok = ~np.isnan(ref)
         assert ref[ok].max() == 1.0 and (ref[ok] < 1).mean() > 0.01
+
+
+LAWS_ALL = ['uniform', 'linear', 'quadratic', 'quadratic-tri', 'nonlinear', 'general', 'square_root', 'logarithmic',
+            'exponential', 'power-2', 'power-2-pm']
+
+
+@pytest.mark.parametrize('law', LAWS_ALL)
+def test_full_flux_path_for_every_ld_law(orc, tab, golden, law):
+    """rr_full for each named limb-darkening law (rrmodel.py:48-58) against the reference's own output, including the
+    laws whose numeric disk integral is NaN / inf as coded (logarithmic: mu log mu at mu = 0; exponential: 1/(1 - e^0)),
+    for which the reference returns NaN in transit."""
+    g = golden('lawsflux')
+    ldc = g[f'{law}__ldc']
+    ldp, istar = orc.evaluate_ld(law, tab.mu, ldc)
+    f = orc.rr_full(tab, g['time'], g['k'], g['t0'], g['p'], g['a'], g['i'], g['e'], g['w'], g['lcids'], g['pbids'], g['epids'],
+                    g['nsamples'], g['exptimes'], ldp, istar)
+    ref = g[f'{law}__flux']
+    assert np.array_equal(np.isnan(f), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    np.testing.assert_allclose(f[ok], ref[ok], rtol=0, atol=FLUX_TOL)
+    if law in ('logarithmic', 'exponential'):
+        assert np.isnan(ref).any() and (ref[ok] == 1.0).all()
+    else:
+        assert ok.all() and (ref < 1).mean() > 0.05
