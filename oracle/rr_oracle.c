@@ -468,6 +468,7 @@ void orc_eclipse_model(const double *times, int64_t npt, const double *k, const 
                        const double *a, const double *inc, const double *e, const double *w, double rstar,
                        int64_t npv, int64_t nlc, int64_t nep, const int64_t *lcids, const int64_t *epids,
                        const int64_t *nsamples, const double *exptimes, double *flux) {
+    (void)nlc;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int64_t ipv = 0; ipv < npv; ++ipv) {
         double *f = flux + ipv * npt;
