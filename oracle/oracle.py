@@ -11,7 +11,6 @@ reads the reference's own host-side broadcasting produces
 from __future__ import annotations
 
 import ctypes as C
-import os
 import subprocess
 from pathlib import Path
 

@@ -9,7 +9,7 @@ The sharding helpers are pure host logic and run under the gloo backend on CPU (
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Sequence, Tuple
+from typing import Callable, Tuple
 
 import numpy as np
 

@@ -2,7 +2,6 @@
 profile model in the style of LDTkLDModel (pytransit/models/ldtkldm.py:29-95)."""
 from __future__ import annotations
 
-import ctypes as C
 from typing import Tuple
 
 import numpy as np

@@ -2,8 +2,6 @@
 (pytransit/models/roadrunner/tsmodel.py:44-136) over the sm_100a kernels of libptb200.so."""
 from __future__ import annotations
 
-import numpy as np
-
 from . import _lib
 from ._lib import LD_PROFILES, check, lib, ptr
 from .ldmodel import LDModel
