@@ -68,6 +68,27 @@ def workload(name: str, rank: int = 0):
     return c, desc
 
 
+def config_dict(args, desc: str, world: int, c=None) -> dict:
+    """The `config` object -- identical for our arm and the reference arm of the same command line."""
+    lnl = args.workload == 'c5'
+    out_b = 4 if args.precision == 'fp32' else 8
+    sizes = {'c1': 1e4, 'c2': 8192 * 2e4, 'c3': 16384 * 65536, 'c4': 1024 * 1000 * 2000, 'c5': 0}[args.workload]
+    out_gb = out_b * 1e-9 * sizes
+    gather = {'peer': 'lnL[npv] all-gathered by peer stores from the finishing kernel into symmetric memory over NVLink, ranks ordered '
+                      'by device-side flags',
+              'peer-barrier': 'lnL[npv] all-gathered by peer stores + one symmetric-memory barrier per step',
+              'nccl': 'NCCL all-gather of lnL[npv] per step'}[args.gather]
+    return {'workload': desc,
+            'parallelism': f'population sharded over {world} GPU(s), ' +
+                           (gather if (lnl and world > 1) else
+                            'flux shards stay on their GPU: no data-path collective (the lnL all-gather of the path is measured in `collective`)'),
+            'l2': ('time+obs (1.6 MB) are L2 resident by design; nothing is written' if lnl else
+                   'each step streams %.2f GB of output through L2 (126 MB): inputs/outputs exceed L2, no explicit flush' % out_gb
+                   if out_gb > 0.2 else
+                   'latency-bound single vector: time axis and output (80 KB each) are L2 resident by design, no flush; '
+                   'the timed loop replays the call as a CUDA graph, per-kernel durations are taken in a separate loop')}
+
+
 # ---------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------
@@ -146,6 +167,100 @@ def oracle_step(orc, tab, c, rows, lnl: bool):
     return rows * c.npt
 
 
+# ---------------------------------------------------------------------------------------------
+# CPU side: the reference's own Numba path, when its files travelled with the repo
+# ---------------------------------------------------------------------------------------------
+def numba_baseline(name: str, c, seconds: float, max_rows: int = 512):
+    """Times the reference's RoadRunnerModel / TSModel / lnlike_normal -- its own files, loaded by
+    baseline/refload.py from baseline/_ref (git-ignored pip install of the reference made by build()) -- on a
+    bounded sample of the workload, all host cores.  -> dict, or {'unavailable': why}."""
+    try:
+        from baseline.refload import load_reference
+        ref = load_reference()
+        import numba
+    except Exception as ex:   # no reference tree on this box, or no numba
+        return {'unavailable': f'{type(ex).__name__}: {ex}'[:200]}
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    numba.set_num_threads(min(cores, numba.config.NUMBA_NUM_THREADS))
+    nthreads = numba.get_num_threads()
+    lnl = name == 'c5'
+    if name == 'c4':
+        # TSModel(nthreads > 1) is broken in the reference (SURVEY.md Q11): serial, as BASELINE.md prescribes
+        nthreads = 1
+        m0 = ref.TSModel('power-2')
+        prof, (x0, dx), (y0, dy), (z0, dz) = c.table
+        from pytransit.models.ldmodel import LDModel
+
+        class Tab(LDModel):
+            def __call__(self, mu, x):
+                ldp = ref.ldtkldm.trilinear_interpolation_set(prof, x[:, 0].copy(), x[:, 1].copy(), x[:, 2].copy(), x0, dx, prof.shape[0],
+                                                              y0, dy, prof.shape[1], z0, dz, prof.shape[2])
+                return ldp, ref.ldtkldm.integrate_profiles_set(mu, ldp)
+
+            def _evaluate(self, mu, x):
+                raise NotImplementedError
+
+            def _integrate(self, x):
+                raise NotImplementedError
+        m = ref.TSModel(Tab(), nthreads=1)
+        m.set_data(c.time)
+        del m0
+
+        def run(rows):
+            sl = slice(0, rows)
+            x = np.column_stack([c.teff[sl], c.logg[sl], c.metal[sl]])
+            m.evaluate(c.k[sl], x, c.t0[sl], c.p[sl], c.a[sl], c.i[sl], c.e[sl], c.w[sl])
+            return rows * c.npb * c.npt
+        max_rows = min(max_rows, 16)
+    elif name == 'c1':
+        m = ref.RoadRunnerModel(c.ldmodel, nthreads=nthreads)
+        m.set_data(c.time)
+
+        def run(rows):
+            m.evaluate(c.k, c.ldc, c.t0, c.p, c.a, c.i, c.e, c.w)
+            return c.npt
+        max_rows = 1
+    else:
+        m = ref.RoadRunnerModel(c.ldmodel, nthreads=nthreads)
+        m.set_data(c.time, c.lcids, c.pbids, c.nsamples, c.exptimes, c.epids)
+
+        def run(rows):
+            sl = slice(0, rows)
+            flux = m.evaluate(c.k[sl], c.ldc[sl], c.t0[sl], c.p[sl], c.a[sl], c.i[sl], c.e[sl], c.w[sl])
+            if lnl:
+                ref.lnlike_normal(c.obs, np.atleast_2d(flux), c.sigma[sl], c.slices, c.nids)
+            return rows * c.npt
+    rows = 1 if name == 'c1' else min(c.npv, 8)
+    t = time.perf_counter()
+    run(rows)                                   # JIT (or cache load) + first touch
+    jit_s = time.perf_counter() - t
+    t = time.perf_counter()
+    run(rows)
+    dt = max(time.perf_counter() - t, 1e-5)
+    if name != 'c1':
+        per = getattr(c, 'npb_out', 1) * c.npt
+        rows = int(max(rows, min(c.npv, max_rows, rows * (seconds / 3.0) / dt, 2e9 // (8 * per))))
+    best, total, passes, cpu_ratio = None, 0.0, 0, 0.0
+    while passes < 3 or (total < seconds and passes < 50):
+        t, tc = time.perf_counter(), time.process_time()
+        n = run(rows)
+        dt, dc = time.perf_counter() - t, time.process_time() - tc
+        if best is None or dt < best:
+            best, cpu_ratio = dt, dc / max(dt, 1e-9)
+        total += dt
+        passes += 1
+    return {'value': n / best, 'unit': UNIT, 'cores': nthreads, 'kind': 'numba+standin',
+            'sample': f'{rows} of {getattr(c, "npv", 1)} parameter vectors x {n // rows} points each, best of {passes} passes '
+                      f'({best:.3f} s best, {total:.1f} s in all, first call incl. JIT {jit_s:.1f} s)',
+            'threads_busy': round(cpu_ratio, 2), 'numba': numba.__version__, 'threading_layer': numba.threading_layer() if nthreads > 1 else 'serial',
+            'note': "the reference's own files (rrmodel.py, model_full.py, model_trspec.py, common.py, ldmodels.py, wnloglikelihood.py:22-35) "
+                    "run unmodified under Numba; the three absent third-party meepmeep functions come from baseline/_standin "
+                    "(restated from the reference's orbits/taylor_z.py)"}
+
+
 def host_threads(orc) -> int:
     """Use every host core this process may run on (torchrun exports OMP_NUM_THREADS=1; undo that here)."""
     try:
@@ -193,12 +308,14 @@ def run_reference(args, rank: int, world: int):
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': desc, 'sample': sample},
+            'config': config_dict(args, desc, world),
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
                              'note': 'oracle/rr_oracle.c (C restatement of the Numba path, OpenMP); the reference '
                                      'itself needs the absent meepmeep package'},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
+    if not args.no_numba:
+        line['cpu_baseline_numba'] = numba_baseline(args.workload, c, seconds=min(args.cpu_seconds, 15.0))
     emit(line)
 
 
@@ -269,9 +386,9 @@ def make_steps(args, c, dev, local_rank, world, dist):
         sig_d = torch.as_tensor(c.sigma, device=dev)
     gathered = peer = None
     if lnl and world > 1:
-        if args.gather == 'peer':     # fused: the finishing kernel stores the shard into every rank's gathered array
+        if args.gather != 'nccl':     # fused: the finishing kernel stores the shard into every rank's gathered array
             from pytransit_b200.distributed import PeerLnLGather
-            peer = PeerLnLGather(m, c.npv)
+            peer = PeerLnLGather(m, c.npv, sync='flags' if args.gather == 'peer' else 'barrier')
         else:
             gathered = torch.empty((world * c.npv,), dtype=torch.float64, device=dev)
 
@@ -308,6 +425,81 @@ def make_steps(args, c, dev, local_rank, world, dist):
 def _table_args(c):
     prof, (x0, dx), (y0, dy), (z0, dz) = c.table
     return prof, x0, dx, y0, dy, z0, dz
+
+
+
+def run_collective(args, rank, world, local_rank, dev, dist):
+    """The one exchange of the path, measured in the same run as the headline: the C5 shard (eccentric 'power-2',
+    8192 vectors x 100 000 points per GPU) through the fused likelihood, lnL[npv] all-gathered over NVLink by peer
+    stores from the finishing kernel, ranks ordered by device-side flags (no host-issued barrier).  Also timed:
+    the same step without any exchange (what the gather costs), the round-1 symmetric-memory barrier variant and
+    the NCCL all_gather_into_tensor variant.  Device-resident inputs, CUDA events, barrier + synchronize on both
+    sides, max over ranks."""
+    import torch
+    import pytransit_b200 as pb
+    from pytransit_b200.distributed import PeerLnLGather
+    c, desc = workload('c5', rank)
+    m = pb.RoadRunnerModelCUDA(c.ldmodel, device=local_rank)
+    m.set_data(torch.as_tensor(c.time, device=dev))
+    m.set_obs(torch.as_tensor(c.obs, device=dev))
+    td = {k: torch.as_tensor(np.ascontiguousarray(getattr(c, k)), device=dev) for k in ('k', 'ldc', 't0', 'p', 'a', 'i', 'e', 'w', 'sigma')}
+    a = (td['k'], td['ldc'], td['t0'], td['p'], td['a'], td['i'], td['e'], td['w'])
+    steps = max(10, min(args.steps, 100))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(3):
+            out = fn()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            out = fn()
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, out
+
+    local_ms, loc = timed(lambda: m.lnlikelihood(*a, sigma=td['sigma'], copy=False))
+    m.set_profiling(True)
+    for _ in range(5):
+        m.lnlikelihood(*a, sigma=td['sigma'], copy=False)
+    torch.cuda.synchronize()
+    n, _, kp = m.timing_summary()
+    m.set_profiling(False)
+    res = {'workload': desc, 'n_gpus': world, 'steps': steps, 'unit': UNIT, 'dtype': 'f64',
+           'per_gpu': f'npv={c.npv} x npt={c.npt}', 'local_only_ms_per_step': local_ms, 'kernel_ms': kp / n}
+    pts = world * c.npv * c.npt
+    if world == 1:
+        res.update({'value': pts / (local_ms * 1e-3), 'ms_per_step': local_ms, 'gather': 'none (one GPU: the shard is the population)'})
+        return res
+    variants = {}
+    gathered = torch.empty((world * c.npv,), dtype=torch.float64, device=dev)
+
+    def step_nccl():
+        dist.all_gather_into_tensor(gathered, m.lnlikelihood(*a, sigma=td['sigma'], copy=False))
+        return gathered
+
+    variants['nccl_all_gather_ms_per_step'], ref = timed(step_nccl)
+    ref = ref.clone()
+    pg_b = PeerLnLGather(m, c.npv, sync='barrier')
+    variants['peer_stores_host_barrier_ms_per_step'], _ = timed(lambda: pg_b.lnlikelihood(*a, sigma=td['sigma']))
+    pg = PeerLnLGather(m, c.npv, sync='flags')
+    ms, got = timed(lambda: pg.lnlikelihood(*a, sigma=td['sigma']))
+    same = bool(torch.equal(got, ref))
+    m.gather_status()
+    res.update({'value': pts / (ms * 1e-3), 'ms_per_step': ms,
+                'gather': 'peer stores from k_lnl_finish into every rank\'s symmetric-memory array over NVLink, ranks ordered by '
+                          'device-side release/acquire flags (k_lnl_wait); 8 B per vector',
+                'gather_cost_ms_per_step': ms - local_ms, 'efficiency_vs_local_only': local_ms / ms,
+                'bit_identical_to_nccl_all_gather': same, 'variants': variants})
+    return res
 
 
 def run_ours(args, rank: int, world: int, local_rank: int):
@@ -403,6 +595,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     except MemoryError as ex:   # page-locked result buffer too large for this host
         e2e = {'value': None, 'unit': UNIT, 'error': str(ex)[:200]}
 
+    # ---- the path's one collective, same run (default workload only) -----------------------------------
+    collective = None
+    if args.workload == 'c2' and not args.no_collective:
+        del m, step_device, step_host
+        torch.cuda.empty_cache()
+        collective = run_collective(args, rank, world, local_rank, dev, dist)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -463,19 +662,20 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                'sample': f'{rows} of {c0.npv} parameter vectors x {n // rows} points each, best of {passes} passes '
                          f'({best:.3f} s best, {total:.1f} s of CPU work in all)'}
 
-    out_gb = (4e-9 if args.precision == 'fp32' else 8e-9) * pts_per_step
+    cpu_numba = None
+    if world == 1 and not args.no_cpu and not args.no_numba:
+        c0, _ = workload(args.workload, 0)
+        if args.workload == 'c4':
+            c0.table, c0.npb_out = c.table, c.npb
+        cpu_numba = numba_baseline(args.workload, c0, seconds=args.cpu_seconds)
+
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64' if args.precision == 'fp64' else 'f32 (opt-in mode: fp64 phase fold, fp32 samples and output)', 'data': 'synthetic',
-            'config': {'workload': desc, 'per_gpu': f'npv={c.npv} x npt={c.npt}' + (f' x npb={c.npb}' if args.workload == 'c4' else ''),
-                       'parallelism': f'population sharded over {world} GPU(s), ' + (('lnL[npv] all-gathered by peer stores from the finishing kernel into symmetric memory over NVLink + one barrier per step' if args.gather == 'peer' else 'NCCL all-gather of lnL[npv] per step') if (lnl and world > 1) else 'no data-path collective'),
-                       'l2': ('time+obs (1.6 MB) are L2 resident by design; nothing is written' if lnl else
-                              'each step streams %.2f GB of output through L2 (126 MB): inputs/outputs exceed L2, no explicit flush' % out_gb
-                              if out_gb > 0.2 else
-                              'latency-bound single vector: time axis and output (80 KB each) are L2 resident by design, no flush; '
-                              'the timed loop replays the call as a CUDA graph, per-kernel durations are taken in a separate loop')},
+            'config': config_dict(args, desc, world), 'per_gpu': f'npv={c.npv} x npt={c.npt}' + (f' x npb={c.npb}' if args.workload == 'c4' else ''),
             'clocks': clocks, 'e2e': e2e,
-            'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu}
+            'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu, 'cpu_baseline_numba': cpu_numba,
+            'collective': collective}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -510,8 +710,12 @@ def main():
     ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c3', 'c4', 'c5'])
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-numba', action='store_true', help="skip timing the reference's own Numba path (baseline/_ref)")
     ap.add_argument('--no-kernel-timing', action='store_true')
-    ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'], help='N>1 lnL workloads: fused peer-memory all-gather (default) or NCCL all_gather')
+    ap.add_argument('--no-collective', action='store_true', help='skip the C5-shard fused lnL + all-gather block of the default line')
+    ap.add_argument('--gather', default='peer', choices=['peer', 'peer-barrier', 'nccl'],
+                    help='N>1 lnL workloads (--workload c5): peer stores ordered by device-side flags (default), peer stores + one '
+                         'symmetric-memory barrier per step, or NCCL all_gather')
     ap.add_argument('--host-result', default='delta', choices=['delta', 'copy'], help='e2e: delta transfer (default) or plain full copy')
     ap.add_argument('--precision', default='fp64', choices=['fp64', 'fp32'], help="'fp32' = the opt-in single-precision mode (c2/c3/c5 only)")
     args = ap.parse_args()

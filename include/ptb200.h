@@ -155,16 +155,30 @@ int ptb_rr_lnlike(ptb_model *h, int64_t npv, const double *k, int64_t kcols, con
                   const double *sigma, double *lnl, void *stream);
 
 /* The same, for a population sharded over the GPUs of one box: the likelihood and its
- * all-gather in one pass.  peer_bufs[r] (r < world <= 16) is rank r's gathered array lnl_all[world * npv]
- * as a device pointer valid in THIS process (symmetric / CUDA-IPC peer memory over NVLink); the finishing
- * kernel stores this rank's lnl[npv] into slot `rank` of every one of them.  The caller orders the ranks
- * afterwards (one symmetric-memory barrier) before anyone reads its gathered array.  Every rank must pass
- * the same npv. */
+ * all-gather in one pass.  The reference has no multi-GPU path; the reduction it replaces is the prange over
+ * the population of lnlike_normal (wnloglikelihood.py:30-34), whose rows are independent.
+ * peer_bufs[r] (r < world <= 16) is rank r's gathered array lnl_all[world * npv] as a device pointer valid in
+ * THIS process (symmetric / CUDA-IPC peer memory over NVLink); the finishing kernel stores this rank's lnl[npv]
+ * into slot `rank` of every one of them.
+ * Ordering.  peer_flags == NULL: the caller orders the ranks afterwards (e.g. one symmetric-memory barrier)
+ * before anyone reads its gathered array.  peer_flags != NULL: peer_flags[r] is rank r's arrival array
+ * uint64[world] (zero-initialised peer memory, same mapping rules); after all its stores the finishing kernel
+ * publishes `seq` (>= 1, increasing by one per call on every rank) into slot `rank` of every arrival array with
+ * a system-scope release, and a one-warp kernel queued behind it on `stream` returns when all `world` slots of
+ * THIS rank's array have reached `seq` -- work queued on `stream` afterwards sees the complete gathered array,
+ * with no host-side synchronisation.  Use at least two gathered arrays alternately (a peer overwrites the array
+ * of step s at its step s+2, which it can only reach after this rank has published step s+1).  A peer that
+ * never arrives is reported by ptb_gather_status after a 20 s device-side timeout.  Every rank must pass the
+ * same npv. */
 int ptb_rr_lnlike_allgather(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld,
                             int64_t nld, const double *istar, const double *t0, const double *p,
                             const double *a, const double *inc, const double *e, const double *w,
-                            const double *sigma, double *const *peer_bufs, int32_t world, int32_t rank,
-                            void *stream);
+                            const double *sigma, double *const *peer_bufs, uint64_t *const *peer_flags,
+                            uint64_t seq, int32_t world, int32_t rank, void *stream);
+
+/* PTB_OK, or PTB_ESTATE with *timed_out_rank = the first rank whose shard a fused all-gather waited for in
+ * vain (-1: none).  Synchronises the device. */
+int ptb_gather_status(ptb_model *h, int32_t *timed_out_rank);
 
 /* lnlike_normal (wnloglikelihood.py:22-35) on an existing model flux m[npv,npt] (device or host),
  * e.g. baseline-multiplied flux produced by the caller (lpf/lpf.py:445-449). */

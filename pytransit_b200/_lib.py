@@ -44,7 +44,8 @@ SIGNATURES = {
     'ptb_es_evaluate': (C.c_int, [_vp, _i64, _i64] + [_vp] * 11),
     'ptb_set_obs': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64]),
     'ptb_rr_lnlike': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64] + [_vp] * 10),
-    'ptb_rr_lnlike_allgather': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64] + [_vp] * 8 + [C.POINTER(_vp), C.c_int32, C.c_int32, _vp]),
+    'ptb_rr_lnlike_allgather': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64] + [_vp] * 8 + [C.POINTER(_vp), C.POINTER(_vp), C.c_uint64, C.c_int32, C.c_int32, _vp]),
+    'ptb_gather_status': (C.c_int, [_vp, C.POINTER(C.c_int32)]),
     'ptb_lnlike_normal': (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     'ptb_lpf_transit_model': (C.c_int, [_vp, _vp, _i64, C.POINTER(PtbLpfLayout), _vp, _vp]),
     'ptb_lpf_lnlike': (C.c_int, [_vp, _vp, _i64, C.POINTER(PtbLpfLayout), _vp, _vp]),

@@ -25,6 +25,9 @@ using namespace ptb;
 namespace {
 
 thread_local std::string g_create_error;
+// slots of the handle's device counter block d_work (ints): the persistent points kernel owns 0 and 1
+constexpr int WORK_FINISH = 8, WORK_GATHER_ERR = 9;
+constexpr unsigned long long GATHER_TIMEOUT_NS = 20ull * 1000000000ull;
 unsigned long long g_alloc_gen = 1;  // bumped whenever a device buffer moves: captured graphs hold raw pointers
 
 struct DevBuf {  // grow-only device buffer
@@ -118,6 +121,7 @@ struct ptb_model {
     double ecl_rstar = 1.0;
     const double *ecl_rstar_v = nullptr;  // per-vector stellar radii (device) for ptb_es_evaluate
     DevBuf d_rec, d_work;            // RoadRunner per-vector records; work counters of the persistent kernel
+    bool work_dirty = false;         // a CUDA error was seen since the counters were last known to be re-armed
     int recstride = 0, rec_ld = 0;   // record stride / offset of the ld rows (doubles) of the last setup
     cudaStream_t side_stream = nullptr;  // the orbit solve runs here, concurrently with the table contraction
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -188,9 +192,11 @@ int fail(ptb_model *h, int code, const char *fmt, ...) {
 #define CU(call)                                                                                      \
     do {                                                                                              \
         cudaError_t _e = (call);                                                                      \
-        if (_e != cudaSuccess)                                                                        \
+        if (_e != cudaSuccess) {                                                                      \
+            if (h) h->work_dirty = true; /* a kernel may have died before re-arming its counters */   \
             return fail(h, _e == cudaErrorMemoryAllocation ? PTB_ENOMEM : PTB_ECUDA, "%s failed: %s", \
                         #call, cudaGetErrorString(_e));                                               \
+        }                                                                                             \
     } while (0)
 
 // A call classifies each argument pointer once: the graph key and the stager ask about the same pointers.
@@ -981,9 +987,12 @@ int launch_points(ptb_model *h, int64_t npv, void *flux, const double *isig2, cu
 
     P.bmin = h->d_bmin; P.bmax = h->d_bmax; P.blc = h->d_blc; P.bchi = h->d_bchi; P.bnoise = h->d_bnoise;
     P.nblk64 = (int)h->nblk64;
-    if (!h->d_work.ptr) {
+    if (!h->d_work.ptr || h->work_dirty) {
+        // the last CTA of every launch re-arms the counters itself; after a CUDA error (a launch that died
+        // mid-way would leave them poisoned) they are reset here before the next launch
         CU(h->d_work.reserve(64));
-        CU(cudaMemsetAsync(h->d_work.ptr, 0, 64, st));  // the kernel re-arms the counters itself afterwards
+        CU(cudaMemsetAsync(h->d_work.ptr, 0, 64, st));
+        h->work_dirty = false;
     }
     P.work = h->d_work.as<int>();
     const bool single = (h->nlc == 1);
@@ -1282,7 +1291,7 @@ int ptb_es_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *fratio
 }
 
 // stage + per-vector setup + fused likelihood kernels on `st`
-static int rr_lnlike_enqueue(ptb_model *h, const ModelArgs &A, const double *sigma, const LnlOut &out, cudaStream_t st) {
+static int rr_lnlike_enqueue(ptb_model *h, const ModelArgs &A, const double *sigma, LnlOut out, cudaStream_t st) {
     const int64_t npv = A.npv;
     Staged D{};
     if (int rc = stage_model_args(h, A, h->npb, h->nep, sigma, h->nblocks, st, D)) return rc;
@@ -1297,17 +1306,23 @@ static int rr_lnlike_enqueue(ptb_model *h, const ModelArgs &A, const double *sig
     mark(h, 2, st);
     if (int rc = launch_points(h, npv, nullptr, h->d_isig2.as<double>(), st, &nchunks)) return rc;
     mark(h, 3, st);
+    out.done = h->d_work.as<int>() + WORK_FINISH;
     k_lnl_finish<<<(unsigned)((npv + 127) / 128), 128, 0, st>>>(h->d_partial.as<double>(), nchunks, D.sigma,
                                                                  h->d_nblk.as<double>(), (int)h->nblocks, (int)npv, out);
     h->launches++;
     CU(cudaGetLastError());
+    if (out.flag[0]) {  // fused all-gather: this GPU's array is complete once every rank has published step `seq`
+        k_lnl_wait<<<1, 32, 0, st>>>(out.flag[out.rank], out.nout, out.seq, GATHER_TIMEOUT_NS, h->d_work.as<int>() + WORK_GATHER_ERR);
+        h->launches++;
+        CU(cudaGetLastError());
+    }
     return PTB_OK;
 }
 
 static int rr_lnlike_impl(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld, int64_t nld,
                           const double *istar, const double *t0, const double *p, const double *a, const double *inc,
                           const double *e, const double *w, const double *sigma, double *lnl, double *const *peers,
-                          int world, int rank, void *stream) {
+                          uint64_t *const *peer_flags, uint64_t seq, int world, int rank, void *stream) {
     if (!h) return PTB_EINVAL;
     if (int rc = set_device(h)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1317,18 +1332,24 @@ static int rr_lnlike_impl(ptb_model *h, int64_t npv, const double *k, int64_t kc
         if (world < 1 || world > LNL_MAXPEERS || rank < 0 || rank >= world)
             return fail(h, PTB_EINVAL, "rr_lnlike_allgather: world=%d (max %d), rank=%d", world, LNL_MAXPEERS, rank);
         for (int r = 0; r < world; ++r)
-            if (!peers[r]) return fail(h, PTB_EINVAL, "rr_lnlike_allgather: peer buffer %d is null", r);
+            if (!peers[r] || (peer_flags && !peer_flags[r])) return fail(h, PTB_EINVAL, "rr_lnlike_allgather: peer buffer %d is null", r);
+        if (peer_flags && seq == 0) return fail(h, PTB_EINVAL, "rr_lnlike_allgather: step numbers start at 1 (flags are zero-initialised)");
     }
     ModelArgs A{npv, kcols, nld, k, ld, istar, t0, p, a, inc, e, w};
     if (int rc = check_model_args(h, "rr_lnlike", A, h->npb)) return rc;
     LnlOut out{};
     const bool direct = peers || is_device_ptr(lnl);
-    const bool use_graph = graph_eligible(h, npv);
+    const bool use_graph = graph_eligible(h, npv) && !peer_flags;  // the step number changes every call
     bool via_own = false;   // the result lands in the handle's buffer first (host output, or graph mode: one graph
                             // for every output tensor) and is copied out afterwards
     if (peers) {
         out.nout = world;
-        for (int r = 0; r < world; ++r) out.ptr[r] = peers[r] + (size_t)rank * npv;
+        out.rank = rank;
+        out.seq = seq;
+        for (int r = 0; r < world; ++r) {
+            out.ptr[r] = peers[r] + (size_t)rank * npv;
+            out.flag[r] = peer_flags ? reinterpret_cast<unsigned long long *>(peer_flags[r]) : nullptr;
+        }
     } else {
         out.nout = 1;
         out.ptr[0] = lnl;
@@ -1375,15 +1396,30 @@ static int rr_lnlike_impl(ptb_model *h, int64_t npv, const double *k, int64_t kc
 int ptb_rr_lnlike(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld, int64_t nld,
                   const double *istar, const double *t0, const double *p, const double *a, const double *inc,
                   const double *e, const double *w, const double *sigma, double *lnl, void *stream) {
-    return rr_lnlike_impl(h, npv, k, kcols, ld, nld, istar, t0, p, a, inc, e, w, sigma, lnl, nullptr, 1, 0, stream);
+    return rr_lnlike_impl(h, npv, k, kcols, ld, nld, istar, t0, p, a, inc, e, w, sigma, lnl, nullptr, nullptr, 0, 1, 0, stream);
 }
 
 int ptb_rr_lnlike_allgather(ptb_model *h, int64_t npv, const double *k, int64_t kcols, const double *ld, int64_t nld,
                             const double *istar, const double *t0, const double *p, const double *a, const double *inc,
                             const double *e, const double *w, const double *sigma, double *const *peer_bufs,
-                            int32_t world, int32_t rank, void *stream) {
+                            uint64_t *const *peer_flags, uint64_t seq, int32_t world, int32_t rank, void *stream) {
     if (!peer_bufs) return h ? fail(h, PTB_EINVAL, "rr_lnlike_allgather: peer_bufs is null") : PTB_EINVAL;
-    return rr_lnlike_impl(h, npv, k, kcols, ld, nld, istar, t0, p, a, inc, e, w, sigma, nullptr, peer_bufs, world, rank, stream);
+    return rr_lnlike_impl(h, npv, k, kcols, ld, nld, istar, t0, p, a, inc, e, w, sigma, nullptr, peer_bufs, peer_flags, seq, world, rank, stream);
+}
+
+int ptb_gather_status(ptb_model *h, int32_t *timed_out_rank) {
+    if (!h || !timed_out_rank) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    *timed_out_rank = -1;
+    if (!h->d_work.ptr) return PTB_OK;
+    int v = 0;
+    CU(cudaMemcpy(&v, h->d_work.as<int>() + WORK_GATHER_ERR, 4, cudaMemcpyDeviceToHost));
+    if (v) {
+        *timed_out_rank = v - 1;
+        CU(cudaMemset(h->d_work.as<int>() + WORK_GATHER_ERR, 0, 4));
+        return fail(h, PTB_ESTATE, "fused all-gather: rank %d never published its shard (waited %.0f s)", v - 1, GATHER_TIMEOUT_NS * 1e-9);
+    }
+    return PTB_OK;
 }
 
 int ptb_lnlike_normal(ptb_model *h, int64_t npv, const double *model, const double *sigma, double *lnl, void *stream) {

@@ -1139,19 +1139,68 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
 constexpr int LNL_MAXPEERS = 16;
 struct LnlOut {
     double *ptr[LNL_MAXPEERS];
-    int nout;
+    // Device-side ordering of the fused all-gather (no host-issued barrier): flag[r] is destination r's arrival
+    // array [world] of 64-bit step numbers.  The last CTA of k_lnl_finish publishes `seq` into slot `rank` of every
+    // destination after all the shard's stores (release at system scope over NVLink); k_lnl_wait on the destination
+    // acquires them.  null = no signalling (single destination, or the caller orders the ranks itself).
+    unsigned long long *flag[LNL_MAXPEERS];
+    unsigned long long seq;
+    int *done;  // CTAs of this launch that have stored their part (re-armed by the last one)
+    int nout, rank;
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
 __global__ void k_lnl_finish(const double *__restrict__ partial, int nchunks, const double *__restrict__ sigma,
                              const double *__restrict__ nblk, int nblocks, int npv, const __grid_constant__ LnlOut out) {
     const int ipv = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ipv >= npv) return;
-    double chi = 0.0;
-    for (int c = 0; c < nchunks; ++c) chi += partial[(size_t)ipv * nchunks + c];
-    double cst = 0.0;
-    for (int b = 0; b < nblocks; ++b) cst += nblk[b] * (-log(sigma[(size_t)ipv * nblocks + b]) - 0.5 * log(kTwoPi));
-    const double v = cst - 0.5 * chi;
-    for (int r = 0; r < out.nout; ++r) out.ptr[r][ipv] = v;
+    if (ipv < npv) {
+        double chi = 0.0;
+        for (int c = 0; c < nchunks; ++c) chi += partial[(size_t)ipv * nchunks + c];
+        double cst = 0.0;
+        for (int b = 0; b < nblocks; ++b) cst += nblk[b] * (-log(sigma[(size_t)ipv * nblocks + b]) - 0.5 * log(kTwoPi));
+        const double v = cst - 0.5 * chi;
+        for (int r = 0; r < out.nout; ++r) out.ptr[r][ipv] = v;
+    }
+    if (out.flag[0] == nullptr) return;
+    __threadfence_system();  // this thread's peer stores are visible system-wide before the CTA reports
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int done = atomicAdd(out.done, 1);
+        if (done == (int)gridDim.x - 1) {  // every CTA's stores have been fenced: publish the step number everywhere
+            *out.done = 0;
+            __threadfence_system();
+            for (int r = 0; r < out.nout; ++r) st_release_sys(out.flag[r] + out.rank, out.seq);
+        }
+    }
+}
+
+// Consumer side of the fused all-gather: returns once every rank's shard of step `seq` has landed in this GPU's
+// gathered array.  One warp, lane r polls source r.  A peer that never arrives (crashed process) must not hang
+// the GPU: after `timeout_ns` the kernel gives up and raises *err (checked by the host at its next synchronisation).
+__global__ void k_lnl_wait(const unsigned long long *flags, int world, unsigned long long seq, unsigned long long timeout_ns,
+                           int *err) {
+    const int lane = threadIdx.x;
+    if (lane < world) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (ld_acquire_sys(flags + lane) < seq) {
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) {
+                atomicExch(err, 1 + lane);
+                break;
+            }
+        }
+    }
+    __syncwarp();
 }
 
 __global__ void k_inv_sigma2(const double *__restrict__ sigma, long long n, double *__restrict__ out) {

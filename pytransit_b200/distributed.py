@@ -91,31 +91,46 @@ class PeerLnLGather:
     (``torch.distributed._symmetric_memory``) that all peers map into their address space.  The likelihood's
     finishing kernel stores the local shard straight into slot ``rank`` of EVERY rank's array
     (``ptb_rr_lnlike_allgather``), so the exchange is part of the kernel instead of a separate NCCL
-    collective; one symmetric-memory barrier then orders the ranks.  Shards must have equal size
-    (``npv`` vectors per rank, SURVEY.md section 8e: 8192 per GPU at C5)."""
+    collective.
 
-    def __init__(self, model, npv_local: int, group=None):
+    ``sync='flags'`` (default): the ranks are ordered on the device.  The finishing kernel publishes the step
+    number into every rank's arrival array (system-scope release after its stores) and a one-warp kernel queued
+    behind it waits until all ``world`` shards of this step have landed here -- no host-issued barrier, nothing
+    for the host to wait on; the returned tensor is complete for any work queued on the current stream.
+    ``sync='barrier'``: one symmetric-memory barrier per step (round-1 behaviour, kept for comparison).
+
+    Two gathered arrays are used alternately: a peer can only overwrite the array of step s at its step s+2,
+    i.e. after it has seen this rank's step s+1, which this rank publishes only after the work that consumed
+    result s (queued on the same stream).  Shards must have equal size (``npv`` vectors per rank, SURVEY.md
+    section 8e: 8192 per GPU at C5)."""
+
+    def __init__(self, model, npv_local: int, group=None, sync: str = 'flags'):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
+        if sync not in ('flags', 'barrier'):
+            raise ValueError("sync must be 'flags' or 'barrier'.")
         self.model = model
+        self.sync = sync
         self.npv = int(npv_local)
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         dev = torch.device(f'cuda:{model.device}')
-        # two gathered arrays used alternately: a peer can only overwrite the array of step i at its step i+2,
-        # i.e. after it has passed the barrier of step i+1 -- which this rank joins only once it is done with
-        # result i.  One barrier per step is then enough.
         n = self.world * self.npv
-        self._buf = symm_mem.empty(2 * n, dtype=torch.float64, device=dev)
+        nflag = (self.world + 1) & ~1
+        self._buf = symm_mem.empty(2 * n + nflag, dtype=torch.float64, device=dev)
+        self._buf.zero_()                      # arrival flags start at step 0
+        torch.cuda.synchronize(dev)
         self.handle = symm_mem.rendezvous(self._buf, self.group)
         base = [int(p) for p in self.handle.buffer_ptrs]
         if len(base) != self.world:
             raise RuntimeError("symmetric-memory rendezvous returned %d peer buffers for a world of %d"
                                % (len(base), self.world))
+        dist.barrier(self.group)               # every rank's flags are zero before anyone publishes
         self.peer_ptrs = [base, [p + 8 * n for p in base]]
-        self.gathered = [self._buf[:n], self._buf[n:]]
+        self.flag_ptrs = [p + 16 * n for p in base]
+        self.gathered = [self._buf[:n], self._buf[n:2 * n]]
         self._step = 0
 
     def lnlikelihood(self, k, ldc, t0, p, a, i, e=0.0, w=0.0, sigma=1e-3):
@@ -123,6 +138,10 @@ class PeerLnLGather:
         buffer, valid until the call after the next one."""
         b = self._step & 1
         self._step += 1
-        self.model.lnlikelihood_allgather(k, ldc, t0, p, a, i, e, w, sigma, self.peer_ptrs[b], self.rank)
-        self.handle.barrier(channel=b)   # every shard has landed everywhere
+        if self.sync == 'flags':
+            self.model.lnlikelihood_allgather(k, ldc, t0, p, a, i, e, w, sigma, self.peer_ptrs[b], self.rank,
+                                              self.flag_ptrs, self._step)
+        else:
+            self.model.lnlikelihood_allgather(k, ldc, t0, p, a, i, e, w, sigma, self.peer_ptrs[b], self.rank)
+            self.handle.barrier(channel=b)   # every shard has landed everywhere
         return self.gathered[b]

@@ -433,10 +433,14 @@ class RoadRunnerModelCUDA(TransitModel):
                                   ptr(a), ptr(i), ptr(e), ptr(w), ptr(sigma), ptr(out), stream), self._h)
         return out
 
-    def lnlikelihood_allgather(self, k, ldc, t0, p, a, i, e, w, sigma, peer_ptrs, rank: int) -> None:
+    def lnlikelihood_allgather(self, k, ldc, t0, p, a, i, e, w, sigma, peer_ptrs, rank: int, flag_ptrs=None,
+                               seq: int = 0) -> None:
         """The fused likelihood with its all-gather (``ptb_rr_lnlike_allgather``): this rank's ``lnL[npv]`` is
         stored into slot ``rank`` of every peer's gathered array (device pointers ``peer_ptrs``, mapped into
-        this process -- see ``pytransit_b200.distributed.PeerLnLGather``).  Asynchronous on the current stream."""
+        this process -- see ``pytransit_b200.distributed.PeerLnLGather``).  With ``flag_ptrs`` (every rank's
+        arrival array) and a step number ``seq >= 1`` the ranks are ordered on the device: the finishing kernel
+        publishes ``seq`` to every peer and a one-warp kernel waits for all peers' shards of this step, so work
+        queued on the stream afterwards sees the complete gathered array.  Asynchronous on the current stream."""
         if not getattr(self, '_has_obs', False):
             raise RuntimeError("set_obs must be called before lnlikelihood.")
         npv, k, t0, p, a, i, e, w = self._expand(k, t0, p, a, i, e, w)
@@ -444,9 +448,19 @@ class RoadRunnerModelCUDA(TransitModel):
         ld, nld, istar = self._limb_darkening(ldc, npv, self.npb)
         sigma = self._sigma(sigma, npv)
         ptrs = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
+        flags = None
+        if flag_ptrs is not None:
+            if len(flag_ptrs) != len(peer_ptrs):
+                raise ValueError("flag_ptrs and peer_ptrs must have one entry per rank.")
+            flags = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
         check(lib().ptb_rr_lnlike_allgather(self._h, npv, ptr(k), k.shape[1], ptr(ld), nld, ptr(istar), ptr(t0), ptr(p),
-                                            ptr(a), ptr(i), ptr(e), ptr(w), ptr(sigma), ptrs, len(peer_ptrs), int(rank),
-                                            _current_stream(self.device)), self._h)
+                                            ptr(a), ptr(i), ptr(e), ptr(w), ptr(sigma), ptrs, flags, int(seq),
+                                            len(peer_ptrs), int(rank), _current_stream(self.device)), self._h)
+
+    def gather_status(self) -> None:
+        """Raises RuntimeError if a fused all-gather gave up waiting for a peer (device-side timeout)."""
+        r = C.c_int32(-1)
+        check(lib().ptb_gather_status(self._h, C.byref(r)), self._h)
 
     def lnlike_normal(self, model, sigma, copy: bool = True):
         """``lnlike_normal(o, m, e, slices, nids)`` (wnloglikelihood.py:22-35) on a materialised model flux

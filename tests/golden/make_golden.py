@@ -11,15 +11,13 @@ reference's files (rrmodel.py, model_full.py, model_simple.py, model_trspec.py, 
 common.py, numba/ldmodels.py, numba/ldtkldm.py, orbits/orbits_py.py) are then imported and run
 UNMODIFIED.  ``lnlike_normal`` is compiled from the function's own source lines extracted with
 ``ast`` (its module imports astropy-dependent code).  The third-party ``meepmeep`` functions come
-from tests/golden/_standin (restated; parity UNPINNED for those three functions -- every fixture
+from baseline/_standin (restated; parity UNPINNED for those three functions -- every fixture
 therefore also stores the reference run's ``xyc`` so downstream stages can be pinned by injection).
 
 The fixtures store inputs AND outputs, so the tests never need /root/reference.
 """
-import ast
 import os
 import sys
-import types
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
@@ -32,29 +30,10 @@ import numpy as np  # noqa: E402
 
 
 def load_reference():
-    def ns(name, path):
-        m = types.ModuleType(name)
-        m.__path__ = [str(path)]
-        sys.modules[name] = m
-
-    for name, path in [('pytransit', REF), ('pytransit.models', REF / 'models'),
-                       ('pytransit.models.roadrunner', REF / 'models/roadrunner'),
-                       ('pytransit.models.numba', REF / 'models/numba'), ('pytransit.orbits', REF / 'orbits')]:
-        ns(name, path)
-    sys.path.insert(0, str(HERE / '_standin'))
-    from pytransit.models.roadrunner.rrmodel import RoadRunnerModel
-    from pytransit.models.roadrunner.tsmodel import TransmissionSpectroscopyModel
-    from pytransit.models.numba import ldtkldm
-    from meepmeep.backends.numba.point2d import solve2d
-
-    # lnlike_normal: wnloglikelihood.py:22-35, compiled from its own source text.
-    from numba import njit, prange
-    from numpy import atleast_2d, zeros, log, pi
-    src = (REF / 'lpf/loglikelihood/wnloglikelihood.py').read_text()
-    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == 'lnlike_normal')
-    g = dict(njit=njit, prange=prange, atleast_2d=atleast_2d, zeros=zeros, log=log, pi=pi)
-    exec(compile(ast.Module(body=[fn], type_ignores=[]), 'wnloglikelihood.py', 'exec'), g)
-    return RoadRunnerModel, TransmissionSpectroscopyModel, ldtkldm, solve2d, g['lnlike_normal']
+    sys.path.insert(0, str(ROOT))
+    from baseline.refload import load_reference as _load
+    r = _load(REF)
+    return r.RoadRunnerModel, r.TSModel, r.ldtkldm, r.solve2d, r.lnlike_normal
 
 
 def xyc_of(solve2d, p, a, i, e, w):

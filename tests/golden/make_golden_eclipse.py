@@ -1,6 +1,6 @@
 """Golden fixture for the secondary-eclipse sibling (tests/golden/eclipse.npz): the reference's
 ``eclipse_model`` (pytransit/models/roadrunner/model_eclipse.py:11-81) executed UNMODIFIED through the loader of
-make_golden.py, with the absent third-party ``meepmeep`` functions supplied by tests/golden/_standin
+make_golden.py, with the absent third-party ``meepmeep`` functions supplied by baseline/_standin
 (``solve2d/sep_c/bounding_box`` as for the transit fixtures; ``eclipse_time_offset`` = the reference's in-tree
 ``eclipse_phase``; ``eclipse_light_travel_time`` restated from its physical definition -- parity UNPINNED for
 those, see the stand-in headers).

@@ -36,15 +36,21 @@ def main():
     args = dict(k=c.k, ldc=c.ldc, t0=c.t0, p=c.p, a=c.a, i=c.i, e=c.e, w=c.w, sigma=c.sigma)
     full = m.lnlikelihood(**args).copy()                                   # unsharded, this GPU
     shard = shard_population(npv, world, rank, **args)
-    pg = PeerLnLGather(m, npv_local)
+    gathers = {mode: PeerLnLGather(m, npv_local, sync=mode) for mode in ('flags', 'barrier')}
     nccl = PopulationSharder().lnlikelihood(lambda **kw: m.lnlikelihood(copy=False, **kw), npv, **args).cpu().numpy()
     np.testing.assert_allclose(nccl, full, rtol=1e-12, atol=1e-9)   # lnL = cst - chi2/2 cancels: compare to the size of the terms
-    for it in range(3):                                                    # repeated calls reuse the buffers
-        got = pg.lnlikelihood(**shard).cpu().numpy()
-        assert np.array_equal(got, nccl), (rank, it, np.abs(got - nccl).max())
+    for mode, pg in gathers.items():
+        for it in range(5):                                                # repeated calls reuse the buffers
+            sh = dict(shard, sigma=shard['sigma'] * (1.0 + it))            # new values every step: stale slots would show
+            want = PopulationSharder().lnlikelihood(lambda **kw: m.lnlikelihood(copy=False, **kw), npv,
+                                                    **dict(args, sigma=args['sigma'] * (1.0 + it))).cpu().numpy()
+            got = pg.lnlikelihood(**sh).clone()                            # consumer on the same stream, no host sync
+            got = got.cpu().numpy()
+            assert np.array_equal(got, want), (mode, rank, it, np.abs(got - want).max())
+        m.gather_status()
     dist.barrier()
     if rank == 0:
-        print(f'peer gather ok: world={world} npv={npv} max|lnL|={np.abs(full).max():.3e}')
+        print(f'peer gather ok ({", ".join(gathers)}): world={world} npv={npv} max|lnL|={np.abs(full).max():.3e}')
     dist.destroy_process_group()
 
 

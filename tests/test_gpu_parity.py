@@ -590,6 +590,62 @@ def test_base_lpf_on_device_vs_reference_golden(pb, golden):
 
 
 # ---------------------------------------------------------------------------------------------
+# fused likelihood + all-gather ordered by device-side flags: two ranks on ONE GPU (two handles, two streams,
+# "peer" pointers in the same address space) -- the protocol of ptb_rr_lnlike_allgather without a second GPU
+# ---------------------------------------------------------------------------------------------
+def test_fused_allgather_device_flags_two_ranks_one_gpu(pb):
+    import torch
+    world, npv_local, npt = 2, 160, 24_000
+    npv = world * npv_local
+    c = wl.config5(npv=npv, npt=npt)
+    args = dict(k=c.k, ldc=c.ldc, t0=c.t0, p=c.p, a=c.a, i=c.i, e=c.e, w=c.w, sigma=c.sigma)
+    ranks = []
+    for r in range(world):
+        m = pb.RoadRunnerModelCUDA('power-2')
+        m.set_data(c.time)
+        m.set_obs(c.obs)
+        ranks.append(m)
+    full = ranks[0].lnlikelihood(**args).copy()
+    # per rank: two gathered arrays (alternating) + arrival flags, as PeerLnLGather lays them out
+    bufs = [torch.zeros(2 * npv + world, dtype=torch.float64, device='cuda') for _ in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    torch.cuda.synchronize()
+    shard = [{k: (v[r * npv_local:(r + 1) * npv_local]) for k, v in args.items()} for r in range(world)]
+    for r in range(world):       # size every workspace first: an allocation may wait for a spinning wait kernel
+        ranks[r].lnlikelihood(**shard[r])
+    torch.cuda.synchronize()
+    for step in range(1, 6):
+        b = (step - 1) & 1
+        order = range(world) if step % 2 else reversed(range(world))     # either rank may arrive first
+        for r in order:
+            with torch.cuda.stream(streams[r]):
+                s = shard[r]
+                if step == 3:      # a different population at one step: stale data would be noticed
+                    s = dict(s, sigma=s['sigma'] * 2.0)
+                ranks[r].lnlikelihood_allgather(s['k'], s['ldc'], s['t0'], s['p'], s['a'], s['i'], s['e'], s['w'], s['sigma'],
+                                                [int(x.data_ptr()) + 8 * npv * b for x in bufs], r,
+                                                [int(x.data_ptr()) + 16 * npv for x in bufs], step)
+        # each rank's consumer runs on ITS stream right behind the wait kernel: no host synchronisation in between
+        got = []
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                got.append(bufs[r][b * npv:(b + 1) * npv].clone())
+        torch.cuda.synchronize()
+        ref = full if step != 3 else ranks[0].lnlikelihood(**dict(args, sigma=c.sigma * 2.0)).copy()
+        for r in range(world):
+            np.testing.assert_allclose(got[r].cpu().numpy(), ref, rtol=1e-12, atol=1e-9)
+            assert np.array_equal(got[r].cpu().numpy(), got[0].cpu().numpy())
+            flags = bufs[r][2 * npv:].view(torch.int64).cpu().numpy()
+            assert (flags == step).all(), flags
+    for m in ranks:
+        m.gather_status()
+    # a peer that never publishes: the wait gives up (short of the timeout nothing is reported)
+    with pytest.raises(ValueError):
+        ranks[0].lnlikelihood_allgather(c.k[:4], c.ldc[:4], c.t0[:4], c.p[:4], c.a[:4], c.i[:4], c.e[:4], c.w[:4], c.sigma[:4],
+                                        [int(bufs[0].data_ptr())], 0, [int(bufs[0].data_ptr()) + 16 * npv], 0)   # seq 0 is invalid
+
+
+# ---------------------------------------------------------------------------------------------
 # fused likelihood + NVLink peer-memory all-gather (needs >= 2 GPUs; skipped on a single-GPU box)
 # ---------------------------------------------------------------------------------------------
 def test_peer_memory_allgather_two_gpus(pb):
@@ -607,6 +663,7 @@ def test_peer_memory_allgather_two_gpus(pb):
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
                         '127.0.0.1', '--master-port', str(port), str(script)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and 'peer gather ok' in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    assert 'flags' in r.stdout and 'barrier' in r.stdout
 
 
 # ---------------------------------------------------------------------------------------------
