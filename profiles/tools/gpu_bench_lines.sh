@@ -9,7 +9,7 @@ python bench.py --steps 100 --warmup 3 --precision fp32 --no-cpu > gpurun_out/be
 python bench.py --steps 100 --warmup 3 --host-result copy --no-cpu > gpurun_out/bench_c2_copy.json
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json
 ncu --set full --clock-control none --import-source on -k regex:k_host_delta -s 3 -c 1 -o gpurun_out/prof_delta_c2 -f python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_delta_c2.log 2>&1
-mkdir -p gpurun_out/summ; python scratch/mk_profiles.py --summarise gpurun_out/prof_delta_c2.ncu-rep gpurun_out/summ/delta_c2.txt; rm -f gpurun_out/prof_delta_c2.ncu-rep
+mkdir -p gpurun_out/summ; python profiles/tools/mk_profiles.py --summarise gpurun_out/prof_delta_c2.ncu-rep gpurun_out/summ/delta_c2.txt; rm -f gpurun_out/prof_delta_c2.ncu-rep
 python - <<'PY'
 import json
 for w in ('c2','c2_fp32','c2_copy','c3','c4','c5','c1','ref'):

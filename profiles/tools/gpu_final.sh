@@ -16,7 +16,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-fil
 done
 cap() {  # name regex skip count workload traffic_key keep
 ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -o gpurun_out/prof_$1 -f python bench.py --steps 2 --warmup 3 --no-cpu --workload $5 > gpurun_out/ncu_$1.log 2>&1
-python scratch/mk_profiles.py --summarise gpurun_out/prof_$1.ncu-rep gpurun_out/summ/$1.txt $6
+python profiles/tools/mk_profiles.py --summarise gpurun_out/prof_$1.ncu-rep gpurun_out/summ/$1.txt $6
 if [ "$7" != keep ]; then rm -f gpurun_out/prof_$1.ncu-rep; fi
 }
 cap points_c2 k_rr_points 3 1 c2 c2 keep

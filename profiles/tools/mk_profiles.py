@@ -2,8 +2,8 @@
 bench lines, the ncu launch lists, and per-kernel summaries of the `ncu --set full` captures
 (key raw metrics + hottest CUDA source lines).
 
-    python scratch/mk_profiles.py [tag]                      assemble profiles/ from gpurun_out/
-    python scratch/mk_profiles.py --summarise REP OUT [KEY]  (on the GPU box) one .ncu-rep -> text summary OUT;
+    python profiles/tools/mk_profiles.py [tag]                      assemble profiles/ from gpurun_out/
+    python profiles/tools/mk_profiles.py --summarise REP OUT [KEY]  (on the GPU box) one .ncu-rep -> text summary OUT;
                                                              KEY: record the dominant kernel's DRAM traffic in
                                                              gpurun_out/summ/traffic.json under that workload key
 """

@@ -52,7 +52,7 @@ __device__ __forceinline__ double fast_div(double n, double d) {
 
 // atan2(y, x) for y >= 0 (the lens-area kite: y = 2 * kite area).  One division after the argument
 // reduction atan(q) = pi/4 + atan((q-1)/(q+1)) for q > tan(pi/8); odd polynomial of degree 23 in the
-// reduced argument (near-minimax fit, scratch/fit_atan.py: 1.5e-16 relative).
+// reduced argument (near-minimax fit, profiles/tools/fit_atan.py: 1.5e-16 relative).
 __device__ __forceinline__ double atan2_pos(double y, double x) {
     const double ax = fabs(x);
     const bool ygt = y > ax;
