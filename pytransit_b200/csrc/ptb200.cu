@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -28,7 +29,7 @@ thread_local std::string g_create_error;
 // slots of the handle's device counter block d_work (ints): the persistent points kernel owns 0 and 1
 constexpr int WORK_FINISH = 8, WORK_GATHER_ERR = 9;
 constexpr unsigned long long GATHER_TIMEOUT_NS = 20ull * 1000000000ull;
-unsigned long long g_alloc_gen = 1;  // bumped whenever a device buffer moves: captured graphs hold raw pointers
+std::atomic<unsigned long long> g_alloc_gen{1};  // bumped whenever a device or pinned buffer moves: captured graphs hold raw pointers
 
 struct DevBuf {  // grow-only device buffer
     void *ptr = nullptr;
@@ -64,6 +65,7 @@ struct PinBuf {  // grow-only pinned host buffer
         const size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMallocHost(&ptr, want);
         if (e == cudaSuccess) cap = want;
+        ++g_alloc_gen;  // a captured copy node may hold the old address
         return e;
     }
     void release() {
@@ -1115,7 +1117,7 @@ static int rr_evaluate_impl(ptb_model *h, int64_t npv, const double *k, int64_t 
         const GKey key{eclipse ? 2ull : 0ull, (unsigned long long)npv, (unsigned long long)kcols, (unsigned long long)nld, pkey(k),
                        pkey(ld), pkey(istar), pkey(t0), pkey(p), pkey(a), pkey(inc), pkey(e), pkey(w),
                        (unsigned long long)reinterpret_cast<uintptr_t>(gflux), eclipse ? rsbits : 0ull,
-                       h->xyc_injected ? 1ull : 0ull, g_alloc_gen, h->data_gen};
+                       h->xyc_injected ? 1ull : 0ull, g_alloc_gen.load(), h->data_gen};
         if (auto *g = graph_find(h, key)) {
             Staged D{};
             if (int rc = stage_model_args(h, A, h->npb, h->nep, nullptr, 0, st, D, true)) return rc;
@@ -1127,7 +1129,7 @@ static int rr_evaluate_impl(ptb_model *h, int64_t npv, const double *k, int64_t 
             h->last_npb = h->npb;
             queued = true;
         } else if (graph_seen(h, key)) {  // second call with this signature: capture while enqueueing
-            const unsigned long long gen0 = g_alloc_gen;
+            const unsigned long long gen0 = g_alloc_gen.load();
             const int64_t l0 = h->launches;
             if (graph_begin(h) == PTB_OK) {
                 const int rc = rr_evaluate_enqueue(h, A, gflux, count, h->cap_stream, eclipse);
@@ -1362,7 +1364,7 @@ static int rr_lnlike_impl(ptb_model *h, int64_t npv, const double *k, int64_t kc
     bool queued = false;
     if (use_graph) {
         GKey key{1ull, (unsigned long long)npv, (unsigned long long)kcols, (unsigned long long)nld, pkey(k), pkey(ld), pkey(istar),
-                 pkey(t0), pkey(p), pkey(a), pkey(inc), pkey(e), pkey(w), pkey(sigma), h->xyc_injected ? 1ull : 0ull, g_alloc_gen,
+                 pkey(t0), pkey(p), pkey(a), pkey(inc), pkey(e), pkey(w), pkey(sigma), h->xyc_injected ? 1ull : 0ull, g_alloc_gen.load(),
                  h->data_gen, (unsigned long long)out.nout};
         for (int r = 0; r < out.nout; ++r) key.push_back((unsigned long long)reinterpret_cast<uintptr_t>(out.ptr[r]));
         if (auto *g = graph_find(h, key)) {
@@ -1376,7 +1378,7 @@ static int rr_lnlike_impl(ptb_model *h, int64_t npv, const double *k, int64_t kc
             h->last_npb = h->npb;
             queued = true;
         } else if (graph_seen(h, key)) {
-            const unsigned long long gen0 = g_alloc_gen;
+            const unsigned long long gen0 = g_alloc_gen.load();
             const int64_t l0 = h->launches;
             if (graph_begin(h) == PTB_OK) {
                 const int rc = rr_lnlike_enqueue(h, A, sigma, out, h->cap_stream);

@@ -28,18 +28,40 @@ def shard_bounds(npv: int, world: int, rank: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
-def _leading(x):
-    return x.shape[0] if hasattr(x, 'shape') and len(x.shape) > 0 else None
+# dimensionality at which an argument carries one entry per parameter vector (leading axis npv); at a lower
+# dimensionality it is shared by the whole population (a per-passband k[npb], ldc[npb, nldc], sigma[nblocks], ...)
+_PER_VECTOR_NDIM = {'k': 2, 'ldc': 3, 't0': 1, 'p': 1, 'a': 1, 'i': 1, 'e': 1, 'w': 1, 'sigma': 2}
+
+
+def _ndim(x) -> int:
+    return len(x.shape) if hasattr(x, 'shape') else 0
 
 
 def shard_population(npv: int, world: int, rank: int, **params):
-    """Slice every array whose leading dimension is `npv`; scalars and shared arrays (e.g. ``ldc[npb, nldc]``
-    or a per-passband ``k[npb]``) pass through.  A 2-D/3-D array with leading dimension 1 is shared too."""
+    """Slice the per-vector arguments of ``evaluate`` / ``lnlikelihood`` to this rank's block.  What is per-vector
+    is decided by argument NAME and rank, never by a coincidence of sizes: ``k`` only as ``[npv, 1|npb]``, ``ldc`` only
+    as ``[npv, npb, nldc]``, ``sigma`` only as ``[npv, nblocks]`` (a 1-D ``sigma[npv]`` with one noise block also
+    counts), ``t0`` as ``[npv]`` or ``[npv, nep]``, the orbital parameters as ``[npv]``.  Scalars, arrays with a
+    leading dimension of 1 and shared arrays (``k[npb]``, ``ldc[npb, nldc]``, ``sigma[nblocks]``) pass through even
+    when ``npb == npv`` or ``nblocks == npv``.  Unknown names are sliced when their leading dimension is npv."""
     lo, hi = shard_bounds(npv, world, rank)
     out = {}
     for name, v in params.items():
-        n = _leading(v)
-        out[name] = v[lo:hi] if (n == npv and npv > 1) else v
+        nd = _ndim(v)
+        if nd == 0 or v.shape[0] != npv or npv == 1:
+            out[name] = v
+            continue
+        need = _PER_VECTOR_NDIM.get(name)
+        if need is None:
+            per_vector = True
+        elif name == 't0':
+            per_vector = nd in (1, 2)
+        elif name == 'sigma':
+            per_vector = nd == 2 or (nd == 1 and params.get('_sigma_blocks', 1) == 1)
+        else:
+            per_vector = nd == need
+        out[name] = v[lo:hi] if per_vector else v
+    out.pop('_sigma_blocks', None)
     return out
 
 
@@ -65,11 +87,17 @@ class PopulationSharder:
 
     def lnlikelihood(self, lnl_fn: Callable, npv: int, **params):
         import torch
-        local = lnl_fn(**self.shard(npv, **params))
+        lo, hi = self.bounds(npv)
+        # more ranks than vectors: a rank with an empty block skips the evaluation and contributes zero rows
+        local = lnl_fn(**self.shard(npv, **params)) if hi > lo else None
         if self.world == 1:
             return local
-        as_numpy = not isinstance(local, torch.Tensor)
-        loc = torch.as_tensor(np.asarray(local)) if as_numpy else local
+        on_gpu = self.dist.get_backend(self.group) == 'nccl'
+        as_numpy = not isinstance(local, torch.Tensor) if local is not None else not on_gpu
+        if local is None:
+            loc = torch.zeros(0, dtype=torch.float64, device='cuda' if on_gpu else 'cpu')
+        else:
+            loc = torch.as_tensor(np.asarray(local)) if as_numpy else local
         loc = loc.reshape(-1).to(torch.float64)
         nmax = -(-npv // self.world)
         pad = torch.full((nmax,), float('nan'), dtype=torch.float64, device=loc.device)
@@ -78,8 +106,8 @@ class PopulationSharder:
         self.dist.all_gather_into_tensor(out, pad, group=self.group)
         parts = []
         for r in range(self.world):
-            lo, hi = shard_bounds(npv, self.world, r)
-            parts.append(out[r * nmax:r * nmax + (hi - lo)])
+            rlo, rhi = shard_bounds(npv, self.world, r)
+            parts.append(out[r * nmax:r * nmax + (rhi - rlo)])
         full = torch.cat(parts)
         return full.cpu().numpy() if as_numpy else full
 

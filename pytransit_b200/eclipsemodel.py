@@ -24,7 +24,7 @@ class EclipseModelCUDA(RoadRunnerModelCUDA):
         super().__init__('uniform', device=device, host_result='copy', **kwargs)
 
     def evaluate(self, k, t0, p, a, i, e=None, w=None, rstar: float = 1.0, copy: bool = True):
-        if self.time is None:
+        if self.time is None or self.time_id is None:   # never registered, or the last set_data failed
             raise RuntimeError("set_data must be called before evaluate.")
         k = _lib.as_f64(k).reshape(-1)                       # atleast_1d (new_eclipse_model.py:62)
         npv = int(k.numel() if _lib.is_torch_tensor(k) else k.size)
@@ -62,7 +62,7 @@ class ESModelCUDA(RoadRunnerModelCUDA):
         self.parallel = parallel
 
     def evaluate(self, f, k, t0, p, a, i, e=0.0, w=0.0, rstar=1.0, copy: bool = True):
-        if self.time is None:
+        if self.time is None or self.time_id is None:   # never registered, or the last set_data failed
             raise RuntimeError("set_data must be called before evaluate.")
         f = _lib.as_f64(f)
         if f.ndim == 1:

@@ -196,13 +196,19 @@ class RoadRunnerModelCUDA(TransitModel):
             return
         self.nep = int(np.unique(self.epids).size)
         if self.epids.min() < 0 or self.epids.max() != self.nep - 1:
-            raise ValueError(f"Epoch indices (`epids`) for {self.nep} unique epochs should be integers between 0 "
-                             f"and {self.nep - 1}.")
+            self.time_id, nep, self.nep = None, self.nep, 0
+            raise ValueError(f"Epoch indices (`epids`) for {nep} unique epochs should be integers between 0 "
+                             f"and {nep - 1}.")
         self._keep = [self.time]
-        check(lib().ptb_set_data(self._h, ptr(self.time), self.npt, ptr(self.lcids) if self.nlc > 1 else None,
-                                 self.nlc, ptr(self.pbids), self.npb, ptr(self.epids), self.nep,
-                                 ptr(self.nsamples), ptr(self.exptimes)), self._h)
         self._has_obs = False
+        try:
+            check(lib().ptb_set_data(self._h, ptr(self.time), self.npt, ptr(self.lcids) if self.nlc > 1 else None,
+                                     self.nlc, ptr(self.pbids), self.npb, ptr(self.epids), self.nep,
+                                     ptr(self.nsamples), ptr(self.exptimes)), self._h)
+        except Exception:
+            self.time_id = None      # the handle still holds the previous dataset: the next set_data must not early-out
+            self.nep = 0
+            raise
 
     # ------------------------------------------------------------------------------------------
     def _limb_darkening(self, ldc, npv: int, npb: int):
@@ -346,7 +352,7 @@ class RoadRunnerModelCUDA(TransitModel):
     # ------------------------------------------------------------------------------------------
     def evaluate(self, k, ldc, t0, p, a, i, e=0.0, w=0.0, copy: bool = True):
         """Evaluate the transit model for a set of scalar or vector parameters (rrmodel.py:175-238)."""
-        if self.time is None:
+        if self.time is None or self.time_id is None:   # never registered, or the last set_data failed
             raise RuntimeError("set_data must be called before evaluate.")
         npv, k, t0, p, a, i, e, w = self._expand(k, t0, p, a, i, e, w)
         self._lastnpv = npv

@@ -36,7 +36,13 @@ class TransitModel:
                 and exptimes is None and epids is None):
             return
 
+        # a failed registration must not look like a registered dataset to the early-out above (the device handle would
+        # still hold the previous one): the identity of `time` is only recorded once everything has validated
+        self.time_id = None
+        self._validate_and_store(time, lcids, pbids, nsamples, exptimes, epids)
         self.time_id = id(time)
+
+    def _validate_and_store(self, time, lcids, pbids, nsamples, exptimes, epids) -> None:
         self.time = _lib.as_f64(time)
         if _lib.is_torch_tensor(self.time):
             self.time = self.time.reshape(-1)

@@ -20,7 +20,7 @@ class TSModelCUDA(RoadRunnerModelCUDA):
     (as in the reference); ``nsamples[0]`` and ``exptimes[0]`` apply to all points."""
 
     def evaluate(self, k, ldc, t0, p, a, i, e=0.0, w=0.0, copy: bool = True):
-        if self.time is None:
+        if self.time is None or self.time_id is None:   # never registered, or the last set_data failed
             raise RuntimeError("set_data must be called before evaluate.")
         if self.precision != 'fp64':
             raise NotImplementedError("TSModelCUDA computes in fp64; the opt-in fp32 mode covers RoadRunnerModelCUDA.")

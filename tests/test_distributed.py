@@ -71,7 +71,7 @@ def _worker(rank, world, port, npv, npt, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('npv', [8, 11])      # even and ragged shards
+@pytest.mark.parametrize('npv', [8, 11, 1])      # even and ragged shards; one vector: rank 1 has an empty block
 def test_allgather_lnl_world2_gloo(npv):
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
@@ -87,3 +87,23 @@ def test_allgather_lnl_world2_gloo(npv):
     assert [r[0] for r in res] == [0, 1]
     assert all(r[1] for r in res), res
     assert all(r[2] == (npv,) for r in res)
+
+
+def test_shard_population_goes_by_name_and_rank_not_by_size():
+    """npb == npv or nblocks == npv must not get the shared arrays sliced."""
+    from pytransit_b200.distributed import shard_population
+    npv = npb = nblocks = 4
+    rng = np.random.default_rng(0)
+    k_shared, ldc_shared, sig_shared = rng.random(npb), rng.random((npb, 2)), rng.random(nblocks)
+    k_pv, ldc_pv, sig_pv = rng.random((npv, npb)), rng.random((npv, npb, 2)), rng.random((npv, nblocks))
+    p = rng.random(npv)
+    s = shard_population(npv, 2, 1, k=k_shared, ldc=ldc_shared, sigma=sig_shared, p=p, t0=rng.random((npv, 3)), _sigma_blocks=nblocks)
+    assert s['k'] is k_shared and s['ldc'] is ldc_shared and s['sigma'] is sig_shared
+    assert s['p'].shape == (2,) and s['t0'].shape == (2, 3) and '_sigma_blocks' not in s
+    s = shard_population(npv, 2, 1, k=k_pv, ldc=ldc_pv, sigma=sig_pv, p=p)
+    assert np.array_equal(s['k'], k_pv[2:]) and np.array_equal(s['ldc'], ldc_pv[2:]) and np.array_equal(s['sigma'], sig_pv[2:])
+    # one noise block: a 1-D sigma[npv] is per vector
+    assert shard_population(npv, 2, 0, sigma=rng.random(npv))['sigma'].shape == (2,)
+    # scalars and leading-1 arrays pass through
+    s = shard_population(npv, 2, 0, e=0.0, k=np.full((1, 1), 0.1))
+    assert s['e'] == 0.0 and s['k'].shape == (1, 1)

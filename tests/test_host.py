@@ -224,3 +224,23 @@ def test_base_lpf_host_logic_with_a_stub_model():
         BaseLPFCUDA('t', ['g'], times, fluxes, pbids=[0, 1, 0], tm=StubTM())        # two passbands used, one named
     with pytest.raises(NotImplementedError):
         BaseLPFCUDA('t', ['g', 'r'], times, fluxes, pbids=[0, 1, 0], tm=StubTM(), lnlikelihood='celerite')
+
+
+def test_failed_set_data_is_not_remembered():
+    """a set_data that raises must not leave the identity of `time` behind -- the next set_data(time) with
+    the same object would return early while the device handle still held the previous dataset."""
+    import numpy as np
+    from pytransit_b200.transitmodel import TransitModel
+    m = TransitModel()
+    t = np.linspace(0, 1, 50)
+    m.set_data(t)
+    assert m.time_id == id(t) and m.npt == 50
+    t2 = np.linspace(0, 1, 80)
+    with pytest.raises(ValueError):
+        m.set_data(t2, lcids=np.full(80, 3))          # light curve ids must be 0..nlc-1
+    assert m.time_id is None
+    with pytest.raises(ValueError):
+        m.set_data(t2, lcids=np.zeros(80, np.int64), pbids=[1])
+    assert m.time_id is None
+    m.set_data(t2)                                     # same object again: fully registered this time
+    assert m.time_id == id(t2) and m.npt == 80 and m.nlc == 1
