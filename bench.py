@@ -565,35 +565,58 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # ---- end to end through the public API with host buffers ("e2e") ---------------------------------
     m.set_profiling(False)
     e2e_steps = max(2, min(args.steps, 20 if args.workload not in ('c3', 'c4') else 4))
-    e2e = None
-    try:
-        for _ in range(3):
-            step_host()
-        barrier()
-        t0 = time.perf_counter()
-        ev0.record()
-        for _ in range(e2e_steps):
-            r = step_host()
-        ev1.record()
-        barrier()
-        e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        d2h, how = int(r.nbytes), 'full copy of the result'
-        if not lnl and getattr(m, 'host_result', '') == 'delta':
-            last, ndelta, nfull = m.host_result_stats
-            d2h = int(last)
-            how = ('delta transfer into the model-owned page-locked host array: the full [npv, npt] result (%d bytes) is '
-                   'current on the host after every step, but only the 16-point blocks that differ from 1.0 now or did '
-                   'after the previous step cross PCIe (written by the GPU); the timed steps alternate between two '
-                   'different populations; %d delta / %d full transfers so far' % (r.nbytes, ndelta, nfull))
-        e2e = {'value': world * pts_per_step * e2e_steps / (float(t.item()) * 1e-3), 'unit': UNIT,
-               'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': d2h, 'result_bytes_per_step': int(r.nbytes),
-               'steps': e2e_steps, 'd2h': how}
-        del r
-    except MemoryError as ex:   # page-locked result buffer too large for this host
-        e2e = {'value': None, 'unit': UNIT, 'error': str(ex)[:200]}
+
+    def measure_e2e(mode):
+        """K calls of the public API with HOST numpy inputs and a host result; every result is read and dropped before the
+        next call, as a consumer would (so one pooled page-locked buffer serves the loop and, in delta mode, has to
+        follow the alternating populations)."""
+        if hasattr(m, 'host_result'):
+            m.host_result = mode
+        try:
+            chk = 0.0
+            for _ in range(3):
+                r = step_host()
+                chk += float(r.reshape(-1)[-1])
+                del r
+            barrier()
+            t0 = time.perf_counter()
+            ev0.record()
+            for _ in range(e2e_steps):
+                r = step_host()
+                nbytes = int(r.nbytes)
+                chk += float(r.reshape(-1)[-1])      # the consumer reads the result ...
+                del r                                # ... and lets go of it before the next call
+            ev1.record()
+            barrier()
+            e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            d2h = nbytes
+            how = "host_result='copy' (the default): one full device-to-host copy of the result per call into a writable array of the caller's own"
+            if lnl:
+                how = 'lnL[npv] only: the flux is never materialised'
+            elif mode == 'delta':
+                last, ndelta, nfull = m.host_result_stats
+                d2h = int(last)
+                how = ("host_result='delta' (documented opt-in of the public API; results are read-only, never aliased): the full "
+                       "result (%d bytes) is current in the caller's page-locked array after every step, but only the 16-point "
+                       "blocks that differ from 1.0 now or did the last time this buffer was written cross PCIe (written by the "
+                       "GPU); the timed steps alternate between two different populations; %d delta / %d full transfers so far"
+                       % (nbytes, ndelta, nfull))
+            return {'value': world * pts_per_step * e2e_steps / (float(t.item()) * 1e-3), 'unit': UNIT,
+                    'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': d2h, 'result_bytes_per_step': nbytes,
+                    'steps': e2e_steps, 'mode': mode if not lnl else 'lnl', 'd2h': how}
+        except MemoryError as ex:   # page-locked result buffer too large for this host
+            return {'value': None, 'unit': UNIT, 'error': str(ex)[:200]}
+
+    e2e = measure_e2e(args.host_result)
+    e2e_copy = None
+    if args.host_result == 'delta' and not lnl and args.workload != 'c4':
+        # the same loop through the DEFAULT mode of the API (plain full copy, writable result): PCIe bound
+        e2e_copy = measure_e2e('copy')
+        if e2e_copy.get('value'):
+            e2e_copy['pcie_gbs'] = e2e_copy['result_bytes_per_step'] * e2e_copy['value'] / (world * pts_per_step) / 1e9
 
     # ---- the path's one collective, same run (default workload only) -----------------------------------
     collective = None
@@ -673,7 +696,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64' if args.precision == 'fp64' else 'f32 (opt-in mode: fp64 phase fold, fp32 samples and output)', 'data': 'synthetic',
             'config': config_dict(args, desc, world), 'per_gpu': f'npv={c.npv} x npt={c.npt}' + (f' x npb={c.npb}' if args.workload == 'c4' else ''),
-            'clocks': clocks, 'e2e': e2e,
+            'clocks': clocks, 'e2e': e2e, 'e2e_copy': e2e_copy,
             'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu, 'cpu_baseline_numba': cpu_numba,
             'collective': collective}
     emit(line)

@@ -216,11 +216,14 @@ int ptb_lpf_lnlike(ptb_model *h, const double *pvp, int64_t npv, const ptb_lpf_l
 
 /* TransmissionSpectroscopyModel.evaluate -> tsmodel_serial (models/roadrunner/tsmodel.py:46-130,
  * model_trspec.py:11-93): k[npv,npb]; ld as above with npb = the spectroscopic channel count;
- * t0,p,a,inc,e,w[npv]; flux[npv,npb,npt].  Uses nsamples[0], exptimes[0] of set_data. */
+ * t0,p,a,inc,e,w[npv]; flux[npv,npb,npt].  Uses nsamples[0], exptimes[0] of set_data.
+ * `flux` is double[], or float[] when the handle was created with precision = 1 (opt-in fp32 output mode:
+ * all arithmetic stays fp64, the stored value is rounded to float -- half the bytes of the write-out that
+ * bounds this model; within 1 ppm of the fp64 result by construction). */
 int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, const double *ld,
                     int64_t nld, const double *istar, const double *t0, const double *p,
                     const double *a, const double *inc, const double *e, const double *w,
-                    double *flux, void *stream);
+                    void *flux, void *stream);
 
 /* LDTkLDModel.__call__ (models/ldtkldm.py:74-89) -> trilinear_interpolation_set +
  * integrate_profiles_set (models/numba/ldtkldm.py:53-60,77-91): profiles[nx,ny,nz3,npb,nmu],
@@ -256,9 +259,15 @@ int ptb_host_free(void *ptr);
  * up to date by DELTA transfer: a transit model is exactly 1.0 outside the transit windows
  * (model_full.py:91), so after the first full copy only the 16-element blocks (128 B) that differ from 1.0
  * now -- or did after the previous call -- are written, by the GPU, straight into `buf` over PCIe.
- * The content of `buf` after each call is identical to a full copy.  NULL unbinds.  Any other host
- * pointer passed as `flux` takes the plain full-copy path. */
+ * The content of `buf` after each call is identical to a full copy.  Up to 8 buffers can be bound at the
+ * same time, each with its own record of what it holds: a caller that still needs the previous result passes
+ * another bound buffer to the next call (the Python layer rotates a small pool, so results never alias).
+ * Binding a bound buffer again invalidates its record (next transfer is a full copy).  NULL unbinds all.  Any
+ * other host pointer passed as `flux` takes the plain full-copy path.  A handle is used by one host thread at
+ * a time and its calls are ordered on the stream they are given. */
 int ptb_bind_host_result(ptb_model *h, void *buf, int64_t count);
+/* Forget `buf` (NULL: every bound buffer).  Waits for the device first. */
+int ptb_unbind_host_result(ptb_model *h, void *buf);
 /* Bytes the last managed transfer moved to the host, and how many delta / full transfers ran. */
 int ptb_host_result_stats(const ptb_model *h, int64_t *last_bytes, int64_t *delta_calls,
                           int64_t *full_calls);

@@ -57,6 +57,7 @@ SIGNATURES = {
     'ptb_host_alloc': (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     'ptb_host_free': (C.c_int, [_vp]),
     'ptb_bind_host_result': (C.c_int, [_vp, _vp, _i64]),
+    'ptb_unbind_host_result': (C.c_int, [_vp, _vp]),
     'ptb_host_result_stats': (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     'ptb_launch_count': (_i64, [_vp]),
     'ptb_set_graphs': (C.c_int, [_vp, C.c_int32]),

@@ -147,12 +147,17 @@ struct ptb_model {
     std::vector<cudaEvent_t> tev;  // TRING x 4 events
     int64_t tcalls = 0;            // timed calls since profiling was enabled
 
-    // managed host result (ptb_bind_host_result): delta transfer of the flux into caller-owned pinned memory
-    void *hr_buf = nullptr, *hr_dev = nullptr;  // host address / its device mapping
-    int64_t hr_count = 0;
-    size_t hr_esize = 0;
-    bool hr_valid = false;           // hr_buf holds the previous result and d_lit its lit-block bitmap
-    DevBuf d_lit;                    // lit bitmap words | 8-byte counter of blocks written
+    // managed host results (ptb_bind_host_result): delta transfer of the flux into caller-owned pinned memory.  Several
+    // buffers can be bound at once (a caller that keeps the previous result alive alternates between two or three);
+    // each carries its own lit-block bitmap describing what IT currently holds.
+    struct HostBinding {
+        void *buf = nullptr, *dev = nullptr;  // host address / its device mapping
+        int64_t count = 0;
+        size_t esize = 0;
+        bool valid = false;              // buf holds a complete previous result and d_lit its lit-block bitmap
+        DevBuf d_lit;                    // lit bitmap words | 8-byte counter of blocks written
+    };
+    std::vector<HostBinding *> hr;
     PinBuf h_hrstat;                 // the counter, read back with the result
     std::vector<cudaEvent_t> ev_part;  // pipelined host delivery: points kernel of part i done / all deltas done
     int64_t hr_last_bytes = 0, hr_delta_calls = 0, hr_full_calls = 0;
@@ -319,40 +324,47 @@ std::vector<double> linspace(double a, double b, int n) {
     return v;
 }
 
+ptb_model::HostBinding *find_binding(ptb_model *h, const void *host, size_t count) {
+    if (!host) return nullptr;
+    for (auto *b : h->hr)
+        if (b->buf == host && (size_t)b->count == count) return b;
+    return nullptr;
+}
+
 // Device result -> host.  Plain buffers get one copy-engine transfer.  The bound managed buffer
 // (ptb_bind_host_result) gets a full transfer the first time and k_host_delta afterwards: only blocks
 // that differ from 1.0 now, or did after the previous call, cross PCIe.  Returns after the data has landed.
 int deliver_host(ptb_model *h, void *host, const void *dsrc, size_t count, size_t esize, cudaStream_t st) {
-    const bool managed = host == h->hr_buf && (int64_t)count == h->hr_count && h->hr_buf != nullptr;
-    if (!managed) {
+    ptb_model::HostBinding *B = find_binding(h, host, count);
+    if (!B) {
         CU(cudaMemcpyAsync(host, dsrc, count * esize, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         return PTB_OK;
     }
     const long long nwords = ((long long)count + 32 * HD_BLOCK - 1) / (32 * HD_BLOCK);
-    const bool delta = h->hr_valid && h->hr_esize == esize;
-    h->hr_valid = false;  // until this transfer has completed
+    const bool delta = B->valid && B->esize == esize;
+    B->valid = false;  // until this transfer has completed
     const size_t lit_bytes = ((size_t)nwords * 4 + 15) & ~size_t(15);
-    if (lit_bytes + 16 > h->d_lit.cap && delta) return fail(h, PTB_ESTATE, "host result: bitmap lost");
-    CU(h->d_lit.reserve(lit_bytes + 16));
+    if (lit_bytes + 16 > B->d_lit.cap && delta) return fail(h, PTB_ESTATE, "host result: bitmap lost");
+    CU(B->d_lit.reserve(lit_bytes + 16));
     CU(h->h_hrstat.reserve(16));
-    unsigned *lit = h->d_lit.as<unsigned>();
-    unsigned long long *nwr = reinterpret_cast<unsigned long long *>(static_cast<char *>(h->d_lit.ptr) + lit_bytes);
+    unsigned *lit = B->d_lit.as<unsigned>();
+    unsigned long long *nwr = reinterpret_cast<unsigned long long *>(static_cast<char *>(B->d_lit.ptr) + lit_bytes);
     CU(cudaMemsetAsync(nwr, 0, 8, st));
     const unsigned grid = (unsigned)std::min<long long>((nwords + 7) / 8, (long long)h->sm_count * 8);
     if (esize == 8)
-        k_host_delta<double><<<grid, 256, 0, st>>>(static_cast<const double *>(dsrc), static_cast<double *>(h->hr_dev), lit, nwr,
+        k_host_delta<double><<<grid, 256, 0, st>>>(static_cast<const double *>(dsrc), static_cast<double *>(B->dev), lit, nwr,
                                                    (long long)count, 0, nwords, delta ? 0 : 1);
     else
-        k_host_delta<float><<<grid, 256, 0, st>>>(static_cast<const float *>(dsrc), static_cast<float *>(h->hr_dev), lit, nwr,
+        k_host_delta<float><<<grid, 256, 0, st>>>(static_cast<const float *>(dsrc), static_cast<float *>(B->dev), lit, nwr,
                                                   (long long)count, 0, nwords, delta ? 0 : 1);
     h->launches++;
     CU(cudaGetLastError());
     if (!delta) CU(cudaMemcpyAsync(host, dsrc, count * esize, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->h_hrstat.ptr, nwr, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    h->hr_esize = esize;
-    h->hr_valid = true;
+    B->esize = esize;
+    B->valid = true;
     if (delta) {
         h->hr_last_bytes = (int64_t)(*static_cast<unsigned long long *>(h->h_hrstat.ptr)) * HD_BLOCK * (int64_t)esize;
         h->hr_delta_calls++;
@@ -487,8 +499,10 @@ void ptb_destroy(ptb_model *h) {
     cudaSetDevice(h->cfg.device);
     for (DevBuf *b : {&h->d_tab, &h->d_W, &h->d_time_own, &h->d_meta, &h->d_obs_own, &h->d_blk, &h->d_nblk, &h->d_orb,
                       &h->d_ldrec, &h->d_ldp, &h->d_istar, &h->d_flux, &h->d_partial, &h->d_isig2, &h->d_lnl, &h->d_xyc,
-                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_sort, &h->d_rec, &h->d_work, &h->d_tsgeo, &h->d_lit, &h->d_lpf, &h->d_cells, &h->d_dummy})
+                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_sort, &h->d_rec, &h->d_work, &h->d_tsgeo, &h->d_lpf, &h->d_cells, &h->d_dummy})
         b->release();
+    for (auto *b : h->hr) { b->d_lit.release(); delete b; }
+    h->hr.clear();
     h->h_stage.release();
     h->h_hrstat.release();
     for (auto &ev : h->ev_part) if (ev) cudaEventDestroy(ev);
@@ -1140,8 +1154,8 @@ static int rr_evaluate_impl(ptb_model *h, int64_t npv, const double *k, int64_t 
     }
     // Large managed host result in its steady state: the population is cut into parts and the delta transfer of
     // part i (PCIe bound, on the side stream) runs under the points kernel of part i+1 (HBM bound).
-    if (!queued && flux && !direct && !eclipse && flux == h->hr_buf && (int64_t)count == h->hr_count && h->hr_valid &&
-        h->hr_esize == esize && count * esize >= ((size_t)64 << 20) && !h->profiling) {
+    ptb_model::HostBinding *B = (!queued && flux && !direct && !eclipse) ? find_binding(h, flux, count) : nullptr;
+    if (B && B->valid && B->esize == esize && count * esize >= ((size_t)64 << 20) && !h->profiling) {
         const long long wordlen = 32LL * HD_BLOCK;                          // elements per bitmap word
         long long g = h->npt, b = wordlen;                                  // rows per part must keep parts word aligned
         while (b) { const long long t = g % b; g = b; b = t; }
@@ -1154,16 +1168,16 @@ static int rr_evaluate_impl(ptb_model *h, int64_t npv, const double *k, int64_t 
             if (int rc = launch_rr_setup(h, A, D, st)) return rc;
             const long long nwords = ((long long)count + wordlen - 1) / wordlen;
             const size_t lit_bytes = ((size_t)nwords * 4 + 15) & ~size_t(15);
-            if (lit_bytes + 16 > h->d_lit.cap) return fail(h, PTB_ESTATE, "host result: bitmap lost");
-            unsigned *lit = h->d_lit.as<unsigned>();
-            unsigned long long *nwr = reinterpret_cast<unsigned long long *>(static_cast<char *>(h->d_lit.ptr) + lit_bytes);
+            if (lit_bytes + 16 > B->d_lit.cap) return fail(h, PTB_ESTATE, "host result: bitmap lost");
+            unsigned *lit = B->d_lit.as<unsigned>();
+            unsigned long long *nwr = reinterpret_cast<unsigned long long *>(static_cast<char *>(B->d_lit.ptr) + lit_bytes);
             const int np = (int)((npv + rows_per - 1) / rows_per);
             while ((int)h->ev_part.size() < np + 1) {
                 cudaEvent_t ev;
                 CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
                 h->ev_part.push_back(ev);
             }
-            h->hr_valid = false;
+            B->valid = false;
             CU(cudaMemsetAsync(nwr, 0, 8, st));
             for (int ip = 0; ip < np; ++ip) {
                 const long long r0 = ip * rows_per, r1 = std::min<long long>(npv, r0 + rows_per);
@@ -1174,10 +1188,10 @@ static int rr_evaluate_impl(ptb_model *h, int64_t npv, const double *k, int64_t 
                 const long long w1 = (r1 == npv) ? nwords : r1 * h->npt / wordlen;
                 const unsigned grid = (unsigned)std::min<long long>((w1 - w0 + 7) / 8, (long long)h->sm_count * 4);
                 if (esize == 8)
-                    k_host_delta<double><<<grid, 256, 0, h->side_stream>>>(static_cast<const double *>(dflux), static_cast<double *>(h->hr_dev),
+                    k_host_delta<double><<<grid, 256, 0, h->side_stream>>>(static_cast<const double *>(dflux), static_cast<double *>(B->dev),
                                                                             lit, nwr, (long long)count, w0, w1, 0);
                 else
-                    k_host_delta<float><<<grid, 256, 0, h->side_stream>>>(static_cast<const float *>(dflux), static_cast<float *>(h->hr_dev),
+                    k_host_delta<float><<<grid, 256, 0, h->side_stream>>>(static_cast<const float *>(dflux), static_cast<float *>(B->dev),
                                                                            lit, nwr, (long long)count, w0, w1, 0);
                 h->launches++;
                 CU(cudaGetLastError());
@@ -1187,7 +1201,7 @@ static int rr_evaluate_impl(ptb_model *h, int64_t npv, const double *k, int64_t 
             CU(h->h_hrstat.reserve(16));
             CU(cudaMemcpyAsync(h->h_hrstat.ptr, nwr, 8, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
-            h->hr_valid = true;
+            B->valid = true;
             h->hr_last_bytes = (int64_t)(*static_cast<unsigned long long *>(h->h_hrstat.ptr)) * HD_BLOCK * (int64_t)esize;
             h->hr_delta_calls++;
             h->last_flux_count = (int64_t)count;
@@ -1521,10 +1535,7 @@ int ptb_flux_device_ptr(ptb_model *h, void **ptr, int64_t *count) {
 int ptb_bind_host_result(ptb_model *h, void *buf, int64_t count) {
     if (!h) return PTB_EINVAL;
     if (int rc = set_device(h)) return rc;
-    h->hr_buf = h->hr_dev = nullptr;
-    h->hr_count = 0;
-    h->hr_valid = false;
-    if (!buf) return PTB_OK;
+    if (!buf) return ptb_unbind_host_result(h, nullptr);
     if (count < 1) return fail(h, PTB_ESHAPE, "bind_host_result: count must be >= 1");
     void *dp = nullptr;
     if (cudaHostGetDevicePointer(&dp, buf, 0) != cudaSuccess || !dp) {
@@ -1532,9 +1543,35 @@ int ptb_bind_host_result(ptb_model *h, void *buf, int64_t count) {
         return fail(h, PTB_EINVAL, "bind_host_result: the buffer is not page-locked memory mapped into the device "
                                    "(allocate it with ptb_host_alloc)");
     }
-    h->hr_buf = buf;
-    h->hr_dev = dp;
-    h->hr_count = count;
+    for (auto *b : h->hr)
+        if (b->buf == buf) {  // re-binding: whatever the buffer held is no longer trusted
+            b->dev = dp;
+            b->count = count;
+            b->valid = false;
+            return PTB_OK;
+        }
+    if (h->hr.size() >= 8) return fail(h, PTB_ESTATE, "bind_host_result: at most 8 host result buffers can be bound (unbind one first)");
+    auto *b = new ptb_model::HostBinding();
+    b->buf = buf;
+    b->dev = dp;
+    b->count = count;
+    h->hr.push_back(b);
+    return PTB_OK;
+}
+
+int ptb_unbind_host_result(ptb_model *h, void *buf) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    for (size_t i = 0; i < h->hr.size();) {
+        if (!buf || h->hr[i]->buf == buf) {
+            CU(cudaDeviceSynchronize());  // a transfer into it may still be running
+            h->hr[i]->d_lit.release();
+            delete h->hr[i];
+            h->hr.erase(h->hr.begin() + i);
+        } else {
+            ++i;
+        }
+    }
     return PTB_OK;
 }
 

@@ -13,9 +13,19 @@ int launch_ts_ldm_t(ptb_model *h, const TsLdmParams &P, size_t smem, unsigned gr
     return PTB_OK;
 }
 
-template <int VEC, bool MULTI>
+template <int VEC, typename TO>
+int launch_ts_flux2_t(ptb_model *h, const TsFlux2Params &P, size_t smem, unsigned grid, cudaStream_t st) {
+    auto kern = k_ts_flux2<VEC, TO>;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, st>>>(P);
+    h->launches++;
+    CU(cudaGetLastError());
+    return PTB_OK;
+}
+
+template <int VEC, bool MULTI, typename TO>
 int launch_ts_flux_t(ptb_model *h, const TsFluxParams &P, size_t smem, unsigned grid, cudaStream_t st) {
-    auto kern = k_ts_flux<VEC, MULTI>;
+    auto kern = k_ts_flux<VEC, MULTI, TO>;
     if (smem > 32 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 256, smem, st>>>(P);
     h->launches++;
@@ -29,7 +39,7 @@ extern "C" {
 
 int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, const double *ld, int64_t nld,
                     const double *istar, const double *t0, const double *p, const double *a, const double *inc,
-                    const double *e, const double *w, double *flux, void *stream) {
+                    const double *e, const double *w, void *flux, void *stream) {
     if (!h) return PTB_EINVAL;
     if (int rc = set_device(h)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -119,15 +129,19 @@ int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, con
 
     // 4. flux
     const size_t count = (size_t)npv * npb * h->npt;
-    double *dflux = flux;
+    // opt-in fp32 output mode (ptb_config.precision = 1): geometry and per-channel arithmetic stay fp64, the flux is
+    // stored as float -- half the HBM and PCIe bytes of the 8 B/point write-out that bounds this model
+    const bool f32 = h->cfg.precision == 1;
+    const size_t esize = f32 ? 4 : 8;
+    void *dflux = flux;
     const bool direct = flux && is_device_ptr(flux);
     if (!direct) {
-        CU(h->d_flux.reserve(count * 8));
-        dflux = h->d_flux.as<double>();
+        CU(h->d_flux.reserve(count * esize));
+        dflux = h->d_flux.ptr;
     }
     const bool multi = ns > 1;
     const bool aligned = !multi && (h->npt % 2 == 0) && ((reinterpret_cast<uintptr_t>(h->d_time) & 15) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(dflux) & 15) == 0);
+                         ((reinterpret_cast<uintptr_t>(dflux) & (f32 ? 7 : 15)) == 0);
     const int vec = aligned ? 2 : 1;
     const size_t geo_bytes = (size_t)npv * h->npt * 28;
     if (!multi && geo_bytes <= (size_t)2 << 30) {
@@ -154,15 +168,9 @@ int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, con
         if (grid > 0x7fffffffLL) return fail(h, PTB_EINVAL, "ts_evaluate: grid too large");
         const size_t smem_fl = (size_t)TS_CH * (ldt + 4) * 8;
         mark(h, 2, st);
-        if (vec == 2) {
-            if (smem_fl > 48 * 1024) CU(cudaFuncSetAttribute(k_ts_flux2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fl));
-            k_ts_flux2<2><<<(unsigned)grid, 256, smem_fl, st>>>(FP);
-        } else {
-            if (smem_fl > 48 * 1024) CU(cudaFuncSetAttribute(k_ts_flux2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fl));
-            k_ts_flux2<1><<<(unsigned)grid, 256, smem_fl, st>>>(FP);
-        }
-        h->launches++;
-        CU(cudaGetLastError());
+        if (vec == 2) rc = f32 ? launch_ts_flux2_t<2, float>(h, FP, smem_fl, (unsigned)grid, st) : launch_ts_flux2_t<2, double>(h, FP, smem_fl, (unsigned)grid, st);
+        else rc = f32 ? launch_ts_flux2_t<1, float>(h, FP, smem_fl, (unsigned)grid, st) : launch_ts_flux2_t<1, double>(h, FP, smem_fl, (unsigned)grid, st);
+        if (rc) return rc;
         mark(h, 3, st);
     } else {
         // ---- supersampled (or very large) case: geometry in registers / shared memory per CTA ------------
@@ -179,15 +187,21 @@ int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, con
         if (grid > 0x7fffffffLL) return fail(h, PTB_EINVAL, "ts_evaluate: grid too large");
         const size_t smem_fl = multi ? (size_t)ns * 256 * sizeof(TsGeo) : 0;
         mark(h, 2, st);
-        if (vec == 2) rc = launch_ts_flux_t<2, false>(h, FP, smem_fl, (unsigned)grid, st);
-        else if (!multi) rc = launch_ts_flux_t<1, false>(h, FP, smem_fl, (unsigned)grid, st);
-        else rc = launch_ts_flux_t<1, true>(h, FP, smem_fl, (unsigned)grid, st);
+        if (f32) {
+            if (vec == 2) rc = launch_ts_flux_t<2, false, float>(h, FP, smem_fl, (unsigned)grid, st);
+            else if (!multi) rc = launch_ts_flux_t<1, false, float>(h, FP, smem_fl, (unsigned)grid, st);
+            else rc = launch_ts_flux_t<1, true, float>(h, FP, smem_fl, (unsigned)grid, st);
+        } else {
+            if (vec == 2) rc = launch_ts_flux_t<2, false, double>(h, FP, smem_fl, (unsigned)grid, st);
+            else if (!multi) rc = launch_ts_flux_t<1, false, double>(h, FP, smem_fl, (unsigned)grid, st);
+            else rc = launch_ts_flux_t<1, true, double>(h, FP, smem_fl, (unsigned)grid, st);
+        }
         if (rc) return rc;
         mark(h, 3, st);
     }
     h->last_npv = 0;  // RoadRunner stage taps do not describe a TS evaluation
     h->last_flux_count = direct ? 0 : (int64_t)count;
-    if (flux && !direct) return deliver_host(h, flux, dflux, count, 8, st);
+    if (flux && !direct) return deliver_host(h, flux, dflux, count, esize, st);
     return PTB_OK;
 }
 

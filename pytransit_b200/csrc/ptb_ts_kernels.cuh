@@ -271,11 +271,20 @@ __global__ void __launch_bounds__(256) k_ts_ldm(const __grid_constant__ TsLdmPar
 // ---------------------------------------------------------------------------------------------
 struct TsFluxParams {
     const double *time, *tsorb, *t0, *tsldm, *tsrec;
-    double *flux;
+    void *flux;   // [npv][npb][npt] fp64, or fp32 in the opt-in fp32 output mode
     long long npt;
     int npv, npb, ng, ldt, ns, ntiles, pbsplit;
     double exptime, dg, inv_dg;
 };
+
+// flux values are computed in fp64; TO is the stored type (double, or float in the opt-in fp32 output mode)
+template <int VEC, typename TO>
+__device__ __forceinline__ void ts_store(TO *p, const double *v) {
+    TO o[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o[j] = (TO)v[j];
+    VecIO<VEC, TO>::store(p, o);
+}
 
 struct TsGeo {
     double alpha, ap0, dadk;
@@ -303,7 +312,7 @@ __device__ __forceinline__ TsGeo ts_geometry(double t, const double *cx, const d
     return G;
 }
 
-template <int VEC, bool MULTI>
+template <int VEC, bool MULTI, typename TO>
 __global__ void __launch_bounds__(256) k_ts_flux(const __grid_constant__ TsFluxParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];  // MULTI: TsGeo[ns][256*VEC]
     const int tid = threadIdx.x;
@@ -318,7 +327,7 @@ __global__ void __launch_bounds__(256) k_ts_flux(const __grid_constant__ TsFluxP
     const bool inr = i0 < npt;
     const int pbper = (P.npb + P.pbsplit - 1) / P.pbsplit;
     const int pb_beg = split * pbper, pb_end = min(P.npb, pb_beg + pbper);
-    double *fbase = P.flux + (size_t)ipv * P.npb * npt + i0;
+    TO *fbase = reinterpret_cast<TO *>(P.flux) + (size_t)ipv * P.npb * npt + i0;
     const double *orb = P.tsorb + (size_t)ipv * TSORB_STRIDE;
 
     if (orb[ORB_GOOD] == 0.0) {  // flux[ipv, :, :] = nan (model_trspec.py:38)
@@ -326,7 +335,7 @@ __global__ void __launch_bounds__(256) k_ts_flux(const __grid_constant__ TsFluxP
             double v[VEC];
 #pragma unroll
             for (int j = 0; j < VEC; ++j) v[j] = nan("");
-            for (int pb = pb_beg; pb < pb_end; ++pb) VecIO<VEC, double>::store(fbase + (size_t)pb * npt, v);
+            for (int pb = pb_beg; pb < pb_end; ++pb) ts_store<VEC, TO>(fbase + (size_t)pb * npt, v);
         }
         return;
     }
@@ -376,7 +385,7 @@ __global__ void __launch_bounds__(256) k_ts_flux(const __grid_constant__ TsFluxP
         double v[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) v[j] = 1.0;
-        for (int pb = pb_beg; pb < pb_end; ++pb) VecIO<VEC, double>::store(fbase + (size_t)pb * npt, v);
+        for (int pb = pb_beg; pb < pb_end; ++pb) ts_store<VEC, TO>(fbase + (size_t)pb * npt, v);
         return;
     }
     for (int pb = pb_beg; pb < pb_end; ++pb) {
@@ -408,7 +417,7 @@ __global__ void __launch_bounds__(256) k_ts_flux(const __grid_constant__ TsFluxP
                 }
             }
         }
-        VecIO<VEC, double>::store(fbase + (size_t)pb * npt, v);
+        ts_store<VEC, TO>(fbase + (size_t)pb * npt, v);
     }
 }
 
@@ -478,13 +487,13 @@ __global__ void __launch_bounds__(256) k_ts_geo(const __grid_constant__ TsGeoPar
 struct TsFlux2Params {
     const double *tsorb, *tsldm, *tsrec, *galpha, *gap0, *gdadk;
     const int *gi0;
-    double *flux;
+    void *flux;
     long long npt;
     int npv, npb, ng, ldt, nchunks;
 };
 constexpr int TS_CH = 32;  // channels per CTA
 
-template <int VEC>
+template <int VEC, typename TO>
 __global__ void __launch_bounds__(256) k_ts_flux2(const __grid_constant__ TsFlux2Params P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];  // [TS_CH][ldt] ld means | [TS_CH][4] records
     __shared__ __align__(8) uint64_t bar;
@@ -494,7 +503,7 @@ __global__ void __launch_bounds__(256) k_ts_flux2(const __grid_constant__ TsFlux
     const int ipv = blockIdx.x / P.nchunks, chunk = blockIdx.x - ipv * P.nchunks;
     const int pb0 = chunk * TS_CH, nch = min(TS_CH, P.npb - pb0);
     const long long npt = P.npt;
-    double *fbase = P.flux + ((size_t)ipv * P.npb + pb0) * npt;
+    TO *fbase = reinterpret_cast<TO *>(P.flux) + ((size_t)ipv * P.npb + pb0) * npt;
     const bool good = P.tsorb[(size_t)ipv * TSORB_STRIDE + ORB_GOOD] != 0.0;
     if (good) {
         if (tid == 0) {
@@ -514,7 +523,7 @@ __global__ void __launch_bounds__(256) k_ts_flux2(const __grid_constant__ TsFlux
         if (!good) {  // flux[ipv, :, :] = nan (model_trspec.py:38)
 #pragma unroll
             for (int j = 0; j < VEC; ++j) v[j] = nan("");
-            for (int c = 0; c < nch; ++c) VecIO<VEC, double>::store(fbase + (size_t)c * npt + i0, v);
+            for (int c = 0; c < nch; ++c) ts_store<VEC, TO>(fbase + (size_t)c * npt + i0, v);
             continue;
         }
         double al[VEC], ap[VEC], da[VEC];
@@ -531,7 +540,7 @@ __global__ void __launch_bounds__(256) k_ts_flux2(const __grid_constant__ TsFlux
         if (!__any_sync(__activemask(), any)) {  // the whole warp is out of transit: ones for every channel
 #pragma unroll
             for (int j = 0; j < VEC; ++j) v[j] = 1.0;
-            for (int c = 0; c < nch; ++c) VecIO<VEC, double>::store(fbase + (size_t)c * npt + i0, v);
+            for (int c = 0; c < nch; ++c) ts_store<VEC, TO>(fbase + (size_t)c * npt + i0, v);
             continue;
         }
         VecIO<VEC, double>::load(P.galpha + gbase + i0, al);
@@ -559,7 +568,7 @@ __global__ void __launch_bounds__(256) k_ts_flux2(const __grid_constant__ TsFlux
                     v[j] = 1.0 - ip * x * r01.x;
                 }
             }
-            VecIO<VEC, double>::store(fbase + (size_t)c * npt + i0, v);
+            ts_store<VEC, TO>(fbase + (size_t)c * npt + i0, v);
         }
     }
 }

@@ -45,7 +45,7 @@ class EclipseModelCUDA(RoadRunnerModelCUDA):
         check(lib().ptb_eclipse_evaluate(self._h, npv, ptr(k), ptr(t0), ptr(p), ptr(a), ptr(i), ptr(e), ptr(w), float(rstar),
                                          ptr(out), _current_stream(self.device)), self._h)
         self._lastnpv = npv
-        return np.squeeze(out) if copy else out.squeeze()
+        return np.squeeze(self._host_view(out)) if copy else out.squeeze()
 
     def __call__(self, k, t0, p, a, i, e=None, w=None, rstar: float = 1.0, copy: bool = True):
         return self.evaluate(k, t0, p, a, i, e, w, rstar, copy)
@@ -80,7 +80,7 @@ class ESModelCUDA(RoadRunnerModelCUDA):
             out = torch.empty(shape, dtype=torch.float64, device=f'cuda:{self.device}')
         check(lib().ptb_es_evaluate(self._h, npv, npb, ptr(f), ptr(k), ptr(t0), ptr(p), ptr(a), ptr(i), ptr(e), ptr(w),
                                     ptr(rstar), ptr(out), _current_stream(self.device)), self._h)
-        return out
+        return self._host_view(out) if copy else out
 
     def __call__(self, f, k, t0, p, a, i, e=0.0, w=0.0, rstar=1.0, copy: bool = True):
         return self.evaluate(f, k, t0, p, a, i, e, w, rstar, copy)

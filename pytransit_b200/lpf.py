@@ -179,4 +179,4 @@ class BaseLPFCUDA:
             out = torch.empty((npv,), dtype=torch.float64, device=f'cuda:{tm.device}')
         check(lib().ptb_lpf_lnlike(tm._h, ptr(pvp), npv, C.byref(self._layout), ptr(out), _current_stream(tm.device)), tm._h)
         tm._lastnpv = npv
-        return out
+        return out.copy() if copy else out     # an array of the caller's own (lnl_old vs lnl_new comparisons in a sampler)

@@ -35,6 +35,64 @@ def _is_scalar(x) -> bool:
     return np.isscalar(x) or (hasattr(x, 'ndim') and x.ndim == 0)
 
 
+class _HostResults:
+    """Page-locked result arrays of one model, handed out by ``evaluate(copy=True)``.
+
+    Every call returns an array that no other live result shares (the reference's ``RoadRunnerModel.evaluate`` returns
+    a fresh array; ``f1 = m.evaluate(a); f2 = m.evaluate(b); f1 - f2`` must work).  Allocating -- and page-locking --
+    gigabytes per call would cost more than the evaluation, so the buffers are pooled: a buffer goes back into
+    circulation only when the caller has dropped every view of it (CPython reference count of the buffer's base
+    array), otherwise a new one is allocated.  In ``'delta'`` mode each buffer is bound to the handle
+    (``ptb_bind_host_result``), which remembers per buffer what it holds, so the delta transfer works whichever buffer
+    the next call lands in."""
+
+    MAX_BUFFERS = 8      # the C handle tracks at most 8 bound buffers
+
+    class _Entry:
+        __slots__ = ('pinned', 'root', 'rc0', 'shape', 'dtype', 'bound')
+
+    def __init__(self, model):
+        self.model = model
+        self.entries = []
+
+    @staticmethod
+    def _idle(e) -> bool:
+        return sys.getrefcount(e.root) <= e.rc0
+
+    def _drop(self, e) -> None:
+        if e.bound and self.model._h:
+            check(lib().ptb_unbind_host_result(self.model._h, e.pinned._ptr), self.model._h)
+        self.entries.remove(e)
+
+    def acquire(self, shape, dtype, delta: bool):
+        shape, dtype = tuple(int(x) for x in shape), np.dtype(dtype)
+        spare = None
+        for e in list(self.entries):
+            if not self._idle(e):
+                continue
+            if e.shape == shape and e.dtype == dtype and e.bound == delta and spare is None:
+                spare = e
+            elif e.shape != shape or e.dtype != dtype or e.bound != delta:
+                self._drop(e)          # an idle buffer of another shape: the population changed
+        if spare is None:
+            if len(self.entries) >= self.MAX_BUFFERS:
+                raise MemoryError(f"{self.MAX_BUFFERS} results of evaluate(copy=True) are still referenced; drop or copy them")
+            e = self._Entry()
+            e.pinned = _lib.PinnedArray(shape, dtype)
+            e.root = e.pinned.array.base if isinstance(e.pinned.array.base, np.ndarray) else e.pinned.array
+            e.shape, e.dtype, e.bound = shape, dtype, delta
+            if delta:
+                check(lib().ptb_bind_host_result(self.model._h, e.pinned._ptr, e.pinned.array.size), self.model._h)
+            e.rc0 = sys.getrefcount(e.root)
+            self.entries.append(e)
+            spare = e
+        return spare.pinned.array
+
+    def clear(self) -> None:
+        for e in list(self.entries):
+            self._drop(e)
+
+
 class RoadRunnerModelCUDA(TransitModel):
     """Drop-in for ``RoadRunnerModel`` (Numba) / ``RoadRunnerModelCL`` (OpenCL) on one B200.
 
@@ -45,15 +103,19 @@ class RoadRunnerModelCUDA(TransitModel):
     ``evaluate(k, ldc, t0, p, a, i, e, w, copy=True)`` broadcasts like the reference *intends* to
     (SURVEY.md Q4-Q7): scalars are expanded to the population size, a 1-D ``t0[npv]`` is one epoch
     per vector, ``k`` is a scalar, ``[npb]``, ``[npv,1]`` or ``[npv,npb]``, ``ldc`` is ``[nldc]``,
-    ``[npb,nldc]`` or ``[npv,npb,nldc]``.  With ``copy=True`` the result is a numpy array in
-    page-locked memory owned by the model (re-used by the next call, like ``RoadRunnerModelCL.f``);
-    with ``copy=False`` it is a ``torch`` CUDA tensor and nothing leaves the device.
+    ``[npb,nldc]`` or ``[npv,npb,nldc]``.  With ``copy=True`` the result is a numpy array that belongs to the caller,
+    as with the reference: no later call touches it (``f1 = m.evaluate(a); f2 = m.evaluate(b); f1 - f2`` is valid).  It
+    lives in page-locked memory drawn from a small per-model pool; its buffer is reused only after every reference
+    to it has been dropped.  With ``copy=False`` it is a ``torch`` CUDA tensor and nothing leaves the device.
 
-    ``host_result='delta'`` (default): the model's host array is kept current by delta transfer -- after the
-    first full copy only the 16-point blocks that differ from 1.0 now, or did after the previous call, cross
-    PCIe (written by the GPU straight into the page-locked array).  Its content after every call is identical
-    to a full copy; it is handed out as a read-only view because the next call relies on it.  ``'copy'``
-    restores the plain full device-to-host copy into a writable array.
+    ``host_result='copy'`` (default): one full device-to-host copy per call into a writable array -- the drop-in
+    behaviour; PCIe bound (C2's 1.31 GB: ~25 ms).  ``host_result='delta'`` (opt-in, for callers that keep evaluating
+    populations on one dataset): the pooled buffers are bound to the handle, which remembers what each one holds, and
+    after a buffer's first full copy only the 16-point blocks that differ from 1.0 now, or did the last time THIS
+    buffer was written, cross PCIe (written by the GPU straight into the page-locked array; a transit model is exactly
+    1.0 outside the transit windows, model_full.py:91).  The content is identical to a full copy and results still do
+    not alias each other, but the arrays are READ-ONLY views (the next delta into the same buffer relies on its
+    content): ``flux *= baseline`` raises, ``flux * baseline`` or ``flux.copy()`` do what the reference's result does.
 
     ``precision='fp32'`` opts into the single-precision mode: the phase fold stays fp64, the per-sample
     geometry / limb-darkening arithmetic and the returned flux are float32 (half the HBM and PCIe
@@ -67,11 +129,11 @@ class RoadRunnerModelCUDA(TransitModel):
                  precompute_weights: bool = False, klims: tuple = (0.005, 0.5), nk: int = 256, nzin: int = 20,
                  nzlimb: int = 20, zcut: float = 0.7, ng: int = 100, nthreads: int = 1,
                  small_planet_limit: float = 0.05, device: Optional[int] = None, precision: str = 'fp64',
-                 host_result: str = 'delta', **kwargs):
+                 host_result: str = 'copy', **kwargs):
         super().__init__()
         self._h = None
         if host_result not in ('delta', 'copy'):
-            raise ValueError("host_result must be 'delta' (default) or 'copy'.")
+            raise ValueError("host_result must be 'copy' (default) or 'delta'.")
         self.host_result = host_result
         if precision not in ('fp64', 'fp32'):
             raise ValueError("precision must be 'fp64' (default) or 'fp32' (opt-in).")
@@ -130,7 +192,7 @@ class RoadRunnerModelCUDA(TransitModel):
         check(lib().ptb_get_tables(h, ptr(self.ze), ptr(self.zm), ptr(self.mu), None, C.byref(dk), C.byref(dg)), h)
         self.dk, self.dg = dk.value, dg.value
         self._weights = None
-        self._out = None        # PinnedArray holding the last host result
+        self._results = _HostResults(self)   # page-locked result arrays (pooled; never shared between live results)
         self._out_lnl = None
         self.nep = 0
         self._keep = []         # objects whose device memory the handle borrows (time, obs)
@@ -139,6 +201,7 @@ class RoadRunnerModelCUDA(TransitModel):
     def __del__(self):
         try:
             if self._h:
+                self._results.entries.clear()      # ptb_destroy forgets the bindings itself
                 lib().ptb_destroy(self._h)
                 self._h = None
         except Exception:
@@ -325,20 +388,21 @@ class RoadRunnerModelCUDA(TransitModel):
         return npv, k, t0, p, a, i, e, w
 
     def _result_buffer(self, shape, attr='_out', dtype=np.float64):
+        """Host destination of a result.  Flux arrays ('_out') come from the pool of page-locked buffers (see
+        _HostResults); the small lnL vectors use one staging array and are copied out by the caller."""
+        if attr == '_out':
+            return self._results.acquire(shape, dtype, self.host_result == 'delta')
         buf = getattr(self, attr)
         if buf is None or buf.shape != tuple(shape) or buf.array.dtype != np.dtype(dtype):
             buf = _lib.PinnedArray(shape, dtype)
             setattr(self, attr, buf)
-            if attr == '_out' and self.host_result == 'delta':
-                # the model's persistent host array (RoadRunnerModelCL.f): kept current by delta transfer
-                check(lib().ptb_bind_host_result(self._h, buf._ptr, buf.array.size), self._h)
         return buf.array
 
     def _host_view(self, out):
-        """What ``evaluate(copy=True)`` hands out: in delta mode a READ-ONLY view -- the library relies on the
-        array still holding the previous result when the next call updates it."""
+        """What ``evaluate(copy=True)`` hands out: a view of the pooled buffer (the pool sees it through the buffer's
+        reference count); read-only in delta mode, where the next transfer into this buffer relies on its content."""
+        out = out.view()
         if self.host_result == 'delta':
-            out = out.view()
             out.flags.writeable = False
         return out
 
@@ -437,7 +501,7 @@ class RoadRunnerModelCUDA(TransitModel):
             out = torch.empty((npv,), dtype=torch.float64, device=f'cuda:{self.device}')
         check(lib().ptb_rr_lnlike(self._h, npv, ptr(k), k.shape[1], ptr(ld), nld, ptr(istar), ptr(t0), ptr(p),
                                   ptr(a), ptr(i), ptr(e), ptr(w), ptr(sigma), ptr(out), stream), self._h)
-        return out
+        return out.copy() if copy else out     # an array of the caller's own, like the reference's lnlikelihood
 
     def lnlikelihood_allgather(self, k, ldc, t0, p, a, i, e, w, sigma, peer_ptrs, rank: int, flag_ptrs=None,
                                seq: int = 0) -> None:
@@ -487,7 +551,7 @@ class RoadRunnerModelCUDA(TransitModel):
             import torch
             out = torch.empty((npv,), dtype=torch.float64, device=f'cuda:{self.device}')
         check(lib().ptb_lnlike_normal(self._h, npv, ptr(model), ptr(sigma), ptr(out), stream), self._h)
-        return out
+        return out.copy() if copy else out
 
     # ------------------------------------------------------------------------------------------
     def stage(self, name: str) -> ndarray:
