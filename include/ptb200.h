@@ -199,18 +199,37 @@ typedef struct ptb_lpf_layout {
     int32_t i_secw, i_sesw;     /* sqrt(e) cos w, sqrt(e) sin w columns; -1 = circular orbit         */
     int32_t inc_mode;           /* 0: i_from_ba (orbits_py.py:674-688); 1: i_from_baew (:654-670)   */
     int32_t i_loge, nloge;      /* log10 sigma columns, one per noise block (lnlike only)            */
+    int32_t ntc;                /* consecutive transit-centre columns starting at i_tc: one per epoch of the
+                                   dataset (TTVLPF, lpf/ttvlpf.py:70-83); 1 for BaseLPF                */
+    int32_t i_bl;               /* first column of the baseline coefficients (ptb_set_baseline); -1 = none */
+    int32_t reserved_;
     double tref;                /* reference time subtracted from tc (lpf/lpf.py:438)                */
 } ptb_lpf_layout;
 
 /* BaseLPF.transit_model (lpf/lpf.py:435-443): k = sqrt(k2), t0 = tc - tref, a = as_from_rhop(rho, p)
  * (orbits_py.py:604-618, G = scipy.constants.G = 6.67430e-11), i = arccos(b/a), ldc = map_ldc(...), all
  * computed on the device from pvp (host or device pointer), then the RoadRunner evaluation of
- * ptb_rr_evaluate.  set_data must describe a single-epoch dataset. */
+ * ptb_rr_evaluate.  lay->ntc must equal the number of epochs of the dataset (t0[npv, nep] = pvp[:, i_tc : i_tc
+ * + ntc] - tref, TTVLPF.transit_model, lpf/ttvlpf.py:78-86). */
 int ptb_lpf_transit_model(ptb_model *h, const double *pvp, int64_t npv, const ptb_lpf_layout *lay,
                           void *flux, void *stream);
+
+/* Multiplicative baseline of the LPF layer (BaseLPF.baseline / flux_model, lpf/lpf.py:418-449) as a linear model in
+ * per-point basis functions: bl[ipv, j] = sum_{c < ncoef[lc(j)]} pvp[ipv, i_bl + cstart[lc(j)] + c] * basis[c][j], and
+ * 1 for light curves with ncoef = 0.  Covers LegendreBaseline (lpf/baselines/legendrebaseline.py:23-40: basis = Legendre
+ * polynomials of the normalised time) and LinearModelBaseline (lpf/baselines/linearbaseline.py:22-36: basis = 1 and the
+ * covariates).  basis[nbasis][npt] (host or device, copied), cstart / ncoef [nlc] with ncoef <= nbasis.  NULL basis
+ * clears.  set_data clears it too (it is tied to the time axis).  fp64 handles only. */
+int ptb_set_baseline(ptb_model *h, const double *basis, int64_t nbasis, const int64_t *cstart, const int64_t *ncoef);
+/* BaseLPF.flux_model (lpf/lpf.py:445-449): baseline * transit_model (+ trends = 0); with only_baseline != 0 the
+ * baseline alone (BaseLPF.baseline).  flux[npv, npt] host or device. */
+int ptb_lpf_flux_model(ptb_model *h, const double *pvp, int64_t npv, const ptb_lpf_layout *lay, int32_t only_baseline,
+                       double *flux, void *stream);
 /* BaseLPF.lnlikelihood with one WNLogLikelihood (lpf/lpf.py:454-475, wnloglikelihood.py:79-81): the same
  * mapping, sigma = 10**pvp[:, i_loge : i_loge + nloge], and the fused model + likelihood of ptb_rr_lnlike.
- * The population never leaves the device when pvp and lnl are device pointers. */
+ * The population never leaves the device when pvp and lnl are device pointers.  With a baseline registered and
+ * lay->i_bl >= 0 the transit flux is materialised on the device and the likelihood kernel multiplies the baseline in on
+ * the fly (the block-skipping fused kernel assumes an out-of-transit model value of exactly 1). */
 int ptb_lpf_lnlike(ptb_model *h, const double *pvp, int64_t npv, const ptb_lpf_layout *lay, double *lnl,
                    void *stream);
 
@@ -233,6 +252,13 @@ int ptb_ldtk_profiles(ptb_model *h, const double *profiles, int64_t nx, int64_t 
                       const double *zs, int64_t npv, double x0, double dx, double y0, double dy,
                       double z0, double dz, const double *mu, double *ldp, double *istar,
                       void *stream);
+
+/* Model derivatives dfdk(k, b, k0, lda, dg, ist) and dfdb(k, b, a, ak, lda, dg, ist) (models/roadrunner/common.py:104-128)
+ * for the population of the LAST ptb_rr_evaluate / ptb_rr_lnlike: b[npv, nb] separations per vector (host or device);
+ * k, the LD-mean row `lda` and I* of passband `pb` are the vector's own, kappa0 / lens area / kite area come from the
+ * device's circle_circle_intersection_area_kite.  dfdk / dfdb [npv, nb], either may be NULL. */
+int ptb_rr_derivatives(ptb_model *h, int64_t npv, int64_t nb, int64_t pb, const double *b, double *dfdk,
+                       double *dfdb, void *stream);
 
 /* Parity taps: copy a per-vector intermediate of the LAST evaluate/lnlike call to out (host or
  * device).  See enum ptb_stage for shapes. */

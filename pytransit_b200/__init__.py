@@ -10,11 +10,11 @@ the package works anywhere, constructing a model needs the built library and a B
 from .eclipsemodel import EclipseModelCUDA, EclipseSpectroscopyModelCUDA, ESModelCUDA
 from .ldmodel import LDModel, TabulatedLDModel
 from .loglikelihood import CUDALogLikelihood
-from .lpf import BaseLPFCUDA
+from .lpf import BaseLPFCUDA, LegendreBaselineCUDA, LinearModelBaselineCUDA, TTVLPFCUDA
 from .rrmodel import RoadRunnerModelCUDA
 from .transitmodel import TransitModel
 from .tsmodel import TSModelCUDA, TransmissionSpectroscopyModelCUDA
 
 __version__ = '0.1.0'
 __all__ = ['TransitModel', 'RoadRunnerModelCUDA', 'TSModelCUDA', 'TransmissionSpectroscopyModelCUDA',
-           'CUDALogLikelihood', 'BaseLPFCUDA', 'EclipseModelCUDA', 'ESModelCUDA', 'EclipseSpectroscopyModelCUDA', 'LDModel', 'TabulatedLDModel']
+           'CUDALogLikelihood', 'BaseLPFCUDA', 'TTVLPFCUDA', 'LegendreBaselineCUDA', 'LinearModelBaselineCUDA', 'EclipseModelCUDA', 'ESModelCUDA', 'EclipseSpectroscopyModelCUDA', 'LDModel', 'TabulatedLDModel']

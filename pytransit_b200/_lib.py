@@ -25,7 +25,12 @@ class PtbConfig(C.Structure):
 
 class PtbLpfLayout(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('npar', 'i_tc', 'i_p', 'i_rho', 'i_b', 'i_k2', 'nk2', 'i_ld', 'nldc', 'ld_map',
-                                         'i_secw', 'i_sesw', 'inc_mode', 'i_loge', 'nloge')] + [('tref', C.c_double)]
+                                         'i_secw', 'i_sesw', 'inc_mode', 'i_loge', 'nloge', 'ntc', 'i_bl', 'reserved_')] + [('tref', C.c_double)]
+
+    def __init__(self, **kw):
+        kw.setdefault('ntc', 1)
+        kw.setdefault('i_bl', -1)
+        super().__init__(**kw)
 
 
 _vp, _i64, _dbl = C.c_void_p, C.c_int64, C.c_double
@@ -49,8 +54,11 @@ SIGNATURES = {
     'ptb_lnlike_normal': (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     'ptb_lpf_transit_model': (C.c_int, [_vp, _vp, _i64, C.POINTER(PtbLpfLayout), _vp, _vp]),
     'ptb_lpf_lnlike': (C.c_int, [_vp, _vp, _i64, C.POINTER(PtbLpfLayout), _vp, _vp]),
+    'ptb_set_baseline': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    'ptb_lpf_flux_model': (C.c_int, [_vp, _vp, _i64, C.POINTER(PtbLpfLayout), C.c_int32, _vp, _vp]),
     'ptb_ts_evaluate': (C.c_int, [_vp, _i64, _i64, _vp, _vp, _i64] + [_vp] * 9),
     'ptb_ldtk_profiles': (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _i64] + [_dbl] * 6 + [_vp] * 4),
+    'ptb_rr_derivatives': (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     'ptb_get_stage': (C.c_int, [_vp, C.c_int32, _vp]),
     'ptb_inject_xyc': (C.c_int, [_vp, _vp, _i64]),
     'ptb_flux_device_ptr': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),

@@ -117,6 +117,8 @@ struct ptb_model {
     DevBuf d_tsw, d_tsrec, d_sort;
     DevBuf d_tsgeo;                  // TSModel geometry pass [npv][npt]
     DevBuf d_lpf;                    // mapped LPF parameters (k_lpf_map)
+    DevBuf d_basis, d_blmeta;        // LPF baseline: basis[nbasis][npt]; cstart[nlc] | ncoef[nlc] (int32)
+    int64_t bl_nbasis = 0;           // 0: no baseline registered
     DevBuf d_cells;                  // per-vector table cells of the tabulated-profile interpolation
     DevBuf d_dummy;                  // zero limb-darkening coefficients of the eclipse model (uniform disk)
     bool ecl_mode = false;           // the next launch_rr_setup expands about mid-eclipse (ptb_eclipse_evaluate)
@@ -499,7 +501,7 @@ void ptb_destroy(ptb_model *h) {
     cudaSetDevice(h->cfg.device);
     for (DevBuf *b : {&h->d_tab, &h->d_W, &h->d_time_own, &h->d_meta, &h->d_obs_own, &h->d_blk, &h->d_nblk, &h->d_orb,
                       &h->d_ldrec, &h->d_ldp, &h->d_istar, &h->d_flux, &h->d_partial, &h->d_isig2, &h->d_lnl, &h->d_xyc,
-                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_sort, &h->d_rec, &h->d_work, &h->d_tsgeo, &h->d_lpf, &h->d_cells, &h->d_dummy})
+                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_sort, &h->d_rec, &h->d_work, &h->d_tsgeo, &h->d_lpf, &h->d_basis, &h->d_blmeta, &h->d_cells, &h->d_dummy})
         b->release();
     for (auto *b : h->hr) { b->d_lit.release(); delete b; }
     h->hr.clear();
@@ -646,7 +648,8 @@ int ptb_set_data(ptb_model *h, const double *time, int64_t npt, const int64_t *l
     h->h_nsamples = hns;
     h->h_exptimes = het;
     h->has_data = true;
-    h->has_obs = false;  // observations are tied to the time axis
+    h->has_obs = false;  // observations and the baseline basis are tied to the time axis
+    h->bl_nbasis = 0;
     h->data_gen++;
     return PTB_OK;
 }
@@ -1454,7 +1457,8 @@ int ptb_lnlike_normal(ptb_model *h, int64_t npv, const double *model, const doub
     CU(h->d_partial.reserve(npv * 8));
     k_inv_sigma2<<<(unsigned)((nsig + 255) / 256), 256, 0, st>>>(ds, nsig, h->d_isig2.as<double>());
     k_lnl_model<<<(unsigned)npv, 256, 0, st>>>(dm, h->d_obs, h->blk_trivial ? nullptr : h->d_blk.as<int32_t>(),
-                                               h->d_isig2.as<double>(), h->npt, (int)h->nblocks, h->d_partial.as<double>());
+                                               h->d_isig2.as<double>(), h->npt, (int)h->nblocks, h->d_partial.as<double>(),
+                                               BaselineParams{});
     const bool direct = is_device_ptr(lnl);
     double *dl = lnl;
     if (!direct) {
@@ -1522,6 +1526,33 @@ int ptb_inject_xyc(ptb_model *h, const double *xyc, int64_t npv) {
     CU(cudaMemcpy(h->d_xyc.ptr, xyc, npv * 80, cudaMemcpyDefault));
     h->xyc_injected = true;
     h->xyc_npv = npv;
+    return PTB_OK;
+}
+
+int ptb_rr_derivatives(ptb_model *h, int64_t npv, int64_t nb, int64_t pb, const double *b, double *dfdk, double *dfdb, void *stream) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (h->last_npv == 0) return fail(h, PTB_ESTATE, "rr_derivatives: no RoadRunner evaluation has run yet");
+    if (npv != h->last_npv) return fail(h, PTB_ESHAPE, "rr_derivatives: npv=%lld but the last evaluation had %lld parameter vectors", (long long)npv, (long long)h->last_npv);
+    if (nb < 1 || !b || (!dfdk && !dfdb)) return fail(h, PTB_EINVAL, "rr_derivatives: null argument or nb < 1");
+    if (pb < 0 || pb >= h->last_npb) return fail(h, PTB_EINVAL, "rr_derivatives: passband %lld outside [0,%lld)", (long long)pb, (long long)h->last_npb);
+    const size_t n = (size_t)npv * nb;
+    Stager S(h, st);
+    auto rb = S.add(b, n * 8);
+    if (int rc = S.commit()) return rc;
+    const bool hk = dfdk && !is_device_ptr(dfdk), hb = dfdb && !is_device_ptr(dfdb);
+    CU(h->d_partial.reserve(2 * n * 8));
+    double *dk = dfdk ? (hk ? h->d_partial.as<double>() : dfdk) : nullptr;
+    double *db = dfdb ? (hb ? h->d_partial.as<double>() + n : dfdb) : nullptr;
+    const int ng = h->cfg.ng, lds = (ng + 4 + 1) & ~1;
+    k_rr_derivs<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->d_rec.as<double>(), h->recstride, h->rec_ld, lds, ng, (int)pb, h->dg,
+                                                              S.get<double>(rb), (int)nb, (int)npv, dk, db);
+    h->launches++;
+    CU(cudaGetLastError());
+    if (hk) CU(cudaMemcpyAsync(dfdk, dk, n * 8, cudaMemcpyDeviceToHost, st));
+    if (hb) CU(cudaMemcpyAsync(dfdb, db, n * 8, cudaMemcpyDeviceToHost, st));
+    if (hk || hb) CU(cudaStreamSynchronize(st));
     return PTB_OK;
 }
 
@@ -1676,15 +1707,16 @@ static_assert(sizeof(LpfLayout) == sizeof(ptb_lpf_layout), "LpfLayout must mirro
 
 // pvp -> device arrays of the RoadRunner arguments (k_lpf_map); returns device pointers in A / sigma
 int lpf_map(ptb_model *h, const char *who, const double *pvp, int64_t npv, const ptb_lpf_layout *lay, bool want_sigma,
-            cudaStream_t st, ModelArgs &A, const double *&sigma) {
+            cudaStream_t st, ModelArgs &A, const double *&sigma, const double **pvp_dev = nullptr) {
     if (!h->has_data) return fail(h, PTB_ESTATE, "%s: call set_data first", who);
     if (!pvp || !lay || npv < 1) return fail(h, PTB_EINVAL, "%s: null argument or npv < 1", who);
-    if (h->nep != 1) return fail(h, PTB_ESTATE, "%s: the LPF mapping needs a single-epoch dataset (nep=%lld)", who, (long long)h->nep);
     if (h->cfg.ldlaw == PTB_LD_PROFILES) return fail(h, PTB_ESTATE, "%s: needs a named limb-darkening law", who);
     const int64_t npb = h->npb;
     const ptb_lpf_layout &L = *lay;
     auto col = [&](int32_t i, int32_t n) { return i >= 0 && n >= 1 && (int64_t)i + n <= L.npar; };
-    if (L.npar < 5 || !col(L.i_tc, 1) || !col(L.i_p, 1) || !col(L.i_rho, 1) || !col(L.i_b, 1))
+    if (L.ntc != h->nep)
+        return fail(h, PTB_ESTATE, "%s: %d transit-centre columns (ntc) for a dataset with %lld epochs", who, L.ntc, (long long)h->nep);
+    if (L.npar < 5 || !col(L.i_tc, L.ntc) || !col(L.i_p, 1) || !col(L.i_rho, 1) || !col(L.i_b, 1))
         return fail(h, PTB_ESHAPE, "%s: orbit columns outside the %d-column parameter array", who, L.npar);
     if (!(L.nk2 == 1 || L.nk2 == npb) || !col(L.i_k2, L.nk2))
         return fail(h, PTB_ESHAPE, "%s: nk2=%d must be 1 or npb=%lld and lie inside the parameter array", who, L.nk2, (long long)npb);
@@ -1700,14 +1732,15 @@ int lpf_map(ptb_model *h, const char *who, const double *pvp, int64_t npv, const
     if (int rc = S.commit()) return rc;
     const size_t n = (size_t)npv;
     const size_t nsig = want_sigma ? (size_t)L.nloge : 0;
-    const size_t total = n * (L.nk2 + npb * L.nldc + 6 + nsig);
+    const size_t total = n * (L.nk2 + npb * L.nldc + L.ntc + 5 + nsig);
     CU(h->d_lpf.reserve(total * 8));
     double *b = h->d_lpf.as<double>();
     LpfMapParams P{};
     P.pvp = S.get<double>(rp);
+    if (pvp_dev) *pvp_dev = P.pvp;
     P.k = b; b += n * L.nk2;
     P.ldc = b; b += n * npb * L.nldc;
-    P.t0 = b; b += n;
+    P.t0 = b; b += n * L.ntc;
     P.p = b; b += n;
     P.a = b; b += n;
     P.inc = b; b += n;
@@ -1721,6 +1754,23 @@ int lpf_map(ptb_model *h, const char *who, const double *pvp, int64_t npv, const
     CU(cudaGetLastError());
     A = ModelArgs{npv, L.nk2, L.nldc, P.k, P.ldc, nullptr, P.t0, P.p, P.a, P.inc, P.e, P.w};
     sigma = P.sigma;
+    return PTB_OK;
+}
+
+// baseline description for the kernels; fails when the layout asks for a baseline that was not registered
+int baseline_params(ptb_model *h, const char *who, const double *pvp_dev, const ptb_lpf_layout *lay, BaselineParams &B) {
+    B = BaselineParams{};
+    if (lay->i_bl < 0) return PTB_OK;
+    if (h->bl_nbasis == 0) return fail(h, PTB_ESTATE, "%s: the layout names baseline columns (i_bl=%d) but no baseline is registered (ptb_set_baseline)", who, lay->i_bl);
+    if (h->cfg.precision != 0) return fail(h, PTB_ESTATE, "%s: the baseline needs an fp64 handle", who);
+    B.pvp = pvp_dev;
+    B.basis = h->d_basis.as<double>();
+    B.lcids = h->d_lcids;
+    B.cstart = h->d_blmeta.as<int32_t>();
+    B.ncoef = B.cstart + h->nlc;
+    B.npt = h->npt;
+    B.npar = lay->npar;
+    B.i_bl = lay->i_bl;
     return PTB_OK;
 }
 
@@ -1741,10 +1791,102 @@ int ptb_lpf_lnlike(ptb_model *h, const double *pvp, int64_t npv, const ptb_lpf_l
     if (!h) return PTB_EINVAL;
     if (int rc = set_device(h)) return rc;
     if (!h->has_obs) return fail(h, PTB_ESTATE, "lpf_lnlike: call set_obs first");
+    if (!lnl) return fail(h, PTB_EINVAL, "lpf_lnlike: lnl is null");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     ModelArgs A{};
-    const double *sigma = nullptr;
-    if (int rc = lpf_map(h, "lpf_lnlike", pvp, npv, lay, true, static_cast<cudaStream_t>(stream), A, sigma)) return rc;
-    return ptb_rr_lnlike(h, npv, A.k, A.kcols, A.ld, A.nld, nullptr, A.t0, A.p, A.a, A.inc, A.e, A.w, sigma, lnl, stream);
+    const double *sigma = nullptr, *pvp_dev = nullptr;
+    if (int rc = lpf_map(h, "lpf_lnlike", pvp, npv, lay, true, st, A, sigma, &pvp_dev)) return rc;
+    if (lay->i_bl < 0)
+        return ptb_rr_lnlike(h, npv, A.k, A.kcols, A.ld, A.nld, nullptr, A.t0, A.p, A.a, A.inc, A.e, A.w, sigma, lnl, stream);
+    // with a baseline: transit flux on the device, then the likelihood of baseline * flux (lpf.py:445-475)
+    BaselineParams B{};
+    if (int rc = baseline_params(h, "lpf_lnlike", pvp_dev, lay, B)) return rc;
+    const size_t count = (size_t)npv * h->npt;
+    CU(h->d_flux.reserve(count * 8));
+    if (int rc = ptb_rr_evaluate(h, npv, A.k, A.kcols, A.ld, A.nld, nullptr, A.t0, A.p, A.a, A.inc, A.e, A.w, h->d_flux.ptr, stream)) return rc;
+    const long long nsig = (long long)npv * h->nblocks;
+    CU(h->d_isig2.reserve(nsig * 8));
+    CU(h->d_partial.reserve(npv * 8));
+    k_inv_sigma2<<<(unsigned)((nsig + 255) / 256), 256, 0, st>>>(sigma, nsig, h->d_isig2.as<double>());
+    k_lnl_model<<<(unsigned)npv, 256, 0, st>>>(h->d_flux.as<double>(), h->d_obs, h->blk_trivial ? nullptr : h->d_blk.as<int32_t>(),
+                                               h->d_isig2.as<double>(), h->npt, (int)h->nblocks, h->d_partial.as<double>(), B);
+    const bool direct = is_device_ptr(lnl);
+    double *dl = lnl;
+    if (!direct) {
+        CU(h->d_lnl.reserve(npv * 8));
+        dl = h->d_lnl.as<double>();
+    }
+    LnlOut out{};
+    out.nout = 1;
+    out.ptr[0] = dl;
+    k_lnl_finish<<<(unsigned)((npv + 127) / 128), 128, 0, st>>>(h->d_partial.as<double>(), 1, sigma, h->d_nblk.as<double>(),
+                                                                 (int)h->nblocks, (int)npv, out);
+    h->launches += 3;
+    CU(cudaGetLastError());
+    if (!direct) {
+        CU(cudaMemcpyAsync(lnl, dl, npv * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return PTB_OK;
+}
+
+int ptb_set_baseline(ptb_model *h, const double *basis, int64_t nbasis, const int64_t *cstart, const int64_t *ncoef) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    h->bl_nbasis = 0;
+    h->data_gen++;
+    if (!basis) return PTB_OK;
+    if (!h->has_data) return fail(h, PTB_ESTATE, "set_baseline: call set_data first");
+    if (nbasis < 1 || nbasis > 64 || !cstart || !ncoef) return fail(h, PTB_EINVAL, "set_baseline: 1..64 basis functions and cstart / ncoef per light curve expected");
+    std::vector<int64_t> cs(h->nlc), nc(h->nlc);
+    CU(cudaMemcpy(cs.data(), cstart, h->nlc * 8, cudaMemcpyDefault));
+    CU(cudaMemcpy(nc.data(), ncoef, h->nlc * 8, cudaMemcpyDefault));
+    std::vector<int32_t> meta(2 * h->nlc);
+    for (int64_t i = 0; i < h->nlc; ++i) {
+        if (nc[i] < 0 || nc[i] > nbasis || cs[i] < 0 || cs[i] > (1 << 20))
+            return fail(h, PTB_EINVAL, "set_baseline: light curve %lld has ncoef=%lld (nbasis=%lld), cstart=%lld", (long long)i, (long long)nc[i], (long long)nbasis, (long long)cs[i]);
+        meta[i] = (int32_t)cs[i];
+        meta[h->nlc + i] = (int32_t)nc[i];
+    }
+    CU(h->d_blmeta.reserve(meta.size() * 4));
+    CU(cudaMemcpy(h->d_blmeta.ptr, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
+    CU(h->d_basis.reserve((size_t)nbasis * h->npt * 8));
+    CU(cudaMemcpy(h->d_basis.ptr, basis, (size_t)nbasis * h->npt * 8, cudaMemcpyDefault));
+    h->bl_nbasis = nbasis;
+    return PTB_OK;
+}
+
+int ptb_lpf_flux_model(ptb_model *h, const double *pvp, int64_t npv, const ptb_lpf_layout *lay, int32_t only_baseline,
+                       double *flux, void *stream) {
+    if (!h) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    if (!flux) return fail(h, PTB_EINVAL, "lpf_flux_model: flux is null");
+    if (h->cfg.precision != 0) return fail(h, PTB_ESTATE, "lpf_flux_model: needs an fp64 handle");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ModelArgs A{};
+    const double *sigma = nullptr, *pvp_dev = nullptr;
+    if (int rc = lpf_map(h, "lpf_flux_model", pvp, npv, lay, false, st, A, sigma, &pvp_dev)) return rc;
+    BaselineParams B{};
+    if (int rc = baseline_params(h, "lpf_flux_model", pvp_dev, lay, B)) return rc;
+    if (only_baseline && !B.basis) return fail(h, PTB_ESTATE, "lpf_flux_model: no baseline registered");
+    const size_t count = (size_t)npv * h->npt;
+    const bool direct = is_device_ptr(flux);
+    double *dflux = flux;
+    if (!direct) {
+        CU(h->d_flux.reserve(count * 8));
+        dflux = h->d_flux.as<double>();
+    }
+    if (!only_baseline)
+        if (int rc = ptb_rr_evaluate(h, npv, A.k, A.kcols, A.ld, A.nld, nullptr, A.t0, A.p, A.a, A.inc, A.e, A.w, dflux, stream)) return rc;
+    if (B.basis) {
+        if (npv > 65535) return fail(h, PTB_EINVAL, "lpf_flux_model: at most 65535 parameter vectors per call with a baseline");
+        k_lpf_baseline<<<dim3((unsigned)((h->npt + 255) / 256), (unsigned)npv), 256, 0, st>>>(B, dflux, only_baseline ? 1 : 0);
+        h->launches++;
+        CU(cudaGetLastError());
+    }
+    h->last_flux_count = direct ? 0 : (int64_t)count;
+    if (!direct) return deliver_host(h, flux, dflux, count, 8, st);
+    return PTB_OK;
 }
 
 }  // extern "C"

@@ -1274,19 +1274,57 @@ __global__ void k_inv_sigma2(const double *__restrict__ sigma, long long n, doub
     }
 }
 
-// lnlike_normal on a materialised model (wnloglikelihood.py:22-35): one CTA per vector.
+// Multiplicative baseline of the LPF layer (lpf/lpf.py:418-428) as a linear model in per-point basis functions:
+//   bl[ipv, j] = sum_c pvp[ipv, i_bl + cstart[lc(j)] + c] * basis[c][j],  c < ncoef[lc(j)]   (1 where ncoef = 0)
+// which covers both baselines of the reference: LegendreBaseline (lpf/baselines/legendrebaseline.py:23-40, basis =
+// Legendre polynomials of the normalised time, summed in the same order) and LinearModelBaseline
+// (lpf/baselines/linearbaseline.py:22-36, basis = 1 and the covariates).
+struct BaselineParams {
+    const double *pvp;      // [npv][npar]
+    const double *basis;    // [nbasis][npt]; null: no baseline
+    const int32_t *lcids;   // [npt], or null with a single light curve
+    const int32_t *cstart, *ncoef;  // [nlc]
+    long long npt;
+    int npar, i_bl;
+};
+
+__device__ __forceinline__ double baseline_at(const BaselineParams &B, const double *pv, long long ipt) {
+    const int lc = B.lcids ? B.lcids[ipt] : 0;
+    const int nc = B.ncoef[lc];
+    if (nc == 0) return 1.0;
+    const double *c = pv + B.i_bl + B.cstart[lc];
+    double bl = 0.0;
+    for (int j = 0; j < nc; ++j) bl += c[j] * B.basis[(size_t)j * B.npt + ipt];
+    return bl;
+}
+
+// flux[ipv, :] *= baseline (BaseLPF.flux_model, lpf.py:445-449, trends = 0), or flux = baseline (BaseLPF.baseline)
+__global__ void __launch_bounds__(256) k_lpf_baseline(const __grid_constant__ BaselineParams B, double *__restrict__ flux, int only_baseline) {
+    const long long j = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (j >= B.npt) return;
+    const int ipv = blockIdx.y;
+    const double bl = baseline_at(B, B.pvp + (size_t)ipv * B.npar, j);
+    double *f = flux + (size_t)ipv * B.npt + j;
+    *f = only_baseline ? bl : bl * *f;
+}
+
+// lnlike_normal on a materialised model (wnloglikelihood.py:22-35): one CTA per vector.  With a baseline the model
+// value is baseline * transit flux (lpf.py:445-449), evaluated on the fly -- the baseline itself is never stored.
 __global__ void __launch_bounds__(256) k_lnl_model(const double *__restrict__ model, const double *__restrict__ obs,
                                                    const int32_t *__restrict__ blk, const double *__restrict__ isig2,
-                                                   long long npt, int nblocks, double *__restrict__ partial) {
+                                                   long long npt, int nblocks, double *__restrict__ partial,
+                                                   const __grid_constant__ BaselineParams B) {
     __shared__ double s_w[8];
     const int ipv = blockIdx.x;
     const double *m = model + (size_t)ipv * npt;
     const double *w = isig2 + (size_t)ipv * nblocks;
+    const double *pv = B.basis ? B.pvp + (size_t)ipv * B.npar : nullptr;
     double chi = 0.0;
     for (long long j = threadIdx.x; j < npt; j += 256) {
         const int b = blk ? blk[j] : 0;
         if (b >= 0) {
-            const double d = obs[j] - m[j];
+            const double mv = pv ? baseline_at(B, pv, j) * m[j] : m[j];
+            const double d = obs[j] - mv;
             chi = fma(d * d, w[b], chi);
         }
     }
@@ -1389,7 +1427,7 @@ __global__ void __launch_bounds__(256) k_host_delta(const T *__restrict__ src, T
 // sigma = 10**pv (wnloglikelihood.py:80).
 // ---------------------------------------------------------------------------------------------
 struct LpfLayout {  // mirror of ptb_lpf_layout (include/ptb200.h)
-    int32_t npar, i_tc, i_p, i_rho, i_b, i_k2, nk2, i_ld, nldc, ld_map, i_secw, i_sesw, inc_mode, i_loge, nloge;
+    int32_t npar, i_tc, i_p, i_rho, i_b, i_k2, nk2, i_ld, nldc, ld_map, i_secw, i_sesw, inc_mode, i_loge, nloge, ntc, i_bl, pad_;
     double tref;
 };
 
@@ -1415,7 +1453,7 @@ __global__ void k_lpf_map(const __grid_constant__ LpfMapParams P) {
         w = atan2(s, c);
     }
     const double inc = (L.inc_mode == 1) ? acos(b / (a * ((1.0 - e * e) / (1.0 + e * sin(w))))) : acos(b / a);
-    P.t0[ipv] = pv[L.i_tc] - L.tref;
+    for (int j = 0; j < L.ntc; ++j) P.t0[(size_t)ipv * L.ntc + j] = pv[L.i_tc + j] - L.tref;   // one per epoch (ttvlpf.py:83)
     P.p[ipv] = per;
     P.a[ipv] = a;
     P.inc[ipv] = inc;
@@ -1435,6 +1473,48 @@ __global__ void k_lpf_map(const __grid_constant__ LpfMapParams P) {
     }
     if (P.sigma)
         for (int j = 0; j < L.nloge; ++j) P.sigma[(size_t)ipv * L.nloge + j] = pow(10.0, pv[L.i_loge + j]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Model derivatives dfdk / dfdb (common.py:104-128), as coded: the partial derivatives of the single-sample flux
+// F = (I* - l(g) A(k, b)) / I*, g = b / (1 + k), with respect to the radius ratio (at fixed l: dA/dk = 2 k kappa0)
+// and to the separation b (dA/db = -2 A_kite / b, dl/db from the two neighbouring LD-mean nodes).  One thread per
+// (vector, separation); the vector's LD-mean row, k and I* come from the records of the last evaluation.  The
+// interpolation weight is `g - ig*dg` as in the reference (not divided by dg, unlike common.py:231).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rr_derivs(const double *__restrict__ rec, int recstride, int rec_ld, int lds, int ng, int pb,
+                                                   double dg, const double *__restrict__ b, int nb, int npv,
+                                                   double *__restrict__ dfdk, double *__restrict__ dfdb) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (long long)npv * nb) return;
+    const int ipv = (int)(idx / nb);
+    const double *row = rec + (size_t)ipv * recstride + rec_ld + (size_t)pb * lds;
+    const double k = row[ng], ist = 1.0 / row[ng + 2], z = b[idx];
+    double dk = 0.0, db = 0.0;
+    if (z < 1.0 + k - 1e-5) {
+        const double g = z / (1.0 + k);
+        const int ig = min(max((int)floor(g / dg), 0), ng - 1), ig1 = min(ig + 1, ng - 1);
+        const double ag = g - ig * dg;
+        const double l1 = row[ig], l2 = row[ig1];
+        const double l = (1.0 - ag) * l1 + ag * l2;
+        // lens area, kappa0 and the kite area (circle_circle_intersection_area_kite, common.py:52-73)
+        double area, kap, akite = 0.0;
+        kite_area<double>(k, k * k, z, area, kap);
+        if (fabs(1.0 - k) < z) {
+            const bool kg = k > 1.0;
+            const double hi = kg ? k : 1.0, lo = kg ? 1.0 : k;
+            const bool c1 = z > hi, c2 = z > lo;
+            const double x = c1 ? z : hi, y = c1 ? hi : (c2 ? z : lo), zz = c2 ? lo : z;
+            akite = 0.5 * sqrt((x + (y + zz)) * (zz - (x - y)) * (zz + (x - y)) * (x + (y - zz)));
+        }
+        dk = -2.0 * k * kap * l / ist;                                   // dfdk, common.py:105-113
+        if (z >= 0.005) {                                                // dfdb, common.py:117-128
+            const double dldb = -(l2 - l1) / (dg * (1.0 + k));
+            db = 2.0 * akite * l / (z * ist) + dldb * area / ist;
+        }
+    }
+    if (dfdk) dfdk[idx] = dk;
+    if (dfdb) dfdb[idx] = db;
 }
 
 // ---------------------------------------------------------------------------------------------

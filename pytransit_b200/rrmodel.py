@@ -553,6 +553,20 @@ class RoadRunnerModelCUDA(TransitModel):
         check(lib().ptb_lnlike_normal(self._h, npv, ptr(model), ptr(sigma), ptr(out), stream), self._h)
         return out.copy() if copy else out
 
+    def derivatives(self, b, pb: int = 0):
+        """``(dfdk, dfdb)`` of the reference's helpers (models/roadrunner/common.py:104-128) for the population of the
+        last ``evaluate`` / ``lnlikelihood``: ``b[npv, nb]`` projected separations per parameter vector; the radius ratio,
+        LD-mean row and disk integral of passband ``pb`` are each vector's own."""
+        npv = getattr(self, '_lastnpv', 0)
+        b = np.ascontiguousarray(np.atleast_2d(np.asarray(b, np.float64)))
+        if b.shape[0] == 1 and npv > 1:
+            b = np.ascontiguousarray(np.broadcast_to(b, (npv, b.shape[1])))
+        if b.shape[0] != npv:
+            raise ValueError(f"b should have shape [npv={npv}, nb].")
+        dk, db = np.zeros_like(b), np.zeros_like(b)
+        check(lib().ptb_rr_derivatives(self._h, npv, b.shape[1], int(pb), ptr(b), ptr(dk), ptr(db), _current_stream(self.device)), self._h)
+        return dk, db
+
     # ------------------------------------------------------------------------------------------
     def stage(self, name: str) -> ndarray:
         """Per-vector intermediates of the last evaluation (parity taps): 'ldp', 'istar', 'ldm', 'xyc',

@@ -673,6 +673,73 @@ def test_base_lpf_on_device_vs_reference_golden(pb, golden):
         lpf.lnlikelihood(pvp[:, :10])
 
 
+def test_model_derivatives_vs_reference_golden(pb, golden):
+    """dfdk / dfdb (common.py:104-128) against the reference's own helpers run on the reference's LD means
+    (tests/golden/make_golden_derivs.py), for the population of the last evaluation."""
+    g = golden('derivs')
+    npv = g['k'].size
+    m = pb.RoadRunnerModelCUDA('quadratic')
+    m.set_data(np.linspace(-0.1, 0.1, 200))
+    m.evaluate(g['k'].reshape(-1, 1), g['ldc'], np.zeros(npv), np.full(npv, 3.0), np.full(npv, 9.0), np.full(npv, 1.55))
+    np.testing.assert_allclose(m.stage('ldm')[:, 0], g['ldm'], rtol=0, atol=1e-13)
+    dk, db = m.derivatives(g['b'])
+    assert np.array_equal(dk == 0, g['dfdk'] == 0) and np.array_equal(db == 0, g['dfdb'] == 0)
+    np.testing.assert_allclose(dk, g['dfdk'], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(db, g['dfdb'], rtol=1e-9, atol=1e-13)
+    assert (dk < 0).sum() > npv * 20 and np.abs(db).max() > 1e-3
+    with pytest.raises(ValueError):
+        m.derivatives(np.zeros((npv + 1, 3)))
+
+
+def test_lpf_baselines_and_ttv_vs_reference_golden(pb, golden):
+    """the reference's two baseline models (lbaseline, linear_model), flux_model = baseline *
+    transit_model, the likelihood of it, and TTVLPF's per-epoch transit centres -- fixture tests/golden/lpf_bl.npz made by
+    the reference's own functions (tests/golden/make_golden_lpf.py)."""
+    import torch
+    g = golden('lpf_bl')
+    times = [g[f'time{i}'] for i in range(4)]
+    fluxes = [g[f'flux{i}'] for i in range(4)]
+    covs = [g[f'cov{i}'] for i in range(4)]
+    kw = dict(pbids=g['pbids'], wnids=g['wnids'], tref=float(g['tref']))
+    # Legendre baseline: block before the wn parameters, as the LegendreBaseline mixin places it
+    lpf = pb.BaseLPFCUDA('leg', ['g', 'r'], times, fluxes, **kw)
+    assert lpf.baseline(g['pvp_leg'][:, :11]) == 1.0
+    lpf._add_baseline_model(pb.LegendreBaselineCUDA(lpf, g['nleg']))
+    assert lpf.npar == g['pvp_leg'].shape[1] and lpf._sl_bl == slice(9, 19) and lpf._sl_wn == slice(19, 21)
+    assert lpf.parameter_names[9:13] == ['bli_0', 'bls_0_1', 'bls_0_2', 'bli_1']
+    bl = lpf.baseline(g['pvp_leg'])
+    assert np.abs(bl - g['bl_leg']).max() <= 1e-14
+    fm = lpf.flux_model(g['pvp_leg'])
+    assert np.abs(fm - g['fm_leg']).max() <= FLUX_TOL and (g['tflux'] < 1).mean() > 0.1
+    assert np.abs(lpf.transit_model(g['pvp_leg']) - g['tflux']).max() <= FLUX_TOL
+    np.testing.assert_allclose(lpf.lnlikelihood(g['pvp_leg']), g['lnl_leg'], rtol=LNL_RTOL)
+    np.testing.assert_allclose(lpf.residuals(g['pvp_leg'][2]), np.concatenate(fluxes) - g['fm_leg'][2], rtol=0, atol=FLUX_TOL)
+    pv_d = torch.as_tensor(g['pvp_leg'], device='cuda')                    # the population stays on the device
+    l_d = lpf.lnlikelihood(pv_d, copy=False)
+    assert l_d.is_cuda and np.allclose(l_d.cpu().numpy(), g['lnl_leg'], rtol=LNL_RTOL, atol=0)
+    f_d = lpf.flux_model(pv_d, copy=False)
+    assert f_d.is_cuda and np.array_equal(f_d.cpu().numpy(), fm)
+    with pytest.raises(NotImplementedError):
+        lpf._add_baseline_model(pb.LegendreBaselineCUDA(lpf, 1))
+    # linear-model baseline on a subset of the light curves: block appended after the wn parameters
+    lpf = pb.BaseLPFCUDA('lm', ['g', 'r'], times, fluxes, covariates=covs, **kw)
+    lpf._add_baseline_model(pb.LinearModelBaselineCUDA(lpf, lcids=g['lm_lcids']))
+    assert lpf.npar == g['pvp_lm'].shape[1] and lpf._sl_lm == slice(11, 21) and lpf._sl_wn == slice(9, 11)
+    assert np.abs(lpf.baseline(g['pvp_lm']) - g['bl_lm']).max() <= 1e-14
+    assert np.abs(lpf.flux_model(g['pvp_lm']) - g['fm_lm']).max() <= FLUX_TOL
+    np.testing.assert_allclose(lpf.lnlikelihood(g['pvp_lm']), g['lnl_lm'], rtol=LNL_RTOL)
+    # TTV: one transit centre per epoch (two light curves share epoch 0)
+    ttv = pb.TTVLPFCUDA('ttv', float(g['zero_epoch']), float(g['period']), ['g', 'r'], times, fluxes, **kw)
+    assert np.array_equal(ttv.epids, g['epids']) and ttv.neps == 3 and ttv._sl_tc == slice(3, 6)
+    assert ttv.parameter_names[:7] == ['p', 'rho', 'b', 'tc_0', 'tc_1', 'tc_2', 'k2'] and ttv.npar == g['pvp_ttv'].shape[1]
+    assert np.abs(ttv.transit_model(g['pvp_ttv']) - g['flux_ttv']).max() <= FLUX_TOL
+    np.testing.assert_allclose(ttv.lnlikelihood(g['pvp_ttv']), g['lnl_ttv'], rtol=LNL_RTOL)
+    with pytest.raises(RuntimeError):      # a single-epoch layout against the multi-epoch dataset
+        lay = pb._lib.PtbLpfLayout(**{f: getattr(ttv._layout, f) for f, _ in ttv._layout._fields_ if f != 'ntc'}, ntc=1)
+        out = np.zeros((1, ttv.tm.npt))
+        pb._lib.check(pb._lib.lib().ptb_lpf_transit_model(ttv.tm._h, pb._lib.ptr(g['pvp_ttv'][:1].copy()), 1, lay, pb._lib.ptr(out), 0), ttv.tm._h)
+
+
 # ---------------------------------------------------------------------------------------------
 # fused likelihood + all-gather ordered by device-side flags: two ranks on ONE GPU (two handles, two streams,
 # "peer" pointers in the same address space) -- the protocol of ptb_rr_lnlike_allgather without a second GPU

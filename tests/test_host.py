@@ -192,8 +192,11 @@ def test_base_lpf_host_logic_with_a_stub_model():
     class StubTM:
         ldmodel, device, npb = 'quadratic', 0, None
 
-        def set_data(self, time, lcids, pbids, nsamples, exptimes):
+        _h = None
+
+        def set_data(self, time, lcids, pbids, nsamples, exptimes, epids=None):
             self.args = (time, lcids, pbids, nsamples, exptimes)
+            self.epids = epids
             self.npb = int(np.unique(pbids).size)
 
         def set_obs(self, obs, slices, nids, nblocks):
@@ -218,8 +221,28 @@ def test_base_lpf_host_logic_with_a_stub_model():
     L = lpf._layout
     assert (L.npar, L.i_tc, L.i_p, L.i_rho, L.i_b, L.i_k2, L.nk2, L.i_ld, L.nldc, L.ld_map, L.i_loge, L.nloge, L.tref) == \
            (11, 0, 1, 2, 3, 4, 1, 5, 2, 1, 9, 2, 0.5)
+    assert (L.ntc, L.i_bl) == (1, -1) and np.array_equal(tm.epids, [0, 0, 0])
     with pytest.raises(ValueError):
         lpf._pvp(np.zeros((3, 10)))
+
+    # TTVLPF host logic (lpf/ttvlpf.py:57-76): epochs of the light curves, parameter order, layout
+    from pytransit_b200.lpf import TTVLPFCUDA, LegendreBaselineCUDA
+    tm2 = StubTM()
+    ttv = TTVLPFCUDA('t', 0.4, 2.5, ['g', 'r'], times, fluxes, pbids=[0, 1, 0], tm=tm2)
+    assert np.array_equal(ttv.epochs, [0, 1, 2]) and np.array_equal(tm2.epids, [0, 1, 2])
+    assert ttv.parameter_names[:7] == ['p', 'rho', 'b', 'tc_0', 'tc_1', 'tc_2', 'k2'] and ttv._sl_tc == slice(3, 6)
+    L = ttv._layout
+    assert (L.i_p, L.i_rho, L.i_b, L.i_tc, L.ntc, L.i_k2, L.i_ld, L.i_loge) == (0, 1, 2, 3, 3, 6, 7, 11)
+    # Legendre basis: the reference's recurrence (legendrebaseline.py:30-39) = numpy's Legendre polynomials
+    bl = LegendreBaselineCUDA(lpf, [2, 0, 3])
+    assert np.array_equal(bl.ncoef, [3, 1, 4]) and np.array_equal(bl.cstart, [0, 3, 4]) and bl.basis.shape == (4, 60)
+    t0 = (times[2] - times[2].mean()) / np.ptp(times[2])
+    for n in range(4):
+        c = np.zeros(n + 1)
+        c[n] = 1.0
+        np.testing.assert_allclose(bl.basis[n, 50:60], np.polynomial.legendre.legval(t0, c), rtol=0, atol=1e-15)
+    assert (bl.basis[1:, 30:50] == 0).all() and (bl.basis[0] == 1).all()
+    assert bl.parameter_names == ['bli_0', 'bls_0_1', 'bls_0_2', 'bli_1', 'bli_2', 'bls_2_1', 'bls_2_2', 'bls_2_3']
     with pytest.raises(ValueError):
         BaseLPFCUDA('t', ['g'], times, fluxes, pbids=[0, 1, 0], tm=StubTM())        # two passbands used, one named
     with pytest.raises(NotImplementedError):
