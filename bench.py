@@ -320,6 +320,62 @@ def run_reference(args, rank: int, world: int):
 
 
 # ---------------------------------------------------------------------------------------------
+# hardware counters of the dominant kernel, measured on this box in this run (a child process under ncu)
+# ---------------------------------------------------------------------------------------------
+NCU_METRICS = ['dram__bytes_read.sum', 'dram__bytes_write.sum', 'sm__inst_executed_pipe_fp64.sum', 'smsp__inst_executed.sum',
+               'sm__cycles_elapsed.avg', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+               'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'gpu__time_duration.sum']
+
+
+def ncu_counters(args, kernel: str, timeout: float = 240.0):
+    """One launch of `kernel` (regex) profiled with ncu in a child process that runs four steps of the same workload.
+    Counters only -- no timing taken under the profiler is used as a bench value.  -> dict or {'unavailable': why}."""
+    import csv
+    import io
+    import shutil
+    import subprocess
+    ncu = shutil.which('ncu') or '/usr/local/cuda/bin/ncu'
+    if not Path(ncu).exists():
+        return {'unavailable': 'ncu not found'}
+    cmd = [ncu, '--metrics', ','.join(NCU_METRICS), '--clock-control', 'none', '-k', f'regex:{kernel}', '--launch-skip', '2', '-c', '1',
+           '--csv', sys.executable, str(Path(__file__).resolve()), '--workload', args.workload, '--precision', args.precision,
+           '--child-profile']
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=dict(os.environ, PTB_GRAPHS='0'))
+    except Exception as ex:
+        return {'unavailable': f'{type(ex).__name__}: {ex}'[:160]}
+    rows = [row for row in csv.reader(io.StringIO(r.stdout)) if len(row) > 14]
+    if not rows or 'Metric Name' not in rows[0]:
+        return {'unavailable': ('ncu produced no counters: ' + (r.stderr or r.stdout)[-200:]).replace('\n', ' ')}
+    h = rows[0]
+    iname, iunit, ival, ikern = h.index('Metric Name'), h.index('Metric Unit'), h.index('Metric Value'), h.index('Kernel Name')
+    mult = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0, 'Tbyte': 1e12, 'msecond': 1.0, 'usecond': 1e-3, 'second': 1e3, 'nsecond': 1e-6}
+    out = {'kernel': rows[1][ikern][:80]}
+    for row in rows[1:]:
+        try:
+            out[row[iname]] = float(row[ival].replace(',', '')) * mult.get(row[iunit], 1.0)
+        except ValueError:
+            pass
+    return out
+
+
+def run_child_profile(args, local_rank: int = 0):
+    """What ncu_counters profiles: four device-resident steps of the workload, nothing else."""
+    import torch
+    torch.cuda.set_device(local_rank)
+    c, _ = workload(args.workload, 0)
+    if args.workload == 'c4':
+        import pytransit_b200 as pb
+        c.table = wl.ldtk_style_table(c.npb, pb.TSModelCUDA('uniform', device=local_rank).mu)
+        c.npb_out = c.npb
+    m, step_device, *_ = make_steps(args, c, f'cuda:{local_rank}', local_rank, 1, None)
+    for _ in range(4):
+        out = step_device()
+    torch.cuda.synchronize()
+    del out
+
+
+# ---------------------------------------------------------------------------------------------
 # GPU side
 # ---------------------------------------------------------------------------------------------
 def measured_peaks():
@@ -340,7 +396,8 @@ def make_steps(args, c, dev, local_rank, world, dist):
     import pytransit_b200 as pb
     name = args.workload
     if name == 'c4':
-        m = pb.TSModelCUDA(pb.TabulatedLDModel(*_table_args(c), device=local_rank), device=local_rank, host_result=args.host_result)
+        m = pb.TSModelCUDA(pb.TabulatedLDModel(*_table_args(c), device=local_rank), device=local_rank, host_result=args.host_result,
+                           precision=args.precision)
         time_d = torch.as_tensor(c.time, device=dev)
         m.set_data(time_d)
         x = np.column_stack([c.teff, c.logg, c.metal])
@@ -358,7 +415,7 @@ def make_steps(args, c, dev, local_rank, world, dist):
             return m.evaluate(c.k, x, t0_alt[nhost[0] & 1], c.p, c.a, c.i, c.e, c.w, copy=True)
 
         h2d = sum(np.asarray(getattr(c, k)).nbytes for k in ('k', 't0', 'p', 'a', 'i', 'e', 'w')) + x.nbytes
-        return m, step_device, step_host, pts, h2d, 'k_ts_flux', 8.0 * pts
+        return m, step_device, step_host, pts, h2d, 'k_ts_flux', (4.0 if args.precision == 'fp32' else 8.0) * pts
     if name == 'c1':
         m = pb.RoadRunnerModelCUDA(c.ldmodel, device=local_rank)
         m.set_data(torch.as_tensor(c.time, device=dev))
@@ -496,7 +553,7 @@ def run_collective(args, rank, world, local_rank, dev, dist):
     m.gather_status()
     res.update({'value': pts / (ms * 1e-3), 'ms_per_step': ms,
                 'gather': 'peer stores from k_lnl_finish into every rank\'s symmetric-memory array over NVLink, ranks ordered by '
-                          'device-side release/acquire flags (k_lnl_wait); 8 B per vector',
+                          'device-side release/acquire flags (the last block of k_lnl_finish waits for all peers); 8 B per vector',
                 'gather_cost_ms_per_step': ms - local_ms, 'efficiency_vs_local_only': local_ms / ms,
                 'bit_identical_to_nccl_all_gather': same, 'variants': variants})
     return res
@@ -508,6 +565,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     torch.cuda.set_device(local_rank)
     dev = f'cuda:{local_rank}'
+    from pytransit_b200.distributed import bind_to_gpu_numa
+    cpus_all = os.sched_getaffinity(0) if hasattr(os, 'sched_getaffinity') else None
+    numa_bound = bind_to_gpu_numa(local_rank)      # page-locked result arrays land on the GPU's NUMA node
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device(dev))
 
@@ -610,13 +670,43 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         except MemoryError as ex:   # page-locked result buffer too large for this host
             return {'value': None, 'unit': UNIT, 'error': str(ex)[:200]}
 
-    e2e = measure_e2e(args.host_result)
+    # concurrent device-to-host copy rate of all ranks (copy engines, sequential 256 MB blocks): the PCIe ceiling the host
+    # delivery is measured against
+    pin = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+    src = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    pin.copy_(src, non_blocking=True)
+    barrier()
+    ev0.record()
+    for _ in range(4):
+        pin.copy_(src, non_blocking=True)
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    pcie_gbs = 4 * (256 << 20) / (float(t.item()) * 1e-3) / 1e9
+    del pin, src
+
+    def with_pcie_roofline(e):
+        if e and e.get('value'):
+            rate = e['d2h_bytes_per_step'] * e['value'] / (world * pts_per_step) / 1e9      # GB/s per GPU that crossed PCIe
+            e['roofline'] = {'bound': 'pcie (device-to-host)', 'achieved': rate, 'peak': pcie_gbs, 'unit': 'GB/s per GPU',
+                             'frac': rate / pcie_gbs,
+                             'peak_source': f'measured in this run: {world} rank(s) copying 256 MB blocks device-to-host concurrently, max over ranks'}
+        return e
+
+    e2e = with_pcie_roofline(measure_e2e(args.host_result))
     e2e_copy = None
     if args.host_result == 'delta' and not lnl and args.workload != 'c4':
         # the same loop through the DEFAULT mode of the API (plain full copy, writable result): PCIe bound
-        e2e_copy = measure_e2e('copy')
-        if e2e_copy.get('value'):
-            e2e_copy['pcie_gbs'] = e2e_copy['result_bytes_per_step'] * e2e_copy['value'] / (world * pts_per_step) / 1e9
+        e2e_copy = with_pcie_roofline(measure_e2e('copy'))
+
+    m_fp64_peak = None
+    if lnl and rank == 0:
+        try:
+            m_fp64_peak = m.measure_fp64_peak()
+        except Exception:
+            m_fp64_peak = None
 
     # ---- the path's one collective, same run (default workload only) -----------------------------------
     collective = None
@@ -636,33 +726,60 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if k_points_ms:
         kp = float(np.mean(k_points_ms))
         ks = float(np.mean(k_setup_ms))
-        if alg_bytes is None:
-            # nothing is written (time + obs stream from L2): the fused likelihood is bound by fp64 arithmetic.
-            # Algorithmic work = SURVEY.md 8(d): 9 (fold + box) + 5 (lnL) + f_in (46 + f_limb (34 + 2 atan2)) ~ 16
-            # source-level fp64 operations per point (div / sqrt / floor / atan2 counted as one each), against the
-            # nominal B200 fp64 rate (MEASURED_PEAKS.json carries no fp64 figure).  The kernel skips the fold for
-            # the ~93 % of points in untouched blocks, so this is an algorithmic rate, not executed instructions.
-            flop_pt, peak_tf = 16.0, 37.0
-            ach = flop_pt * pts_per_step / (kp * 1e-3) / 1e12
-            roof = {'bound': 'fp64', 'kernel': kname, 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                    'frac': ach / peak_tf, 'traffic': None,
-                    'peak_source': 'nominal B200 fp64 (no measured fp64 peak available); algorithmic flops = 16 per point (SURVEY.md 8d)',
-                    'algorithmic_flops_per_launch': flop_pt * pts_per_step, 'gpoints_per_s': pts_per_step / (kp * 1e-3) / 1e9,
-                    'kernel_ms': kp, 'setup_ms': ks, 'kernel_share_of_step': kp / (ms_max / args.steps)}
+        counters = None
+        if world == 1 and not args.no_counters:
+            counters = ncu_counters(args, 'k_ts_flux' if args.workload == 'c4' else 'k_rr_points')
+        have = counters is not None and 'unavailable' not in counters
+        traffic, traffic_src = None, None
+        if have and 'dram__bytes_write.sum' in counters:
+            traffic = counters['dram__bytes_read.sum'] + counters['dram__bytes_write.sum']
+            traffic_src = 'dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu child process of this run'
         else:
-            ach = alg_bytes / (kp * 1e-3) / 1e9
-            roof = {'bound': 'hbm', 'kernel': kname, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-                    'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
-                    'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': kp, 'setup_ms': ks,
-                    'kernel_share_of_step': kp / (ms_max / args.steps)}
             tr = ROOT / 'profiles' / 'traffic.json'
             if tr.exists():
                 try:
-                    roof['traffic'] = json.loads(tr.read_text()).get(args.workload)
+                    traffic = json.loads(tr.read_text()).get(args.workload)
+                    traffic_src = 'profiles/traffic.json (earlier ncu --set full capture; no counters in this run: %s)' % \
+                                  ((counters or {}).get('unavailable', 'N > 1 or --no-counters'))
                 except Exception:
                     pass
+        if alg_bytes is None:
+            # Fused likelihood: nothing is written, time + obs (1.6 MB) stream from L2 -- the kernel is bound by instruction
+            # issue on the fp64 pipe.  Roofline on EXECUTED work: fp64-pipe warp instructions of one launch (ncu counter)
+            # x 32 lanes x 2 flop per FMA slot, over the kernel's event-timed duration, against the DFMA throughput
+            # measured on this GPU (ptb_measure_fp64_peak).  The algorithmic gain of skipping untouched blocks (their
+            # chi^2 is pre-summed) is reported separately as points per second; it is not part of the fraction.
+            peak_tf = m_fp64_peak
+            roof = {'bound': 'fp64 pipe (instruction issue); no HBM or tensor-core bound applies: nothing is written', 'kernel': kname,
+                    'peak': peak_tf, 'unit': 'TFLOP/s', 'peak_source': 'measured on this GPU: DFMA microbenchmark k_dfma_peak (ptb_measure_fp64_peak)',
+                    'traffic': traffic, 'traffic_source': traffic_src, 'kernel_ms': kp, 'setup_ms': ks,
+                    'kernel_share_of_step': kp / (ms_max / args.steps), 'gpoints_per_s': pts_per_step / (kp * 1e-3) / 1e9}
+            if have and 'sm__inst_executed_pipe_fp64.sum' in counters:
+                f64 = counters['sm__inst_executed_pipe_fp64.sum']
+                ach = f64 * 32 * 2 / (kp * 1e-3) / 1e12
+                roof.update({'achieved': ach, 'frac': ach / peak_tf if peak_tf else None,
+                             'executed_fp64_warp_inst_per_launch': f64, 'executed_warp_inst_per_launch': counters.get('smsp__inst_executed.sum'),
+                             'fp64_pipe_active_pct': counters.get('sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active'),
+                             'issue_active_pct': counters.get('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+                             'executed_fp64_lane_ops_per_point': f64 * 32 / pts_per_step,
+                             'note': 'achieved = executed fp64-pipe warp instructions x 64 flop / kernel time; the kernel folds only the '
+                                     '~7 % of points in blocks a transit window touches'})
+            else:
+                roof.update({'achieved': None, 'frac': None, 'note': 'no counters in this run: ' + str((counters or {}).get('unavailable', 'N > 1 or --no-counters'))})
+        else:
+            ach = alg_bytes / (kp * 1e-3) / 1e9
+            roof = {'bound': 'hbm', 'kernel': kname, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                    'frac': ach / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': kp, 'setup_ms': ks,
+                    'kernel_share_of_step': kp / (ms_max / args.steps),
+                    'step_frac_of_peak': alg_bytes / (ms_max / args.steps * 1e-3) / 1e9 / peak}
+            if have:
+                roof['issue_active_pct'] = counters.get('smsp__issue_active.avg.pct_of_peak_sustained_active')
+                roof['fp64_pipe_active_pct'] = counters.get('sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active')
 
     # ---- CPU baseline on a bounded sample (N=1 only) -----------------------------------------------
+    if cpus_all is not None:
+        os.sched_setaffinity(0, cpus_all)          # the CPU arms use every host core again
     cpu = None
     if world == 1 and not args.no_cpu:
         from oracle import oracle as orc
@@ -696,7 +813,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64' if args.precision == 'fp64' else 'f32 (opt-in mode: fp64 phase fold, fp32 samples and output)', 'data': 'synthetic',
             'config': config_dict(args, desc, world), 'per_gpu': f'npv={c.npv} x npt={c.npt}' + (f' x npb={c.npb}' if args.workload == 'c4' else ''),
-            'clocks': clocks, 'e2e': e2e, 'e2e_copy': e2e_copy,
+            'clocks': clocks, 'e2e': e2e, 'e2e_copy': e2e_copy, 'numa_bound': numa_bound,
             'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu, 'cpu_baseline_numba': cpu_numba,
             'collective': collective}
     emit(line)
@@ -735,6 +852,8 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-numba', action='store_true', help="skip timing the reference's own Numba path (baseline/_ref)")
     ap.add_argument('--no-kernel-timing', action='store_true')
+    ap.add_argument('--no-counters', action='store_true', help='skip the ncu child process that measures DRAM traffic / executed instructions of the dominant kernel')
+    ap.add_argument('--child-profile', action='store_true', help=argparse.SUPPRESS)
     ap.add_argument('--no-collective', action='store_true', help='skip the C5-shard fused lnL + all-gather block of the default line')
     ap.add_argument('--gather', default='peer', choices=['peer', 'peer-barrier', 'nccl'],
                     help='N>1 lnL workloads (--workload c5): peer stores ordered by device-side flags (default), peer stores + one '
@@ -745,7 +864,9 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
-    if args.impl == 'reference':
+    if args.child_profile:
+        run_child_profile(args, local_rank)
+    elif args.impl == 'reference':
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)

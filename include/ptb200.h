@@ -164,8 +164,8 @@ int ptb_rr_lnlike(ptb_model *h, int64_t npv, const double *k, int64_t kcols, con
  * before anyone reads its gathered array.  peer_flags != NULL: peer_flags[r] is rank r's arrival array
  * uint64[world] (zero-initialised peer memory, same mapping rules); after all its stores the finishing kernel
  * publishes `seq` (>= 1, increasing by one per call on every rank) into slot `rank` of every arrival array with
- * a system-scope release, and a one-warp kernel queued behind it on `stream` returns when all `world` slots of
- * THIS rank's array have reached `seq` -- work queued on `stream` afterwards sees the complete gathered array,
+ * a system-scope release, and the kernel's last thread block then waits until all `world` slots of THIS rank's
+ * array have reached `seq` -- work queued on `stream` afterwards sees the complete gathered array,
  * with no host-side synchronisation.  Use at least two gathered arrays alternately (a peer overwrites the array
  * of step s at its step s+2, which it can only reach after this rank has published step s+1).  A peer that
  * never arrives is reported by ptb_gather_status after a 20 s device-side timeout.  Every rank must pass the
@@ -301,6 +301,10 @@ int ptb_host_result_stats(const ptb_model *h, int64_t *last_bytes, int64_t *delt
 /* Kernels launched by this handle since creation (bench.py's gpu_launches evidence; kernels inside a replayed
  * CUDA graph are counted). */
 int64_t ptb_launch_count(const ptb_model *h);
+
+/* Measured fp64 FMA throughput of the handle's GPU in TFLOP/s (8 independent DFMA chains per thread, no memory
+ * traffic; best of 4 timed launches): the roofline denominator bench.py uses for the fused-likelihood kernel. */
+int ptb_measure_fp64_peak(ptb_model *h, double *tflops);
 
 /* CUDA-graph replay of launch-bound calls.  For populations of up to 2048 vectors the kernel sequence of
  * ptb_rr_evaluate / ptb_rr_lnlike / ptb_eclipse_evaluate (argument copy, orbit solve on its side stream,

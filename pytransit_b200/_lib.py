@@ -68,6 +68,7 @@ SIGNATURES = {
     'ptb_unbind_host_result': (C.c_int, [_vp, _vp]),
     'ptb_host_result_stats': (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     'ptb_launch_count': (_i64, [_vp]),
+    'ptb_measure_fp64_peak': (C.c_int, [_vp, C.POINTER(_dbl)]),
     'ptb_set_graphs': (C.c_int, [_vp, C.c_int32]),
     'ptb_graph_stats': (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     'ptb_synchronize': (C.c_int, [_vp, _vp]),

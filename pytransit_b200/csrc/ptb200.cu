@@ -7,6 +7,7 @@
 #include "../../include/ptb200.h"
 
 #include <cuda_runtime.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <atomic>
@@ -15,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -1326,15 +1328,13 @@ static int rr_lnlike_enqueue(ptb_model *h, const ModelArgs &A, const double *sig
     if (int rc = launch_points(h, npv, nullptr, h->d_isig2.as<double>(), st, &nchunks)) return rc;
     mark(h, 3, st);
     out.done = h->d_work.as<int>() + WORK_FINISH;
+    out.err = h->d_work.as<int>() + WORK_GATHER_ERR;
+    out.timeout_ns = GATHER_TIMEOUT_NS;
+    // with arrival flags (fused all-gather) the kernel's last CTA also waits for every peer's shard of this step
     k_lnl_finish<<<(unsigned)((npv + 127) / 128), 128, 0, st>>>(h->d_partial.as<double>(), nchunks, D.sigma,
                                                                  h->d_nblk.as<double>(), (int)h->nblocks, (int)npv, out);
     h->launches++;
     CU(cudaGetLastError());
-    if (out.flag[0]) {  // fused all-gather: this GPU's array is complete once every rank has published step `seq`
-        k_lnl_wait<<<1, 32, 0, st>>>(out.flag[out.rank], out.nout, out.seq, GATHER_TIMEOUT_NS, h->d_work.as<int>() + WORK_GATHER_ERR);
-        h->launches++;
-        CU(cudaGetLastError());
-    }
     return PTB_OK;
 }
 
@@ -1614,8 +1614,44 @@ int ptb_host_result_stats(const ptb_model *h, int64_t *last_bytes, int64_t *delt
     return PTB_OK;
 }
 
+// Page-locked host memory for results.  Large buffers (>= 32 MB) are carved from 2 MB-aligned anonymous memory with
+// transparent huge pages requested (madvise) and then registered with CUDA: the delta transfer writes 128-byte bursts
+// scattered over the whole array, and every 4 KB page it touches costs an IOMMU / PCIe address translation -- 512x
+// fewer with 2 MB pages.  First touch happens here, on the calling thread, so the memory lands on the NUMA node the
+// caller is bound to (see pytransit_b200.distributed.bind_to_gpu_numa).  PTB_HOST_HUGEPAGES=0 restores cudaMallocHost.
+namespace {
+struct HostBlock { void *p; size_t bytes; };
+std::vector<HostBlock> g_host_blocks;   // registered (mmap-backed) allocations; everything else is cudaMallocHost memory
+std::mutex g_host_mu;
+}  // namespace
+
 int ptb_host_alloc(void **ptr, size_t bytes) {
     if (!ptr) return PTB_EINVAL;
+    static const bool huge = [] {
+        const char *e = getenv("PTB_HOST_HUGEPAGES");
+        return !(e && atoi(e) == 0);
+    }();
+    if (huge && bytes >= ((size_t)32 << 20)) {
+        const size_t two_mb = (size_t)2 << 20, len = (bytes + two_mb - 1) & ~(two_mb - 1);
+        void *raw = mmap(nullptr, len + two_mb, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (raw != MAP_FAILED) {
+            char *p = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(raw) + two_mb - 1) & ~(uintptr_t)(two_mb - 1));
+            // give back the unaligned head and tail so that munmap(p, len) frees everything later
+            if (p > static_cast<char *>(raw)) munmap(raw, p - static_cast<char *>(raw));
+            char *end = static_cast<char *>(raw) + len + two_mb;
+            if (end > p + len) munmap(p + len, end - (p + len));
+            madvise(p, len, MADV_HUGEPAGE);
+            for (size_t o = 0; o < len; o += 4096) p[o] = 0;   // first touch (NUMA placement, huge-page faults)
+            if (cudaHostRegister(p, len, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess) {
+                std::lock_guard<std::mutex> lk(g_host_mu);
+                g_host_blocks.push_back({p, len});
+                *ptr = p;
+                return PTB_OK;
+            }
+            cudaGetLastError();
+            munmap(p, len);
+        }
+    }
     cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -1627,10 +1663,47 @@ int ptb_host_alloc(void **ptr, size_t bytes) {
 
 int ptb_host_free(void *ptr) {
     if (!ptr) return PTB_OK;
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        for (size_t i = 0; i < g_host_blocks.size(); ++i)
+            if (g_host_blocks[i].p == ptr) {
+                const size_t len = g_host_blocks[i].bytes;
+                g_host_blocks.erase(g_host_blocks.begin() + i);
+                const bool ok = cudaHostUnregister(ptr) == cudaSuccess;
+                munmap(ptr, len);
+                return ok ? PTB_OK : PTB_ECUDA;
+            }
+    }
     return cudaFreeHost(ptr) == cudaSuccess ? PTB_OK : PTB_ECUDA;
 }
 
 int64_t ptb_launch_count(const ptb_model *h) { return h ? h->launches : 0; }
+
+int ptb_measure_fp64_peak(ptb_model *h, double *tflops) {
+    if (!h || !tflops) return PTB_EINVAL;
+    if (int rc = set_device(h)) return rc;
+    CU(h->d_dummy.reserve(64));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int iters = 4096, grid = h->sm_count * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0, 0));
+        k_dfma_peak<<<grid, 256>>>(h->d_dummy.as<double>(), iters, 0.999999, 1e-9);
+        CU(cudaEventRecord(e1, 0));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 64.0 * iters * 256.0 * grid / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;   // first launch: warm-up
+    }
+    h->launches += 5;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return PTB_OK;
+}
 
 int ptb_set_graphs(ptb_model *h, int32_t enabled) {
     if (!h) return PTB_EINVAL;

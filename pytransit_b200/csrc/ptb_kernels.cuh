@@ -1204,11 +1204,13 @@ struct LnlOut {
     double *ptr[LNL_MAXPEERS];
     // Device-side ordering of the fused all-gather (no host-issued barrier): flag[r] is destination r's arrival
     // array [world] of 64-bit step numbers.  The last CTA of k_lnl_finish publishes `seq` into slot `rank` of every
-    // destination after all the shard's stores (release at system scope over NVLink); k_lnl_wait on the destination
+    // destination after all the shard's stores (release at system scope over NVLink); the last CTA of the destination's own k_lnl_finish
     // acquires them.  null = no signalling (single destination, or the caller orders the ranks itself).
     unsigned long long *flag[LNL_MAXPEERS];
     unsigned long long seq;
+    unsigned long long timeout_ns;  // a peer that never arrives must not hang the GPU: give up and raise *err
     int *done;  // CTAs of this launch that have stored their part (re-armed by the last one)
+    int *err;
     int nout, rank;
 };
 
@@ -1223,6 +1225,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 
 __global__ void k_lnl_finish(const double *__restrict__ partial, int nchunks, const double *__restrict__ sigma,
                              const double *__restrict__ nblk, int nblocks, int npv, const __grid_constant__ LnlOut out) {
+    __shared__ int s_last;
     const int ipv = blockIdx.x * blockDim.x + threadIdx.x;
     if (ipv < npv) {
         double chi = 0.0;
@@ -1233,37 +1236,37 @@ __global__ void k_lnl_finish(const double *__restrict__ partial, int nchunks, co
         for (int r = 0; r < out.nout; ++r) out.ptr[r][ipv] = v;
     }
     if (out.flag[0] == nullptr) return;
+    // ---- fused all-gather, ordered on the device -------------------------------------------------------------
     __threadfence_system();  // this thread's peer stores are visible system-wide before the CTA reports
     __syncthreads();
     if (threadIdx.x == 0) {
         const int done = atomicAdd(out.done, 1);
-        if (done == (int)gridDim.x - 1) {  // every CTA's stores have been fenced: publish the step number everywhere
+        s_last = (done == (int)gridDim.x - 1);
+        if (s_last) {        // every CTA's stores have been fenced: publish the step number everywhere
             *out.done = 0;
             __threadfence_system();
             for (int r = 0; r < out.nout; ++r) st_release_sys(out.flag[r] + out.rank, out.seq);
         }
     }
-}
-
-// Consumer side of the fused all-gather: returns once every rank's shard of step `seq` has landed in this GPU's
-// gathered array.  One warp, lane r polls source r.  A peer that never arrives (crashed process) must not hang
-// the GPU: after `timeout_ns` the kernel gives up and raises *err (checked by the host at its next synchronisation).
-__global__ void k_lnl_wait(const unsigned long long *flags, int world, unsigned long long seq, unsigned long long timeout_ns,
-                           int *err) {
-    const int lane = threadIdx.x;
-    if (lane < world) {
+    __syncthreads();
+    // The last CTA stays until every rank's shard of this step has landed in THIS GPU's gathered array (lane r polls
+    // source r): when the kernel retires, work queued behind it on the stream sees the complete array.  No separate
+    // wait kernel, nothing for the host to do.
+    if (s_last && (int)threadIdx.x < out.nout) {
+        const unsigned long long *mine = out.flag[out.rank] + threadIdx.x;
         unsigned long long t0, t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        while (ld_acquire_sys(flags + lane) < seq) {
-            __nanosleep(200);
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > timeout_ns) {
-                atomicExch(err, 1 + lane);
-                break;
+        int spins = 0;
+        while (ld_acquire_sys(mine) < out.seq) {
+            if ((++spins & 1023) == 0) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > out.timeout_ns) {
+                    atomicExch(out.err, 1 + (int)threadIdx.x);
+                    break;
+                }
             }
         }
     }
-    __syncwarp();
 }
 
 __global__ void k_inv_sigma2(const double *__restrict__ sigma, long long n, double *__restrict__ out) {
@@ -1473,6 +1476,24 @@ __global__ void k_lpf_map(const __grid_constant__ LpfMapParams P) {
     }
     if (P.sigma)
         for (int j = 0; j < L.nloge; ++j) P.sigma[(size_t)ipv * L.nloge + j] = pow(10.0, pv[L.i_loge + j]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_dfma_peak -- measured fp64 FMA throughput of this GPU (the roofline denominator of the fused-likelihood kernel,
+// whose bound is instruction issue on the fp64 pipe, not memory): 8 independent DFMA chains per thread, no memory
+// traffic.  2 flop per DFMA.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678) out[0] = s;   // never true: keeps the chains alive
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -13,9 +13,9 @@ int launch_ts_ldm_t(ptb_model *h, const TsLdmParams &P, size_t smem, unsigned gr
     return PTB_OK;
 }
 
-template <int VEC, typename TO>
+template <int VEC, typename TO, bool FUSED, int NT>
 int launch_ts_flux2_t(ptb_model *h, const TsFlux2Params &P, size_t smem, unsigned grid, cudaStream_t st) {
-    auto kern = k_ts_flux2<VEC, TO>;
+    auto kern = k_ts_flux2<VEC, TO, FUSED, NT>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 256, smem, st>>>(P);
     h->launches++;
@@ -108,23 +108,35 @@ int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, con
         ldp = h->d_ldp.as<double>();
     }
 
-    // 3. dense LD contraction (DMMA)
-    TsLdmParams MP{};
-    MP.tsw = h->d_tsw.as<double>(); MP.ldp = ldp; MP.istar = ist; MP.k = D.k; MP.tsorb = h->d_orb.as<double>();
-    MP.tsldm = h->d_ldrec.as<double>(); MP.tsrec = h->d_tsrec.as<double>();
-    MP.npv = (int)npv; MP.npb = (int)npb; MP.ng = ng; MP.nz = nz; MP.ldt = ldt; MP.rs = rs;
-    const size_t smem_ldm = (size_t)(nt * 8 + 2 * TSL_PB) * rs * 8;
-    const long long ntile_ldm = (npb + TSL_PB - 1) / TSL_PB;
-    MP.tpc = (int)std::min<long long>(4, ntile_ldm);
-    const unsigned grid_ldm = (unsigned)(npv * ((ntile_ldm + MP.tpc - 1) / MP.tpc));
-    int rc;
-    switch (nt) {
-    case 4: rc = launch_ts_ldm_t<4>(h, MP, smem_ldm, grid_ldm, st); break;
-    case 8: rc = launch_ts_ldm_t<8>(h, MP, smem_ldm, grid_ldm, st); break;
-    case 13: rc = launch_ts_ldm_t<13>(h, MP, smem_ldm, grid_ldm, st); break;
-    default: rc = launch_ts_ldm_t<16>(h, MP, smem_ldm, grid_ldm, st); break;
+    // 3. dense LD contraction (DMMA): fused into the flux kernel's prologue in the common case (one sample per point,
+    //    default grid) -- the ld means then never touch HBM (0.83 GB written + 0.91 GB read back at C4) and a launch goes
+    const bool multi = ns > 1;
+    const size_t geo_bytes = (size_t)npv * h->npt * 28;
+    const bool two_pass = !multi && geo_bytes <= (size_t)2 << 30;
+    static const bool fuse_env = [] {
+        const char *e = getenv("PTB_TS_FUSE");
+        return !(e && atoi(e) == 0);
+    }();
+    const size_t smem_fused = std::max((size_t)ng * rs + (size_t)TS_CH * nz, (size_t)TS_CH * (ldt + 4)) * 8;
+    const bool fused = fuse_env && two_pass && nt == 13 && (nz & 3) == 0 && smem_fused <= 200 * 1024;
+    int rc = PTB_OK;
+    if (!fused) {
+        TsLdmParams MP{};
+        MP.tsw = h->d_tsw.as<double>(); MP.ldp = ldp; MP.istar = ist; MP.k = D.k; MP.tsorb = h->d_orb.as<double>();
+        MP.tsldm = h->d_ldrec.as<double>(); MP.tsrec = h->d_tsrec.as<double>();
+        MP.npv = (int)npv; MP.npb = (int)npb; MP.ng = ng; MP.nz = nz; MP.ldt = ldt; MP.rs = rs;
+        const size_t smem_ldm = (size_t)(nt * 8 + 2 * TSL_PB) * rs * 8;
+        const long long ntile_ldm = (npb + TSL_PB - 1) / TSL_PB;
+        MP.tpc = (int)std::min<long long>(4, ntile_ldm);
+        const unsigned grid_ldm = (unsigned)(npv * ((ntile_ldm + MP.tpc - 1) / MP.tpc));
+        switch (nt) {
+        case 4: rc = launch_ts_ldm_t<4>(h, MP, smem_ldm, grid_ldm, st); break;
+        case 8: rc = launch_ts_ldm_t<8>(h, MP, smem_ldm, grid_ldm, st); break;
+        case 13: rc = launch_ts_ldm_t<13>(h, MP, smem_ldm, grid_ldm, st); break;
+        default: rc = launch_ts_ldm_t<16>(h, MP, smem_ldm, grid_ldm, st); break;
+        }
+        if (rc) return rc;
     }
-    if (rc) return rc;
     mark(h, 1, st);
 
     // 4. flux
@@ -139,12 +151,10 @@ int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, con
         CU(h->d_flux.reserve(count * esize));
         dflux = h->d_flux.ptr;
     }
-    const bool multi = ns > 1;
     const bool aligned = !multi && (h->npt % 2 == 0) && ((reinterpret_cast<uintptr_t>(h->d_time) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(dflux) & (f32 ? 7 : 15)) == 0);
     const int vec = aligned ? 2 : 1;
-    const size_t geo_bytes = (size_t)npv * h->npt * 28;
-    if (!multi && geo_bytes <= (size_t)2 << 30) {
+    if (two_pass) {
         // ---- one sample per point: geometry pass + channel-chunk flux pass ------------------------------
         const size_t npts = (size_t)npv * h->npt;
         CU(h->d_tsgeo.reserve(geo_bytes + 64));
@@ -164,12 +174,17 @@ int ptb_ts_evaluate(ptb_model *h, int64_t npv, int64_t npb, const double *k, con
         FP.galpha = GP.galpha; FP.gap0 = GP.gap0; FP.gdadk = GP.gdadk; FP.gi0 = GP.gi0; FP.flux = dflux;
         FP.npt = h->npt; FP.npv = (int)npv; FP.npb = (int)npb; FP.ng = ng; FP.ldt = ldt;
         FP.nchunks = (int)((npb + TS_CH - 1) / TS_CH);
+        FP.tsw = h->d_tsw.as<double>(); FP.ldp = ldp; FP.istar = ist; FP.k = D.k; FP.nz = nz; FP.rs = rs;
         const long long grid = (long long)npv * FP.nchunks;
         if (grid > 0x7fffffffLL) return fail(h, PTB_EINVAL, "ts_evaluate: grid too large");
-        const size_t smem_fl = (size_t)TS_CH * (ldt + 4) * 8;
+        const size_t smem_fl = fused ? smem_fused : (size_t)TS_CH * (ldt + 4) * 8;
         mark(h, 2, st);
-        if (vec == 2) rc = f32 ? launch_ts_flux2_t<2, float>(h, FP, smem_fl, (unsigned)grid, st) : launch_ts_flux2_t<2, double>(h, FP, smem_fl, (unsigned)grid, st);
-        else rc = f32 ? launch_ts_flux2_t<1, float>(h, FP, smem_fl, (unsigned)grid, st) : launch_ts_flux2_t<1, double>(h, FP, smem_fl, (unsigned)grid, st);
+#define PTB_TS_FLUX2(V, T)                                                                         \
+    (fused ? launch_ts_flux2_t<V, T, true, 13>(h, FP, smem_fl, (unsigned)grid, st)                \
+           : launch_ts_flux2_t<V, T, false, 16>(h, FP, smem_fl, (unsigned)grid, st))
+        if (vec == 2) rc = f32 ? PTB_TS_FLUX2(2, float) : PTB_TS_FLUX2(2, double);
+        else rc = f32 ? PTB_TS_FLUX2(1, float) : PTB_TS_FLUX2(1, double);
+#undef PTB_TS_FLUX2
         if (rc) return rc;
         mark(h, 3, st);
     } else {

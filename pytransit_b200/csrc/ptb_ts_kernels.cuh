@@ -255,7 +255,9 @@ __global__ void __launch_bounds__(256) k_ts_ldm(const __grid_constant__ TsLdmPar
             const int q = pb0 + tid;
             const double kk = P.k[(size_t)ipv * P.npb + q];
             double *rec = P.tsrec + ((size_t)ipv * P.npb + q) * 4;
-            rec[0] = 1.0 / P.istar[(size_t)ipv * P.npb + q];
+            // a disk integral that is not finite makes every in-box point NaN in the reference: (I* - x) / I* (model_trspec.py:91)
+            const double is = P.istar[(size_t)ipv * P.npb + q];
+            rec[0] = isfinite(is) ? 1.0 / is : nan("");
             rec[1] = (kk * kk) / (kmean * kmean);
             rec[2] = kk - kmean;
             rec[3] = 0.0;
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(256) k_ts_flux(const __grid_constant__ TsFluxP
 struct TsGeoParams {
     const double *time, *tsorb, *t0;
     double *galpha, *gap0, *gdadk;  // [npv][npt]
-    int *gi0;                       // [npv][npt]: ld-mean node | TS_FULL, or -1 (flux exactly 1)
+    int *gi0;                       // [npv][npt]: ld-mean node | TS_FULL; -1: outside the box (flux exactly 1); -2: in the box, off the disk
     long long npt;
     int npv, ng;
     double exptime, dg, inv_dg;
@@ -473,6 +475,8 @@ __global__ void __launch_bounds__(256) k_ts_geo(const __grid_constant__ TsGeoPar
                 if (g.i0 >= 0) {
                     al[j] = g.alpha; ap[j] = g.ap0; da[j] = g.dadk;
                     id[j] = g.i0 | (g.full ? TS_FULL : 0);
+                } else {
+                    id[j] = -2;   // inside the box, planet off the disk: (I* - 0) / I* = 1, or NaN when I* is not finite
                 }
             }
         }
@@ -490,12 +494,19 @@ struct TsFlux2Params {
     void *flux;
     long long npt;
     int npv, npb, ng, ldt, nchunks;
+    // fused contraction (FUSED): the CTA computes its chunk's LD means itself from the vector's weight matrix and the
+    // chunk's limb-darkening profiles, and the per-channel records from k and I*
+    const double *tsw, *ldp, *istar, *k;
+    int nz, rs;
 };
 constexpr int TS_CH = 32;  // channels per CTA
 
-template <int VEC, typename TO>
+template <int VEC, typename TO, bool FUSED, int NT>
 __global__ void __launch_bounds__(256) k_ts_flux2(const __grid_constant__ TsFlux2Params P) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];  // [TS_CH][ldt] ld means | [TS_CH][4] records
+    // shared memory: [TS_CH][ldt] ld means | [TS_CH][4] records.  FUSED: the prologue's operands -- the vector's weight
+    // matrix [ng][rs] and the chunk's profiles [TS_CH][nz] -- use the same bytes first (they are dead once the
+    // accumulators sit in registers), so the kernel keeps its ~45 KB footprint and five resident CTAs per SM.
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     double *sLdm = reinterpret_cast<double *>(smem_raw);
     double *sRec = sLdm + (size_t)TS_CH * P.ldt;
@@ -504,8 +515,9 @@ __global__ void __launch_bounds__(256) k_ts_flux2(const __grid_constant__ TsFlux
     const int pb0 = chunk * TS_CH, nch = min(TS_CH, P.npb - pb0);
     const long long npt = P.npt;
     TO *fbase = reinterpret_cast<TO *>(P.flux) + ((size_t)ipv * P.npb + pb0) * npt;
-    const bool good = P.tsorb[(size_t)ipv * TSORB_STRIDE + ORB_GOOD] != 0.0;
-    if (good) {
+    const double *orb = P.tsorb + (size_t)ipv * TSORB_STRIDE;
+    const bool good = orb[ORB_GOOD] != 0.0;
+    if (good && !FUSED) {
         if (tid == 0) {
             mbar_init(&bar, 1);
             const uint32_t b1 = (uint32_t)nch * P.ldt * 8u, b2 = (uint32_t)nch * 32u;
@@ -515,6 +527,60 @@ __global__ void __launch_bounds__(256) k_ts_flux2(const __grid_constant__ TsFlux
         }
         __syncthreads();
         mbar_wait(&bar, 0);
+    }
+    if (good && FUSED) {
+        // ---- prologue: ldm[c][ig] = sum_iz ldp[c][iz] W[ig][iz] for the chunk's channels on the fp64 tensor-core path ----
+        // (model_trspec.py:58-59; mma.sync.m8n8k4: a warp owns 8 channels x half of the g-node tiles; nz % 4 == 0)
+        const int nz = P.nz, rs = P.rs, lane = tid & 31, warp = tid >> 5;
+        double *sW = reinterpret_cast<double *>(smem_raw);       // [ng][rs]   (rows padded with zeros in global memory)
+        double *sA = sW + (size_t)P.ng * rs;                      // [TS_CH][nz]
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            const uint32_t wb = (uint32_t)P.ng * rs * 8u, ab = (uint32_t)nch * nz * 8u;
+            mbar_expect_tx(&bar, wb + ab);
+            tma_load_1d(sW, P.tsw + (size_t)ipv * P.ng * rs, wb, &bar);
+            tma_load_1d(sA, P.ldp + ((size_t)ipv * P.npb + pb0) * nz, ab, &bar);
+        }
+        // per-channel records (model_trspec.py:43,87,91) while the copies are in flight
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+        if (tid < nch) {
+            const double kmean = orb[TSORB_KMEAN];
+            const double kk = P.k[(size_t)ipv * P.npb + pb0 + tid];
+            const double is = P.istar[(size_t)ipv * P.npb + pb0 + tid];
+            r0 = isfinite(is) ? 1.0 / is : nan("");   // a non-finite disk integral: NaN for every in-box point, (I* - x) / I*
+            r1 = (kk * kk) / (kmean * kmean);
+            r2 = kk - kmean;
+        }
+        __syncthreads();
+        mbar_wait(&bar, 0);
+        const int fr = lane >> 2, fc = lane & 3;
+        const int cg = warp & 3, half = warp >> 2;                 // channel group (8 channels), first / second half of the tiles
+        constexpr int NH = (NT + 1) / 2;
+        const int n0 = half * NH, n1 = min(NT, n0 + NH);
+        double acc[NH][2];
+#pragma unroll
+        for (int n = 0; n < NH; ++n) acc[n][0] = acc[n][1] = 0.0;
+        const double *arow = sA + (size_t)(cg * 8 + fr) * nz + fc;   // rows beyond nch: stale bytes, results never read
+        for (int ks = 0; ks < nz / 4; ++ks) {
+            const double av = arow[ks * 4];
+#pragma unroll
+            for (int n = 0; n < NH; ++n) {
+                const int ig = min((n0 + n) * 8 + fr, P.ng - 1);     // g nodes beyond ng alias the last row: never read
+                dmma_m8n8k4(acc[n][0], acc[n][1], av, sW[(size_t)ig * rs + ks * 4 + fc]);
+            }
+        }
+        __syncthreads();   // every warp is done with the operands: their bytes become the ld means and records
+#pragma unroll
+        for (int n = 0; n < NH; ++n)
+            if (n0 + n < n1)
+                *reinterpret_cast<double2 *>(sLdm + (size_t)(cg * 8 + fr) * P.ldt + (n0 + n) * 8 + fc * 2) = make_double2(acc[n][0], acc[n][1]);
+        if (tid < nch) {
+            sRec[tid * 4 + 0] = r0;
+            sRec[tid * 4 + 1] = r1;
+            sRec[tid * 4 + 2] = r2;
+            sRec[tid * 4 + 3] = 0.0;
+        }
+        __syncthreads();
     }
     const int ngm1 = P.ng - 1;
     const size_t gbase = (size_t)ipv * npt;
@@ -536,7 +602,7 @@ __global__ void __launch_bounds__(256) k_ts_flux2(const __grid_constant__ TsFlux
         }
         bool any = false;
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) any |= id[j] >= 0;
+        for (int j = 0; j < VEC; ++j) any |= id[j] != -1;
         if (!__any_sync(__activemask(), any)) {  // the whole warp is out of transit: ones for every channel
 #pragma unroll
             for (int j = 0; j < VEC; ++j) v[j] = 1.0;
@@ -566,6 +632,8 @@ __global__ void __launch_bounds__(256) k_ts_flux2(const __grid_constant__ TsFlux
                     const double ip = (1.0 - al[j]) * row[n0[j]] + al[j] * row[n1[j]];
                     const double x = full[j] ? ap[j] * r01.y : ap[j] + dkk * da[j];
                     v[j] = 1.0 - ip * x * r01.x;
+                } else if (id[j] == -2) {
+                    v[j] = fma(0.0, r01.x, 1.0);
                 }
             }
             ts_store<VEC, TO>(fbase + (size_t)c * npt + i0, v);

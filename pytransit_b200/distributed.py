@@ -13,9 +13,23 @@ from typing import Callable, Tuple
 
 import numpy as np
 
-__all__ = ['shard_bounds', 'shard_population', 'PopulationSharder', 'PeerLnLGather']
+__all__ = ['shard_bounds', 'shard_population', 'PopulationSharder', 'PeerLnLGather', 'bind_to_gpu_numa']
 
 _POP_ARGS = ('k', 'ldc', 't0', 'p', 'a', 'i', 'e', 'w', 'sigma')
+
+
+def bind_to_gpu_numa(device: int) -> bool:
+    """Bind the calling process to the CPUs NVML reports as closest to GPU `device` (its NUMA node), so that the
+    page-locked result arrays this process allocates -- first touched by it -- sit on the memory the GPU writes with the
+    fewest hops.  One process per GPU (torchrun) leaves the ranks unbound otherwise: all eight result arrays may land on
+    node 0.  Returns False when NVML is unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(int(device)))
+        return True
+    except Exception:
+        return False
 
 
 def shard_bounds(npv: int, world: int, rank: int) -> Tuple[int, int]:
@@ -122,8 +136,8 @@ class PeerLnLGather:
     collective.
 
     ``sync='flags'`` (default): the ranks are ordered on the device.  The finishing kernel publishes the step
-    number into every rank's arrival array (system-scope release after its stores) and a one-warp kernel queued
-    behind it waits until all ``world`` shards of this step have landed here -- no host-issued barrier, nothing
+    number into every rank's arrival array (system-scope release after its stores) and its last thread block then
+    waits until all ``world`` shards of this step have landed here -- no host-issued barrier, nothing
     for the host to wait on; the returned tensor is complete for any work queued on the current stream.
     ``sync='barrier'``: one symmetric-memory barrier per step (round-1 behaviour, kept for comparison).
 

@@ -231,6 +231,12 @@ class RoadRunnerModelCUDA(TransitModel):
         check(lib().ptb_graph_stats(self._h, C.byref(a), C.byref(b)), self._h)
         return a.value, b.value
 
+    def measure_fp64_peak(self) -> float:
+        """Measured fp64 FMA throughput of this GPU in TFLOP/s (a DFMA microbenchmark inside the library)."""
+        v = C.c_double()
+        check(lib().ptb_measure_fp64_peak(self._h, C.byref(v)), self._h)
+        return v.value
+
     def set_profiling(self, enabled: bool = True) -> None:
         """Record CUDA events around the setup kernel(s) and the dominant kernel of every call."""
         check(lib().ptb_set_profiling(self._h, int(enabled)), self._h)
@@ -509,7 +515,7 @@ class RoadRunnerModelCUDA(TransitModel):
         stored into slot ``rank`` of every peer's gathered array (device pointers ``peer_ptrs``, mapped into
         this process -- see ``pytransit_b200.distributed.PeerLnLGather``).  With ``flag_ptrs`` (every rank's
         arrival array) and a step number ``seq >= 1`` the ranks are ordered on the device: the finishing kernel
-        publishes ``seq`` to every peer and a one-warp kernel waits for all peers' shards of this step, so work
+        publishes ``seq`` to every peer and its last thread block waits for all peers' shards of this step, so work
         queued on the stream afterwards sees the complete gathered array.  Asynchronous on the current stream."""
         if not getattr(self, '_has_obs', False):
             raise RuntimeError("set_obs must be called before lnlikelihood.")

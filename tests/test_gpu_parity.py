@@ -499,6 +499,37 @@ def test_fp32_mode_population_lnlike_and_device_output(pb, orc, tab):
     assert np.abs(f1.astype(np.float64) - ref[:8, :4999]).max() <= FP32_TOL
 
 
+def test_tsmodel_non_finite_disk_integral(pb, orc, tab):
+    """a channel whose disk integral I* is not finite (the numeric integral of 'logarithmic' /
+    'exponential' as coded) makes the reference return NaN for EVERY point inside the bounding box of that channel --
+    (I* - x) / I*, model_trspec.py:91 -- including the in-box points where the planet does not touch the disk, and 1.0
+    outside the box.  One and several samples per point."""
+    c = wl.config4(npv=5, npb=6, npt=900)
+    c.time = np.linspace(-0.25, 0.25, c.npt)
+    mu = pb.TSModelCUDA('uniform').mu
+    ldp = np.tile(1.0 - 0.4 * (1.0 - mu), (c.npv, c.npb, 1))
+    istar = np.full((c.npv, c.npb), 2.0 * np.pi * (0.5 - 0.4 / 6.0))
+    istar[:, 1] = np.inf
+    istar[:, 3] = np.nan
+    istar[2, 4] = -np.inf
+
+    class Tab(pb.LDModel):
+        def __call__(self, mu, x):
+            return ldp, istar
+    for ns, et in ((1, 0.0), (3, 0.01)):
+        m = pb.TSModelCUDA(Tab())
+        m.set_data(c.time, nsamples=[ns], exptimes=[et])
+        f = m.evaluate(c.k, np.zeros((c.npv, c.npb, 1)), c.t0, c.p, c.a, c.i, c.e, c.w)
+        ref = orc.tsmodel(tab, c.time, c.k, c.t0, c.p, c.a, c.i, c.e, c.w, ns, et, ldp, istar)
+        assert np.array_equal(np.isnan(f), np.isnan(ref)), (ns, np.isnan(f).sum(), np.isnan(ref).sum())
+        ok = ~np.isnan(ref)
+        assert np.abs(f[ok] - ref[ok]).max() <= TIGHT
+        bad = np.isnan(ref[:, 1])
+        assert bad.any() and not bad.all()                     # NaN inside the box only
+        assert np.isnan(ref[:, 3]).sum() == bad.sum() and not np.isnan(ref[:, 0]).any()
+        assert (ref[:, 0][bad] == 1.0).any()                   # in-box points without overlap exist: they are NaN in the bad channels
+
+
 def test_tsmodel_fp32_output_mode(pb, golden):
     """TSModelCUDA(precision='fp32') (north_star: opt-in fp32 mode <= 1 ppm): float32 flux within 1 ppm of the reference's
     tsmodel_serial output for both weight modes, one and several samples per point, NaN block, odd npt (scalar stores),
@@ -671,6 +702,40 @@ def test_base_lpf_on_device_vs_reference_golden(pb, golden):
     assert f_d.is_cuda and np.array_equal(f_d.cpu().numpy(), flux, equal_nan=True)
     with pytest.raises(ValueError):
         lpf.lnlikelihood(pvp[:, :10])
+
+
+def test_epoch_fold_with_wide_boxes_close_in_orbits(pb, orc, tab):
+    """the phase fold multiplies by 1/p instead of dividing (model_full.py:88); the two can only
+    differ half a period from mid-transit.  The bounding box is widest for a -> 1+ and large k: the contact search
+    brackets at 2/vx = p/(pi a) < 0.32 p, so with the 0.003 d pad it stays inside +-p/2 for any a > 1.  Checked here
+    where it is tightest: a/R* in (1, 1.5], k up to 0.5, short periods, a time axis covering many whole periods, grazing
+    to central -- against the oracle's division-based fold, point for point."""
+    rng = np.random.default_rng(73)
+    npv, npt = 96, 9000
+    time = np.sort(rng.uniform(0.0, 12.0, npt))
+    k = rng.uniform(0.1, 0.5, (npv, 1))
+    t0 = rng.uniform(0.0, 1.0, (npv, 1))
+    p = rng.uniform(0.5, 2.0, npv)
+    a = rng.uniform(1.001, 1.5, npv)
+    b = rng.uniform(0.0, 1.0, npv)
+    inc = np.arccos(np.clip(b / a, 0, 1))
+    e, w = np.zeros(npv), np.zeros(npv)
+    e[::3] = rng.uniform(0.0, 0.2, e[::3].size)          # some eccentric ones (periastron may dip below the surface)
+    w[::3] = rng.uniform(0, 2 * np.pi, w[::3].size)
+    ldc = np.tile([0.3, 0.2], (npv, 1, 1))
+    m = pb.RoadRunnerModelCUDA('quadratic')
+    m.set_data(time)
+    flux = m.evaluate(k, ldc, t0, p, a, inc, e, w)
+    ldp, istar = orc.evaluate_ld('quadratic', tab.mu, ldc)
+    z1 = np.zeros(1, np.int64)
+    ref = orc.rr_full(tab, time, k, t0, p, a, inc, e, w, np.zeros(npt, np.int64), z1, z1, np.ones(1, np.int64), np.zeros(1), ldp, istar)
+    assert np.array_equal(np.isnan(flux), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert np.abs(flux[ok] - ref[ok]).max() <= FLUX_TOL
+    box = m.stage('bbox')
+    half = np.abs(box).max(axis=1) + 0.003
+    assert (half < 0.5 * p).all() and (half / p).max() > 0.25        # wide boxes, still inside half a period
+    assert (ref[ok] < 1).mean() > 0.3                                   # a third of all points are in transit
 
 
 def test_model_derivatives_vs_reference_golden(pb, golden):
