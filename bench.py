@@ -194,10 +194,13 @@ def numba_baseline(name: str, c, seconds: float, max_rows: int = 512):
         prof, (x0, dx), (y0, dy), (z0, dz) = c.table
         from pytransit.models.ldmodel import LDModel
 
-        class Tab(LDModel):
+        class Tab(LDModel):      # stellar parameters -> profiles, as LDTkLDModel.__call__ does (models/ldtkldm.py:74-89)
+            rows = 1
+
             def __call__(self, mu, x):
-                ldp = ref.ldtkldm.trilinear_interpolation_set(prof, x[:, 0].copy(), x[:, 1].copy(), x[:, 2].copy(), x0, dx, prof.shape[0],
-                                                              y0, dy, prof.shape[1], z0, dz, prof.shape[2])
+                sl = slice(0, self.rows)
+                ldp = ref.ldtkldm.trilinear_interpolation_set(prof, c.teff[sl].copy(), c.logg[sl].copy(), c.metal[sl].copy(), x0, dx,
+                                                              prof.shape[0], y0, dy, prof.shape[1], z0, dz, prof.shape[2])
                 return ldp, ref.ldtkldm.integrate_profiles_set(mu, ldp)
 
             def _evaluate(self, mu, x):
@@ -205,14 +208,16 @@ def numba_baseline(name: str, c, seconds: float, max_rows: int = 512):
 
             def _integrate(self, x):
                 raise NotImplementedError
-        m = ref.TSModel(Tab(), nthreads=1)
+        tab = Tab()
+        m = ref.TSModel(tab, nthreads=1)
         m.set_data(c.time)
         del m0
 
         def run(rows):
             sl = slice(0, rows)
-            x = np.column_stack([c.teff[sl], c.logg[sl], c.metal[sl]])
-            m.evaluate(c.k[sl], x, c.t0[sl], c.p[sl], c.a[sl], c.i[sl], c.e[sl], c.w[sl])
+            tab.rows = rows
+            # the reference insists on a 3-D coefficient array for a population; the tabulated model does not read it
+            m.evaluate(c.k[sl], np.zeros((rows, c.npb, 3)), c.t0[sl], c.p[sl], c.a[sl], c.i[sl], c.e[sl], c.w[sl])
             return rows * c.npb * c.npt
         max_rows = min(max_rows, 16)
     elif name == 'c1':

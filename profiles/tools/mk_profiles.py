@@ -9,7 +9,7 @@ bench lines, the ncu launch lists, and per-kernel summaries of the `ncu --set fu
 """
 import csv, io, json, shutil, subprocess, sys
 from pathlib import Path
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 G, P = ROOT / 'gpurun_out', ROOT / 'profiles'
 SUMM = len(sys.argv) > 1 and sys.argv[1] == '--summarise'
 tag = sys.argv[1] if (len(sys.argv) > 1 and not SUMM) else 'r01'
