@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "ptb_kernels.cuh"
+#include "ptb_ss_kernels.cuh"
 #include "ptb_ts_kernels.cuh"
 
 using namespace ptb;
@@ -975,7 +976,10 @@ int launch_rr_setup(ptb_model *h, const ModelArgs &A, const Staged &D, cudaStrea
 
 template <int VEC, bool SINGLE, bool LNL, bool S1, typename T>
 int launch_points_t(ptb_model *h, const PointsParams &P, size_t smem, cudaStream_t st) {
-    auto kern = k_rr_points<VEC, SINGLE, LNL, S1, T>;
+    // one sample per point: k_rr_points; supersampled data sets: k_rr_points_ss (ptb_ss_kernels.cuh)
+    void (*kern)(PointsParams);
+    if constexpr (S1) kern = k_rr_points<VEC, SINGLE, LNL, T>;
+    else kern = k_rr_points_ss<VEC, SINGLE, LNL, T>;
     const int slot = (sizeof(T) == 4 ? 16 : 0) + (S1 ? 8 : 0) + (VEC == 2 ? 4 : 0) + (SINGLE ? 2 : 0) + (LNL ? 1 : 0);
     if (h->pt_occ[slot] == 0 || h->pt_occ_smem[slot] != smem) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1056,8 +1060,8 @@ int launch_points(ptb_model *h, int64_t npv, void *flux, const double *isig2, cu
     P.frac_tab = ((long long)h->nlc * h->ns_max <= PT_FRAC_MAX) ? 1 : 0;
     const bool s1 = (h->ns_max == 1);
     const size_t nfrac = P.frac_tab ? (size_t)h->nlc * h->ns_max : 0;
-    const size_t shared_bytes = ((((size_t)h->nlc) * 8 + ((size_t)h->nlc + nfrac) * tsize + 3 * (size_t)h->nlc * 4) + 127) & ~size_t(127);
-    const size_t smem = shared_bytes + pt_warp_bytes(s1 ? 0 : P.ssc, h->recstride, tsize) * PT_WARPS;
+    const size_t smem = s1 ? pt_shared_bytes((int)h->nlc, tsize) + pt_warp_bytes(h->recstride, tsize) * PT_WARPS
+                           : ss_shared_bytes((int)h->nlc, (int)nfrac, tsize) + ss_warp_bytes(P.ssc, h->recstride, tsize) * PT_WARPS;
     if (smem > 220 * 1024)
         return fail(h, PTB_EINVAL, "npb=%lld passbands x nlc=%lld light curves need %zu bytes of shared memory (> 220 KB)",
                     (long long)h->npb, (long long)h->nlc, smem);

@@ -520,19 +520,10 @@ struct PointsParams {
     double dg, inv_dg;
 };
 
-// resident CTAs per SM: three for the one-sample kernels (<= 85 registers, no spills), two for the
-// supersampled ones (the sub-sample loop keeps more state live)
+// resident CTAs per SM of the one-sample kernel (<= 85 registers); the supersampled kernel has its own bound
+// (ptb_ss_kernels.cuh)
 #ifndef PT_MINB_S1
 #define PT_MINB_S1 3
-#endif
-#ifndef PT_MINB_SS
-#define PT_MINB_SS 2
-#endif
-// record slots per warp of the supersampled kernels: 1 = fetched at the start of the item (their items are tens of
-// thousands of points long, the fetch is noise; measured on C3: 5.86 ms against 6.28 ms with the prefetching
-// double slot, whose bookkeeping costs registers in a kernel that spills at its 128-register cap), 2 = prefetched
-#ifndef PT_NREC_SS
-#define PT_NREC_SS 1
 #endif
 constexpr int PT_THREADS = 256;
 constexpr int PT_WARPS = PT_THREADS / 32;
@@ -540,7 +531,7 @@ constexpr int PT_BLOCK = 64;           // points per classification block
 constexpr int PT_MAXBLK = 2048;        // blocks per item (hit bitmap in shared memory)
 constexpr int PT_QCAP = 96;            // in-box point queue: < 32 carried + 64 from one block
 constexpr int PT_LCAP = 64;            // limb sample queue: < 32 carried + 32 from one sub-sample step
-constexpr int PT_COLS = 33;             // stride of the supersampled kernels' per-lane limb columns (odd: a lane's samples and
+constexpr int PT_COLS = 33;            // stride of the supersampled kernel's per-lane limb columns (odd: a lane's samples and
                                        // consecutive lanes' samples fall into different banks)
 #ifndef PT_SSC_MAX_
 #define PT_SSC_MAX_ 12
@@ -549,30 +540,33 @@ constexpr int PT_SSC_MAX = PT_SSC_MAX_;  // exposure sub-samples buffered per pa
 constexpr int PT_FRAC_MAX = 1024;      // entries of the tabulated sub-sample offsets
 constexpr double PT_EPS = 1e-9;        // classification margin, in periods (>> rounding, << the 0.003 d pad)
 
-// Warp-private shared memory: queues, two record slots, the hit bitmap, two mbarriers, the
-// sub-sample buffer (none when every point has one sample) and, in fp32 mode, the record converted to
-// float.  T is the sample arithmetic / output type (double, or float in the opt-in fp32 mode).
-__host__ __device__ inline int pt_nrec(int ssc) { return ssc == 0 ? 2 : PT_NREC_SS; }
-__host__ __device__ inline int pt_lcap(int ssc) { return ssc == 0 ? PT_LCAP : 0; }   // limb queue: one-sample kernels only
-__host__ __device__ inline size_t pt_warp_bytes(int ssc, int recstride, int tsize) {
+// Warp-private shared memory of k_rr_points: queues, two record slots (double buffered), the hit bitmap, two
+// mbarriers and, in fp32 mode, the record converted to float.  T is the sample arithmetic / output type (double, or
+// float in the opt-in fp32 mode).
+__host__ __device__ inline size_t pt_warp_bytes(int recstride, int tsize) {
     const size_t rec_t = (tsize == 4) ? (((size_t)recstride * 4 + 15) & ~size_t(15)) : 0;
-    const size_t n = (size_t)(PT_QCAP + 2 * pt_lcap(ssc) + 2 * PT_COLS * ssc) * tsize + (size_t)(2 * PT_QCAP + 2 * pt_lcap(ssc)) * 4 + PT_MAXBLK / 8 + 16 +
-                     (size_t)pt_nrec(ssc) * recstride * 8 + rec_t;
+    const size_t n = (size_t)(PT_QCAP + 2 * PT_LCAP) * tsize + (size_t)(2 * PT_QCAP + 2 * PT_LCAP) * 4 + PT_MAXBLK / 8 + 16 +
+                     (size_t)2 * recstride * 8 + rec_t;
     return (n + 15) & ~size_t(15);   // the next warp's mbarriers and TMA record slots stay 16-byte aligned
+}
+// CTA-wide part: the per-light-curve tables
+__host__ __device__ inline size_t pt_shared_bytes(int nlc, int tsize) {
+    (void)tsize;
+    return (((size_t)nlc) * 8 + 2 * (size_t)nlc * 4 + 127) & ~size_t(127);   // box pad, ld-row offset, epoch id
 }
 
 template <typename T>
 struct WarpScratch {
     unsigned char *base;
     int nrec;  // record slots (2: double buffered)
-    int lcap;  // entries of the limb queue (0 in the supersampled kernels)
+    int lcap;  // entries of the limb queue
     __device__ __forceinline__ WarpScratch(unsigned char *b, int nrec_, int lcap_) : base(b), nrec(nrec_), lcap(lcap_) {}
     __device__ __forceinline__ T *q_tc() const { return reinterpret_cast<T *>(base); }
     __device__ __forceinline__ T *l_z() const { return q_tc() + PT_QCAP; }
     __device__ __forceinline__ T *l_ip() const { return l_z() + lcap; }
     __device__ __forceinline__ int *q_ipt() const { return reinterpret_cast<int *>(l_ip() + lcap); }
     __device__ __forceinline__ int *q_lc() const { return q_ipt() + PT_QCAP; }
-    __device__ __forceinline__ int *l_slot() const { return q_lc() + PT_QCAP; }   // S1: the point index
+    __device__ __forceinline__ int *l_slot() const { return q_lc() + PT_QCAP; }   // the point index
     __device__ __forceinline__ int *l_row() const { return l_slot() + lcap; }
     __device__ __forceinline__ unsigned *hit() const { return reinterpret_cast<unsigned *>(l_row() + lcap); }
     __device__ __forceinline__ uint64_t *bar() const { return reinterpret_cast<uint64_t *>(hit() + PT_MAXBLK / 32); }
@@ -581,12 +575,6 @@ struct WarpScratch {
     }
     // fp32 mode: the current record converted to float (16-byte aligned); fp64: unused
     __device__ __forceinline__ T *rec_t(int recstride) const { return reinterpret_cast<T *>(rec(nrec, recstride)); }
-    // supersampled kernels: per-lane columns [ssc][PT_COLS] of the limb samples' separations (replaced by their flux
-    // values) and LD means
-    __device__ __forceinline__ T *cols(int recstride) const {
-        const size_t rt = (sizeof(T) == 4) ? (((size_t)recstride * 4 + 15) & ~size_t(15)) : 0;
-        return reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(rec(nrec, recstride)) + rt);
-    }
 };
 
 // VEC consecutive points per lane: time stamps are always fp64, fluxes are T.
@@ -627,10 +615,8 @@ struct VecIO<2, float> {
 template <typename T>
 struct DrainCtx {
     const PointsParams *P;
-    const T *sEt, *sFrac;          // per light curve: exposure time; tabulated (s+1-0.5)/ns-0.5 or null
-    const int *sNs, *sRow;         // per light curve: nsamples, offset of the passband row in the ld block
-    int ns1, row1;                 // single light curve: the same as scalars
-    T et1;
+    const int *sRow;               // per light curve: offset of the passband row in the ld block
+    int row1;                      // single light curve: the same as a scalar
     int lane;
 };
 
@@ -752,151 +738,23 @@ __device__ __forceinline__ double drain_points(const DrainCtx<T> &c, const WarpS
     return chi;
 }
 
-// Supersampled drain (nsamples > 1): `n` (<= 32) queued in-box points starting at queue slot `base`, one point per
-// lane; the lane walks its exposure sub-samples in order (model_full.py:93-99).  Lean straight-line step: the
-// sub-sample offset exptime*((s-0.5)/ns-0.5) comes from a shared-memory table built with the reference's own
-// operations, the per-point constants (1+k, |1-k|, full-overlap area / I*, the no-overlap value) are hoisted, and
-// everything off the limb is accumulated in a register.  A sample on the limb (sqrt + 2 atan2 lens area, ~1/4 of
-// them) only drops its separation and LD mean into the lane's own shared-memory column -- no ballot, no
-// compaction in the step.  After the pass an inclusive scan of the per-lane counts numbers the limb samples of the
-// warp; lane q of each lens-area pass finds sample q's owner by a 5-step search over the scanned counts (shuffles),
-// evaluates it and writes the value back into the owner's column, and every lane then adds its column in exposure
-// order.  A point's arithmetic depends on nothing but the point: results are bit-reproducible across chunkings.
-template <bool SINGLE_LC, bool LNL, typename T>
-__device__ __forceinline__ double drain_points_ss(const DrainCtx<T> &c, const WarpScratch<T> &ws, const T *rt, T *frow,
-                                                  const double *isig2, int base, int n) {
-    const PointsParams &P = *c.P;
-    const int lane = c.lane, ng = P.ng, S = P.ns_max, SSC = P.ssc;
-    const T dg = (T)P.dg, inv_dg = (T)P.inv_dg, one = T(1), pi = T(kPi), qnan = T(nan(""));
-    const T *ld = rt + P.rec_ld;
-    T *colz = ws.cols(P.recstride), *colip = colz + PT_COLS * SSC;
-    T cx[5], cy[5];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) { cx[j] = rt[j]; cy[j] = rt[5 + j]; }
-
-    const bool valid = lane < n;
-    int ipt = 0, lc = 0, ns = 0, rowoff = c.row1;
-    T tc = T(0), et = T(0);
-    if (valid) {
-        ipt = ws.q_ipt()[base + lane];
-        tc = ws.q_tc()[base + lane];
-        if (SINGLE_LC) {
-            ns = c.ns1;
-            et = c.et1;
-        } else {
-            lc = ws.q_lc()[base + lane];
-            ns = c.sNs[lc];
-            et = c.sEt[lc];
-            rowoff = c.sRow[lc];
-        }
-    }
-    const T *row = ld + rowoff;
-    const T k = row[ng], inv1k = row[ng + 1], inv_istar = row[ng + 2], k2 = row[ng + 3];
-    // per-point constants of the area cases that need no lens formula (common.py:52-73)
-    const T zout = one + k, zin = fabs(one - k);
-    const T qfull = ((k > one) ? pi : pi * k2) * inv_istar;   // planet covers the star: area pi; else pi k^2
-    const T c_out = fma(T(0), inv_istar, one);                 // no overlap: (I* - 0) / I* = 1, NaN when 1/I* is NaN
-    const T *off = c.sFrac ? c.sFrac + (size_t)lc * S : nullptr;
-
-    T sum = T(0);
-    for (int s0 = 0; s0 < S; s0 += SSC) {
-        const int SS = min(min(SSC, S - s0), ns - s0);   // ns = 0 for lanes without a point
-        int cnt = 0;                                      // this lane's limb samples of the pass
-        T *mz = colz + lane, *mip = colip + lane;
-        for (int j = 0; j < SS; ++j) {
-            // exposure offset exptime*((s+1-0.5)/ns - 0.5) (model_full.py:94), tabulated per light curve
-            T t;
-            if (off) t = tc + off[s0 + j];
-            else t = tc + (T)__dmul_rn((double)et, ((s0 + j + 1) - 0.5) / ns - 0.5);
-            const T z = sep_poly<T>(t, cx, cy);
-            const T g = z * inv1k;       // >= 0, or NaN; a negative g needs k < -1: k_rr_ldm stores NaN rows for that
-            const T fl = floor(g * inv_dg);
-            const T a = (g - fl * dg) * inv_dg;
-            const int i = (int)fl;       // saturating conversion; NaN -> 0
-            const int i0 = min(i, ng - 1), i1 = min(i + 1, ng - 1);   // i >= 0; g > 1 means z > 1 + k: value unused
-            const T ip = (one - a) * row[i0] + a * row[i1];
-            if (zout <= z) {
-                sum += c_out;
-            } else if (zin < z) {        // on the limb: deferred
-                *mz = z;
-                *mip = ip;
-                mz += PT_COLS;
-                mip += PT_COLS;
-                ++cnt;
-            } else {
-                sum += (z <= zin) ? fma(-ip, qfull, one) : qnan;
-            }
-        }
-        // number the warp's limb samples: inclusive scan of the per-lane counts
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        __syncwarp();
-        for (int q0 = 0; q0 < total; q0 += 32) {
-            const int q = q0 + lane;
-            int o = 0;   // owner of sample q: the number of lanes whose inclusive count is <= q
-#pragma unroll
-            for (int st = 16; st > 0; st >>= 1) {
-                const int v = __shfl_sync(0xffffffffu, incl, o + st - 1);
-                if (v <= q) o += st;
-            }
-            o = min(o, 31);
-            const int r = q - (__shfl_sync(0xffffffffu, incl, o) - __shfl_sync(0xffffffffu, cnt, o));
-            const int ro = SINGLE_LC ? 0 : __shfl_sync(0xffffffffu, rowoff, o);
-            if (q < total) {
-                const T *r2 = SINGLE_LC ? row : ld + ro;
-                T *slot = colz + r * PT_COLS + o;
-                T area, kap;
-                kite_area<T>(r2[ng], r2[ng + 3], *slot, area, kap);
-                *slot = one - colip[r * PT_COLS + o] * area * r2[ng + 2];
-            }
-        }
-        __syncwarp();
-        for (int r = 0; r < cnt; ++r) sum += colz[r * PT_COLS + lane];   // this lane's limb values, in exposure order
-        __syncwarp();
-    }
-    double chi = 0.0;
-    if (valid) {
-        const T f = sum / ns;
-        if (LNL) {
-            const int b = P.blk ? P.blk[ipt] : 0;
-            if (b >= 0) {
-                const double d = P.obs[ipt] - (double)f;
-                chi = d * d * isig2[b];
-            }
-        } else {
-            frow[ipt] = f;
-        }
-    }
-    return chi;
-}
-
-template <int VEC, bool SINGLE_LC, bool LNL, bool S1, typename T>
-__global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr_points(const __grid_constant__ PointsParams P) {
+template <int VEC, bool SINGLE_LC, bool LNL, typename T>
+__global__ void __launch_bounds__(PT_THREADS, PT_MINB_S1) k_rr_points(const __grid_constant__ PointsParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr bool F32 = sizeof(T) == 4;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long npt = P.npt;
-    const int S = P.ns_max, nlc = P.nlc;
+    const int nlc = P.nlc;
     const long long nitems = (long long)P.npv * P.nchunks;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    // dynamic smem: [per-light-curve tables] [sub-sample offsets] [warp-private area x 8]
+    // dynamic smem: [per-light-curve tables] [warp-private area x 8]
     double *sPad = reinterpret_cast<double *>(smem_raw);
-    T *sEt = reinterpret_cast<T *>(sPad + nlc);
-    T *sFrac = sEt + nlc;
-    const int nfrac = P.frac_tab ? nlc * S : 0;
-    int *sNs = reinterpret_cast<int *>(sFrac + nfrac);
-    int *sRow = sNs + nlc;
+    int *sRow = reinterpret_cast<int *>(sPad + nlc);
     int *sEp = sRow + nlc;
-    const size_t shared_bytes = ((((size_t)nlc) * 8 + ((size_t)nlc + nfrac) * sizeof(T) + 3 * (size_t)nlc * 4) + 127) & ~size_t(127);
-    constexpr int NREC = S1 ? 2 : PT_NREC_SS;
-    const WarpScratch<T> ws(smem_raw + shared_bytes + (size_t)warp * pt_warp_bytes(S1 ? 0 : P.ssc, P.recstride, (int)sizeof(T)), NREC, S1 ? PT_LCAP : 0);
+    constexpr int NREC = 2;
+    const WarpScratch<T> ws(smem_raw + pt_shared_bytes(nlc, (int)sizeof(T)) + (size_t)warp * pt_warp_bytes(P.recstride, (int)sizeof(T)), NREC, PT_LCAP);
     unsigned *s_hit = ws.hit();
     uint64_t *bar = ws.bar();
 
@@ -915,21 +773,13 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
     // item-independent per-light-curve tables
     for (int lc = tid; lc < nlc; lc += PT_THREADS) {
         sPad[lc] = 0.003 + P.exptimes[lc];  // model_full.py:69-70
-        sEt[lc] = (T)P.exptimes[lc];
-        sNs[lc] = P.nsamples[lc];
         sRow[lc] = P.pbids[lc] * P.lds;
         sEp[lc] = P.epids[lc];
-    }
-    for (int i = tid; i < nfrac; i += PT_THREADS) {   // exptimes[ilc]*((isample-0.5)/nsamples[ilc] - 0.5), model_full.py:94
-        const int lc = i / S, s = i - lc * S;
-        sFrac[i] = (T)__dmul_rn(P.exptimes[lc], ((s + 1) - 0.5) / P.nsamples[lc] - 0.5);
     }
     __syncthreads();  // the only CTA-wide barrier: from here on the warps are independent workers
 
     DrainCtx<T> dctx;
-    dctx.P = &P; dctx.sEt = sEt; dctx.sFrac = P.frac_tab ? sFrac : nullptr; dctx.sNs = sNs; dctx.sRow = sRow;
-    dctx.ns1 = sNs[0]; dctx.row1 = sRow[0]; dctx.et1 = sEt[0];
-    dctx.lane = lane;
+    dctx.P = &P; dctx.sRow = sRow; dctx.row1 = sRow[0]; dctx.lane = lane;
     const double pad1 = sPad[0];
     const int ep1 = sEp[0];
     T *flux = reinterpret_cast<T *>(P.flux);
@@ -1169,8 +1019,7 @@ __global__ void __launch_bounds__(PT_THREADS, S1 ? PT_MINB_S1 : PT_MINB_SS) k_rr
             while (qn >= 32 || (!live && (qn > 0 || nl > 0))) {
                 const int n = min(qn, 32);
                 qn -= n;
-                if (S1) chi += drain_points<SINGLE_LC, LNL, T>(dctx, ws, rt, frow, isig2, qn, n, nl, !live && qn == 0);
-                else chi += drain_points_ss<SINGLE_LC, LNL, T>(dctx, ws, rt, frow, isig2, qn, n);
+                chi += drain_points<SINGLE_LC, LNL, T>(dctx, ws, rt, frow, isig2, qn, n, nl, !live && qn == 0);
             }
             if (!live) break;
         }

@@ -1,0 +1,599 @@
+// ptb_ss_kernels.cuh -- the npv x npt pass for supersampled data sets (some light curve has nsamples > 1):
+// phase fold, box test, the exposure-averaged flux (model_full.py:76-99) and the optional fused chi^2.
+//
+// Same decomposition as k_rr_points (ptb_kernels.cuh): a persistent grid whose warps pull items (parameter vector x
+// chunk of the time axis) from a global counter, classify the item's 64-point blocks against the transit windows,
+// fill the untouched ones with 1.0 and fold the touched ones point by point.  What differs is where the time goes:
+// with ten sub-samples per point the kernel is bound by instruction issue in the per-sample arithmetic, not by the
+// flux store, so this kernel is organised around the sample loop's registers and occupancy:
+//
+//   * fold and sample evaluation alternate in long PHASES instead of block by block: the fold phase walks touched
+//     blocks until the warp's queue holds ~SS_QCAP in-box points (4 bytes each: only the point index is queued, the
+//     folded time is recomputed by the drain), the drain phase then evaluates them 32 at a time.  Each phase is a real
+//     function (`ss_fold`, `ss_drain_phase`: __noinline__) with its own register allocation; what survives a phase
+//     boundary is warp-uniform and lives in a small shared-memory frame, so the driver loop keeps nothing alive
+//     across the calls: 80 registers, three CTAs of 256 threads per SM (the block-by-block version needed 128, with
+//     the fold state spilled around the sample loop);
+//   * everything the phases need that does not depend on the item lives in shared memory (a copy of the kernel
+//     parameters, the per-light-curve tables, the warp's record slot);
+//   * the fold step handles a block inside one light curve with block-constant window and transit centre, two points
+//     per lane and ONE compaction for both; blocks that straddle light curves take a separate general path;
+//   * the sample step is straight fp64 arithmetic: separation (two Horner quartics, rsqrt + one coupled Newton
+//     step: 2^-43), LD-mean node by a float->int floor conversion, lerp as one fused multiply-add on the node
+//     difference; a sample on the stellar limb only drops its separation into the lane's shared-memory column;
+//   * limb samples (sqrt + 2 atan2 lens area, common.py:52-73) are numbered by a warp scan and evaluated 32 at a
+//     time by full warps, each value written back into its owner's column; every lane then adds its column in
+//     exposure order.  A point's arithmetic depends on nothing but the point.
+#pragma once
+#include "ptb_kernels.cuh"
+
+namespace ptb {
+
+#ifndef PT_MINB_SS2
+#define PT_MINB_SS2 3
+#endif
+#ifndef SS_QCAP_
+#define SS_QCAP_ 256
+#endif
+constexpr int SS_QCAP = SS_QCAP_;   // in-box points queued per fold phase (a fold step adds up to 64)
+constexpr int SS_FRAME = 16;        // ints of the warp's phase frame
+
+// Warp-private shared memory of the supersampled kernel: limb columns, point queue (index + light curve), hit bitmap,
+// phase frame, mbarrier, record slot (+ its float copy in fp32 mode).
+__host__ __device__ inline size_t ss_tpart(int ssc, int tsize) { return ((size_t)(ssc * PT_COLS) * tsize + 15) & ~size_t(15); }
+__host__ __device__ inline size_t ss_warp_bytes(int ssc, int recstride, int tsize) {
+    const size_t rec_t = (tsize == 4) ? (((size_t)recstride * 4 + 15) & ~size_t(15)) : 0;
+    return ss_tpart(ssc, tsize) + (size_t)2 * SS_QCAP * 4 + PT_MAXBLK / 8 + SS_FRAME * 4 + 16 + (size_t)recstride * 8 + rec_t;
+}
+// CTA-wide part: a copy of the kernel parameters, then the per-light-curve tables
+constexpr size_t SS_PARAM_BYTES = (sizeof(PointsParams) + 127) & ~size_t(127);
+__host__ __device__ inline size_t ss_shared_bytes(int nlc, int nfrac, int tsize) {
+    return SS_PARAM_BYTES + ((((size_t)nlc) * 8 + ((size_t)nlc + nfrac) * tsize + 3 * (size_t)nlc * 4 + 127) & ~size_t(127));
+}
+
+template <typename T>
+struct SsWarp {
+    unsigned char *base;
+    int ssc, recstride;
+    __device__ __forceinline__ SsWarp(unsigned char *b, int ssc_, int recstride_) : base(b), ssc(ssc_), recstride(recstride_) {}
+    __device__ __forceinline__ T *colz() const { return reinterpret_cast<T *>(base); }   // per-lane columns [ssc][PT_COLS] of limb samples
+    __device__ __forceinline__ int *q_ipt() const { return reinterpret_cast<int *>(base + ss_tpart(ssc, (int)sizeof(T))); }
+    __device__ __forceinline__ int *q_lc() const { return q_ipt() + SS_QCAP; }
+    __device__ __forceinline__ unsigned *hit() const { return reinterpret_cast<unsigned *>(q_lc() + SS_QCAP); }
+    __device__ __forceinline__ volatile int *frame() const { return reinterpret_cast<volatile int *>(hit() + PT_MAXBLK / 32); }
+    __device__ __forceinline__ uint64_t *bar() const { return reinterpret_cast<uint64_t *>(hit() + PT_MAXBLK / 32 + SS_FRAME); }
+    __device__ __forceinline__ double *rec() const { return reinterpret_cast<double *>(bar() + 2); }
+    __device__ __forceinline__ T *rec_t() const { return reinterpret_cast<T *>(rec() + recstride); }   // fp32 mode only
+};
+// slots of the phase frame (warp-uniform values)
+enum : int { FR_WI = 0, FR_WBITS, FR_CUR, FR_QN, FR_DONE, FR_IPV, FR_CHUNK, FR_BBEG, FR_BEND, FR_NEXT_LO, FR_NEXT_HI, FR_ITER };
+
+// the per-light-curve tables behind the parameter copy
+template <typename T>
+struct SsTables {
+    double *sPad;
+    T *sEt, *sFrac;
+    int *sNs, *sRow, *sEp;
+    int nfrac;
+    __device__ __forceinline__ SsTables(unsigned char *smem, int nlc, int S, int frac_tab) {
+        sPad = reinterpret_cast<double *>(smem + SS_PARAM_BYTES);
+        sEt = reinterpret_cast<T *>(sPad + nlc);
+        sFrac = sEt + nlc;
+        nfrac = frac_tab ? nlc * S : 0;
+        sNs = reinterpret_cast<int *>(sFrac + nfrac);
+        sRow = sNs + nlc;
+        sEp = sRow + nlc;
+    }
+};
+
+// what every phase function starts with: the parameter copy, the tables and the warp's private area
+#define SS_PHASE_PROLOGUE(T)                                                                                                   \
+    extern __shared__ __align__(128) unsigned char smem_raw[];                                                                 \
+    const PointsParams &P = *reinterpret_cast<const PointsParams *>(smem_raw);                                                 \
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                                                                \
+    const SsTables<T> tb(smem_raw, P.nlc, P.ns_max, P.frac_tab);                                                               \
+    const SsWarp<T> ws(smem_raw + ss_shared_bytes(P.nlc, tb.nfrac, (int)sizeof(T)) +                                           \
+                           (size_t)warp * ss_warp_bytes(P.ssc, P.recstride, (int)sizeof(T)),                                   \
+                       P.ssc, P.recstride);                                                                                    \
+    volatile int *fr = ws.frame()
+
+// sqrt for the separation: the operand is a sum of squares (+0, positive, or NaN).  MUFU.RSQ64H + one coupled Newton
+// step (2^-43 relative); +0 and subnormal operands are lifted to the smallest normal number by an integer max on the
+// high word (the separation becomes 1.5e-154 instead of 0), NaN passes through.
+__device__ __forceinline__ double sqrt_sep(double x) {
+    const unsigned hi = max((unsigned)__double2hiint(x), 0x00100000u);
+    x = __hiloint2double((int)hi, __double2loint(x));
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double g = x * r, h = 0.5 * r;
+    return fma(g, fma(-h, g, 0.5), g);
+}
+__device__ __forceinline__ float sqrt_sep(float x) { return sqrtf(x); }
+
+__device__ __forceinline__ int floor_to_int(double x) { return __double2int_rd(x); }   // saturating, NaN -> 0
+__device__ __forceinline__ int floor_to_int(float x) { return __float2int_rd(x); }
+
+// next set bit of the item's hit bitmap (-1: none left)
+__device__ __forceinline__ int ss_next_block(int &wi, unsigned &wbits, int nwords, const unsigned *s_hit) {
+    while (wbits == 0u) {
+        if (++wi >= nwords) return -1;
+        wbits = s_hit[wi];
+    }
+    const int j = __ffs(wbits) - 1;
+    wbits &= wbits - 1;
+    return wi * 32 + j;
+}
+
+// ---- fold phase: exact per-point fold + box test over touched blocks (model_full.py:88-91) until the queue holds
+// more than SS_QCAP - 64 in-box points or the item's blocks are exhausted.  The fluxes of the blocks' points are set
+// to 1.0 here (the drain overwrites the in-box ones); in likelihood mode the out-of-box points add their chi^2 here.
+// Returns the lane's chi^2 increment.
+template <int VEC, bool SINGLE_LC, bool LNL, typename T>
+__device__ __noinline__ double ss_fold() {
+    SS_PHASE_PROLOGUE(T);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned *s_hit = ws.hit();
+    int *q_ipt = ws.q_ipt(), *q_lc = ws.q_lc();
+    int qn = fr[FR_QN];
+    const int ipv = fr[FR_IPV], bbeg = fr[FR_BBEG], nwords = (fr[FR_BEND] - bbeg + 31) >> 5;
+    int wi = fr[FR_WI];
+    unsigned wbits = (unsigned)fr[FR_WBITS];
+    int cur = fr[FR_CUR];
+    const double *rec = ws.rec();
+    const double p = rec[ORB_P], invp = rec[ORB_INVP], T1 = rec[ORB_T1], T4 = rec[ORB_T4];
+    const double *t0v = rec + ORB_STRIDE;
+    // this lane's corner of the item: 64-bit addresses once per phase, 32-bit offsets per block
+    const long long lbase = (long long)bbeg * PT_BLOCK + lane * VEC;
+    const double *tl = P.time + lbase;
+    const double *ol = LNL ? P.obs + lbase : nullptr;
+    T *fl = LNL ? nullptr : reinterpret_cast<T *>(P.flux) + (size_t)ipv * P.npt + lbase;
+    const int32_t *bl = P.blc + bbeg;
+    const long long left = P.npt - lbase;                                   // offsets < rem are inside the time axis
+    const int rem = (int)(left > 0x7fffffffll ? 0x7fffffffll : left);     // (VEC == 2 requires an even npt: vectors are all-in or all-out)
+    const int ipt0 = (int)lbase;
+    const double *isig2 = LNL ? P.isig2 + (size_t)ipv * P.nblocks : nullptr;
+    const double w_one = (LNL && !P.blk) ? isig2[0] : 0.0;  // single noise block: its weight is an item constant
+    double chi = 0.0;
+
+    T ones[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) ones[j] = T(1);
+    // A lane folds two points of every 64-point block: A and B are neighbours (VEC == 2, one 16-byte load) or 32
+    // points apart (VEC == 1, odd npt or unaligned arrays).  Scalars, not arrays: they must stay in registers.
+    constexpr int DB = (VEC == 2) ? 1 : 32;
+    double tnA = 0.0, tnB = 0.0, onA = 1.0, onB = 1.0;   // the prefetched block: time stamps, (likelihood) observed fluxes
+    int lcn = 0;                                          // its light curve (-1: mixed, per-point lookup)
+    auto load_block = [&](int bb) {
+        const int off = bb * PT_BLOCK;
+        if (!SINGLE_LC) lcn = __ldg(bl + bb);
+        tnA = 0.0; tnB = 0.0;
+        if (LNL) { onA = 1.0; onB = 1.0; }
+        if (VEC == 2) {
+            if (off < rem) {
+                const double2 t = __ldg(reinterpret_cast<const double2 *>(tl + off));
+                tnA = t.x; tnB = t.y;
+                if (LNL) {
+                    const double2 o = __ldg(reinterpret_cast<const double2 *>(ol + off));
+                    onA = o.x; onB = o.y;
+                }
+            }
+        } else {
+            if (off < rem) { tnA = __ldg(tl + off); if (LNL) onA = __ldg(ol + off); }
+            if (off + DB < rem) { tnB = __ldg(tl + off + DB); if (LNL) onB = __ldg(ol + off + DB); }
+        }
+    };
+
+    if (cur == -2) cur = ss_next_block(wi, wbits, nwords, s_hit);   // -2: nothing taken from the bitmap yet
+    if (cur >= 0) load_block(cur);
+    int lc_last = -2;   // the block constants below belong to this light curve
+    double lob = 0.0, hib = 0.0, t0b = 0.0;
+    if (SINGLE_LC) {
+        const double pd = tb.sPad[0];
+        lob = T1 - pd;
+        hib = T4 + pd;
+        t0b = t0v[tb.sEp[0]];
+    }
+
+    while (cur >= 0 && qn <= SS_QCAP - PT_BLOCK) {
+        const int offA = cur * PT_BLOCK, offB = offA + DB;
+        const double tA = tnA, tB = tnB, oA = onA, oB = onB;
+        const int lcb = SINGLE_LC ? 0 : lcn;
+        if (!SINGLE_LC && lcb >= 0 && lcb != lc_last) {   // window and transit centre of the block's light curve
+            const double pd = tb.sPad[lcb];
+            lob = T1 - pd;
+            hib = T4 + pd;
+            t0b = t0v[tb.sEp[lcb]];
+            lc_last = lcb;
+        }
+        cur = ss_next_block(wi, wbits, nwords, s_hit);
+        if (cur >= 0) load_block(cur);  // in flight while this block is folded
+        const bool inrA = offA < rem, inrB = offB < rem;
+        bool inA, inB;
+        int lcA = lcb, lcB = lcb;
+        // epoch = floor((t - t0 + p/2)/p); tc = t - (t0 + epoch p)  (model_full.py:88-89).  The division is a
+        // multiplication by 1/p: the two can only disagree half a period away from the transit, where the
+        // point is outside the box either way.  Always fp64: time stamps need all their digits.
+        if (SINGLE_LC || lcb >= 0) {   // the rule: window and transit centre are block constants
+            const double eA = floor(fma(tA - t0b, invp, 0.5)), eB = floor(fma(tB - t0b, invp, 0.5));
+            const double tcA = tA - __dadd_rn(t0b, __dmul_rn(eA, p)), tcB = tB - __dadd_rn(t0b, __dmul_rn(eB, p));
+            inA = inrA && (lob <= tcA) && (tcA <= hib);
+            inB = inrB && (lob <= tcB) && (tcB <= hib);
+        } else {                       // a block that straddles light curves: per-point lookup
+            lcA = inrA ? P.lcids[(long long)ipt0 + offA] : 0;
+            lcB = inrB ? P.lcids[(long long)ipt0 + offB] : 0;
+            const double pdA = tb.sPad[lcA], t0A = t0v[tb.sEp[lcA]], pdB = tb.sPad[lcB], t0B = t0v[tb.sEp[lcB]];
+            const double eA = floor(fma(tA - t0A, invp, 0.5)), eB = floor(fma(tB - t0B, invp, 0.5));
+            const double tcA = tA - __dadd_rn(t0A, __dmul_rn(eA, p)), tcB = tB - __dadd_rn(t0B, __dmul_rn(eB, p));
+            inA = inrA && (T1 - pdA <= tcA) && (tcA <= T4 + pdA);
+            inB = inrB && (T1 - pdB <= tcB) && (tcB <= T4 + pdB);
+        }
+        if (LNL) {
+            if (inrA && !inA) {
+                const double d = oA - 1.0;
+                const int nb = P.blk ? P.blk[(long long)ipt0 + offA] : 0;
+                if (nb >= 0) chi = fma(d * d, P.blk ? isig2[nb] : w_one, chi);
+            }
+            if (inrB && !inB) {
+                const double d = oB - 1.0;
+                const int nb = P.blk ? P.blk[(long long)ipt0 + offB] : 0;
+                if (nb >= 0) chi = fma(d * d, P.blk ? isig2[nb] : w_one, chi);
+            }
+        }
+        // one compaction for the lane's two points
+        const unsigned mA = __ballot_sync(0xffffffffu, inA), mB = __ballot_sync(0xffffffffu, inB);
+        int pos = qn + __popc(mA & lt_mask) + __popc(mB & lt_mask);
+        qn += __popc(mA) + __popc(mB);
+        if (inA) {
+            q_ipt[pos] = ipt0 + offA;
+            if (!SINGLE_LC) q_lc[pos] = lcA;
+            ++pos;
+        }
+        if (inB) {
+            q_ipt[pos] = ipt0 + offB;
+            if (!SINGLE_LC) q_lc[pos] = lcB;
+        }
+        // 1.0 for the block's points, default cache policy (not evict-first): the line is still in L2 when the drain
+        // updates its in-box points, so it reaches DRAM once
+        if (!LNL) {
+            if (VEC == 2) {
+                if (inrA) VecIO<VEC, T>::store_keep(fl + offA, ones);
+            } else {
+                if (inrA) fl[offA] = T(1);
+                if (inrB) fl[offB] = T(1);
+            }
+        }
+    }
+    fr[FR_QN] = qn;
+    fr[FR_DONE] = cur < 0;
+    fr[FR_WI] = wi; fr[FR_WBITS] = (int)wbits; fr[FR_CUR] = cur;   // `cur` is taken from the bitmap but not folded yet
+    return chi;
+}
+
+// The drain of `n` (<= 32) queued in-box points starting at queue slot `base`, one point per lane; the lane folds its
+// point again (the same fp64 operations as the fold phase) and walks its exposure sub-samples in order
+// (model_full.py:88-99).  Returns the lane's chi^2 increment (likelihood); the flux goes to the row of vector `ipv`.
+template <bool SINGLE_LC, bool LNL, typename T>
+__device__ __forceinline__ double ss_drain(const PointsParams &P, const SsTables<T> &tb, const SsWarp<T> &ws, int ipv, int base,
+                                           int n, int lane) {
+    const int ng = P.ng, S = P.ns_max, SSC = P.ssc;
+    const double *rec = ws.rec();
+    const T *rt = (sizeof(T) == 4) ? ws.rec_t() : reinterpret_cast<const T *>(rec);
+    const T *ld = rt + P.rec_ld;
+    T *colz = ws.colz();
+    const T inv_dg = (T)P.inv_dg, one = T(1), pi = T(kPi);
+
+    const bool valid = lane < n;
+    int ipt = 0, lc = 0, ns = 0, rowoff = tb.sRow[0];
+    T tc = T(0), et = T(0);
+    if (valid) {
+        ipt = ws.q_ipt()[base + lane];
+        if (!SINGLE_LC) {
+            lc = ws.q_lc()[base + lane];
+            rowoff = tb.sRow[lc];
+        }
+        ns = tb.sNs[lc];
+        et = tb.sEt[lc];
+        // epoch = floor((t - t0 + p/2)/p); tc = t - (t0 + epoch p)  (model_full.py:88-89), as in the fold phase
+        const double t = __ldg(P.time + ipt), t0 = rec[ORB_STRIDE + tb.sEp[lc]];
+        const double epoch = floor(fma(t - t0, rec[ORB_INVP], 0.5));
+        tc = (T)(t - __dadd_rn(t0, __dmul_rn(epoch, rec[ORB_P])));
+    }
+    const T *row = ld + rowoff;
+    const T k = row[ng], inv1k = row[ng + 1], inv_istar = row[ng + 2], k2 = row[ng + 3];
+    // per-point constants of the area cases that need no lens formula (common.py:52-73)
+    const T zout = one + k, zin = fabs(one - k);
+    const T qfull = ((k > one) ? pi : pi * k2) * inv_istar;   // planet covers the star: area pi; else pi k^2
+    const T c_out = fma(T(0), inv_istar, one);                 // no overlap: (I* - 0) / I* = 1, NaN when 1/I* is NaN
+    const T xs = inv1k * inv_dg;                               // separation -> position on the LD-mean grid
+    const T *off = tb.nfrac ? tb.sFrac + lc * S : nullptr;
+    T cx[5], cy[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { cx[j] = rt[j]; cy[j] = rt[5 + j]; }
+
+    T sum = T(0);
+    for (int s0 = 0; s0 < S; s0 += SSC) {
+        const int SS = min(min(SSC, S - s0), ns - s0);   // ns = 0 for lanes without a point
+        T *mz = colz + lane;
+        int cnt = 0;                                      // this lane's limb samples of the pass
+        // one exposure sub-sample at offset `o` from the point's folded time
+        auto step = [&](T o) {
+            const T t = tc + o;
+            const T px = fma(t, fma(t, fma(t, fma(t, cx[4], cx[3]), cx[2]), cx[1]), cx[0]);
+            const T py = fma(t, fma(t, fma(t, fma(t, cy[4], cy[3]), cy[2]), cy[1]), cy[0]);
+            const T z = sqrt_sep(fma(px, px, py * py));      // sep_c (taylor_z.py:229-255)
+            // LD-mean lerp (common.py:225-233): node i = floor(g/dg), weight g/dg - i; the upper node is clamped
+            // to the last one (the reference reads one element past the row for g in (1-1e-7, 1])
+            const T x = z * xs;
+            const int i0 = min(floor_to_int(x), ng - 2);     // >= 0; NaN -> 0 (the weight stays NaN)
+            const T r0 = row[i0], r1 = row[i0 + 1];
+            const T ip = fma(x - (T)i0, r1 - r0, r0);
+            if (zout <= z) {
+                sum += c_out;
+            } else if (zin < z) {        // on the limb: deferred to the lens-area passes
+                *mz = z;
+                mz += PT_COLS;
+                ++cnt;
+            } else {                     // full overlap; a NaN separation lands here with a NaN weight
+                sum += fma(-ip, qfull, one);
+            }
+        };
+        // exposure offset exptime*((s+1-0.5)/ns - 0.5) (model_full.py:94): tabulated per light curve, or on the fly
+        if (off) {
+            const T *o = off + s0;
+            for (int j = 0; j < SS; ++j) step(o[j]);
+        } else {
+            for (int j = 0; j < SS; ++j) step((T)__dmul_rn((double)et, ((s0 + j + 1) - 0.5) / ns - 0.5));
+        }
+        // number the warp's limb samples: inclusive scan of the per-lane counts
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        for (int q0 = 0; q0 < total; q0 += 32) {
+            const int q = q0 + lane;
+            int o = 0;   // owner of sample q: the number of lanes whose inclusive count is <= q
+#pragma unroll
+            for (int st = 16; st > 0; st >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, incl, o + st - 1);
+                if (v <= q) o += st;
+            }
+            o = min(o, 31);
+            const int r = q - (__shfl_sync(0xffffffffu, incl, o) - __shfl_sync(0xffffffffu, cnt, o));
+            const int ro = SINGLE_LC ? 0 : __shfl_sync(0xffffffffu, rowoff, o);
+            if (q < total) {
+                const T *r2 = SINGLE_LC ? row : ld + ro;
+                T *slot = colz + r * PT_COLS + o;
+                const T z = *slot;
+                const T x = z * (r2[ng + 1] * inv_dg);
+                const int i0 = min(floor_to_int(x), ng - 2);
+                const T r0 = r2[i0], r1 = r2[i0 + 1];
+                const T ip = fma(x - (T)i0, r1 - r0, r0);
+                T area, kap;
+                kite_area<T>(r2[ng], r2[ng + 3], z, area, kap);
+                *slot = one - ip * area * r2[ng + 2];
+            }
+        }
+        __syncwarp();
+        for (int r = 0; r < cnt; ++r) sum += colz[r * PT_COLS + lane];   // this lane's limb values, in exposure order
+        __syncwarp();
+    }
+    double chi = 0.0;
+    if (valid) {
+        const T f = sum / ns;
+        if (LNL) {
+            const int b = P.blk ? P.blk[ipt] : 0;
+            if (b >= 0) {
+                const double d = P.obs[ipt] - (double)f;
+                chi = d * d * (P.isig2 + (size_t)ipv * P.nblocks)[b];
+            }
+        } else {
+            (reinterpret_cast<T *>(P.flux) + (size_t)ipv * P.npt)[ipt] = f;
+        }
+    }
+    return chi;
+}
+
+// ---- drain phase: full warps of points from the top of the queue; a remainder (< 32) waits for the next fold phase
+// unless that was the item's last one.  Returns the lane's chi^2 increment.
+template <bool SINGLE_LC, bool LNL, typename T>
+__device__ __noinline__ double ss_drain_phase() {
+    SS_PHASE_PROLOGUE(T);
+    int qn = fr[FR_QN];
+    const int done = fr[FR_DONE], ipv = fr[FR_IPV];
+    double chi = 0.0;
+    while (qn >= 32 || (done && qn > 0)) {
+        const int n = min(qn, 32);
+        qn -= n;
+        chi += ss_drain<SINGLE_LC, LNL, T>(P, tb, ws, ipv, qn, n, lane);
+    }
+    fr[FR_QN] = qn;
+    return chi;
+}
+
+template <int VEC, bool SINGLE_LC, bool LNL, typename T>
+__global__ void __launch_bounds__(PT_THREADS, PT_MINB_SS2) k_rr_points_ss(const __grid_constant__ PointsParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr bool F32 = sizeof(T) == 4;
+    constexpr int NH = 2 / VEC;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long npt = P.npt;
+    const int S = P.ns_max, nlc = P.nlc;
+    const long long nitems = (long long)P.npv * P.nchunks;
+
+    // dynamic smem: [parameter copy] [per-light-curve tables] [sub-sample offsets] [warp-private area x 8]
+    {
+        const int *src = reinterpret_cast<const int *>(&P);
+        int *dst = reinterpret_cast<int *>(smem_raw);
+        for (int i = tid; i < (int)(sizeof(PointsParams) / 4); i += PT_THREADS) dst[i] = src[i];
+    }
+    const SsTables<T> tb(smem_raw, nlc, S, P.frac_tab);
+    double *sPad = tb.sPad;
+    int *sEp = tb.sEp;
+    const SsWarp<T> ws(smem_raw + ss_shared_bytes(nlc, tb.nfrac, (int)sizeof(T)) + (size_t)warp * ss_warp_bytes(P.ssc, P.recstride, (int)sizeof(T)),
+                       P.ssc, P.recstride);
+    unsigned *s_hit = ws.hit();
+    uint64_t *bar = ws.bar();
+    volatile int *fr = ws.frame();
+
+    const uint32_t rec_bytes = (uint32_t)P.recstride * 8u;
+    long long item = 0;
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        item = atomicAdd(&P.work[0], 1);
+    }
+    item = __shfl_sync(0xffffffffu, item, 0);
+    // item-independent per-light-curve tables
+    for (int lc = tid; lc < nlc; lc += PT_THREADS) {
+        sPad[lc] = 0.003 + P.exptimes[lc];  // model_full.py:69-70
+        tb.sEt[lc] = (T)P.exptimes[lc];
+        tb.sNs[lc] = P.nsamples[lc];
+        tb.sRow[lc] = P.pbids[lc] * P.lds;
+        sEp[lc] = P.epids[lc];
+    }
+    for (int i = tid; i < tb.nfrac; i += PT_THREADS) {   // exptimes[ilc]*((isample-0.5)/nsamples[ilc] - 0.5), model_full.py:94
+        const int lc = i / S, s = i - lc * S;
+        tb.sFrac[i] = (T)__dmul_rn(P.exptimes[lc], ((s + 1) - 0.5) / P.nsamples[lc] - 0.5);
+    }
+    __syncthreads();  // the only CTA-wide barrier: from here on the warps are independent workers
+
+    int iter = 0;
+    while (item < nitems) {
+        const double *rec = ws.rec();
+        double chi = 0.0;
+        {   // ---- item header; what the phases and the item's end need is parked in the frame ------------------
+            // this item's record: one TMA bulk copy into the warp's slot (every lane left the slot at the end of the
+            // last item; the items are tens of thousands of sub-samples long, the fetch is noise)
+            long long next = 0;
+            if (lane == 0) {
+                mbar_expect_tx(&bar[0], rec_bytes);
+                tma_load_1d(ws.rec(), P.rec + (size_t)(item / P.nchunks) * P.recstride, rec_bytes, &bar[0]);
+                next = atomicAdd(&P.work[0], 1);
+            }
+            next = __shfl_sync(0xffffffffu, next, 0);
+            const int ipv = (int)(item / P.nchunks);
+            const int chunk = (int)(item - (long long)ipv * P.nchunks);
+            const int bbeg = chunk * P.blocks_per_chunk;
+            const int bend = min(P.nblk64, bbeg + P.blocks_per_chunk);
+            const int nbc = bend - bbeg;
+            fr[FR_IPV] = ipv; fr[FR_CHUNK] = chunk; fr[FR_BBEG] = bbeg; fr[FR_BEND] = bend;
+            fr[FR_NEXT_LO] = (int)(unsigned)(next & 0xffffffffll); fr[FR_NEXT_HI] = (int)(next >> 32);
+            fr[FR_ITER] = iter + 1;
+            T *frow = LNL ? nullptr : reinterpret_cast<T *>(P.flux) + (size_t)ipv * npt;
+            const double *isig2 = LNL ? P.isig2 + (size_t)ipv * P.nblocks : nullptr;
+
+            mbar_wait(&bar[0], iter & 1);
+            if (rec[ORB_GOOD] == 0.0 || rec[ORB_LDNAN] != 0.0) {  // invalid parameter vector: NaN row (model_full.py:40,80-82)
+                if (LNL) {
+                    if (lane == 0) P.partial[(size_t)ipv * P.nchunks + chunk] = nan("");
+                } else {
+                    T v[VEC];
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) v[j] = T(nan(""));
+                    const long long cend = min(npt, (long long)bend * PT_BLOCK);
+                    for (long long i = (long long)bbeg * PT_BLOCK + (long long)lane * VEC; i < cend; i += 32 * VEC)
+                        VecIO<VEC, T>::store(frow + i, v);
+                }
+                __syncwarp();
+                item = next;
+                ++iter;
+                continue;
+            }
+            if (F32) {   // the record in the arithmetic type, converted once per item
+                T *dst = ws.rec_t();
+                for (int i = lane; i < P.recstride; i += 32) dst[i] = (T)rec[i];
+            }
+
+            const double p = rec[ORB_P], invp = rec[ORB_INVP], T1 = rec[ORB_T1], T4 = rec[ORB_T4];
+            const double *t0v = rec + ORB_STRIDE;
+            const double w_one = (LNL && !P.blk) ? isig2[0] : 0.0;  // single noise block: its weight is an item constant
+
+            // ---- 1. classification of every block of this item (see k_rr_points) ------------------------------
+            for (int bb0 = 0; bb0 < nbc; bb0 += 32) {
+                const int bb = bb0 + lane, b = bbeg + bb;
+                bool hit = false;
+                if (bb < nbc) {
+                    hit = true;
+                    const int lcb = SINGLE_LC ? 0 : P.blc[b];
+                    int nz_id = 0;
+                    if (LNL && P.blk) nz_id = P.bnoise ? P.bnoise[b] : 0;
+                    const bool partial = (b == P.nblk64 - 1) && (npt % PT_BLOCK != 0);
+                    if (lcb >= 0 && nz_id != -2 && !partial) {
+                        const double pd = sPad[lcb], t0 = t0v[sEp[lcb]];
+                        const double n1 = ceil(fma(P.bmin[b] - t0 - (T4 + pd), invp, -PT_EPS));
+                        const double n2 = floor(fma(P.bmax[b] - t0 - (T1 - pd), invp, PT_EPS));
+                        hit = !(n1 > n2) || !(p > 0.0);  // NaNs and p <= 0 fall through to the exact per-point path
+                    }
+                    if (LNL && !hit && nz_id >= 0) chi = fma(P.bchi[b], P.blk ? isig2[nz_id] : w_one, chi);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) s_hit[bb0 >> 5] = m;
+            }
+            __syncwarp();
+
+            // ---- 2. untouched blocks: 64 fluxes of exactly 1.0, vectorised streaming stores ---------------------
+            if (!LNL) {
+                T one[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) one[j] = T(1);
+                const int ngroups = (nbc + 7) >> 3;
+                for (int g = 0; g < ngroups; ++g) {
+                    const unsigned bits = (s_hit[g >> 2] >> ((g & 3) * 8)) & 0xffu;
+                    const int b0 = bbeg + g * 8;
+                    T *fb = frow + (long long)b0 * PT_BLOCK + lane * VEC;
+                    if (bits == 0u && b0 + 8 <= bend) {  // the common case: eight untouched blocks, no predicates
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                            for (int h = 0; h < NH; ++h) VecIO<VEC, T>::store(fb + j * PT_BLOCK + h * 32 * VEC, one);
+                        }
+                    } else if (bits != 0xffu) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (!((bits >> j) & 1u) && b0 + j < bend) {
+#pragma unroll
+                                for (int h = 0; h < NH; ++h) VecIO<VEC, T>::store(fb + j * PT_BLOCK + h * 32 * VEC, one);
+                            }
+                        }
+                    }
+                }
+            }
+            fr[FR_WI] = 0; fr[FR_WBITS] = (int)s_hit[0]; fr[FR_CUR] = -2; fr[FR_QN] = 0; fr[FR_DONE] = 0;
+        }
+        __syncwarp();
+
+        // ---- 3. touched blocks: fold and drain phases alternate until the item's blocks are exhausted ------------
+        do {
+            chi += ss_fold<VEC, SINGLE_LC, LNL, T>();
+            __syncwarp();
+            chi += ss_drain_phase<SINGLE_LC, LNL, T>();
+            __syncwarp();
+        } while (!fr[FR_DONE]);
+
+        if (LNL) {
+            chi = warp_sum(chi);
+            if (lane == 0) P.partial[(size_t)fr[FR_IPV] * P.nchunks + fr[FR_CHUNK]] = chi;
+        }
+        item = ((long long)fr[FR_NEXT_HI] << 32) | (long long)(unsigned)fr[FR_NEXT_LO];
+        iter = fr[FR_ITER];
+        __syncwarp();  // every lane is done with this record slot and frame before the next item refills them
+    }
+
+    // the last CTA to leave re-arms the work counters for the next launch
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const int done = atomicAdd(&P.work[1], 1);
+        if (done == (int)gridDim.x - 1) {
+            P.work[0] = 0;
+            P.work[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+}  // namespace ptb
