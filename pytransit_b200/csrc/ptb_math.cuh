@@ -53,6 +53,10 @@ __device__ __forceinline__ double fast_div(double n, double d) {
 // atan2(y, x) for y >= 0 (the lens-area kite: y = 2 * kite area).  One division after the argument
 // reduction atan(q) = pi/4 + atan((q-1)/(q+1)) for q > tan(pi/8); odd polynomial of degree 23 in the
 // reduced argument (near-minimax fit, profiles/tools/fit_atan.py: 1.5e-16 relative).
+#define PTB_ATAN_COEFFS(X)                                                                                                        \
+    X(3.79652574538659332e-02) X(-5.03510245660155203e-02) X(5.84687829733087222e-02) X(-6.66295181362919070e-02)               \
+    X(7.69204533090222520e-02) X(-9.09089680906402658e-02) X(1.11111107449196583e-01) X(-1.42857142792502445e-01)               \
+    X(1.99999999999408928e-01) X(-3.33333333333331205e-01)
 __device__ __forceinline__ double atan2_pos(double y, double x) {
     const double ax = fabs(x);
     const bool ygt = y > ax;
@@ -63,22 +67,47 @@ __device__ __forceinline__ double atan2_pos(double y, double x) {
     const double t = (den > 0.0) ? fast_div(num, den) : 0.0;
     const double u = t * t;
     double q = -1.78053972054194459e-02;
-    q = fma(q, u, 3.79652574538659332e-02);
-    q = fma(q, u, -5.03510245660155203e-02);
-    q = fma(q, u, 5.84687829733087222e-02);
-    q = fma(q, u, -6.66295181362919070e-02);
-    q = fma(q, u, 7.69204533090222520e-02);
-    q = fma(q, u, -9.09089680906402658e-02);
-    q = fma(q, u, 1.11111107449196583e-01);
-    q = fma(q, u, -1.42857142792502445e-01);
-    q = fma(q, u, 1.99999999999408928e-01);
-    q = fma(q, u, -3.33333333333331205e-01);
+#define PTB_STEP(c) q = fma(q, u, c);
+    PTB_ATAN_COEFFS(PTB_STEP)
+#undef PTB_STEP
     double r = fma(t * u, q, t);                 // atan(t)
     r = big ? r + 0.78539816339744830962 : r;    // atan(mn / mx)
     r = ygt ? kHalfPi - r : r;
     return (x < 0.0) ? kPi - r : r;
 }
 __device__ __forceinline__ float atan2_pos(float y, float x) { return atan2f(y, x); }
+
+// The lens area needs two of them with the same y: atan2(y, xa) and atan2(y, xb).  Evaluated side by side: the two
+// dependency chains interleave, and every coefficient (an fp64 immediate costs two moves) is materialised once
+// (constant-memory coefficients were measured: the LDC latency in front of the polynomial costs more than the moves).
+__device__ __forceinline__ void atan2_pos2(double y, double xa, double xb, double &ra, double &rb) {
+    const double axa = fabs(xa), axb = fabs(xb);
+    const bool ygta = y > axa, ygtb = y > axb;
+    const double mxa = ygta ? y : axa, mna = ygta ? axa : y, mxb = ygtb ? y : axb, mnb = ygtb ? axb : y;
+    const double thr = 0.41421356237309503;
+    const bool biga = mna > thr * mxa, bigb = mnb > thr * mxb;
+    const double numa = biga ? mna - mxa : mna, dena = biga ? mna + mxa : mxa;
+    const double numb = bigb ? mnb - mxb : mnb, denb = bigb ? mnb + mxb : mxb;
+    const double ta = (dena > 0.0) ? fast_div(numa, dena) : 0.0, tb = (denb > 0.0) ? fast_div(numb, denb) : 0.0;
+    const double ua = ta * ta, ub = tb * tb;
+    double qa = -1.78053972054194459e-02, qb = qa;
+#define PTB_STEP(c) { const double cc = c; qa = fma(qa, ua, cc); qb = fma(qb, ub, cc); }
+    PTB_ATAN_COEFFS(PTB_STEP)
+#undef PTB_STEP
+    ra = fma(ta * ua, qa, ta);
+    rb = fma(tb * ub, qb, tb);
+    const double q4 = 0.78539816339744830962, h = kHalfPi, pi = kPi;
+    ra = biga ? ra + q4 : ra;
+    rb = bigb ? rb + q4 : rb;
+    ra = ygta ? h - ra : ra;
+    rb = ygtb ? h - rb : rb;
+    ra = (xa < 0.0) ? pi - ra : ra;
+    rb = (xb < 0.0) ? pi - rb : rb;
+}
+__device__ __forceinline__ void atan2_pos2(float y, float xa, float xb, float &ra, float &rb) {
+    ra = atan2f(y, xa);
+    rb = atan2f(y, xb);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Geometry (models/roadrunner/common.py)
@@ -120,8 +149,8 @@ __device__ __forceinline__ void kite_area(T k, T k2, T z, T &area, T &kappa0) {
         const T zz = c2 ? lo : z;
         const T akite = half * fast_sqrt((x + (y + zz)) * (zz - (x - y)) * (zz + (x - y)) * (x + (y - zz)));
         const T z2 = z * z;
-        const T k0 = atan2_pos(two * akite, (k - one) * (k + one) + z2);
-        const T k1 = atan2_pos(two * akite, (one - k) * (one + k) + z2);
+        T k0, k1;
+        atan2_pos2(two * akite, (k - one) * (k + one) + z2, (one - k) * (one + k) + z2, k0, k1);
         area = k1 + k2 * k0 - akite;
         kappa0 = k0;
     } else if (z <= one - k) {

@@ -32,6 +32,9 @@ namespace ptb {
 #ifndef PT_MINB_SS2
 #define PT_MINB_SS2 3
 #endif
+#ifndef SS_BRANCHY_TAIL
+#define SS_BRANCHY_TAIL 0
+#endif
 #ifndef SS_QCAP_
 #define SS_QCAP_ 256
 #endif
@@ -314,7 +317,6 @@ __device__ __forceinline__ double ss_drain(const PointsParams &P, const SsTables
     for (int s0 = 0; s0 < S; s0 += SSC) {
         const int SS = min(min(SSC, S - s0), ns - s0);   // ns = 0 for lanes without a point
         T *mz = colz + lane;
-        int cnt = 0;                                      // this lane's limb samples of the pass
         // one exposure sub-sample at offset `o` from the point's folded time
         auto step = [&](T o) {
             const T t = tc + o;
@@ -327,15 +329,26 @@ __device__ __forceinline__ double ss_drain(const PointsParams &P, const SsTables
             const int i0 = min(floor_to_int(x), ng - 2);     // >= 0; NaN -> 0 (the weight stays NaN)
             const T r0 = row[i0], r1 = row[i0 + 1];
             const T ip = fma(x - (T)i0, r1 - r0, r0);
+#if SS_BRANCHY_TAIL
             if (zout <= z) {
                 sum += c_out;
-            } else if (zin < z) {        // on the limb: deferred to the lens-area passes
+            } else if (zin < z) {
                 *mz = z;
                 mz += PT_COLS;
-                ++cnt;
-            } else {                     // full overlap; a NaN separation lands here with a NaN weight
+            } else {
                 sum += fma(-ip, qfull, one);
             }
+#else
+            // straight-line tail (selects and predicated stores: consecutive steps interleave): no overlap, limb
+            // (deferred to the lens-area passes), or full overlap -- a NaN separation lands there with a NaN weight
+            const bool out = zout <= z, limb = !out && (zin < z);
+            const T v = out ? c_out : fma(-ip, qfull, one);
+            if (!limb) sum += v;
+            if (limb) {
+                *mz = z;
+                mz += PT_COLS;
+            }
+#endif
         };
         // exposure offset exptime*((s+1-0.5)/ns - 0.5) (model_full.py:94): tabulated per light curve, or on the fly
         if (off) {
@@ -344,6 +357,7 @@ __device__ __forceinline__ double ss_drain(const PointsParams &P, const SsTables
         } else {
             for (int j = 0; j < SS; ++j) step((T)__dmul_rn((double)et, ((s0 + j + 1) - 0.5) / ns - 0.5));
         }
+        const int cnt = (int)((smem_u32(mz) - smem_u32(colz + lane)) / (unsigned)(PT_COLS * sizeof(T)));   // this lane's limb samples of the pass
         // number the warp's limb samples: inclusive scan of the per-lane counts
         int incl = cnt;
 #pragma unroll
