@@ -102,6 +102,12 @@ struct ptb_model {
     DevBuf d_bmeta;                    // bmin[nblk64] | bmax[nblk64] | blc[nblk64]
     double *d_bmin = nullptr, *d_bmax = nullptr;
     int32_t *d_blc = nullptr;
+    // the same at 16-point granularity ("cells"): the supersampled kernel classifies finer (a Kepler long-cadence block
+    // of 64 points spans 1.3 d, more than a third of a hot Jupiter's period); built only when some nsamples > 1
+    int64_t ncell = 0;
+    DevBuf d_cmeta, d_cobs;            // cmin | cmax | clc ; cchi | cnoise
+    double *d_cmin = nullptr, *d_cmax = nullptr, *d_cchi = nullptr;
+    int32_t *d_clc = nullptr, *d_cnoise = nullptr;
     std::vector<int32_t> h_lcids;      // host copy (empty when nlc == 1)
     std::vector<int64_t> h_nsamples;
     std::vector<double> h_exptimes;
@@ -504,7 +510,7 @@ void ptb_destroy(ptb_model *h) {
     cudaSetDevice(h->cfg.device);
     for (DevBuf *b : {&h->d_tab, &h->d_W, &h->d_time_own, &h->d_meta, &h->d_obs_own, &h->d_blk, &h->d_nblk, &h->d_orb,
                       &h->d_ldrec, &h->d_ldp, &h->d_istar, &h->d_flux, &h->d_partial, &h->d_isig2, &h->d_lnl, &h->d_xyc,
-                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_sort, &h->d_rec, &h->d_work, &h->d_tsgeo, &h->d_lpf, &h->d_basis, &h->d_blmeta, &h->d_cells, &h->d_dummy})
+                      &h->d_tsw, &h->d_tsrec, &h->d_stage, &h->d_bmeta, &h->d_bobs, &h->d_cmeta, &h->d_cobs, &h->d_sort, &h->d_rec, &h->d_work, &h->d_tsgeo, &h->d_lpf, &h->d_basis, &h->d_blmeta, &h->d_cells, &h->d_dummy})
         b->release();
     for (auto *b : h->hr) { b->d_lit.release(); delete b; }
     h->hr.clear();
@@ -614,13 +620,13 @@ int ptb_set_data(ptb_model *h, const double *time, int64_t npt, const int64_t *l
         CU(cudaMemcpy(h->d_time_own.ptr, time, npt * 8, cudaMemcpyHostToDevice));
         h->d_time = h->d_time_own.as<double>();
     }
-    // per 64-point block: time range and light curve (k_rr_points block classification)
-    {
-        const int64_t nb = (npt + 63) / 64;
+    // per block of `bs` points: time range and light curve (block classification of the points kernels)
+    auto build_blocks = [&](int64_t bs, DevBuf &buf, double *&dmin, double *&dmax, int32_t *&dlc, int64_t &nb_out) -> int {
+        const int64_t nb = (npt + bs - 1) / bs;
         std::vector<double> bm(2 * nb);
         std::vector<int32_t> bl(nb, 0);
         for (int64_t b = 0; b < nb; ++b) {
-            const int64_t j0 = b * 64, j1 = std::min<int64_t>(npt, j0 + 64);
+            const int64_t j0 = b * bs, j1 = std::min<int64_t>(npt, j0 + bs);
             double mn = ht[j0], mx = ht[j0];
             bool nanv = false;
             int32_t lc = lcids ? meta[j0] : 0;
@@ -635,14 +641,19 @@ int ptb_set_data(ptb_model *h, const double *time, int64_t npt, const int64_t *l
             bm[nb + b] = mx;
             bl[b] = lc;
         }
-        CU(h->d_bmeta.reserve(nb * 20 + 64));
-        CU(cudaMemcpy(h->d_bmeta.ptr, bm.data(), nb * 16, cudaMemcpyHostToDevice));
-        h->d_bmin = h->d_bmeta.as<double>();
-        h->d_bmax = h->d_bmin + nb;
-        h->d_blc = reinterpret_cast<int32_t *>(h->d_bmax + nb);
-        CU(cudaMemcpy(h->d_blc, bl.data(), nb * 4, cudaMemcpyHostToDevice));
-        h->nblk64 = nb;
-    }
+        CU(buf.reserve(nb * 20 + 64));
+        CU(cudaMemcpy(buf.ptr, bm.data(), nb * 16, cudaMemcpyHostToDevice));
+        dmin = buf.as<double>();
+        dmax = dmin + nb;
+        dlc = reinterpret_cast<int32_t *>(dmax + nb);
+        CU(cudaMemcpy(dlc, bl.data(), nb * 4, cudaMemcpyHostToDevice));
+        nb_out = nb;
+        return PTB_OK;
+    };
+    if (int rc = build_blocks(PT_BLOCK, h->d_bmeta, h->d_bmin, h->d_bmax, h->d_blc, h->nblk64)) return rc;
+    h->ncell = 0;
+    if (nsmax > 1)
+        if (int rc = build_blocks(SS_CELL, h->d_cmeta, h->d_cmin, h->d_cmax, h->d_clc, h->ncell)) return rc;
     h->npt = npt;
     h->nlc = nlc;
     h->npb = npb;
@@ -706,13 +717,12 @@ int ptb_set_obs(ptb_model *h, const double *obs, const int64_t *slices, const in
         CU(cudaMemcpy(h->d_obs_own.ptr, obs, npt * 8, cudaMemcpyHostToDevice));
         h->d_obs = h->d_obs_own.as<double>();
     }
-    // per 64-point block: sum of (obs-1)^2 and the block's noise id (k_rr_points likelihood fast path)
-    {
-        const int64_t nb = h->nblk64;
+    // per block of `bs` points: sum of (obs-1)^2 and the block's noise id (likelihood fast path of the points kernels)
+    auto build_obs_blocks = [&](int64_t bs, int64_t nb, DevBuf &buf, double *&dchi, int32_t *&dnoise) -> int {
         std::vector<double> bc(nb, 0.0);
         std::vector<int32_t> bn(nb, -1);
         for (int64_t b = 0; b < nb; ++b) {
-            const int64_t j0 = b * 64, j1 = std::min<int64_t>(npt, j0 + 64);
+            const int64_t j0 = b * bs, j1 = std::min<int64_t>(npt, j0 + bs);
             int32_t id = -1;
             bool mixed = false;
             double sum = 0.0;
@@ -727,12 +737,16 @@ int ptb_set_obs(ptb_model *h, const double *obs, const int64_t *slices, const in
             bc[b] = sum;
             bn[b] = mixed ? -2 : id;
         }
-        CU(h->d_bobs.reserve(nb * 12 + 64));
-        h->d_bchi = h->d_bobs.as<double>();
-        h->d_bnoise = reinterpret_cast<int32_t *>(h->d_bchi + nb);
-        CU(cudaMemcpy(h->d_bchi, bc.data(), nb * 8, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(h->d_bnoise, bn.data(), nb * 4, cudaMemcpyHostToDevice));
-    }
+        CU(buf.reserve(nb * 12 + 64));
+        dchi = buf.as<double>();
+        dnoise = reinterpret_cast<int32_t *>(dchi + nb);
+        CU(cudaMemcpy(dchi, bc.data(), nb * 8, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dnoise, bn.data(), nb * 4, cudaMemcpyHostToDevice));
+        return PTB_OK;
+    };
+    if (int rc = build_obs_blocks(PT_BLOCK, h->nblk64, h->d_bobs, h->d_bchi, h->d_bnoise)) return rc;
+    if (h->ncell > 0)
+        if (int rc = build_obs_blocks(SS_CELL, h->ncell, h->d_cobs, h->d_cchi, h->d_cnoise)) return rc;
     h->blk_trivial = trivial;
     h->nblocks = nblocks;
     h->has_obs = true;
@@ -1012,6 +1026,7 @@ int launch_points(ptb_model *h, int64_t npv, void *flux, const double *isig2, cu
 
     P.bmin = h->d_bmin; P.bmax = h->d_bmax; P.blc = h->d_blc; P.bchi = h->d_bchi; P.bnoise = h->d_bnoise;
     P.nblk64 = (int)h->nblk64;
+    P.cmin = h->d_cmin; P.cmax = h->d_cmax; P.clc = h->d_clc; P.cchi = h->d_cchi; P.cnoise = h->d_cnoise; P.ncell = (int)h->ncell;
     if (!h->d_work.ptr || h->work_dirty) {
         // the last CTA of every launch re-arms the counters itself; after a CUDA error (a launch that died
         // mid-way would leave them poisoned) they are reset here before the next launch
@@ -1045,9 +1060,11 @@ int launch_points(ptb_model *h, int64_t npv, void *flux, const double *isig2, cu
     // a population too small to give every warp an item: cut finer (down to two blocks per item) -- the
     // single-vector call is latency bound and wants all the parallelism there is
     if (npv * nchunks < workers) nchunks = std::min<long long>(std::max<long long>(1, nb / 2), (workers + npv - 1) / npv);
-    nchunks = std::max<long long>(nchunks, (nb + PT_MAXBLK - 1) / PT_MAXBLK);
+    // the hit bitmap holds PT_MAXBLK bits: 64-point blocks, or (supersampled kernel) 16-point cells
+    const long long maxblk = (h->ns_max == 1) ? PT_MAXBLK : PT_MAXBLK * SS_CELL / PT_BLOCK;
+    nchunks = std::max<long long>(nchunks, (nb + maxblk - 1) / maxblk);
     long long bpc = (nb + nchunks - 1) / nchunks;
-    bpc = std::min<long long>(bpc >= 8 ? (bpc + 7) / 8 * 8 : bpc, PT_MAXBLK);
+    bpc = std::min<long long>(bpc >= 8 ? (bpc + 7) / 8 * 8 : bpc, maxblk);
     nchunks = (nb + bpc - 1) / bpc;
     P.nchunks = (int)nchunks;
     P.blocks_per_chunk = (int)bpc;

@@ -513,10 +513,14 @@ struct PointsParams {
     const int32_t *blc;         // light curve of the block, -1 when it straddles light curves
     const double *bchi;         // likelihood: sum of (obs-1)^2 over the block's points
     const int32_t *bnoise;      // likelihood: noise id of the block, -1 none, -2 mixed (slow path)
+    const double *cmin, *cmax;  // the same per 16-point cell (supersampled kernel, ptb_ss_kernels.cuh)
+    const int32_t *clc;
+    const double *cchi;
+    const int32_t *cnoise;
     int *work;                  // [0] next item, [1] CTAs finished (the last one re-arms both)
     long long npt;
     int npv, nlc, npb, nep, ng, lds, nblocks, ns_max, nchunks, blocks_per_chunk, nblk64;
-    int recstride, rec_ld, ssc, frac_tab;
+    int recstride, rec_ld, ssc, frac_tab, ncell;
     double dg, inv_dg;
 };
 
@@ -528,6 +532,7 @@ struct PointsParams {
 constexpr int PT_THREADS = 256;
 constexpr int PT_WARPS = PT_THREADS / 32;
 constexpr int PT_BLOCK = 64;           // points per classification block
+constexpr int SS_CELL = 16;            // ... of the supersampled kernel
 constexpr int PT_MAXBLK = 2048;        // blocks per item (hit bitmap in shared memory)
 constexpr int PT_QCAP = 96;            // in-box point queue: < 32 carried + 64 from one block
 constexpr int PT_LCAP = 64;            // limb sample queue: < 32 carried + 32 from one sub-sample step

@@ -90,10 +90,29 @@ __device__ __forceinline__ void atan2_pos2(double y, double xa, double xb, doubl
     const double numb = bigb ? mnb - mxb : mnb, denb = bigb ? mnb + mxb : mxb;
     const double ta = (dena > 0.0) ? fast_div(numa, dena) : 0.0, tb = (denb > 0.0) ? fast_div(numb, denb) : 0.0;
     const double ua = ta * ta, ub = tb * tb;
+#ifndef PTB_ATAN_ESTRIN
+#define PTB_ATAN_ESTRIN 1
+#endif
+#if PTB_ATAN_ESTRIN
+    // the degree-10 polynomial in u as two interleaved Horner chains in u^2 (even / odd coefficients): half the depth
+    const double c0 = -1.78053972054194459e-02, c1 = 3.79652574538659332e-02, c2 = -5.03510245660155203e-02,
+                 c3 = 5.84687829733087222e-02, c4 = -6.66295181362919070e-02, c5 = 7.69204533090222520e-02,
+                 c6 = -9.09089680906402658e-02, c7 = 1.11111107449196583e-01, c8 = -1.42857142792502445e-01,
+                 c9 = 1.99999999999408928e-01, c10 = -3.33333333333331205e-01;
+    const double va = ua * ua, vb = ub * ub;
+    // q = c0 u^10 + c1 u^9 + ... + c10 = E(v) + u O(v),  E = c0 v^5 + c2 v^4 + ... + c10,  O = c1 v^4 + c3 v^3 + ... + c9
+    double ea = fma(c0, va, c2), eb = fma(c0, vb, c2), oa = fma(c1, va, c3), ob = fma(c1, vb, c3);
+    ea = fma(ea, va, c4); eb = fma(eb, vb, c4); oa = fma(oa, va, c5); ob = fma(ob, vb, c5);
+    ea = fma(ea, va, c6); eb = fma(eb, vb, c6); oa = fma(oa, va, c7); ob = fma(ob, vb, c7);
+    ea = fma(ea, va, c8); eb = fma(eb, vb, c8); oa = fma(oa, va, c9); ob = fma(ob, vb, c9);
+    ea = fma(ea, va, c10); eb = fma(eb, vb, c10);
+    const double qa = fma(oa, ua, ea), qb = fma(ob, ub, eb);
+#else
     double qa = -1.78053972054194459e-02, qb = qa;
 #define PTB_STEP(c) { const double cc = c; qa = fma(qa, ua, cc); qb = fma(qb, ub, cc); }
     PTB_ATAN_COEFFS(PTB_STEP)
 #undef PTB_STEP
+#endif
     ra = fma(ta * ua, qa, ta);
     rb = fma(tb * ub, qb, tb);
     const double q4 = 0.78539816339744830962, h = kHalfPi, pi = kPi;

@@ -16,8 +16,10 @@
 //     the fold state spilled around the sample loop);
 //   * everything the phases need that does not depend on the item lives in shared memory (a copy of the kernel
 //     parameters, the per-light-curve tables, the warp's record slot);
-//   * the fold step handles a block inside one light curve with block-constant window and transit centre, two points
-//     per lane and ONE compaction for both; blocks that straddle light curves take a separate general path;
+//   * classification works on CELLS of 16 points, not on 64-point blocks (a Kepler long-cadence block spans 1.3 d:
+//     42 % of the blocks of a 3.5 d orbit are touched, against 14 % of the cells); touched cells are compacted into a
+//     small ring buffer and a fold step takes four of them (eight lanes each, two points per lane, ONE warp-wide
+//     compaction for all 64 points); cells that straddle light curves take a separate general path;
 //   * the sample step is straight fp64 arithmetic: separation (two Horner quartics, rsqrt + one coupled Newton
 //     step: 2^-43), LD-mean node by a float->int floor conversion, lerp as one fused multiply-add on the node
 //     difference; a sample on the stellar limb only drops its separation into the lane's shared-memory column;
@@ -40,13 +42,15 @@ namespace ptb {
 #endif
 constexpr int SS_QCAP = SS_QCAP_;   // in-box points queued per fold phase (a fold step adds up to 64)
 constexpr int SS_FRAME = 16;        // ints of the warp's phase frame
+constexpr int SS_LIST = 128;        // ring buffer of touched cells (16-bit indices relative to the item's first cell)
+constexpr int SS_CPB = PT_BLOCK / SS_CELL;   // cells per 64-point block
 
-// Warp-private shared memory of the supersampled kernel: limb columns, point queue (index + light curve), hit bitmap,
-// phase frame, mbarrier, record slot (+ its float copy in fp32 mode).
+// Warp-private shared memory of the supersampled kernel: limb columns, point queue (index + light curve), hit bitmap
+// (one bit per cell), phase frame, ring of touched cells, mbarrier, record slot (+ its float copy in fp32 mode).
 __host__ __device__ inline size_t ss_tpart(int ssc, int tsize) { return ((size_t)(ssc * PT_COLS) * tsize + 15) & ~size_t(15); }
 __host__ __device__ inline size_t ss_warp_bytes(int ssc, int recstride, int tsize) {
     const size_t rec_t = (tsize == 4) ? (((size_t)recstride * 4 + 15) & ~size_t(15)) : 0;
-    return ss_tpart(ssc, tsize) + (size_t)2 * SS_QCAP * 4 + PT_MAXBLK / 8 + SS_FRAME * 4 + 16 + (size_t)recstride * 8 + rec_t;
+    return ss_tpart(ssc, tsize) + (size_t)2 * SS_QCAP * 4 + PT_MAXBLK / 8 + SS_FRAME * 4 + SS_LIST * 2 + 16 + (size_t)recstride * 8 + rec_t;
 }
 // CTA-wide part: a copy of the kernel parameters, then the per-light-curve tables
 constexpr size_t SS_PARAM_BYTES = (sizeof(PointsParams) + 127) & ~size_t(127);
@@ -64,12 +68,13 @@ struct SsWarp {
     __device__ __forceinline__ int *q_lc() const { return q_ipt() + SS_QCAP; }
     __device__ __forceinline__ unsigned *hit() const { return reinterpret_cast<unsigned *>(q_lc() + SS_QCAP); }
     __device__ __forceinline__ volatile int *frame() const { return reinterpret_cast<volatile int *>(hit() + PT_MAXBLK / 32); }
-    __device__ __forceinline__ uint64_t *bar() const { return reinterpret_cast<uint64_t *>(hit() + PT_MAXBLK / 32 + SS_FRAME); }
+    __device__ __forceinline__ unsigned short *clist() const { return reinterpret_cast<unsigned short *>(hit() + PT_MAXBLK / 32 + SS_FRAME); }
+    __device__ __forceinline__ uint64_t *bar() const { return reinterpret_cast<uint64_t *>(clist() + SS_LIST); }
     __device__ __forceinline__ double *rec() const { return reinterpret_cast<double *>(bar() + 2); }
     __device__ __forceinline__ T *rec_t() const { return reinterpret_cast<T *>(rec() + recstride); }   // fp32 mode only
 };
 // slots of the phase frame (warp-uniform values)
-enum : int { FR_WI = 0, FR_WBITS, FR_CUR, FR_QN, FR_DONE, FR_IPV, FR_CHUNK, FR_BBEG, FR_BEND, FR_NEXT_LO, FR_NEXT_HI, FR_ITER };
+enum : int { FR_WI = 0, FR_LHEAD, FR_LTAIL, FR_QN, FR_DONE, FR_IPV, FR_CHUNK, FR_BBEG, FR_NCL, FR_NEXT_LO, FR_NEXT_HI, FR_ITER };
 
 // the per-light-curve tables behind the parameter copy
 template <typename T>
@@ -116,114 +121,145 @@ __device__ __forceinline__ float sqrt_sep(float x) { return sqrtf(x); }
 __device__ __forceinline__ int floor_to_int(double x) { return __double2int_rd(x); }   // saturating, NaN -> 0
 __device__ __forceinline__ int floor_to_int(float x) { return __float2int_rd(x); }
 
-// next set bit of the item's hit bitmap (-1: none left)
-__device__ __forceinline__ int ss_next_block(int &wi, unsigned &wbits, int nwords, const unsigned *s_hit) {
-    while (wbits == 0u) {
-        if (++wi >= nwords) return -1;
-        wbits = s_hit[wi];
-    }
-    const int j = __ffs(wbits) - 1;
-    wbits &= wbits - 1;
-    return wi * 32 + j;
+// LD-mean lerp (common.py:225-233) at grid position x = g/dg >= 0: node i = floor(x), weight x - i, upper node clamped to
+// the last one (the reference reads one element past the row for g in (1-1e-7, 1]).  fp64: no conversion instructions
+// (F2I / I2F run on the quarter-rate pipe) -- adding 1.5 * 2^52 rounds x - 0.5 to the nearest integer, which is
+// floor(x) except when x is an integer (then it may be x - 1 with weight 1: the same value); the node index is the low
+// word of the sum.  A position that is NaN or beyond the row gives a clamped node and a meaningless (NaN for NaN) weight:
+// such samples are outside the stellar disk and their value is not used.
+#ifndef SS_MAGIC_FLOOR
+#define SS_MAGIC_FLOOR 1
+#endif
+__device__ __forceinline__ double ld_lerp(double x, const double *row, int ng) {
+#if SS_MAGIC_FLOOR
+    const double m = (x - 0.5) + 6755399441055744.0;            // 1.5 * 2^52: the sum stays in [2^52, 2^53), ulp 1
+    const int i0 = (int)min((unsigned)__double2loint(m), (unsigned)(ng - 2));
+    const double a = x - (m - 6755399441055744.0);
+#else
+    const int i0 = min(floor_to_int(x), ng - 2);
+    const double a = x - (double)i0;
+#endif
+    const double r0 = row[i0], r1 = row[i0 + 1];
+    return fma(a, r1 - r0, r0);
+}
+__device__ __forceinline__ float ld_lerp(float x, const float *row, int ng) {
+    const int i0 = min(floor_to_int(x), ng - 2);     // >= 0; NaN -> 0 (the weight stays NaN)
+    const float r0 = row[i0], r1 = row[i0 + 1];
+    return fmaf(x - (float)i0, r1 - r0, r0);
 }
 
-// ---- fold phase: exact per-point fold + box test over touched blocks (model_full.py:88-91) until the queue holds
-// more than SS_QCAP - 64 in-box points or the item's blocks are exhausted.  The fluxes of the blocks' points are set
-// to 1.0 here (the drain overwrites the in-box ones); in likelihood mode the out-of-box points add their chi^2 here.
+// ---- fold phase: exact per-point fold + box test over touched cells (model_full.py:88-91) until the queue holds
+// more than SS_QCAP - 64 in-box points or the item's cells are exhausted.  The fluxes of the cells' points are set to
+// 1.0 here (the drain overwrites the in-box ones); in likelihood mode the out-of-box points add their chi^2 here.
 // Returns the lane's chi^2 increment.
 template <int VEC, bool SINGLE_LC, bool LNL, typename T>
 __device__ __noinline__ double ss_fold() {
     SS_PHASE_PROLOGUE(T);
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned *s_hit = ws.hit();
+    unsigned short *clist = ws.clist();
     int *q_ipt = ws.q_ipt(), *q_lc = ws.q_lc();
     int qn = fr[FR_QN];
-    const int ipv = fr[FR_IPV], bbeg = fr[FR_BBEG], nwords = (fr[FR_BEND] - bbeg + 31) >> 5;
-    int wi = fr[FR_WI];
-    unsigned wbits = (unsigned)fr[FR_WBITS];
-    int cur = fr[FR_CUR];
+    const int ipv = fr[FR_IPV], bbeg = fr[FR_BBEG], nwords = (fr[FR_NCL] + 31) >> 5;
+    int wi = fr[FR_WI], head = fr[FR_LHEAD], tail = fr[FR_LTAIL];   // next bitmap word; ring positions (monotonic)
     const double *rec = ws.rec();
     const double p = rec[ORB_P], invp = rec[ORB_INVP], T1 = rec[ORB_T1], T4 = rec[ORB_T4];
     const double *t0v = rec + ORB_STRIDE;
-    // this lane's corner of the item: 64-bit addresses once per phase, 32-bit offsets per block
-    const long long lbase = (long long)bbeg * PT_BLOCK + lane * VEC;
-    const double *tl = P.time + lbase;
-    const double *ol = LNL ? P.obs + lbase : nullptr;
-    T *fl = LNL ? nullptr : reinterpret_cast<T *>(P.flux) + (size_t)ipv * P.npt + lbase;
-    const int32_t *bl = P.blc + bbeg;
-    const long long left = P.npt - lbase;                                   // offsets < rem are inside the time axis
+    // the item's corner of the arrays: 64-bit addresses once per phase, 32-bit offsets per cell
+    const long long pbase = (long long)bbeg * PT_BLOCK;
+    const double *tl = P.time + pbase;
+    const double *ol = LNL ? P.obs + pbase : nullptr;
+    T *fl = LNL ? nullptr : reinterpret_cast<T *>(P.flux) + (size_t)ipv * P.npt + pbase;
+    const int32_t *cl = P.clc + bbeg * SS_CPB;
+    const long long left = P.npt - pbase;                                   // offsets < rem are inside the time axis
     const int rem = (int)(left > 0x7fffffffll ? 0x7fffffffll : left);     // (VEC == 2 requires an even npt: vectors are all-in or all-out)
-    const int ipt0 = (int)lbase;
+    const int ipt0 = (int)pbase;
     const double *isig2 = LNL ? P.isig2 + (size_t)ipv * P.nblocks : nullptr;
     const double w_one = (LNL && !P.blk) ? isig2[0] : 0.0;  // single noise block: its weight is an item constant
     double chi = 0.0;
-
+    // A fold step takes four cells, eight lanes each; a lane folds two points of its cell: A and B are neighbours
+    // (VEC == 2, one 16-byte load) or 8 points apart (VEC == 1, odd npt or unaligned arrays).
+    constexpr int DB = (VEC == 2) ? 1 : 8;
+    const int g = lane >> 3, loff = (lane & 7) * VEC;
     T ones[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) ones[j] = T(1);
-    // A lane folds two points of every 64-point block: A and B are neighbours (VEC == 2, one 16-byte load) or 32
-    // points apart (VEC == 1, odd npt or unaligned arrays).  Scalars, not arrays: they must stay in registers.
-    constexpr int DB = (VEC == 2) ? 1 : 32;
-    double tnA = 0.0, tnB = 0.0, onA = 1.0, onB = 1.0;   // the prefetched block: time stamps, (likelihood) observed fluxes
-    int lcn = 0;                                          // its light curve (-1: mixed, per-point lookup)
-    auto load_block = [&](int bb) {
-        const int off = bb * PT_BLOCK;
-        if (!SINGLE_LC) lcn = __ldg(bl + bb);
-        tnA = 0.0; tnB = 0.0;
+
+    // the set bits of the next bitmap words go to the ring while it has room for a whole word
+    auto refill = [&]() {
+        while (tail - head <= SS_LIST - 32 && wi < nwords) {
+            const unsigned w = s_hit[wi];
+            if ((w >> lane) & 1u) clist[(tail + __popc(w & lt_mask)) & (SS_LIST - 1)] = (unsigned short)(wi * 32 + lane);
+            tail += __popc(w);
+            ++wi;
+        }
+        __syncwarp();
+    };
+    // the next group of up to four cells with its time stamps (and observed fluxes) in flight
+    int celln = -1, cntn = 0, lcn = 0;
+    double tnA = 0.0, tnB = 0.0, onA = 1.0, onB = 1.0;
+    auto fetch = [&]() {
+        cntn = min(4, tail - head);
+        celln = (g < cntn) ? (int)clist[(head + g) & (SS_LIST - 1)] : -1;
+        head += cntn;
+        tnA = 0.0; tnB = 0.0; lcn = 0;
         if (LNL) { onA = 1.0; onB = 1.0; }
-        if (VEC == 2) {
-            if (off < rem) {
-                const double2 t = __ldg(reinterpret_cast<const double2 *>(tl + off));
-                tnA = t.x; tnB = t.y;
-                if (LNL) {
-                    const double2 o = __ldg(reinterpret_cast<const double2 *>(ol + off));
-                    onA = o.x; onB = o.y;
+        if (celln >= 0) {
+            const int off = celln * SS_CELL + loff;
+            if (!SINGLE_LC) lcn = __ldg(cl + celln);
+            if (VEC == 2) {
+                if (off < rem) {
+                    const double2 t = __ldg(reinterpret_cast<const double2 *>(tl + off));
+                    tnA = t.x; tnB = t.y;
+                    if (LNL) {
+                        const double2 o = __ldg(reinterpret_cast<const double2 *>(ol + off));
+                        onA = o.x; onB = o.y;
+                    }
                 }
+            } else {
+                if (off < rem) { tnA = __ldg(tl + off); if (LNL) onA = __ldg(ol + off); }
+                if (off + DB < rem) { tnB = __ldg(tl + off + DB); if (LNL) onB = __ldg(ol + off + DB); }
             }
-        } else {
-            if (off < rem) { tnA = __ldg(tl + off); if (LNL) onA = __ldg(ol + off); }
-            if (off + DB < rem) { tnB = __ldg(tl + off + DB); if (LNL) onB = __ldg(ol + off + DB); }
         }
     };
 
-    if (cur == -2) cur = ss_next_block(wi, wbits, nwords, s_hit);   // -2: nothing taken from the bitmap yet
-    if (cur >= 0) load_block(cur);
-    int lc_last = -2;   // the block constants below belong to this light curve
-    double lob = 0.0, hib = 0.0, t0b = 0.0;
+    double lob = 0.0, hib = 0.0, t0b = 0.0;   // window and transit centre of the lane's cell
     if (SINGLE_LC) {
         const double pd = tb.sPad[0];
         lob = T1 - pd;
         hib = T4 + pd;
         t0b = t0v[tb.sEp[0]];
     }
-
-    while (cur >= 0 && qn <= SS_QCAP - PT_BLOCK) {
-        const int offA = cur * PT_BLOCK, offB = offA + DB;
+    refill();
+    int head0 = head;   // ring position of the first cell that has not been folded
+    fetch();
+    while (cntn > 0 && qn <= SS_QCAP - PT_BLOCK) {
+        const int cell = celln, lcb = lcn;
         const double tA = tnA, tB = tnB, oA = onA, oB = onB;
-        const int lcb = SINGLE_LC ? 0 : lcn;
-        if (!SINGLE_LC && lcb >= 0 && lcb != lc_last) {   // window and transit centre of the block's light curve
-            const double pd = tb.sPad[lcb];
-            lob = T1 - pd;
-            hib = T4 + pd;
-            t0b = t0v[tb.sEp[lcb]];
-            lc_last = lcb;
-        }
-        cur = ss_next_block(wi, wbits, nwords, s_hit);
-        if (cur >= 0) load_block(cur);  // in flight while this block is folded
-        const bool inrA = offA < rem, inrB = offB < rem;
+        head0 = head;
+        refill();
+        fetch();  // in flight while this group is folded
+        const int offA = (cell >= 0 ? cell : 0) * SS_CELL + loff, offB = offA + DB;
+        const bool inrA = cell >= 0 && offA < rem, inrB = cell >= 0 && offB < rem;
         bool inA, inB;
         int lcA = lcb, lcB = lcb;
         // epoch = floor((t - t0 + p/2)/p); tc = t - (t0 + epoch p)  (model_full.py:88-89).  The division is a
         // multiplication by 1/p: the two can only disagree half a period away from the transit, where the
         // point is outside the box either way.  Always fp64: time stamps need all their digits.
-        if (SINGLE_LC || lcb >= 0) {   // the rule: window and transit centre are block constants
+        if (SINGLE_LC || !__any_sync(0xffffffffu, lcb < 0)) {   // the rule: window and transit centre are cell constants
+            if (!SINGLE_LC) {
+                const double pd = tb.sPad[lcb];
+                lob = T1 - pd;
+                hib = T4 + pd;
+                t0b = t0v[tb.sEp[lcb]];
+            }
             const double eA = floor(fma(tA - t0b, invp, 0.5)), eB = floor(fma(tB - t0b, invp, 0.5));
             const double tcA = tA - __dadd_rn(t0b, __dmul_rn(eA, p)), tcB = tB - __dadd_rn(t0b, __dmul_rn(eB, p));
             inA = inrA && (lob <= tcA) && (tcA <= hib);
             inB = inrB && (lob <= tcB) && (tcB <= hib);
-        } else {                       // a block that straddles light curves: per-point lookup
-            lcA = inrA ? P.lcids[(long long)ipt0 + offA] : 0;
-            lcB = inrB ? P.lcids[(long long)ipt0 + offB] : 0;
+        } else {                       // some cell of the group straddles light curves: per-point lookup
+            lcA = lcb >= 0 ? lcb : (inrA ? P.lcids[(long long)ipt0 + offA] : 0);
+            lcB = lcb >= 0 ? lcb : (inrB ? P.lcids[(long long)ipt0 + offB] : 0);
             const double pdA = tb.sPad[lcA], t0A = t0v[tb.sEp[lcA]], pdB = tb.sPad[lcB], t0B = t0v[tb.sEp[lcB]];
             const double eA = floor(fma(tA - t0A, invp, 0.5)), eB = floor(fma(tB - t0B, invp, 0.5));
             const double tcA = tA - __dadd_rn(t0A, __dmul_rn(eA, p)), tcB = tB - __dadd_rn(t0B, __dmul_rn(eB, p));
@@ -242,7 +278,7 @@ __device__ __noinline__ double ss_fold() {
                 if (nb >= 0) chi = fma(d * d, P.blk ? isig2[nb] : w_one, chi);
             }
         }
-        // one compaction for the lane's two points
+        // one compaction for the warp's 64 points
         const unsigned mA = __ballot_sync(0xffffffffu, inA), mB = __ballot_sync(0xffffffffu, inB);
         int pos = qn + __popc(mA & lt_mask) + __popc(mB & lt_mask);
         qn += __popc(mA) + __popc(mB);
@@ -255,7 +291,7 @@ __device__ __noinline__ double ss_fold() {
             q_ipt[pos] = ipt0 + offB;
             if (!SINGLE_LC) q_lc[pos] = lcB;
         }
-        // 1.0 for the block's points, default cache policy (not evict-first): the line is still in L2 when the drain
+        // 1.0 for the cells' points, default cache policy (not evict-first): the line is still in L2 when the drain
         // updates its in-box points, so it reaches DRAM once
         if (!LNL) {
             if (VEC == 2) {
@@ -267,8 +303,10 @@ __device__ __noinline__ double ss_fold() {
         }
     }
     fr[FR_QN] = qn;
-    fr[FR_DONE] = cur < 0;
-    fr[FR_WI] = wi; fr[FR_WBITS] = (int)wbits; fr[FR_CUR] = cur;   // `cur` is taken from the bitmap but not folded yet
+    fr[FR_DONE] = cntn == 0;                  // nothing fetched: ring and bitmap are exhausted
+    fr[FR_WI] = wi;
+    fr[FR_LHEAD] = cntn > 0 ? head0 : head;   // a group fetched but not folded (queue full) is fetched again
+    fr[FR_LTAIL] = tail;
     return chi;
 }
 
@@ -323,12 +361,7 @@ __device__ __forceinline__ double ss_drain(const PointsParams &P, const SsTables
             const T px = fma(t, fma(t, fma(t, fma(t, cx[4], cx[3]), cx[2]), cx[1]), cx[0]);
             const T py = fma(t, fma(t, fma(t, fma(t, cy[4], cy[3]), cy[2]), cy[1]), cy[0]);
             const T z = sqrt_sep(fma(px, px, py * py));      // sep_c (taylor_z.py:229-255)
-            // LD-mean lerp (common.py:225-233): node i = floor(g/dg), weight g/dg - i; the upper node is clamped
-            // to the last one (the reference reads one element past the row for g in (1-1e-7, 1])
-            const T x = z * xs;
-            const int i0 = min(floor_to_int(x), ng - 2);     // >= 0; NaN -> 0 (the weight stays NaN)
-            const T r0 = row[i0], r1 = row[i0 + 1];
-            const T ip = fma(x - (T)i0, r1 - r0, r0);
+            const T ip = ld_lerp(z * xs, row, ng);
 #if SS_BRANCHY_TAIL
             if (zout <= z) {
                 sum += c_out;
@@ -382,10 +415,7 @@ __device__ __forceinline__ double ss_drain(const PointsParams &P, const SsTables
                 const T *r2 = SINGLE_LC ? row : ld + ro;
                 T *slot = colz + r * PT_COLS + o;
                 const T z = *slot;
-                const T x = z * (r2[ng + 1] * inv_dg);
-                const int i0 = min(floor_to_int(x), ng - 2);
-                const T r0 = r2[i0], r1 = r2[i0 + 1];
-                const T ip = fma(x - (T)i0, r1 - r0, r0);
+                const T ip = ld_lerp(z * (r2[ng + 1] * inv_dg), r2, ng);
                 T area, kap;
                 kite_area<T>(r2[ng], r2[ng + 3], z, area, kap);
                 *slot = one - ip * area * r2[ng + 2];
@@ -493,8 +523,9 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB_SS2) k_rr_points_ss(const 
             const int chunk = (int)(item - (long long)ipv * P.nchunks);
             const int bbeg = chunk * P.blocks_per_chunk;
             const int bend = min(P.nblk64, bbeg + P.blocks_per_chunk);
-            const int nbc = bend - bbeg;
-            fr[FR_IPV] = ipv; fr[FR_CHUNK] = chunk; fr[FR_BBEG] = bbeg; fr[FR_BEND] = bend;
+            const int cbeg = bbeg * SS_CPB;                      // the item's cells
+            const int ncl = min(P.ncell, bend * SS_CPB) - cbeg;
+            fr[FR_IPV] = ipv; fr[FR_CHUNK] = chunk; fr[FR_BBEG] = bbeg; fr[FR_NCL] = ncl;
             fr[FR_NEXT_LO] = (int)(unsigned)(next & 0xffffffffll); fr[FR_NEXT_HI] = (int)(next >> 32);
             fr[FR_ITER] = iter + 1;
             T *frow = LNL ? nullptr : reinterpret_cast<T *>(P.flux) + (size_t)ipv * npt;
@@ -526,57 +557,59 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB_SS2) k_rr_points_ss(const 
             const double *t0v = rec + ORB_STRIDE;
             const double w_one = (LNL && !P.blk) ? isig2[0] : 0.0;  // single noise block: its weight is an item constant
 
-            // ---- 1. classification of every block of this item (see k_rr_points) ------------------------------
-            for (int bb0 = 0; bb0 < nbc; bb0 += 32) {
-                const int bb = bb0 + lane, b = bbeg + bb;
+            // ---- 1. classification of every cell of this item (see k_rr_points) -------------------------------
+            for (int cc0 = 0; cc0 < ncl; cc0 += 32) {
+                const int cc = cc0 + lane, c = cbeg + cc;
                 bool hit = false;
-                if (bb < nbc) {
+                if (cc < ncl) {
                     hit = true;
-                    const int lcb = SINGLE_LC ? 0 : P.blc[b];
+                    const int lcb = SINGLE_LC ? 0 : P.clc[c];
                     int nz_id = 0;
-                    if (LNL && P.blk) nz_id = P.bnoise ? P.bnoise[b] : 0;
-                    const bool partial = (b == P.nblk64 - 1) && (npt % PT_BLOCK != 0);
+                    if (LNL && P.blk) nz_id = P.cnoise ? P.cnoise[c] : 0;
+                    const bool partial = (c == P.ncell - 1) && (npt % SS_CELL != 0);
                     if (lcb >= 0 && nz_id != -2 && !partial) {
                         const double pd = sPad[lcb], t0 = t0v[sEp[lcb]];
-                        const double n1 = ceil(fma(P.bmin[b] - t0 - (T4 + pd), invp, -PT_EPS));
-                        const double n2 = floor(fma(P.bmax[b] - t0 - (T1 - pd), invp, PT_EPS));
+                        const double n1 = ceil(fma(P.cmin[c] - t0 - (T4 + pd), invp, -PT_EPS));
+                        const double n2 = floor(fma(P.cmax[c] - t0 - (T1 - pd), invp, PT_EPS));
                         hit = !(n1 > n2) || !(p > 0.0);  // NaNs and p <= 0 fall through to the exact per-point path
                     }
-                    if (LNL && !hit && nz_id >= 0) chi = fma(P.bchi[b], P.blk ? isig2[nz_id] : w_one, chi);
+                    if (LNL && !hit && nz_id >= 0) chi = fma(P.cchi[c], P.blk ? isig2[nz_id] : w_one, chi);
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (lane == 0) s_hit[bb0 >> 5] = m;
+                if (lane == 0) s_hit[cc0 >> 5] = m;
             }
             __syncwarp();
 
-            // ---- 2. untouched blocks: 64 fluxes of exactly 1.0, vectorised streaming stores ---------------------
+            // ---- 2. untouched cells: 16 fluxes of exactly 1.0 each, vectorised streaming stores; a bitmap word
+            //         covers 32 cells = 512 points = eight 64-point rows -------------------------------------------
             if (!LNL) {
                 T one[VEC];
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) one[j] = T(1);
-                const int ngroups = (nbc + 7) >> 3;
-                for (int g = 0; g < ngroups; ++g) {
-                    const unsigned bits = (s_hit[g >> 2] >> ((g & 3) * 8)) & 0xffu;
-                    const int b0 = bbeg + g * 8;
-                    T *fb = frow + (long long)b0 * PT_BLOCK + lane * VEC;
-                    if (bits == 0u && b0 + 8 <= bend) {  // the common case: eight untouched blocks, no predicates
+                const int nw = (ncl + 31) >> 5;
+                T *f0 = frow + (long long)cbeg * SS_CELL + lane * VEC;
+                for (int w = 0; w < nw; ++w) {
+                    const unsigned bits = s_hit[w];
+                    T *fw = f0 + w * (32 * SS_CELL);
+                    if (bits == 0u && (w + 1) * 32 <= ncl) {  // the common case: 32 untouched cells, no predicates
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
 #pragma unroll
-                            for (int h = 0; h < NH; ++h) VecIO<VEC, T>::store(fb + j * PT_BLOCK + h * 32 * VEC, one);
+                            for (int h = 0; h < NH; ++h) VecIO<VEC, T>::store(fw + j * PT_BLOCK + h * 32 * VEC, one);
                         }
-                    } else if (bits != 0xffu) {
+                    } else if (bits != 0xffffffffu) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            if (!((bits >> j) & 1u) && b0 + j < bend) {
 #pragma unroll
-                                for (int h = 0; h < NH; ++h) VecIO<VEC, T>::store(fb + j * PT_BLOCK + h * 32 * VEC, one);
+                            for (int h = 0; h < NH; ++h) {
+                                const int ci = (j * PT_BLOCK + h * 32 * VEC + lane * VEC) / SS_CELL;   // cell within the word
+                                if (!((bits >> ci) & 1u) && w * 32 + ci < ncl) VecIO<VEC, T>::store(fw + j * PT_BLOCK + h * 32 * VEC, one);
                             }
                         }
                     }
                 }
             }
-            fr[FR_WI] = 0; fr[FR_WBITS] = (int)s_hit[0]; fr[FR_CUR] = -2; fr[FR_QN] = 0; fr[FR_DONE] = 0;
+            fr[FR_WI] = 0; fr[FR_LHEAD] = 0; fr[FR_LTAIL] = 0; fr[FR_QN] = 0; fr[FR_DONE] = 0;
         }
         __syncwarp();
 

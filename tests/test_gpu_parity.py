@@ -1117,6 +1117,53 @@ def test_supersampling_and_layout_corner_cases_vs_oracle(pb, orc, tab):
     run(t3, lc3, np.arange(nlc) % 8, np.arange(nlc) % 5, np.full(nlc, 30), np.full(nlc, 0.0204), npv=12)   # + likelihood
 
 
+def test_supersampled_kernel_phases_cells_and_centre_crossing(pb, orc, tab):
+    """Structure of k_rr_points_ss (ptb_ss_kernels.cuh) that the fixtures do not pin: (1) an item whose in-box points
+    exceed the fold phase's queue many times over (every point of a long in-transit stretch: the fold / drain phases
+    alternate and resume from the ring of touched cells), (2) a time axis that is not a multiple of the 16-point cell
+    (the partial last cell takes the exact path) with NaN time stamps inside a cell, (3) central transits (b = 0, the
+    separation passes through zero: LD-mean grid positions below half a node) and a planet larger than the star,
+    (4) the fp32 mode of the same kernel -- all against the oracle."""
+    rng = np.random.default_rng(1234)
+
+    def check(time, nsamples, exptime, k, t0, p, a, b, tol=FLUX_TOL, precision='fp64', law='quadratic'):
+        npv = k.shape[0]
+        i = np.arccos(b / a)
+        e = np.zeros(npv)
+        w = np.zeros(npv)
+        ldc = rng.uniform(0.1, 0.5, size=(npv, 1, 2))
+        lcids = np.zeros(time.size, np.int64)
+        m = pb.RoadRunnerModelCUDA(law, precision=precision)
+        m.set_data(time, nsamples=nsamples, exptimes=exptime)
+        f = np.atleast_2d(m.evaluate(k, ldc, t0, p, a, i, e, w)).astype(np.float64)
+        ldp, istar = orc.evaluate_ld(law, tab.mu, ldc)
+        ref = orc.rr_full(tab, time, k, t0, p, a, i, e, w, lcids, np.zeros(1, np.int64), np.zeros(1, np.int64),
+                          np.array([nsamples], np.int64), np.array([exptime]), ldp, istar)
+        assert np.array_equal(np.isnan(f), np.isnan(ref))
+        err = np.nanmax(np.abs(f - ref))
+        assert err <= tol, err
+        return ref
+
+    # (1) + (3): 20 000 points inside ONE transit of a long-period planet, b = 0 for half of the vectors
+    npv = 8
+    t = np.linspace(-0.3, 0.3, 20_000)
+    k = rng.uniform(0.05, 0.15, size=(npv, 1))
+    k[-1] = 1.3                                                     # planet larger than the star
+    b = np.where(np.arange(npv) % 2 == 0, 0.0, rng.uniform(0.0, 0.9, npv))
+    ref = check(t, 10, 0.02, k, np.zeros((npv, 1)), np.full(npv, 30.0), np.full(npv, 12.0), b)
+    assert (ref < 1).mean() > 0.9
+    # (2): 6010 points (not a multiple of 16), NaN time stamps in the middle of a cell and in the last, partial cell
+    t = np.arange(6010) * 0.0204
+    t[[1000, 1001, 6005]] = np.nan
+    k = rng.uniform(0.05, 0.15, size=(npv, 1))
+    check(t, 10, 0.0204, k, rng.normal(1.0, 0.01, size=(npv, 1)), rng.normal(3.5, 0.01, npv), rng.normal(10.0, 0.5, npv),
+          rng.uniform(0.0, 0.9, npv))
+    # (4): the same kernel in the fp32 mode
+    t = np.arange(6000) * 0.0204
+    check(t, 10, 0.0204, k, rng.normal(1.0, 0.01, size=(npv, 1)), rng.normal(3.5, 0.01, npv), rng.normal(10.0, 0.5, npv),
+          rng.uniform(0.0, 0.9, npv), tol=FP32_TOL, precision='fp32')
+
+
 @pytest.mark.parametrize('law', ['uniform', 'linear', 'quadratic', 'quadratic-tri', 'nonlinear', 'general', 'square_root',
                                  'logarithmic', 'exponential', 'power-2', 'power-2-pm'])
 def test_full_flux_path_for_every_ld_law(pb, golden, law):
