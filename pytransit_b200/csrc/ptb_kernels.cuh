@@ -625,22 +625,18 @@ struct DrainCtx {
     int lane;
 };
 
-// One exposure sub-sample at time `t` from mid-transit, straight-line code (selects only, so that two
-// samples of one lane interleave): separation (taylor_z.py:229-255), LD-mean lerp
-// (common.py:225-233) and the area cases that need no lens formula (common.py:52-73).  `limb` marks a
-// sample on the limb: its contribution comes from limb_pass.
+// One sample at time `t` from mid-transit, straight-line code (selects only): separation (taylor_z.py:229-255; rsqrt +
+// one coupled Newton step, 2^-43), LD-mean lerp (common.py:225-233) at grid position z * xs (xs = 1/((1+k) dg)) and the
+// area cases that need no lens formula (common.py:52-73).  `limb` marks a sample on the limb: its contribution comes
+// from limb_pass.
 template <typename T>
-__device__ __forceinline__ void sample_eval(T t, const T *cx, const T *cy, const T *row, int ng, T k, T inv1k, T inv_istar,
-                                            T k2, T dg, T inv_dg, T &z, T &ip, T &cc, bool &limb) {
+__device__ __forceinline__ void sample_eval(T t, const T *cx, const T *cy, const T *row, int ng, T k, T xs, T inv_istar,
+                                            T k2, T &z, T &ip, T &cc, bool &limb) {
     const T one = T(1), pi = T(kPi), qnan = T(nan(""));
-    z = sep_poly<T>(t, cx, cy);
-    const T g = z * inv1k;       // >= 0, or NaN; a negative g needs k < -1: k_rr_ldm stores NaN rows for that
-    const T fl = floor(g * inv_dg);
-    const T a = (g - fl * dg) * inv_dg;
-    const int i = (int)fl;  // saturating conversion; NaN -> 0
-    const int i0 = min(max(i, 0), ng - 1), i1 = min(max(i + 1, 0), ng - 1);
-    const T v = (one - a) * row[i0] + a * row[i1];
-    ip = (g > one) ? T(0) : v;
+    const T px = fma(t, fma(t, fma(t, fma(t, cx[4], cx[3]), cx[2]), cx[1]), cx[0]);
+    const T py = fma(t, fma(t, fma(t, fma(t, cy[4], cy[3]), cy[2]), cy[1]), cy[0]);
+    z = sqrt_sep(fma(px, px, py * py));
+    ip = ld_lerp(z * xs, row, ng);                            // used only where the planet overlaps the disk
     const bool out = (one + k <= z);
     limb = !out && (fabs(one - k) < z);
     const bool covers = (z <= k - one);                       // planet covers the star: area pi; else pi k^2
@@ -665,9 +661,9 @@ __device__ __forceinline__ double limb_pass(const PointsParams &P, const WarpScr
         const int ipt = ws.l_slot()[q];
         if (LNL) {
             const int b = P.blk ? P.blk[ipt] : 0;
-            if (b >= 0) {
-                const double d = P.obs[ipt] - (double)v;
-                chi = d * d * isig2[b];
+            if (b >= 0) {   // the point's (obs - 1)^2 is already in the block baseline: swap it for (obs - model)^2
+                const double o = P.obs[ipt], d1 = o - (double)v, d0 = o - 1.0;
+                chi = fma(d1, d1, -d0 * d0) * isig2[b];
             }
         } else {
             frow[ipt] = v;
@@ -684,7 +680,7 @@ __device__ __forceinline__ double drain_points(const DrainCtx<T> &c, const WarpS
                                                const double *isig2, int base, int n, int &nl, bool flush) {
     const PointsParams &P = *c.P;
     const int lane = c.lane, ng = P.ng;
-    const T dg = (T)P.dg, inv_dg = (T)P.inv_dg;
+    const T inv_dg = (T)P.inv_dg;
     const unsigned lt_mask = (1u << lane) - 1u;
     const T *ld = rt + P.rec_ld;
     T cx[5], cy[5];
@@ -707,7 +703,7 @@ __device__ __forceinline__ double drain_points(const DrainCtx<T> &c, const WarpS
     T z, ip, cc;
     bool limb;
     // the exposure offset exptime*((1-0.5)/1 - 0.5) is exactly 0 (model_full.py:94), as the reference's own product is
-    sample_eval<T>(tc, cx, cy, row, ng, k, inv1k, inv_istar, k2, dg, inv_dg, z, ip, cc, limb);
+    sample_eval<T>(tc, cx, cy, row, ng, k, inv1k * inv_dg, inv_istar, k2, z, ip, cc, limb);
     limb = limb && valid;
     const unsigned m = __ballot_sync(0xffffffffu, limb);
     if (m) {
@@ -724,9 +720,9 @@ __device__ __forceinline__ double drain_points(const DrainCtx<T> &c, const WarpS
     if (valid && !limb) {   // everything that is not on the limb is final
         if (LNL) {
             const int b = P.blk ? P.blk[ipt] : 0;
-            if (b >= 0) {
-                const double d = P.obs[ipt] - (double)cc;
-                chi += d * d * isig2[b];
+            if (b >= 0) {   // swap the baseline's (obs - 1)^2 for (obs - model)^2
+                const double o = P.obs[ipt], d1 = o - (double)cc, d0 = o - 1.0;
+                chi += fma(d1, d1, -d0 * d0) * isig2[b];
             }
         } else {
             frow[ipt] = cc;
@@ -865,7 +861,9 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB_S1) k_rr_points(const __gr
                     const double n2 = floor(fma(P.bmax[b] - t0 - lo, invp, PT_EPS));
                     hit = !(n1 > n2) || !(p > 0.0);  // NaNs and p <= 0 fall through to the exact per-point path
                 }
-                if (LNL && !hit && nz_id >= 0) chi = fma(P.bchi[b], P.blk ? isig2[nz_id] : w_one, chi);
+                // likelihood baseline: sum of (obs - 1)^2 of EVERY block that has one noise id, touched or not (the
+                // drain swaps the in-box points' terms for (obs - model)^2); blocks with several ids: per point, below
+                if (LNL && nz_id >= 0) chi = fma(P.bchi[b], P.blk ? isig2[nz_id] : w_one, chi);
             }
             const unsigned m = __ballot_sync(0xffffffffu, hit);
             if (lane == 0) s_hit[bb0 >> 5] = m;
@@ -920,103 +918,116 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB_S1) k_rr_points(const __gr
             return wi * 32 + j;
         };
         int cur = next_block();
-        double tvn[2 / VEC][VEC];
-        double obn[2 / VEC][VEC];  // likelihood: the observed fluxes of the prefetched block travel with its time stamps
-        int lcbn = 0;  // light curve of the prefetched block (-1: mixed, per-point lookup)
+        // A lane folds two points of every 64-point block: A and B are neighbours (VEC == 2, one 16-byte load) or 32
+        // points apart (VEC == 1, odd npt or unaligned arrays).  Scalars and 32-bit offsets from the lane's corner of
+        // the item (64-bit addresses once per item).
+        constexpr int DB = (VEC == 2) ? 1 : 32;
+        const long long lbase = (long long)bbeg * PT_BLOCK + lane * VEC;
+        const double *tl = P.time + lbase;
+        const double *ol = LNL ? P.obs + lbase : nullptr;
+        T *fl = LNL ? nullptr : frow + lbase;
+        const int32_t *bl = SINGLE_LC ? nullptr : P.blc + bbeg;
+        const long long left = npt - lbase;                                   // offsets < rem are inside the time axis
+        const int rem = (int)(left > 0x7fffffffll ? 0x7fffffffll : left);   // (VEC == 2 requires an even npt: vectors are all-in or all-out)
+        const int ipt0 = (int)lbase;
+        double tnA = 0.0, tnB = 0.0;   // the prefetched block: time stamps,
+        int lcbn = 0, nzn = 0;         // its light curve (-1: mixed, per-point lookup) and (likelihood) noise id (-2: mixed)
+        const bool nz_lookup = LNL && P.blk && P.bnoise;
         auto load_block = [&](int bb) {
-            const long long base = (long long)(bbeg + bb) * PT_BLOCK;
-            if (!SINGLE_LC) lcbn = __ldg(P.blc + bbeg + bb);
-#pragma unroll
-            for (int h = 0; h < 2 / VEC; ++h) {
-                const long long i0 = base + (long long)(h * 32 + lane) * VEC;
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) tvn[h][j] = 0.0;
-                if (i0 < npt) VecIO<VEC, T>::load(P.time + i0, tvn[h]);
-                if (LNL) {
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) obn[h][j] = 1.0;
-                    if (i0 < npt) VecIO<VEC, T>::load(P.obs + i0, obn[h]);
+            const int off = bb * PT_BLOCK;
+            if (!SINGLE_LC) lcbn = __ldg(bl + bb);
+            if (nz_lookup) nzn = __ldg(P.bnoise + bbeg + bb);
+            tnA = 0.0; tnB = 0.0;
+            if (VEC == 2) {
+                if (off < rem) {
+                    const double2 t = __ldg(reinterpret_cast<const double2 *>(tl + off));
+                    tnA = t.x; tnB = t.y;
                 }
+            } else {
+                if (off < rem) tnA = __ldg(tl + off);
+                if (off + DB < rem) tnB = __ldg(tl + off + DB);
             }
         };
         if (cur >= 0) load_block(cur);
+        int lc_last = SINGLE_LC ? 0 : -2;           // the block constants below belong to this light curve
+        double lob = lo1, hib = hi1, t0b = t01;
+        T ones[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) ones[j] = T(1);
         for (;;) {
             const bool live = cur >= 0;
             if (live) {
-                const long long base = (long long)(bbeg + cur) * PT_BLOCK;
-                double tv[2 / VEC][VEC];
-#pragma unroll
-                for (int h = 0; h < 2 / VEC; ++h)
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) tv[h][j] = tvn[h][j];
-                double ob[2 / VEC][VEC];
-                if (LNL) {
-#pragma unroll
-                    for (int h = 0; h < 2 / VEC; ++h)
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j) ob[h][j] = obn[h][j];
-                }
-                // a block inside one light curve (the rule): window and epoch are block constants
-                const int lcb = SINGLE_LC ? 0 : lcbn;
-                double lob = lo1, hib = hi1, t0b = t01;
-                if (!SINGLE_LC && lcb >= 0) {
+                const int offA = cur * PT_BLOCK, offB = offA + DB;
+                const double tA = tnA, tB = tnB;
+                const int lcb = SINGLE_LC ? 0 : lcbn, nzb = nzn;
+                if (!SINGLE_LC && lcb >= 0 && lcb != lc_last) {   // window and transit centre of the block's light curve
                     const double pd = sPad[lcb];
                     lob = T1 - pd;
                     hib = T4 + pd;
                     t0b = t0v[sEp[lcb]];
+                    lc_last = lcb;
                 }
                 cur = next_block();
                 if (cur >= 0) load_block(cur);  // in flight while this block is folded
-#pragma unroll
-                for (int h = 0; h < 2 / VEC; ++h) {
-                    const long long i0 = base + (long long)(h * 32 + lane) * VEC;
-                    T fv[VEC];
-                    const bool inr = i0 < npt;  // VEC == 2 requires an even npt: vectors are all-in or all-out
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        bool inbox = false;
-                        double tc = 0.0;
-                        int lc = 0;
-                        fv[j] = T(1);
-                        if (inr) {
-                            double lo = lob, hi = hib, t0 = t0b;
-                            if (!SINGLE_LC) lc = lcb;
-                            if (!SINGLE_LC && lcb < 0) {
-                                lc = P.lcids[i0 + j];
-                                const double pd = sPad[lc];
-                                lo = T1 - pd;
-                                hi = T4 + pd;
-                                t0 = t0v[sEp[lc]];
-                            }
-                            // epoch = floor((t - t0 + p/2)/p); tc = t - (t0 + epoch p)  (model_full.py:88-89)
-                            // The division is a multiplication by 1/p: the two can only disagree half a
-                            // period away from the transit, where the point is outside the box either way.
-                            // Always fp64: time stamps need all their digits; tc itself is small.
-                            const double epoch = floor(fma(tv[h][j] - t0, invp, 0.5));
-                            tc = tv[h][j] - __dadd_rn(t0, __dmul_rn(epoch, p));
-                            inbox = (lo <= tc) && (tc <= hi);
-                            if (LNL && !inbox) {
-                                const double d = ob[h][j] - 1.0;
-                                if (!P.blk) {
-                                    chi = fma(d * d, w_one, chi);
-                                } else {
-                                    const int nb = P.blk[i0 + j];
-                                    if (nb >= 0) chi = fma(d * d, isig2[nb], chi);
-                                }
-                            }
-                        }
-                        const unsigned m = __ballot_sync(0xffffffffu, inbox);
-                        if (inbox) {
-                            const int pos = qn + __popc(m & lt_mask);
-                            ws.q_ipt()[pos] = (int)(i0 + j);
-                            ws.q_tc()[pos] = (T)tc;
-                            if (!SINGLE_LC) ws.q_lc()[pos] = lc;
-                        }
-                        qn += __popc(m);
+                const bool inrA = offA < rem, inrB = offB < rem;
+                bool inA, inB;
+                int lcA = lcb, lcB = lcb;
+                double tcA, tcB;
+                // epoch = floor((t - t0 + p/2)/p); tc = t - (t0 + epoch p)  (model_full.py:88-89).  The division is a
+                // multiplication by 1/p: the two can only disagree half a period away from the transit, where the
+                // point is outside the box either way.  Always fp64: time stamps need all their digits; tc is small.
+                if (SINGLE_LC || lcb >= 0) {   // the rule: window and transit centre are block constants
+                    const double eA = floor(fma(tA - t0b, invp, 0.5)), eB = floor(fma(tB - t0b, invp, 0.5));
+                    tcA = tA - __dadd_rn(t0b, __dmul_rn(eA, p));
+                    tcB = tB - __dadd_rn(t0b, __dmul_rn(eB, p));
+                    inA = inrA && (lob <= tcA) && (tcA <= hib);
+                    inB = inrB && (lob <= tcB) && (tcB <= hib);
+                } else {                       // a block that straddles light curves: per-point lookup
+                    lcA = inrA ? P.lcids[(long long)ipt0 + offA] : 0;
+                    lcB = inrB ? P.lcids[(long long)ipt0 + offB] : 0;
+                    const double pdA = sPad[lcA], t0A = t0v[sEp[lcA]], pdB = sPad[lcB], t0B = t0v[sEp[lcB]];
+                    const double eA = floor(fma(tA - t0A, invp, 0.5)), eB = floor(fma(tB - t0B, invp, 0.5));
+                    tcA = tA - __dadd_rn(t0A, __dmul_rn(eA, p));
+                    tcB = tB - __dadd_rn(t0B, __dmul_rn(eB, p));
+                    inA = inrA && (T1 - pdA <= tcA) && (tcA <= T4 + pdA);
+                    inB = inrB && (T1 - pdB <= tcB) && (tcB <= T4 + pdB);
+                }
+                if (LNL && nzb == -2) {   // several noise ids in this block: its baseline, point by point
+                    if (inrA) {
+                        const int nb = P.blk[(long long)ipt0 + offA];
+                        const double d = ol[offA] - 1.0;
+                        if (nb >= 0) chi = fma(d * d, isig2[nb], chi);
                     }
-                    // default cache policy (not evict-first): the line is still in L2 when the drain updates its
-                    // in-box points, so it reaches DRAM once
-                    if (!LNL && inr) VecIO<VEC, T>::store_keep(frow + i0, fv);
+                    if (inrB) {
+                        const int nb = P.blk[(long long)ipt0 + offB];
+                        const double d = ol[offB] - 1.0;
+                        if (nb >= 0) chi = fma(d * d, isig2[nb], chi);
+                    }
+                }
+                // one compaction for the lane's two points
+                const unsigned mA = __ballot_sync(0xffffffffu, inA), mB = __ballot_sync(0xffffffffu, inB);
+                int pos = qn + __popc(mA & lt_mask) + __popc(mB & lt_mask);
+                qn += __popc(mA) + __popc(mB);
+                if (inA) {
+                    ws.q_ipt()[pos] = ipt0 + offA;
+                    ws.q_tc()[pos] = (T)tcA;
+                    if (!SINGLE_LC) ws.q_lc()[pos] = lcA;
+                    ++pos;
+                }
+                if (inB) {
+                    ws.q_ipt()[pos] = ipt0 + offB;
+                    ws.q_tc()[pos] = (T)tcB;
+                    if (!SINGLE_LC) ws.q_lc()[pos] = lcB;
+                }
+                // 1.0 for the block's points, default cache policy (not evict-first): the line is still in L2 when the
+                // drain updates its in-box points, so it reaches DRAM once
+                if (!LNL) {
+                    if (VEC == 2) {
+                        if (inrA) VecIO<VEC, T>::store_keep(fl + offA, ones);
+                    } else {
+                        if (inrA) fl[offA] = T(1);
+                        if (inrB) fl[offB] = T(1);
+                    }
                 }
                 __syncwarp();
             }

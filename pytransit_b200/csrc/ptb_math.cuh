@@ -326,6 +326,49 @@ __device__ __forceinline__ T sep_poly(T t, const T *cx, const T *cy) {
     return fast_sqrt(fma(px, px, py * py));
 }
 
+// sqrt for the separation: the operand is a sum of squares (+0, positive, or NaN).  MUFU.RSQ64H + one coupled Newton
+// step (2^-43 relative); +0 and subnormal operands are lifted to the smallest normal number by an integer max on the
+// high word (the separation becomes 1.5e-154 instead of 0), NaN passes through.
+__device__ __forceinline__ double sqrt_sep(double x) {
+    const unsigned hi = max((unsigned)__double2hiint(x), 0x00100000u);
+    x = __hiloint2double((int)hi, __double2loint(x));
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double g = x * r, h = 0.5 * r;
+    return fma(g, fma(-h, g, 0.5), g);
+}
+__device__ __forceinline__ float sqrt_sep(float x) { return sqrtf(x); }
+
+__device__ __forceinline__ int floor_to_int(double x) { return __double2int_rd(x); }   // saturating, NaN -> 0
+__device__ __forceinline__ int floor_to_int(float x) { return __float2int_rd(x); }
+
+// LD-mean lerp (common.py:225-233) at grid position x = g/dg >= 0: node i = floor(x), weight x - i, upper node clamped to
+// the last one (the reference reads one element past the row for g in (1-1e-7, 1]).  fp64: no conversion instructions
+// (F2I / I2F run on the quarter-rate pipe) -- adding 1.5 * 2^52 rounds x - 0.5 to the nearest integer, which is
+// floor(x) except when x is an integer (then it may be x - 1 with weight 1: the same value); the node index is the low
+// word of the sum.  A position that is NaN or beyond the row gives a clamped node and a meaningless (NaN for NaN) weight:
+// such samples are outside the stellar disk and their value is not used.
+#ifndef SS_MAGIC_FLOOR
+#define SS_MAGIC_FLOOR 1
+#endif
+__device__ __forceinline__ double ld_lerp(double x, const double *row, int ng) {
+#if SS_MAGIC_FLOOR
+    const double m = (x - 0.5) + 6755399441055744.0;            // 1.5 * 2^52: the sum stays in [2^52, 2^53), ulp 1
+    const int i0 = (int)min((unsigned)__double2loint(m), (unsigned)(ng - 2));
+    const double a = x - (m - 6755399441055744.0);
+#else
+    const int i0 = min(floor_to_int(x), ng - 2);
+    const double a = x - (double)i0;
+#endif
+    const double r0 = row[i0], r1 = row[i0 + 1];
+    return fma(a, r1 - r0, r0);
+}
+__device__ __forceinline__ float ld_lerp(float x, const float *row, int ng) {
+    const int i0 = min(floor_to_int(x), ng - 2);     // >= 0; NaN -> 0 (the weight stays NaN)
+    const float r0 = row[i0], r1 = row[i0 + 1];
+    return fmaf(x - (float)i0, r1 - r0, r0);
+}
+
 // find_contact_point for points 1 (s=-1) and 4 (s=+1), target z = 1 + k (taylor_z.py:298-328).
 __device__ __forceinline__ double contact_point(double k, double s, const double *cx, const double *cy) {
     const double zt = 1.0 + k;

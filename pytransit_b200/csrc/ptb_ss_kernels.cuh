@@ -105,49 +105,6 @@ struct SsTables {
                        P.ssc, P.recstride);                                                                                    \
     volatile int *fr = ws.frame()
 
-// sqrt for the separation: the operand is a sum of squares (+0, positive, or NaN).  MUFU.RSQ64H + one coupled Newton
-// step (2^-43 relative); +0 and subnormal operands are lifted to the smallest normal number by an integer max on the
-// high word (the separation becomes 1.5e-154 instead of 0), NaN passes through.
-__device__ __forceinline__ double sqrt_sep(double x) {
-    const unsigned hi = max((unsigned)__double2hiint(x), 0x00100000u);
-    x = __hiloint2double((int)hi, __double2loint(x));
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    const double g = x * r, h = 0.5 * r;
-    return fma(g, fma(-h, g, 0.5), g);
-}
-__device__ __forceinline__ float sqrt_sep(float x) { return sqrtf(x); }
-
-__device__ __forceinline__ int floor_to_int(double x) { return __double2int_rd(x); }   // saturating, NaN -> 0
-__device__ __forceinline__ int floor_to_int(float x) { return __float2int_rd(x); }
-
-// LD-mean lerp (common.py:225-233) at grid position x = g/dg >= 0: node i = floor(x), weight x - i, upper node clamped to
-// the last one (the reference reads one element past the row for g in (1-1e-7, 1]).  fp64: no conversion instructions
-// (F2I / I2F run on the quarter-rate pipe) -- adding 1.5 * 2^52 rounds x - 0.5 to the nearest integer, which is
-// floor(x) except when x is an integer (then it may be x - 1 with weight 1: the same value); the node index is the low
-// word of the sum.  A position that is NaN or beyond the row gives a clamped node and a meaningless (NaN for NaN) weight:
-// such samples are outside the stellar disk and their value is not used.
-#ifndef SS_MAGIC_FLOOR
-#define SS_MAGIC_FLOOR 1
-#endif
-__device__ __forceinline__ double ld_lerp(double x, const double *row, int ng) {
-#if SS_MAGIC_FLOOR
-    const double m = (x - 0.5) + 6755399441055744.0;            // 1.5 * 2^52: the sum stays in [2^52, 2^53), ulp 1
-    const int i0 = (int)min((unsigned)__double2loint(m), (unsigned)(ng - 2));
-    const double a = x - (m - 6755399441055744.0);
-#else
-    const int i0 = min(floor_to_int(x), ng - 2);
-    const double a = x - (double)i0;
-#endif
-    const double r0 = row[i0], r1 = row[i0 + 1];
-    return fma(a, r1 - r0, r0);
-}
-__device__ __forceinline__ float ld_lerp(float x, const float *row, int ng) {
-    const int i0 = min(floor_to_int(x), ng - 2);     // >= 0; NaN -> 0 (the weight stays NaN)
-    const float r0 = row[i0], r1 = row[i0 + 1];
-    return fmaf(x - (float)i0, r1 - r0, r0);
-}
-
 // ---- fold phase: exact per-point fold + box test over touched cells (model_full.py:88-91) until the queue holds
 // more than SS_QCAP - 64 in-box points or the item's cells are exhausted.  The fluxes of the cells' points are set to
 // 1.0 here (the drain overwrites the in-box ones); in likelihood mode the out-of-box points add their chi^2 here.
@@ -175,7 +132,6 @@ __device__ __noinline__ double ss_fold() {
     const int rem = (int)(left > 0x7fffffffll ? 0x7fffffffll : left);     // (VEC == 2 requires an even npt: vectors are all-in or all-out)
     const int ipt0 = (int)pbase;
     const double *isig2 = LNL ? P.isig2 + (size_t)ipv * P.nblocks : nullptr;
-    const double w_one = (LNL && !P.blk) ? isig2[0] : 0.0;  // single noise block: its weight is an item constant
     double chi = 0.0;
     // A fold step takes four cells, eight lanes each; a lane folds two points of its cell: A and B are neighbours
     // (VEC == 2, one 16-byte load) or 8 points apart (VEC == 1, odd npt or unaligned arrays).
@@ -196,29 +152,27 @@ __device__ __noinline__ double ss_fold() {
         __syncwarp();
     };
     // the next group of up to four cells with its time stamps (and observed fluxes) in flight
-    int celln = -1, cntn = 0, lcn = 0;
-    double tnA = 0.0, tnB = 0.0, onA = 1.0, onB = 1.0;
+    int celln = -1, cntn = 0, lcn = 0, nzn = 0;   // cells, count, light curve (-1 mixed), (likelihood) noise id (-2 mixed)
+    double tnA = 0.0, tnB = 0.0;
+    const bool nz_lookup = LNL && P.blk && P.cnoise;
+    const int32_t *cnz = nz_lookup ? P.cnoise + bbeg * SS_CPB : nullptr;
     auto fetch = [&]() {
         cntn = min(4, tail - head);
         celln = (g < cntn) ? (int)clist[(head + g) & (SS_LIST - 1)] : -1;
         head += cntn;
-        tnA = 0.0; tnB = 0.0; lcn = 0;
-        if (LNL) { onA = 1.0; onB = 1.0; }
+        tnA = 0.0; tnB = 0.0; lcn = 0; nzn = 0;
         if (celln >= 0) {
             const int off = celln * SS_CELL + loff;
             if (!SINGLE_LC) lcn = __ldg(cl + celln);
+            if (nz_lookup) nzn = __ldg(cnz + celln);
             if (VEC == 2) {
                 if (off < rem) {
                     const double2 t = __ldg(reinterpret_cast<const double2 *>(tl + off));
                     tnA = t.x; tnB = t.y;
-                    if (LNL) {
-                        const double2 o = __ldg(reinterpret_cast<const double2 *>(ol + off));
-                        onA = o.x; onB = o.y;
-                    }
                 }
             } else {
-                if (off < rem) { tnA = __ldg(tl + off); if (LNL) onA = __ldg(ol + off); }
-                if (off + DB < rem) { tnB = __ldg(tl + off + DB); if (LNL) onB = __ldg(ol + off + DB); }
+                if (off < rem) tnA = __ldg(tl + off);
+                if (off + DB < rem) tnB = __ldg(tl + off + DB);
             }
         }
     };
@@ -234,8 +188,8 @@ __device__ __noinline__ double ss_fold() {
     int head0 = head;   // ring position of the first cell that has not been folded
     fetch();
     while (cntn > 0 && qn <= SS_QCAP - PT_BLOCK) {
-        const int cell = celln, lcb = lcn;
-        const double tA = tnA, tB = tnB, oA = onA, oB = onB;
+        const int cell = celln, lcb = lcn, nzb = nzn;
+        const double tA = tnA, tB = tnB;
         head0 = head;
         refill();
         fetch();  // in flight while this group is folded
@@ -266,16 +220,16 @@ __device__ __noinline__ double ss_fold() {
             inA = inrA && (T1 - pdA <= tcA) && (tcA <= T4 + pdA);
             inB = inrB && (T1 - pdB <= tcB) && (tcB <= T4 + pdB);
         }
-        if (LNL) {
-            if (inrA && !inA) {
-                const double d = oA - 1.0;
-                const int nb = P.blk ? P.blk[(long long)ipt0 + offA] : 0;
-                if (nb >= 0) chi = fma(d * d, P.blk ? isig2[nb] : w_one, chi);
+        if (LNL && nzb == -2) {   // several noise ids in this cell: its baseline, point by point
+            if (inrA) {
+                const int nb = P.blk[(long long)ipt0 + offA];
+                const double d = ol[offA] - 1.0;
+                if (nb >= 0) chi = fma(d * d, isig2[nb], chi);
             }
-            if (inrB && !inB) {
-                const double d = oB - 1.0;
-                const int nb = P.blk ? P.blk[(long long)ipt0 + offB] : 0;
-                if (nb >= 0) chi = fma(d * d, P.blk ? isig2[nb] : w_one, chi);
+            if (inrB) {
+                const int nb = P.blk[(long long)ipt0 + offB];
+                const double d = ol[offB] - 1.0;
+                if (nb >= 0) chi = fma(d * d, isig2[nb], chi);
             }
         }
         // one compaction for the warp's 64 points
@@ -430,9 +384,9 @@ __device__ __forceinline__ double ss_drain(const PointsParams &P, const SsTables
         const T f = sum / ns;
         if (LNL) {
             const int b = P.blk ? P.blk[ipt] : 0;
-            if (b >= 0) {
-                const double d = P.obs[ipt] - (double)f;
-                chi = d * d * (P.isig2 + (size_t)ipv * P.nblocks)[b];
+            if (b >= 0) {   // the point's (obs - 1)^2 is already in the cell baseline: swap it for (obs - model)^2
+                const double o = P.obs[ipt], d1 = o - (double)f, d0 = o - 1.0;
+                chi = fma(d1, d1, -d0 * d0) * (P.isig2 + (size_t)ipv * P.nblocks)[b];
             }
         } else {
             (reinterpret_cast<T *>(P.flux) + (size_t)ipv * P.npt)[ipt] = f;
@@ -573,7 +527,9 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB_SS2) k_rr_points_ss(const 
                         const double n2 = floor(fma(P.cmax[c] - t0 - (T1 - pd), invp, PT_EPS));
                         hit = !(n1 > n2) || !(p > 0.0);  // NaNs and p <= 0 fall through to the exact per-point path
                     }
-                    if (LNL && !hit && nz_id >= 0) chi = fma(P.cchi[c], P.blk ? isig2[nz_id] : w_one, chi);
+                    // likelihood baseline: sum of (obs - 1)^2 of EVERY cell that has one noise id, touched or not (the
+                    // drain swaps the in-box points' terms for (obs - model)^2); cells with several ids: per point, in ss_fold
+                    if (LNL && nz_id >= 0) chi = fma(P.cchi[c], P.blk ? isig2[nz_id] : w_one, chi);
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, hit);
                 if (lane == 0) s_hit[cc0 >> 5] = m;
