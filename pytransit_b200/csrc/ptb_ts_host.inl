@@ -259,7 +259,7 @@ int ptb_ldtk_profiles(ptb_model *h, const double *profiles, int64_t nx, int64_t 
         const int nchunks = (int)((npb + chunk - 1) / chunk);
         const long long want = (long long)h->sm_count * 4;
         const int vsplit = (int)std::max<long long>(1, std::min<long long>((npv + 63) / 64, (want + nchunks - 1) / nchunks));
-        const size_t smem = (nodes * chunk * nmu + ((nmu + 1) & ~(size_t)1) + (size_t)LDS_WARPS * chunk * nmu) * 8;
+        const size_t smem = (nodes * chunk * nmu + ((nmu + 1) & ~(size_t)1) + nodes * chunk) * 8;
         CU(cudaFuncSetAttribute(k_ldtk_profiles_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_ldtk_profiles_slab<<<(unsigned)(nchunks * vsplit), LDS_THREADS, smem, st>>>(P, cells, chunk, vsplit);
         h->launches += 2;

@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(LDS_THREADS, 2) k_ldtk_profiles_slab(const __g
     const int ne = nch * nmu;            // live elements per node / per vector
     double *sT = reinterpret_cast<double *>(smem_raw);   // [nodes][chunk][nmu]
     double *sZ = sT + (size_t)nodes * slab;               // [nmu]  z = sqrt(1 - mu^2)
-    double *sTerm = sZ + ((nmu + 1) & ~1);                // [LDS_WARPS][slab] trapezoid terms
+    double *sI = sZ + ((nmu + 1) & ~1);                   // [nodes][chunk] disk integral of every node profile
 
     const bool tma_ok = ((nmu & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.profiles) & 15) == 0);
     if (tma_ok) {
@@ -776,40 +776,32 @@ __global__ void __launch_bounds__(LDS_THREADS, 2) k_ldtk_profiles_slab(const __g
     __syncthreads();
     if (tma_ok) mbar_wait(&bar, 0);
 
-    double *term = sTerm + (size_t)warp * slab;
-    const int i_first = lane % nmu;   // mu node of this lane's first element; advanced by 32 (mod nmu) per pass
+    // The trapezoid rule (integrate_profiles_set, ldtkldm.py:86-89) is linear in the profile and the interpolated
+    // profile is a weighted sum of eight node profiles: the disk integral of every (node, channel) of the slab is
+    // taken ONCE per CTA, and a vector's integral is the same weighted sum of eight of them.
+    for (int idx = tid; idx < nodes * nch; idx += LDS_THREADS) {
+        const int n = idx / nch, ch = idx - n * nch;
+        const double *pr = sT + (size_t)n * slab + ch * nmu;
+        double sum = 0.0;
+        for (int i = 1; i < nmu; ++i) sum += (sZ[i] - sZ[i - 1]) * 0.5 * (sZ[i] * pr[i] + sZ[i - 1] * pr[i - 1]);
+        sI[n * chunk + ch] = 2.0 * kPi * sum;
+    }
+    __syncthreads();
+
     for (long long ipv = (long long)isplit * LDS_WARPS + warp; ipv < P.npv; ipv += (long long)LDS_WARPS * vsplit) {
         const LdtkCell c = cells[ipv];   // uniform across the warp
         const double *t0 = sT + (size_t)c.node[0] * slab, *t1 = sT + (size_t)c.node[1] * slab, *t2 = sT + (size_t)c.node[2] * slab,
                      *t3 = sT + (size_t)c.node[3] * slab, *t4 = sT + (size_t)c.node[4] * slab, *t5 = sT + (size_t)c.node[5] * slab,
                      *t6 = sT + (size_t)c.node[6] * slab, *t7 = sT + (size_t)c.node[7] * slab;
         double *out = P.ldp + ((size_t)ipv * P.npb + pb0) * nmu;
-        double carry = 0.0;  // value of the element before this pass's first
-        int i = i_first;
-        for (int e0 = 0; e0 < ne; e0 += 32) {
-            const int e = e0 + lane;
-            double v = 0.0;
-            if (e < ne) {
-                v = t0[e] * c.w[0] + t1[e] * c.w[1] + t2[e] * c.w[2] + t3[e] * c.w[3] + t4[e] * c.w[4] + t5[e] * c.w[5] +
-                    t6[e] * c.w[6] + t7[e] * c.w[7];
-                out[e] = v;
-            }
-            double vp = __shfl_up_sync(0xffffffffu, v, 1);
-            if (lane == 0) vp = carry;
-            carry = __shfl_sync(0xffffffffu, v, 31);
-            // trapezoid term between nodes i-1 and i (integrate_profiles_set, ldtkldm.py:86-89)
-            if (e < ne) term[e] = i > 0 ? (sZ[i] - sZ[i - 1]) * 0.5 * (sZ[i] * v + sZ[i - 1] * vp) : 0.0;
-            i += 32;
-            while (i >= nmu) i -= nmu;
-        }
-        __syncwarp();
-        for (int ch = 0; ch < nch; ++ch) {   // the warp sums one channel's terms at a time
-            double sum = 0.0;
-            for (int j = lane; j < nmu; j += 32) sum += term[ch * nmu + j];
-            sum = warp_sum(sum);
-            if (lane == 0) P.istar[(size_t)ipv * P.npb + pb0 + ch] = 2.0 * kPi * sum;
-        }
-        __syncwarp();
+        for (int e = lane; e < ne; e += 32)   // the term order of trilinear_interpolation (ldtkldm.py:45-50)
+            out[e] = t0[e] * c.w[0] + t1[e] * c.w[1] + t2[e] * c.w[2] + t3[e] * c.w[3] + t4[e] * c.w[4] + t5[e] * c.w[5] +
+                     t6[e] * c.w[6] + t7[e] * c.w[7];
+        for (int ch = lane; ch < nch; ch += 32)
+            P.istar[(size_t)ipv * P.npb + pb0 + ch] =
+                sI[c.node[0] * chunk + ch] * c.w[0] + sI[c.node[1] * chunk + ch] * c.w[1] + sI[c.node[2] * chunk + ch] * c.w[2] +
+                sI[c.node[3] * chunk + ch] * c.w[3] + sI[c.node[4] * chunk + ch] * c.w[4] + sI[c.node[5] * chunk + ch] * c.w[5] +
+                sI[c.node[6] * chunk + ch] * c.w[6] + sI[c.node[7] * chunk + ch] * c.w[7];
     }
 }
 
