@@ -695,6 +695,7 @@ __device__ __forceinline__ double drain_points(const DrainCtx<T> &c, const WarpS
         tc = ws.q_tc()[base + lane];
         if (!SINGLE_LC) rowoff = c.sRow[ws.q_lc()[base + lane]];
     }
+    __syncwarp();   // the queue slots are read: the next fold step may reuse them
     const T *row1 = ld + c.row1;
     const T *row = ld + rowoff;
     const T k = row[ng], inv1k = row[ng + 1], inv_istar = row[ng + 2], k2 = row[ng + 3];

@@ -143,13 +143,16 @@ __device__ __noinline__ double ss_fold() {
 
     // the set bits of the next bitmap words go to the ring while it has room for a whole word
     auto refill = [&]() {
-        while (tail - head <= SS_LIST - 32 && wi < nwords) {
-            const unsigned w = s_hit[wi];
-            if ((w >> lane) & 1u) clist[(tail + __popc(w & lt_mask)) & (SS_LIST - 1)] = (unsigned short)(wi * 32 + lane);
-            tail += __popc(w);
-            ++wi;
+        if (tail - head <= SS_LIST - 32 && wi < nwords) {
+            __syncwarp();   // the slots about to be reused have been read by every lane
+            do {
+                const unsigned w = s_hit[wi];
+                if ((w >> lane) & 1u) clist[(tail + __popc(w & lt_mask)) & (SS_LIST - 1)] = (unsigned short)(wi * 32 + lane);
+                tail += __popc(w);
+                ++wi;
+            } while (tail - head <= SS_LIST - 32 && wi < nwords);
+            __syncwarp();
         }
-        __syncwarp();
     };
     // the next group of up to four cells with its time stamps (and observed fluxes) in flight
     int celln = -1, cntn = 0, lcn = 0, nzn = 0;   // cells, count, light curve (-1 mixed), (likelihood) noise id (-2 mixed)
@@ -256,11 +259,14 @@ __device__ __noinline__ double ss_fold() {
             }
         }
     }
-    fr[FR_QN] = qn;
-    fr[FR_DONE] = cntn == 0;                  // nothing fetched: ring and bitmap are exhausted
-    fr[FR_WI] = wi;
-    fr[FR_LHEAD] = cntn > 0 ? head0 : head;   // a group fetched but not folded (queue full) is fetched again
-    fr[FR_LTAIL] = tail;
+    __syncwarp();   // every lane has read the frame (and left the ring) before lane 0 rewrites it
+    if (lane == 0) {
+        fr[FR_QN] = qn;
+        fr[FR_DONE] = cntn == 0;                  // nothing fetched: ring and bitmap are exhausted
+        fr[FR_WI] = wi;
+        fr[FR_LHEAD] = cntn > 0 ? head0 : head;   // a group fetched but not folded (queue full) is fetched again
+        fr[FR_LTAIL] = tail;
+    }
     return chi;
 }
 
@@ -293,6 +299,7 @@ __device__ __forceinline__ double ss_drain(const PointsParams &P, const SsTables
         const double epoch = floor(fma(t - t0, rec[ORB_INVP], 0.5));
         tc = (T)(t - __dadd_rn(t0, __dmul_rn(epoch, rec[ORB_P])));
     }
+    __syncwarp();   // queue and frame are read
     const T *row = ld + rowoff;
     const T k = row[ng], inv1k = row[ng + 1], inv_istar = row[ng + 2], k2 = row[ng + 3];
     // per-point constants of the area cases that need no lens formula (common.py:52-73)
@@ -408,7 +415,8 @@ __device__ __noinline__ double ss_drain_phase() {
         qn -= n;
         chi += ss_drain<SINGLE_LC, LNL, T>(P, tb, ws, ipv, qn, n, lane);
     }
-    fr[FR_QN] = qn;
+    __syncwarp();   // every lane has read the frame before lane 0 rewrites it
+    if (lane == 0) fr[FR_QN] = qn;
     return chi;
 }
 
@@ -479,9 +487,12 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB_SS2) k_rr_points_ss(const 
             const int bend = min(P.nblk64, bbeg + P.blocks_per_chunk);
             const int cbeg = bbeg * SS_CPB;                      // the item's cells
             const int ncl = min(P.ncell, bend * SS_CPB) - cbeg;
-            fr[FR_IPV] = ipv; fr[FR_CHUNK] = chunk; fr[FR_BBEG] = bbeg; fr[FR_NCL] = ncl;
-            fr[FR_NEXT_LO] = (int)(unsigned)(next & 0xffffffffll); fr[FR_NEXT_HI] = (int)(next >> 32);
-            fr[FR_ITER] = iter + 1;
+            if (lane == 0) {
+                fr[FR_IPV] = ipv; fr[FR_CHUNK] = chunk; fr[FR_BBEG] = bbeg; fr[FR_NCL] = ncl;
+                fr[FR_NEXT_LO] = (int)(unsigned)(next & 0xffffffffll); fr[FR_NEXT_HI] = (int)(next >> 32);
+                fr[FR_ITER] = iter + 1;
+                fr[FR_WI] = 0; fr[FR_LHEAD] = 0; fr[FR_LTAIL] = 0; fr[FR_QN] = 0; fr[FR_DONE] = 0;
+            }
             T *frow = LNL ? nullptr : reinterpret_cast<T *>(P.flux) + (size_t)ipv * npt;
             const double *isig2 = LNL ? P.isig2 + (size_t)ipv * P.nblocks : nullptr;
 
@@ -565,7 +576,6 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB_SS2) k_rr_points_ss(const 
                     }
                 }
             }
-            fr[FR_WI] = 0; fr[FR_LHEAD] = 0; fr[FR_LTAIL] = 0; fr[FR_QN] = 0; fr[FR_DONE] = 0;
         }
         __syncwarp();
 
