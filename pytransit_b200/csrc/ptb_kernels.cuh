@@ -650,7 +650,7 @@ __device__ __forceinline__ void sample_eval(T t, const T *cx, const T *cy, const
 // writes the flux / accumulates chi^2 directly.
 template <bool SINGLE_LC, bool LNL, typename T>
 __device__ __forceinline__ double limb_pass(const PointsParams &P, const WarpScratch<T> &ws, const T *ld, const T *row1,
-                                            T *frow, const double *isig2, int lane, int first, int take) {
+                                            T *frow, const double *isig2, double w_one, int lane, int first, int take) {
     double chi = 0.0;
     if (lane < take) {
         const int q = first + lane, ng = P.ng;
@@ -663,7 +663,7 @@ __device__ __forceinline__ double limb_pass(const PointsParams &P, const WarpScr
             const int b = P.blk ? P.blk[ipt] : 0;
             if (b >= 0) {   // the point's (obs - 1)^2 is already in the block baseline: swap it for (obs - model)^2
                 const double o = P.obs[ipt], d1 = o - (double)v, d0 = o - 1.0;
-                chi = fma(d1, d1, -d0 * d0) * isig2[b];
+                chi = fma(d1, d1, -d0 * d0) * (P.blk ? isig2[b] : w_one);
             }
         } else {
             frow[ipt] = v;
@@ -677,7 +677,7 @@ __device__ __forceinline__ double limb_pass(const PointsParams &P, const WarpScr
 // carried across calls; `flush` empties it.  Inlined at its single call site.  Returns the lane's chi^2 increment.
 template <bool SINGLE_LC, bool LNL, typename T>
 __device__ __forceinline__ double drain_points(const DrainCtx<T> &c, const WarpScratch<T> &ws, const T *rt, T *frow,
-                                               const double *isig2, int base, int n, int &nl, bool flush) {
+                                               const double *isig2, double w_one, int base, int n, int &nl, bool flush) {
     const PointsParams &P = *c.P;
     const int lane = c.lane, ng = P.ng;
     const T inv_dg = (T)P.inv_dg;
@@ -723,7 +723,7 @@ __device__ __forceinline__ double drain_points(const DrainCtx<T> &c, const WarpS
             const int b = P.blk ? P.blk[ipt] : 0;
             if (b >= 0) {   // swap the baseline's (obs - 1)^2 for (obs - model)^2
                 const double o = P.obs[ipt], d1 = o - (double)cc, d0 = o - 1.0;
-                chi += fma(d1, d1, -d0 * d0) * isig2[b];
+                chi += fma(d1, d1, -d0 * d0) * (P.blk ? isig2[b] : w_one);   // one noise block: its weight is an item constant
             }
         } else {
             frow[ipt] = cc;
@@ -734,7 +734,7 @@ __device__ __forceinline__ double drain_points(const DrainCtx<T> &c, const WarpS
     while (nl >= 32 || (flush && nl > 0)) {
         const int take = min(nl, 32);
         nl -= take;
-        chi += limb_pass<SINGLE_LC, LNL, T>(P, ws, ld, row1, frow, isig2, lane, nl, take);
+        chi += limb_pass<SINGLE_LC, LNL, T>(P, ws, ld, row1, frow, isig2, w_one, lane, nl, take);
         __syncwarp();
     }
     return chi;
@@ -1036,7 +1036,7 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB_S1) k_rr_points(const __gr
             while (qn >= 32 || (!live && (qn > 0 || nl > 0))) {
                 const int n = min(qn, 32);
                 qn -= n;
-                chi += drain_points<SINGLE_LC, LNL, T>(dctx, ws, rt, frow, isig2, qn, n, nl, !live && qn == 0);
+                chi += drain_points<SINGLE_LC, LNL, T>(dctx, ws, rt, frow, isig2, w_one, qn, n, nl, !live && qn == 0);
             }
             if (!live) break;
         }

@@ -393,7 +393,7 @@ __device__ __forceinline__ double ss_drain(const PointsParams &P, const SsTables
             const int b = P.blk ? P.blk[ipt] : 0;
             if (b >= 0) {   // the point's (obs - 1)^2 is already in the cell baseline: swap it for (obs - model)^2
                 const double o = P.obs[ipt], d1 = o - (double)f, d0 = o - 1.0;
-                chi = fma(d1, d1, -d0 * d0) * (P.isig2 + (size_t)ipv * P.nblocks)[b];
+                chi = fma(d1, d1, -d0 * d0) * (P.isig2 + (size_t)ipv * P.nblocks)[P.blk ? b : 0];
             }
         } else {
             (reinterpret_cast<T *>(P.flux) + (size_t)ipv * P.npt)[ipt] = f;
