@@ -3,7 +3,8 @@
 model flux points/s (npv x npt) on configs[1]: RoadRunnerModel('power-2') population npv=8192 x 20 000
 TESS 2-min cadence points, single passband, fp64.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4|c5]
+                    [--precision fp64|fp32] [--host-result delta|copy] [--gather peer|peer-barrier|nccl]
 
 One "step" = one pass of the hot path over the whole population: per-vector setup (limb-darkening
 profile, LD-mean contraction, Kepler/Taylor orbit, contact times) + the npv x npt flux kernel.
@@ -11,18 +12,24 @@ profile, LD-mean contraction, Kepler/Taylor orbit, contact times) + the npv x np
 Our arm prints ONE JSON line:
   value     whole-job flux points/s, parameters + time axis resident in HBM, flux written to HBM
             (device-resident output, `evaluate(copy=False)`), CUDA-event timed, max over ranks;
-  e2e       same metric through the public API with HOST numpy inputs and a host result: the pinned
-            H2D parameter copy and the D2H copy of the [npv, npt] flux are inside the timed region;
-  roofline  the dominant kernel (k_rr_points) against the measured HBM copy bandwidth
-            (MEASURED_PEAKS.json), algorithmic bytes = 8 B per flux point (DESIGN.md);
-  cpu_baseline  the CPU oracle port (oracle/rr_oracle.c, OpenMP, all host threads) on a bounded
-            sample of the same workload (N=1, rank 0).
+  e2e       same metric through the public API with HOST numpy inputs and a host result, H2D and D2H inside the
+            timed region, in the opt-in delta mode (`host_result='delta'`); e2e_copy: the default mode (one full
+            D2H copy into an array of the caller's own); both with a roofline against the device-to-host rate
+            measured in the same run with every rank copying concurrently;
+  roofline  the dominant kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json), algorithmic
+            bytes = 8 B per flux point; `traffic` and the executed-instruction counters are measured
+            in the run by an ncu child process (--no-counters skips it); C5 (nothing written): executed fp64 work
+            against a DFMA peak measured on the same GPU;
+  cpu_baseline        the CPU oracle port (oracle/rr_oracle.c, OpenMP, all host threads),
+  cpu_baseline_numba  the reference's own Numba path (baseline/_ref), threads = cores -- both on bounded samples
+            of the same workload (N=1, rank 0);
+  collective  (default line) the C5 shard's fused lnL + all-gather measured in the same run: peer stores ordered
+            by device-side flags, with the host-barrier and NCCL variants and a bit-identity check.
 N > 1 (torchrun): the population is sharded, 8192 vectors per GPU (weak scaling), no data-path
 collective for the flux; timing is barrier + synchronize bracketed, max over ranks.
 
-`--impl reference` times the reference's CPU implementation of the path.  The reference is pure
-Python + Numba and its third-party orbit dependency (meepmeep) is absent, so this is the oracle port
-(kind "port"), all host threads, on a bounded sample of the same workload per step.
+`--impl reference` times the reference's CPU implementation of the path: the oracle port (kind "port") with all
+host threads, and the reference's own Numba path beside it, on a bounded sample of the same workload per step.
 """
 from __future__ import annotations
 
