@@ -695,6 +695,14 @@ __device__ __forceinline__ double drain_points(const DrainCtx<T> &c, const WarpS
         tc = ws.q_tc()[base + lane];
         if (!SINGLE_LC) rowoff = c.sRow[ws.q_lc()[base + lane]];
     }
+    // likelihood: the observed flux (and noise id) of the lane's point, requested now so that the load is in flight
+    // under the sample evaluation instead of in front of the chi^2 update
+    double obs_v = 1.0;
+    int nz_b = 0;
+    if (LNL && valid) {
+        obs_v = __ldg(P.obs + ipt);
+        if (P.blk) nz_b = __ldg(P.blk + ipt);
+    }
     __syncwarp();   // the queue slots are read: the next fold step may reuse them
     const T *row1 = ld + c.row1;
     const T *row = ld + rowoff;
@@ -720,10 +728,9 @@ __device__ __forceinline__ double drain_points(const DrainCtx<T> &c, const WarpS
     }
     if (valid && !limb) {   // everything that is not on the limb is final
         if (LNL) {
-            const int b = P.blk ? P.blk[ipt] : 0;
-            if (b >= 0) {   // swap the baseline's (obs - 1)^2 for (obs - model)^2
-                const double o = P.obs[ipt], d1 = o - (double)cc, d0 = o - 1.0;
-                chi += fma(d1, d1, -d0 * d0) * (P.blk ? isig2[b] : w_one);   // one noise block: its weight is an item constant
+            if (nz_b >= 0) {   // swap the baseline's (obs - 1)^2 for (obs - model)^2
+                const double d1 = obs_v - (double)cc, d0 = obs_v - 1.0;
+                chi += fma(d1, d1, -d0 * d0) * (P.blk ? isig2[nz_b] : w_one);   // one noise block: its weight is an item constant
             }
         } else {
             frow[ipt] = cc;
