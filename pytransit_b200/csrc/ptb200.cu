@@ -1055,7 +1055,9 @@ int launch_points(ptb_model *h, int64_t npv, void *flux, const double *isig2, cu
         return (long long)((e && atoi(e) > 0) ? atoi(e) : 16);
     }();
     const long long workers = (long long)h->sm_count * 3 * PT_WARPS;
-    const long long want = (long long)(workers * items_per_warp);
+    // the supersampled kernel's items are ~10x heavier: four times as many keep its tail short (measured on C3:
+    // 3.99 ms with 8 items per warp, 3.83 with 16, 3.81 with 32, 3.87 with 64; C2 loses with more than 8)
+    const long long want = (long long)(workers * items_per_warp * (h->ns_max > 1 ? 4 : 1));
     long long nchunks = std::min<long long>(std::max<long long>(1, nb / min_item_blocks), std::max<long long>(1, (want + npv - 1) / npv));
     // a population too small to give every warp an item: cut finer (down to two blocks per item) -- the
     // single-vector call is latency bound and wants all the parallelism there is
