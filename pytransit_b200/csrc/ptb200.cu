@@ -995,18 +995,19 @@ int launch_points_t(ptb_model *h, const PointsParams &P, size_t smem, cudaStream
     if constexpr (S1) kern = k_rr_points<VEC, SINGLE, LNL, T>;
     else kern = k_rr_points_ss<VEC, SINGLE, LNL, T>;
     const int slot = (sizeof(T) == 4 ? 16 : 0) + (S1 ? 8 : 0) + (VEC == 2 ? 4 : 0) + (SINGLE ? 2 : 0) + (LNL ? 1 : 0);
+    constexpr int threads = S1 ? PT_THREADS : SS_THREADS, warps = threads / 32;
     if (h->pt_occ[slot] == 0 || h->pt_occ_smem[slot] != smem) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PT_THREADS, smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
         if (occ < 1) return fail(h, PTB_EINVAL, "k_rr_points does not fit on an SM with %zu bytes of shared memory", smem);
         h->pt_occ[slot] = occ;
         h->pt_occ_smem[slot] = smem;
     }
     // persistent grid: one wave of CTAs; every warp pulls items from the work counter
     const long long nitems = (long long)P.npv * P.nchunks;
-    const long long grid = std::min<long long>((nitems + PT_WARPS - 1) / PT_WARPS, (long long)h->sm_count * h->pt_occ[slot]);
-    kern<<<(unsigned)grid, PT_THREADS, smem, st>>>(P);
+    const long long grid = std::min<long long>((nitems + warps - 1) / warps, (long long)h->sm_count * h->pt_occ[slot]);
+    kern<<<(unsigned)grid, threads, smem, st>>>(P);
     h->launches++;
     CU(cudaGetLastError());
     return PTB_OK;
@@ -1080,7 +1081,7 @@ int launch_points(ptb_model *h, int64_t npv, void *flux, const double *isig2, cu
     const bool s1 = (h->ns_max == 1);
     const size_t nfrac = P.frac_tab ? (size_t)h->nlc * h->ns_max : 0;
     const size_t smem = s1 ? pt_shared_bytes((int)h->nlc, tsize) + pt_warp_bytes(h->recstride, tsize) * PT_WARPS
-                           : ss_shared_bytes((int)h->nlc, (int)nfrac, tsize) + ss_warp_bytes(P.ssc, h->recstride, tsize) * PT_WARPS;
+                           : ss_shared_bytes((int)h->nlc, (int)nfrac, tsize) + ss_warp_bytes(P.ssc, h->recstride, tsize) * SS_WARPS;
     if (smem > 220 * 1024)
         return fail(h, PTB_EINVAL, "npb=%lld passbands x nlc=%lld light curves need %zu bytes of shared memory (> 220 KB)",
                     (long long)h->npb, (long long)h->nlc, smem);

@@ -31,9 +31,17 @@
 
 namespace ptb {
 
+// CTA shape.  Measured on C3 (profiles/tools/ss_variants.sh): 256 threads x 3 CTAs (80 registers, 256-entry queue)
+// 3.78 ms; 128 x 6 (80 registers) 3.78 ms with the 256-entry queue, 3.91 ms with 128 entries; 128 x 7 (72 registers,
+// 128 entries: 28 warps instead of 24) 4.06 ms -- the extra warps do not pay for the spills and the shorter phases.
+#ifndef SS_THREADS_
+#define SS_THREADS_ 256
+#endif
 #ifndef PT_MINB_SS2
 #define PT_MINB_SS2 3
 #endif
+constexpr int SS_THREADS = SS_THREADS_;
+constexpr int SS_WARPS = SS_THREADS / 32;
 #ifndef SS_BRANCHY_TAIL
 #define SS_BRANCHY_TAIL 0
 #endif
@@ -45,12 +53,12 @@ constexpr int SS_FRAME = 16;        // ints of the warp's phase frame
 constexpr int SS_LIST = 128;        // ring buffer of touched cells (16-bit indices relative to the item's first cell)
 constexpr int SS_CPB = PT_BLOCK / SS_CELL;   // cells per 64-point block
 
-// Warp-private shared memory of the supersampled kernel: limb columns, point queue (index + light curve), hit bitmap
+// Warp-private shared memory of the supersampled kernel: limb columns, point queue (point indices), hit bitmap
 // (one bit per cell), phase frame, ring of touched cells, mbarrier, record slot (+ its float copy in fp32 mode).
 __host__ __device__ inline size_t ss_tpart(int ssc, int tsize) { return ((size_t)(ssc * PT_COLS) * tsize + 15) & ~size_t(15); }
 __host__ __device__ inline size_t ss_warp_bytes(int ssc, int recstride, int tsize) {
     const size_t rec_t = (tsize == 4) ? (((size_t)recstride * 4 + 15) & ~size_t(15)) : 0;
-    return ss_tpart(ssc, tsize) + (size_t)2 * SS_QCAP * 4 + PT_MAXBLK / 8 + SS_FRAME * 4 + SS_LIST * 2 + 16 + (size_t)recstride * 8 + rec_t;
+    return ss_tpart(ssc, tsize) + (size_t)SS_QCAP * 4 + PT_MAXBLK / 8 + SS_FRAME * 4 + SS_LIST * 2 + 16 + (size_t)recstride * 8 + rec_t;
 }
 // CTA-wide part: a copy of the kernel parameters, then the per-light-curve tables
 constexpr size_t SS_PARAM_BYTES = (sizeof(PointsParams) + 127) & ~size_t(127);
@@ -65,8 +73,7 @@ struct SsWarp {
     __device__ __forceinline__ SsWarp(unsigned char *b, int ssc_, int recstride_) : base(b), ssc(ssc_), recstride(recstride_) {}
     __device__ __forceinline__ T *colz() const { return reinterpret_cast<T *>(base); }   // per-lane columns [ssc][PT_COLS] of limb samples
     __device__ __forceinline__ int *q_ipt() const { return reinterpret_cast<int *>(base + ss_tpart(ssc, (int)sizeof(T))); }
-    __device__ __forceinline__ int *q_lc() const { return q_ipt() + SS_QCAP; }
-    __device__ __forceinline__ unsigned *hit() const { return reinterpret_cast<unsigned *>(q_lc() + SS_QCAP); }
+    __device__ __forceinline__ unsigned *hit() const { return reinterpret_cast<unsigned *>(q_ipt() + SS_QCAP); }
     __device__ __forceinline__ volatile int *frame() const { return reinterpret_cast<volatile int *>(hit() + PT_MAXBLK / 32); }
     __device__ __forceinline__ unsigned short *clist() const { return reinterpret_cast<unsigned short *>(hit() + PT_MAXBLK / 32 + SS_FRAME); }
     __device__ __forceinline__ uint64_t *bar() const { return reinterpret_cast<uint64_t *>(clist() + SS_LIST); }
@@ -115,7 +122,7 @@ __device__ __noinline__ double ss_fold() {
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned *s_hit = ws.hit();
     unsigned short *clist = ws.clist();
-    int *q_ipt = ws.q_ipt(), *q_lc = ws.q_lc();
+    int *q_ipt = ws.q_ipt();
     int qn = fr[FR_QN];
     const int ipv = fr[FR_IPV], bbeg = fr[FR_BBEG], nwords = (fr[FR_NCL] + 31) >> 5;
     int wi = fr[FR_WI], head = fr[FR_LHEAD], tail = fr[FR_LTAIL];   // next bitmap word; ring positions (monotonic)
@@ -199,7 +206,6 @@ __device__ __noinline__ double ss_fold() {
         const int offA = (cell >= 0 ? cell : 0) * SS_CELL + loff, offB = offA + DB;
         const bool inrA = cell >= 0 && offA < rem, inrB = cell >= 0 && offB < rem;
         bool inA, inB;
-        int lcA = lcb, lcB = lcb;
         // epoch = floor((t - t0 + p/2)/p); tc = t - (t0 + epoch p)  (model_full.py:88-89).  The division is a
         // multiplication by 1/p: the two can only disagree half a period away from the transit, where the
         // point is outside the box either way.  Always fp64: time stamps need all their digits.
@@ -215,8 +221,8 @@ __device__ __noinline__ double ss_fold() {
             inA = inrA && (lob <= tcA) && (tcA <= hib);
             inB = inrB && (lob <= tcB) && (tcB <= hib);
         } else {                       // some cell of the group straddles light curves: per-point lookup
-            lcA = lcb >= 0 ? lcb : (inrA ? P.lcids[(long long)ipt0 + offA] : 0);
-            lcB = lcb >= 0 ? lcb : (inrB ? P.lcids[(long long)ipt0 + offB] : 0);
+            const int lcA = lcb >= 0 ? lcb : (inrA ? P.lcids[(long long)ipt0 + offA] : 0);
+            const int lcB = lcb >= 0 ? lcb : (inrB ? P.lcids[(long long)ipt0 + offB] : 0);
             const double pdA = tb.sPad[lcA], t0A = t0v[tb.sEp[lcA]], pdB = tb.sPad[lcB], t0B = t0v[tb.sEp[lcB]];
             const double eA = floor(fma(tA - t0A, invp, 0.5)), eB = floor(fma(tB - t0B, invp, 0.5));
             const double tcA = tA - __dadd_rn(t0A, __dmul_rn(eA, p)), tcB = tB - __dadd_rn(t0B, __dmul_rn(eB, p));
@@ -239,15 +245,8 @@ __device__ __noinline__ double ss_fold() {
         const unsigned mA = __ballot_sync(0xffffffffu, inA), mB = __ballot_sync(0xffffffffu, inB);
         int pos = qn + __popc(mA & lt_mask) + __popc(mB & lt_mask);
         qn += __popc(mA) + __popc(mB);
-        if (inA) {
-            q_ipt[pos] = ipt0 + offA;
-            if (!SINGLE_LC) q_lc[pos] = lcA;
-            ++pos;
-        }
-        if (inB) {
-            q_ipt[pos] = ipt0 + offB;
-            if (!SINGLE_LC) q_lc[pos] = lcB;
-        }
+        if (inA) q_ipt[pos++] = ipt0 + offA;   // only the index is queued: the drain looks the light curve up again
+        if (inB) q_ipt[pos] = ipt0 + offB;
         // 1.0 for the cells' points, default cache policy (not evict-first): the line is still in L2 when the drain
         // updates its in-box points, so it reaches DRAM once
         if (!LNL) {
@@ -288,8 +287,9 @@ __device__ __forceinline__ double ss_drain(const PointsParams &P, const SsTables
     T tc = T(0), et = T(0);
     if (valid) {
         ipt = ws.q_ipt()[base + lane];
-        if (!SINGLE_LC) {
-            lc = ws.q_lc()[base + lane];
+        if (!SINGLE_LC) {   // the point's light curve: its cell's, or (cell straddling light curves) its own
+            lc = __ldg(P.clc + (ipt >> 4));
+            if (lc < 0) lc = __ldg(P.lcids + ipt);
             rowoff = tb.sRow[lc];
         }
         ns = tb.sNs[lc];
@@ -421,7 +421,7 @@ __device__ __noinline__ double ss_drain_phase() {
 }
 
 template <int VEC, bool SINGLE_LC, bool LNL, typename T>
-__global__ void __launch_bounds__(PT_THREADS, PT_MINB_SS2) k_rr_points_ss(const __grid_constant__ PointsParams P) {
+__global__ void __launch_bounds__(SS_THREADS, PT_MINB_SS2) k_rr_points_ss(const __grid_constant__ PointsParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr bool F32 = sizeof(T) == 4;
     constexpr int NH = 2 / VEC;
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB_SS2) k_rr_points_ss(const 
     {
         const int *src = reinterpret_cast<const int *>(&P);
         int *dst = reinterpret_cast<int *>(smem_raw);
-        for (int i = tid; i < (int)(sizeof(PointsParams) / 4); i += PT_THREADS) dst[i] = src[i];
+        for (int i = tid; i < (int)(sizeof(PointsParams) / 4); i += SS_THREADS) dst[i] = src[i];
     }
     const SsTables<T> tb(smem_raw, nlc, S, P.frac_tab);
     double *sPad = tb.sPad;
@@ -454,14 +454,14 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB_SS2) k_rr_points_ss(const 
     }
     item = __shfl_sync(0xffffffffu, item, 0);
     // item-independent per-light-curve tables
-    for (int lc = tid; lc < nlc; lc += PT_THREADS) {
+    for (int lc = tid; lc < nlc; lc += SS_THREADS) {
         sPad[lc] = 0.003 + P.exptimes[lc];  // model_full.py:69-70
         tb.sEt[lc] = (T)P.exptimes[lc];
         tb.sNs[lc] = P.nsamples[lc];
         tb.sRow[lc] = P.pbids[lc] * P.lds;
         sEp[lc] = P.epids[lc];
     }
-    for (int i = tid; i < tb.nfrac; i += PT_THREADS) {   // exptimes[ilc]*((isample-0.5)/nsamples[ilc] - 0.5), model_full.py:94
+    for (int i = tid; i < tb.nfrac; i += SS_THREADS) {   // exptimes[ilc]*((isample-0.5)/nsamples[ilc] - 0.5), model_full.py:94
         const int lc = i / S, s = i - lc * S;
         tb.sFrac[i] = (T)__dmul_rn(P.exptimes[lc], ((s + 1) - 0.5) / P.nsamples[lc] - 0.5);
     }
