@@ -1,3 +1,4 @@
+# (belongs to the warp-role experiment recorded in DESIGN.md section 8; the PTB_FILL_WARPS switch is not in the tree)
 # Sweep of the fill-role warp count of k_rr_points (flux mode) on C2 (run on the GPU box)
 b() { python bench.py --steps 50 --warmup 3 --workload $1 $3 --no-cpu --no-numba --no-counters --no-collective 2> gpurun_out/$1.err | python -c "
 import sys,json
