@@ -1164,6 +1164,67 @@ def test_supersampled_kernel_phases_cells_and_centre_crossing(pb, orc, tab):
           rng.uniform(0.0, 0.9, npv), tol=FP32_TOL, precision='fp32')
 
 
+@pytest.mark.parametrize('seed', range(8))
+def test_randomized_layouts_vs_oracle(pb, orc, tab, seed):
+    """Random data-set layouts against the oracle, flux and fused likelihood: 1-5 light curves of random lengths (odd and
+    even totals, not multiples of the 16-point cell or the 64-point block), nsamples 1-12 per light curve (both points
+    kernels: all-ones -> k_rr_points, otherwise k_rr_points_ss), random passband / epoch assignment, sorted or randomly
+    interleaved time stamps, NaN time stamps, noise-block slices that cut through cells and leave gaps, eccentric orbits,
+    an invalid vector."""
+    rng = np.random.default_rng(9000 + seed)
+    nlc = int(rng.integers(1, 6))
+    lens = rng.integers(40, 900, nlc)
+    lens[0] = 900                                    # at least one light curve longer than a period at either cadence
+    cad = rng.choice([2.0 / 1440.0, 0.0204])
+    time = np.concatenate([rng.uniform(0, 3) + j * 0.4 + np.arange(n) * cad for j, n in enumerate(lens)])
+    lcids = np.repeat(np.arange(nlc), lens)
+    nsamples = np.ones(nlc, np.int64) if seed % 4 == 0 else rng.integers(1, 13, nlc)
+    exptimes = np.where(nsamples > 1, cad, 0.0)
+    npb = int(rng.integers(1, nlc + 1))
+    nep = int(rng.integers(1, 3))
+    pbids = rng.permutation(np.arange(nlc) % npb)          # every passband / epoch index is used (the reference insists)
+    nep = min(nep, nlc)
+    epids = rng.permutation(np.arange(nlc) % nep)
+    contiguous = seed % 2 == 0
+    if not contiguous:
+        perm = rng.permutation(time.size)
+        time, lcids = time[perm], lcids[perm]
+    time[rng.integers(0, time.size, 3)] = np.nan
+    npv = 10
+    k = rng.uniform(0.05, 0.15, size=(npv, npb))
+    t0 = rng.normal(1.0, 0.01, size=(npv, 1)) + rng.normal(0, 0.002, size=(npv, nep))
+    p = rng.normal(0.9, 0.01, npv)
+    a = rng.normal(5.0, 0.4, npv)
+    b = rng.uniform(0.0, 0.9, npv)
+    e = rng.uniform(0.0, 0.2, npv)
+    w = rng.uniform(0.0, 2 * np.pi, npv)
+    i = np.arccos(np.clip(b / a * (1 + e * np.sin(w)) / (1 - e ** 2), 0.0, 1.0))
+    a[3] = 0.7                                       # invalid vector: NaN row / NaN lnL
+    ldc = rng.uniform(0.1, 0.5, size=(npv, npb, 2))
+    m = pb.RoadRunnerModelCUDA('quadratic')
+    m.set_data(time, lcids, pbids, nsamples, exptimes, epids)
+    f = np.atleast_2d(m.evaluate(k, ldc, t0, p, a, i, e, w)).copy()
+    ldp, istar = orc.evaluate_ld('quadratic', tab.mu, ldc)
+    ref = orc.rr_full(tab, time, k, t0, p, a, i, e, w, lcids.astype(np.int64), pbids.astype(np.int64), epids.astype(np.int64),
+                      nsamples.astype(np.int64), exptimes.astype(float), ldp, istar)
+    assert np.array_equal(np.isnan(f), np.isnan(ref))
+    assert np.isnan(ref[3]).all() and (np.nanmin(ref) < 0.999)
+    assert np.nanmax(np.abs(f - ref)) <= FLUX_TOL
+    # likelihood: three slices with odd boundaries and a gap, two noise blocks
+    n = time.size
+    c1, c2 = int(n * 0.3) | 1, int(n * 0.7) | 1
+    slices = np.array([[0, c1], [c1, c2], [c2 + 5, n]], np.int64)
+    nids = np.array([0, 1, 0], np.int64)
+    obs = 1 + rng.normal(0, 1e-3, n)
+    sigma = 10 ** rng.uniform(-3.2, -2.8, size=(npv, 2))
+    m.set_obs(obs, slices, nids, 2)
+    lnl = m.lnlikelihood(k, ldc, t0, p, a, i, e, w, sigma=sigma).copy()
+    refl = orc.lnlike_normal(obs, ref, sigma, slices, nids)
+    ok = np.isfinite(refl)
+    assert np.array_equal(np.isnan(lnl), np.isnan(refl)) and ok.sum() >= npv - 4
+    np.testing.assert_allclose(lnl[ok], refl[ok], rtol=LNL_RTOL)
+
+
 @pytest.mark.parametrize('law', ['uniform', 'linear', 'quadratic', 'quadratic-tri', 'nonlinear', 'general', 'square_root',
                                  'logarithmic', 'exponential', 'power-2', 'power-2-pm'])
 def test_full_flux_path_for_every_ld_law(pb, golden, law):
