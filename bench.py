@@ -488,7 +488,8 @@ def make_steps(args, c, dev, local_rank, world, dist):
 
     h2d = sum(np.asarray(getattr(c, k)).nbytes for k in ('k', 'ldc', 't0', 'p', 'a', 'i', 'e', 'w')) + (c.sigma.nbytes if lnl else 0)
     pts = c.npv * c.npt
-    return m, step_device, step_host, pts, h2d, ('k_rr_points<LNL>' if lnl else 'k_rr_points'), (None if lnl else float(esize) * pts)
+    kname = 'k_rr_points_ss' if int(np.max(c.nsamples)) > 1 else 'k_rr_points'     # supersampled data sets have their own kernel
+    return m, step_device, step_host, pts, h2d, (kname + '<LNL>' if lnl else kname), (None if lnl else float(esize) * pts)
 
 
 def _table_args(c):
