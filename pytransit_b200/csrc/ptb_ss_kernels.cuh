@@ -2,14 +2,14 @@
 // phase fold, box test, the exposure-averaged flux (model_full.py:76-99) and the optional fused chi^2.
 //
 // Same decomposition as k_rr_points (ptb_kernels.cuh): a persistent grid whose warps pull items (parameter vector x
-// chunk of the time axis) from a global counter, classify the item's 64-point blocks against the transit windows,
-// fill the untouched ones with 1.0 and fold the touched ones point by point.  What differs is where the time goes:
+// chunk of the time axis) from a global counter, classify the item's time axis against the transit windows (here in 16-point
+// cells), fill the untouched cells with 1.0 and fold the touched ones point by point.  What differs is where the time goes:
 // with ten sub-samples per point the kernel is bound by instruction issue in the per-sample arithmetic, not by the
 // flux store, so this kernel is organised around the sample loop's registers and occupancy:
 //
 //   * fold and sample evaluation alternate in long PHASES instead of block by block: the fold phase walks touched
-//     blocks until the warp's queue holds ~SS_QCAP in-box points (4 bytes each: only the point index is queued, the
-//     folded time is recomputed by the drain), the drain phase then evaluates them 32 at a time.  Each phase is a real
+//     cells until the warp's queue holds ~SS_QCAP in-box points (4 bytes each: only the point index is queued, the
+//     folded time and the light curve are recomputed / looked up by the drain), the drain phase then evaluates them 32 at a time.  Each phase is a real
 //     function (`ss_fold`, `ss_drain_phase`: __noinline__) with its own register allocation; what survives a phase
 //     boundary is warp-uniform and lives in a small shared-memory frame, so the driver loop keeps nothing alive
 //     across the calls: 80 registers, three CTAs of 256 threads per SM (the block-by-block version needed 128, with
@@ -21,7 +21,7 @@
 //     small ring buffer and a fold step takes four of them (eight lanes each, two points per lane, ONE warp-wide
 //     compaction for all 64 points); cells that straddle light curves take a separate general path;
 //   * the sample step is straight fp64 arithmetic: separation (two Horner quartics, rsqrt + one coupled Newton
-//     step: 2^-43), LD-mean node by a float->int floor conversion, lerp as one fused multiply-add on the node
+//     step: 2^-43), LD-mean node and weight by adding 1.5 * 2^52 (no conversion instructions), lerp as one fused multiply-add on the node
 //     difference; a sample on the stellar limb only drops its separation into the lane's shared-memory column;
 //   * limb samples (sqrt + 2 atan2 lens area, common.py:52-73) are numbered by a warp scan and evaluated 32 at a
 //     time by full warps, each value written back into its owner's column; every lane then adds its column in
