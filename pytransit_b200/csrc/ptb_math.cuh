@@ -328,7 +328,9 @@ __device__ __forceinline__ T sep_poly(T t, const T *cx, const T *cy) {
 
 // sqrt for the separation: the operand is a sum of squares (+0, positive, or NaN).  MUFU.RSQ64H + one coupled Newton
 // step (2^-43 relative); +0 and subnormal operands are lifted to the smallest normal number by an integer max on the
-// high word (the separation becomes 1.5e-154 instead of 0), NaN passes through.
+// high word (the separation becomes 1.5e-154 instead of 0), NaN passes through.  A sum of squares that overflows to +inf
+// (sky-plane coordinates beyond 1e154 stellar radii) gives NaN where the reference's sqrt gives +inf: not a model any
+// caller evaluates, and the one place the straight-line version departs from IEEE sqrt.
 __device__ __forceinline__ double sqrt_sep(double x) {
     const unsigned hi = max((unsigned)__double2hiint(x), 0x00100000u);
     x = __hiloint2double((int)hi, __double2loint(x));
