@@ -655,9 +655,7 @@ __device__ __forceinline__ double limb_pass(const PointsParams &P, const WarpScr
     if (lane < take) {
         const int q = first + lane, ng = P.ng;
         const T *r2 = SINGLE_LC ? row1 : ld + ws.l_row()[q];
-        T area, kap;
-        kite_area<T>(r2[ng], r2[ng + 3], ws.l_z()[q], area, kap);
-        const T v = T(1) - ws.l_ip()[q] * area * r2[ng + 2];
+        const T v = T(1) - ws.l_ip()[q] * kite_area_limb<T>(r2[ng], r2[ng + 3], ws.l_z()[q]) * r2[ng + 2];
         const int ipt = ws.l_slot()[q];
         if (LNL) {
             const int b = P.blk ? P.blk[ipt] : 0;

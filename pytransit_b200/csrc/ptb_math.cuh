@@ -184,6 +184,24 @@ __device__ __forceinline__ void kite_area(T k, T k2, T z, T &area, T &kappa0) {
     }
 }
 
+// The lens-area branch of kite_area alone, for a separation that is known to be on the limb (|1 - k| < z < 1 + k):
+// straight-line code, so that the evaluations of two samples in one lane interleave.  Same arithmetic as above.
+template <typename T>
+__device__ __forceinline__ T kite_area_limb(T k, T k2, T z) {
+    const T one = T(1), two = T(2), half = T(0.5);
+    const bool kg = k > one;
+    const T hi = kg ? k : one, lo = kg ? one : k;
+    const bool c1 = z > hi, c2 = z > lo;
+    const T x = c1 ? z : hi;
+    const T y = c1 ? hi : (c2 ? z : lo);
+    const T zz = c2 ? lo : z;
+    const T akite = half * fast_sqrt((x + (y + zz)) * (zz - (x - y)) * (zz + (x - y)) * (x + (y - zz)));
+    const T z2 = z * z;
+    T k0, k1;
+    atan2_pos2(two * akite, (k - one) * (k + one) + z2, (one - k) * (one + k) + z2, k0, k1);
+    return k1 + k2 * k0 - akite;
+}
+
 // interpolate_mean_limb_darkening_s (common.py:225-233) with inv_dg = 1/dg hoisted and the upper
 // node clamped to ng-1 (the reference reads lda[ng] for g in (1-1e-7, 1]; that term multiplies a
 // lens area < 1e-10).  `row` may point to shared or global memory.

@@ -361,25 +361,29 @@ __device__ __forceinline__ double ss_drain(const PointsParams &P, const SsTables
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         __syncwarp();
-        for (int q0 = 0; q0 < total; q0 += 32) {
-            const int q = q0 + lane;
-            int o = 0;   // owner of sample q: the number of lanes whose inclusive count is <= q
+        // owner (lane) and row (position in the owner's column) of limb sample q: the owner is the number of lanes whose
+        // inclusive count is <= q
+        auto locate = [&](int q, int &o, int &r, int &ro) {
+            o = 0;
 #pragma unroll
             for (int st = 16; st > 0; st >>= 1) {
                 const int v = __shfl_sync(0xffffffffu, incl, o + st - 1);
                 if (v <= q) o += st;
             }
             o = min(o, 31);
-            const int r = q - (__shfl_sync(0xffffffffu, incl, o) - __shfl_sync(0xffffffffu, cnt, o));
-            const int ro = SINGLE_LC ? 0 : __shfl_sync(0xffffffffu, rowoff, o);
+            r = q - (__shfl_sync(0xffffffffu, incl, o) - __shfl_sync(0xffffffffu, cnt, o));
+            ro = SINGLE_LC ? 0 : __shfl_sync(0xffffffffu, rowoff, o);
+        };
+        for (int q0 = 0; q0 < total; q0 += 32) {
+            const int q = q0 + lane;
+            int o, r, ro;
+            locate(q, o, r, ro);
             if (q < total) {
                 const T *r2 = SINGLE_LC ? row : ld + ro;
                 T *slot = colz + r * PT_COLS + o;
                 const T z = *slot;
                 const T ip = ld_lerp(z * (r2[ng + 1] * inv_dg), r2, ng);
-                T area, kap;
-                kite_area<T>(r2[ng], r2[ng + 3], z, area, kap);
-                *slot = one - ip * area * r2[ng + 2];
+                *slot = one - ip * kite_area_limb<T>(r2[ng], r2[ng + 3], z) * r2[ng + 2];
             }
         }
         __syncwarp();
