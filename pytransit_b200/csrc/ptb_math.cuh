@@ -38,6 +38,21 @@ __device__ __forceinline__ double fast_sqrt(double x) {
 }
 __device__ __forceinline__ float fast_sqrt(float x) { return sqrtf(x); }
 
+// sqrt for the separation: the operand is a sum of squares (+0, positive, or NaN).  MUFU.RSQ64H + one coupled Newton
+// step (2^-43 relative); +0 and subnormal operands are lifted to the smallest normal number by an integer max on the
+// high word (the separation becomes 1.5e-154 instead of 0), NaN passes through.  A sum of squares that overflows to +inf
+// (sky-plane coordinates beyond 1e154 stellar radii) gives NaN where the reference's sqrt gives +inf: not a model any
+// caller evaluates, and the one place the straight-line version departs from IEEE sqrt.
+__device__ __forceinline__ double sqrt_sep(double x) {
+    const unsigned hi = max((unsigned)__double2hiint(x), 0x00100000u);
+    x = __hiloint2double((int)hi, __double2loint(x));
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double g = x * r, h = 0.5 * r;
+    return fma(g, fma(-h, g, 0.5), g);
+}
+__device__ __forceinline__ float sqrt_sep(float x) { return sqrtf(x); }
+
 // n / d for finite, normal d (not 0)
 __device__ __forceinline__ double fast_div(double n, double d) {
     double r;
@@ -195,7 +210,9 @@ __device__ __forceinline__ T kite_area_limb(T k, T k2, T z) {
     const T x = c1 ? z : hi;
     const T y = c1 ? hi : (c2 ? z : lo);
     const T zz = c2 ? lo : z;
-    const T akite = half * fast_sqrt((x + (y + zz)) * (zz - (x - y)) * (zz + (x - y)) * (x + (y - zz)));
+    // (2^-43 is ample for an area that enters the flux with a weight of ~0.1; a product that rounding made negative
+    //  gives NaN, as the reference's sqrt does)
+    const T akite = half * sqrt_sep((x + (y + zz)) * (zz - (x - y)) * (zz + (x - y)) * (x + (y - zz)));
     const T z2 = z * z;
     T k0, k1;
     atan2_pos2(two * akite, (k - one) * (k + one) + z2, (one - k) * (one + k) + z2, k0, k1);
@@ -344,20 +361,6 @@ __device__ __forceinline__ T sep_poly(T t, const T *cx, const T *cy) {
     return fast_sqrt(fma(px, px, py * py));
 }
 
-// sqrt for the separation: the operand is a sum of squares (+0, positive, or NaN).  MUFU.RSQ64H + one coupled Newton
-// step (2^-43 relative); +0 and subnormal operands are lifted to the smallest normal number by an integer max on the
-// high word (the separation becomes 1.5e-154 instead of 0), NaN passes through.  A sum of squares that overflows to +inf
-// (sky-plane coordinates beyond 1e154 stellar radii) gives NaN where the reference's sqrt gives +inf: not a model any
-// caller evaluates, and the one place the straight-line version departs from IEEE sqrt.
-__device__ __forceinline__ double sqrt_sep(double x) {
-    const unsigned hi = max((unsigned)__double2hiint(x), 0x00100000u);
-    x = __hiloint2double((int)hi, __double2loint(x));
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    const double g = x * r, h = 0.5 * r;
-    return fma(g, fma(-h, g, 0.5), g);
-}
-__device__ __forceinline__ float sqrt_sep(float x) { return sqrtf(x); }
 
 __device__ __forceinline__ int floor_to_int(double x) { return __double2int_rd(x); }   // saturating, NaN -> 0
 __device__ __forceinline__ int floor_to_int(float x) { return __float2int_rd(x); }

@@ -112,6 +112,10 @@ struct SsTables {
                        P.ssc, P.recstride);                                                                                    \
     volatile int *fr = ws.frame()
 
+// sum / ns by the straight-line division (<= 1 ulp from the IEEE quotient; CUDA's '/' carries a slow-path call)
+__device__ __forceinline__ double ss_mean(double sum, int ns) { return fast_div(sum, (double)ns); }
+__device__ __forceinline__ float ss_mean(float sum, int ns) { return sum / (float)ns; }
+
 // ---- fold phase: exact per-point fold + box test over touched cells (model_full.py:88-91) until the queue holds
 // more than SS_QCAP - 64 in-box points or the item's cells are exhausted.  The fluxes of the cells' points are set to
 // 1.0 here (the drain overwrites the in-box ones); in likelihood mode the out-of-box points add their chi^2 here.
@@ -392,7 +396,7 @@ __device__ __forceinline__ double ss_drain(const PointsParams &P, const SsTables
     }
     double chi = 0.0;
     if (valid) {
-        const T f = sum / ns;
+        const T f = ss_mean(sum, ns);   // flux / nsamples (model_full.py:99)
         if (LNL) {
             const int b = P.blk ? P.blk[ipt] : 0;
             if (b >= 0) {   // the point's (obs - 1)^2 is already in the cell baseline: swap it for (obs - model)^2
