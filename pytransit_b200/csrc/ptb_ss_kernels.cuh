@@ -391,7 +391,10 @@ __device__ __forceinline__ double ss_drain(const PointsParams &P, const SsTables
             }
         }
         __syncwarp();
-        for (int r = 0; r < cnt; ++r) sum += colz[r * PT_COLS + lane];   // this lane's limb values, in exposure order
+        // this lane's limb values, in exposure order (fixed trip count, predicated: the per-lane counts differ)
+#pragma unroll
+        for (int r = 0; r < PT_SSC_MAX; ++r)
+            if (r < cnt) sum += colz[r * PT_COLS + lane];
         __syncwarp();
     }
     double chi = 0.0;
